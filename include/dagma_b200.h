@@ -1,0 +1,120 @@
+/*
+ * dagma_b200.h -- C ABI of libdagma_b200.so: the B200 (sm_100a) implementation of
+ * DAGMA's inner-optimisation hot path.
+ *
+ * The reference (fbleile/midagma) has no FFI: its boundary is the Python method
+ * surface of DagmaLinear / DagmaMLP / DagmaNonlinear / notreks.  Each
+ * entry point below names the reference code it replaces (paths relative to the
+ * reference root, file:line).  All matrices are FP64, row-major, caller-owned.
+ * Pointers named *_dev are device pointers; everything else is host data.
+ * Every function returns 0 on success, <0 on API misuse / CUDA error (the text is
+ * available from dagma_last_error()); numerical failure is reported through
+ * per-problem status words, never through the return code -- mirroring the
+ * reference, where leaving the M-matrix domain is a return flag, not an exception
+ * (src/dagma/linear.py:230-233).  Nothing here has a CPU fallback.
+ */
+#ifndef DAGMA_B200_H
+#define DAGMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dagma_stream_t;            /* a cudaStream_t (0 = default stream) */
+
+#define DAGMA_SMALL_MAX_D   64           /* fused on-chip fit path: d <= 64      */
+#define DAGMA_ONCHIP_INV_MAX_D 128       /* on-chip logdet+inverse: d <= 128     */
+#define DAGMA_MAX_STAGES    16
+
+/* per-problem status bits written by the fit / minimize kernels */
+#define DAGMA_ST_OK            0
+#define DAGMA_ST_OUT_OF_DOMAIN 1         /* minimize returned (W, False)  linear.py:231-233 */
+#define DAGMA_ST_LR_UNDERFLOW  2         /* lr <= 1e-16 exit              linear.py:237-238 */
+#define DAGMA_ST_RETRY_LIMIT   4         /* more than 64 stage retries (reference would spin) */
+
+/* ---- library / device ---------------------------------------------------------- */
+int         dagma_version(void);
+const char* dagma_last_error(void);
+/* 0 iff the current device is compute capability 10.x; anything else is an error
+ * (there is no other code path).  Optionally returns the SM count. */
+int         dagma_device_check(int* sm_count);
+
+/* ---- (i) fused slogdet + inverse ------------------------------------------------
+ * Replaces: DagmaLinear._h            src/dagma/linear.py:113-115  (square_input=1)
+ *           DagmaMLP.h_func           src/dagma/nonlinear.py:82-85 (A built by caller)
+ *           logdet_acyc_value_gradA   src/notreks/notreks.py:263-274 (square_input=0)
+ * For each problem b:  M = s*I - (square_input ? A*A (Hadamard) : A);
+ *   logabsdet[b] = log|det M|,  h[b] = -logabsdet + d*log(s),
+ *   minv_dev  (optional) = M^{-1},
+ *   grad_dev  (optional) = square_input ? 2*A o M^{-T} : M^{-T},
+ *   min_entry[b] = min(M^{-1}),  info[b] = 0 ok | 1 non-positive pivot (not an M-matrix)
+ *                                          | 2 negative entry: min(M^{-1}) + 1e-16 < 0.
+ * d <= 128 runs one persistent CTA per problem (Gauss-Jordan in registers);
+ * larger d runs the blocked multi-CTA path (batch is then looped).               */
+int dagma_logdet_inv_f64(dagma_stream_t stream, int batch, int d, double s,
+                         const double* a_dev, int lda, int square_input,
+                         double* logabsdet_dev, double* h_dev,
+                         double* minv_dev, double* grad_dev, int ldo,
+                         double* min_entry_dev, int* info_dev);
+
+/* ---- (iii) the inner loop / whole path-following fit, small d, batched -----------
+ * Replaces: DagmaLinear.minimize  src/dagma/linear.py:165-333 (l2 loss, trek_reg None)
+ *           DagmaLinear.fit       src/dagma/linear.py:441-457 (the stage loop + retries)
+ * One persistent CTA per problem runs `n_stages` calls of minimize back to back
+ * without leaving the SM: W, the Adam moments, cov and M^{-1} stay in registers /
+ * shared memory.  Problems are pulled from an atomic work queue.                 */
+typedef struct dagma_small_fit_args {
+    int32_t batch;            /* number of independent problems                          */
+    int32_t d;                /* nodes, 1..DAGMA_SMALL_MAX_D                              */
+    int32_t n_stages;         /* T (fit) or 1 (minimize)                                  */
+    int32_t checkpoint;       /* convergence-check interval          linear.py:279        */
+    int32_t retry_on_fail;    /* 1: fit semantics (lr/2, s+0.1, redo) linear.py:446-451
+                                 0: minimize semantics (stop, status OUT_OF_DOMAIN)       */
+    int32_t ckpt_log_cap;     /* rows available per problem in ckpt_log_dev (0 = none)    */
+    double  lr;               /* initial Adam step of every stage    linear.py:444        */
+    double  tol;              /* relative objective tolerance        linear.py:328        */
+    double  beta1, beta2;     /* Adam                                linear.py:158-162    */
+    double  mu[DAGMA_MAX_STAGES];      /* mu_t (already multiplied out, Q7)               */
+    double  s[DAGMA_MAX_STAGES];       /* s_t                                             */
+    int32_t iters[DAGMA_MAX_STAGES];   /* max inner iterations of stage t                 */
+    const double*  cov_dev;       /* [batch][d][d]  X^T X / n          linear.py:428      */
+    const double*  lambda1_dev;   /* [batch]                                              */
+    double*        w_dev;         /* [batch][d][d]  in: start point, out: raw W           */
+    const uint8_t* mask_exc_dev;  /* [d][d] 1 = excluded edge, shared by the batch, or 0  */
+    const uint8_t* mask_inc_dev;  /* [d][d] 1 = included edge, shared by the batch, or 0  */
+    /* outputs */
+    int32_t* status_dev;          /* [batch] DAGMA_ST_* bits                              */
+    double*  stage_stats_dev;     /* [batch][n_stages][8]: iters done, final lr, final s,
+                                     obj, score, h, retries, back-tracks                  */
+    double*  final_dev;           /* [batch][2]: h(W, s=1) and score(W)  linear.py:456-457 */
+    double*  ckpt_log_dev;        /* [batch][cap][6]: stage, iter, obj, score, h, lr       */
+    int32_t* ckpt_count_dev;      /* [batch]                                               */
+    uint32_t* work_counter_dev;   /* one zero-initialised uint32 (work queue head)         */
+} dagma_small_fit_args;
+
+int dagma_linear_fit_small_f64(dagma_stream_t stream, const dagma_small_fit_args* args);
+/* launch geometry chosen for (d): CTAs, threads, dynamic shared memory bytes */
+int dagma_linear_fit_small_geometry(int d, int batch, int* ctas, int* threads, size_t* smem_bytes);
+
+/* ---- host-buffer convenience: the call a reference user makes --------------------
+ * Replaces: DagmaLinear.fit for a batch of problems given host covariances; does
+ * H2D, the fit and D2H on `stream`, then synchronises.  w_host in/out [batch][d][d].  */
+int dagma_linear_fit_small_host_f64(dagma_stream_t stream, const dagma_small_fit_args* args_host_ptrs);
+
+/* ---- data staging in front of the path ---------------------------------------------
+ * Replaces: X -= X.mean(0) (in place) and cov = X^T X / n   src/dagma/linear.py:410-411, 428
+ * x_dev [batch][n][d] (centred in place when center != 0), cov_dev [batch][d][d].     */
+int dagma_center_cov_f64(dagma_stream_t stream, int batch, int n, int d, double* x_dev,
+                         int center, double* cov_dev);
+
+/* ---- FP64 pipe yardsticks used by bench.py for the roofline denominator ---------- */
+int dagma_bench_fp64_fma(dagma_stream_t stream, int ctas, int threads, int iters, double* sink_dev);
+int dagma_bench_fp64_dmma(dagma_stream_t stream, int ctas, int threads, int iters, double* sink_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAGMA_B200_H */

@@ -1,0 +1,402 @@
+"""Drop-in ``DagmaLinear`` on the B200 kernels (reference: src/dagma/linear.py).
+
+Same constructor, methods, defaults, return values and side effects as the
+reference class (numpy in / numpy out, ``minimize`` mutates and returns its ``W``,
+``fit`` centres the caller's ``X`` in place for the l2 loss, failure is a return
+flag).  All arithmetic is done by libdagma_b200.so:
+
+* d <= 64, l2 loss: one persistent CTA runs whole ``minimize`` stages -- and for
+  ``fit`` the whole path-following loop including retries -- in one kernel launch
+  (``dagma_linear_fit_small_f64``).
+* larger d and the logistic loss: the multi-CTA path in ``_large.py`` (blocked
+  inverse + score GEMMs + fused Adam), one CUDA-graph replay per inner iteration.
+
+``fit_batch`` / ``minimize_batch`` are the batched entry points (independent
+problems: seeds, lambda1 grids, bootstrap replicates) that the reference can only
+express as a Python loop over ``DagmaLinear.fit``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+import typing
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["DagmaLinear", "fit_batch", "minimize_batch"]
+
+
+def _mu_schedule(mu_init: float, mu_factor: float, T: int) -> list:
+    mus, mu = [], mu_init
+    for _ in range(int(T)):
+        mus.append(mu)
+        mu *= mu_factor                     # repeated multiplication (linear.py:453, Q7)
+    return mus
+
+
+def _edge_mask(edges, d: int, device) -> typing.Optional[torch.Tensor]:
+    if edges is None:
+        return None
+    m = np.zeros((d, d), dtype=np.uint8)
+    r, c = zip(*edges)
+    m[list(r), list(c)] = 1
+    return torch.from_numpy(m).to(device)
+
+
+class SmallFitResult(typing.NamedTuple):
+    W: torch.Tensor             # [batch, d, d] raw (un-thresholded) result, device
+    status: torch.Tensor        # [batch] int32
+    stage_stats: torch.Tensor   # [batch, n_stages, 8]
+    final: torch.Tensor         # [batch, 2] (h(W, s=1), score(W))
+    ckpt_log: typing.Optional[torch.Tensor]
+    ckpt_count: typing.Optional[torch.Tensor]
+
+
+def _run_small(cov: torch.Tensor, W: torch.Tensor, lambda1: torch.Tensor, mus, ss, iters, *, lr, tol,
+               beta1, beta2, checkpoint, retry, mask_exc=None, mask_inc=None, ckpt_log_cap=0,
+               want_final=True) -> SmallFitResult:
+    """Launch ``dagma_linear_fit_small_f64`` on device tensors (W is updated in place)."""
+    _lib.require_device()
+    lib = _lib.load()
+    batch, d, _ = cov.shape
+    T = len(mus)
+    assert T <= _lib.MAX_STAGES, f"at most {_lib.MAX_STAGES} stages per launch"
+    assert cov.is_cuda and W.is_cuda and cov.dtype == torch.float64 and W.dtype == torch.float64
+    assert cov.is_contiguous() and W.is_contiguous() and lambda1.is_contiguous()
+    dev = cov.device
+    a = _lib.SmallFitArgs()
+    a.batch, a.d, a.n_stages, a.checkpoint = batch, d, T, int(checkpoint)
+    a.retry_on_fail, a.ckpt_log_cap = int(bool(retry)), int(ckpt_log_cap)
+    a.lr, a.tol, a.beta1, a.beta2 = float(lr), float(tol), float(beta1), float(beta2)
+    for t in range(T):
+        a.mu[t], a.s[t], a.iters[t] = float(mus[t]), float(ss[t]), int(iters[t])
+    status = torch.zeros(batch, dtype=torch.int32, device=dev)
+    stats = torch.zeros(batch, max(T, 1), 8, dtype=torch.float64, device=dev)
+    final = torch.zeros(batch, 2, dtype=torch.float64, device=dev)
+    counter = torch.zeros(16, dtype=torch.int32, device=dev)
+    log = cnt = None
+    if ckpt_log_cap > 0:
+        log = torch.zeros(batch, ckpt_log_cap, 6, dtype=torch.float64, device=dev)
+        cnt = torch.zeros(batch, dtype=torch.int32, device=dev)
+    a.cov, a.lambda1, a.w = cov.data_ptr(), lambda1.data_ptr(), W.data_ptr()
+    a.mask_exc = mask_exc.data_ptr() if mask_exc is not None else None
+    a.mask_inc = mask_inc.data_ptr() if mask_inc is not None else None
+    a.status, a.stage_stats = status.data_ptr(), stats.data_ptr()
+    a.final = final.data_ptr() if want_final else None
+    a.ckpt_log = log.data_ptr() if log is not None else None
+    a.ckpt_count = cnt.data_ptr() if cnt is not None else None
+    a.work_counter = counter.data_ptr()
+    _lib.check(lib.dagma_linear_fit_small_f64(_lib.stream_ptr(), C.byref(a)), "dagma_linear_fit_small_f64")
+    return SmallFitResult(W, status, stats, final, log, cnt)
+
+
+def center_cov(X: torch.Tensor, center: bool) -> torch.Tensor:
+    """cov = X^T X / n on device ([batch, n, d] -> [batch, d, d]); X centred in place if asked."""
+    _lib.require_device()
+    assert X.is_cuda and X.dtype == torch.float64 and X.is_contiguous() and X.dim() == 3
+    batch, n, d = X.shape
+    cov = torch.empty(batch, d, d, dtype=torch.float64, device=X.device)
+    _lib.check(_lib.load().dagma_center_cov_f64(_lib.stream_ptr(), batch, n, d, X.data_ptr(), int(center),
+                                                cov.data_ptr()), "dagma_center_cov_f64")
+    return cov
+
+
+def logdet_inv(A: torch.Tensor, s: float = 1.0, square_input: bool = True, want_inv=False, want_grad=True):
+    """Fused slogdet + inverse of ``sI - A∘A`` (or ``sI - A``) for a batch ``[b, d, d]`` on device.
+
+    Returns dict(logabsdet, h, minv, grad, min_entry, info) of device tensors."""
+    _lib.require_device()
+    assert A.is_cuda and A.dtype == torch.float64 and A.dim() == 3 and A.is_contiguous()
+    b, d, _ = A.shape
+    dev = A.device
+    out = {
+        "logabsdet": torch.empty(b, dtype=torch.float64, device=dev),
+        "h": torch.empty(b, dtype=torch.float64, device=dev),
+        "minv": torch.empty(b, d, d, dtype=torch.float64, device=dev) if want_inv else None,
+        "grad": torch.empty(b, d, d, dtype=torch.float64, device=dev) if want_grad else None,
+        "min_entry": torch.empty(b, dtype=torch.float64, device=dev),
+        "info": torch.empty(b, dtype=torch.int32, device=dev),
+    }
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    _lib.check(_lib.load().dagma_logdet_inv_f64(
+        _lib.stream_ptr(), b, d, float(s), A.data_ptr(), d, int(bool(square_input)),
+        ptr(out["logabsdet"]), ptr(out["h"]), ptr(out["minv"]), ptr(out["grad"]), d,
+        ptr(out["min_entry"]), ptr(out["info"])), "dagma_logdet_inv_f64")
+    return out
+
+
+# =============================================================================
+# batched entry points
+# =============================================================================
+def _as_dev(x, device, dtype=torch.float64) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device)
+
+
+def minimize_batch(W, cov, lambda1, mu, max_iter, s, lr, *, tol=1e-6, beta_1=0.99, beta_2=0.999,
+                   checkpoint=1000, device=None):
+    """One ``DagmaLinear.minimize`` call (linear.py:165-333, l2 loss) for a batch of
+    independent problems.  ``W``/``cov``: [batch, d, d] numpy (pinned or not) or torch
+    tensors on host or device; results come back in the same kind of container.
+    Returns ``(W, success[batch], stats)``."""
+    device = torch.device(device or "cuda")
+    host_in = not (isinstance(W, torch.Tensor) and W.is_cuda)
+    Wd = _as_dev(W, device)
+    if Wd.data_ptr() == (W.data_ptr() if isinstance(W, torch.Tensor) else 0) and not host_in:
+        pass   # in place on the caller's device tensor, like the reference's in-place W
+    covd = _as_dev(cov, device)
+    batch, d, _ = covd.shape
+    assert d <= _lib.SMALL_MAX_D, "minimize_batch uses the on-chip path (d <= 64)"
+    lam = _as_dev(np.broadcast_to(np.asarray(lambda1, dtype=np.float64), (batch,)), device)
+    res = _run_small(covd, Wd, lam, [mu], [s], [max_iter], lr=lr, tol=tol, beta1=beta_1, beta2=beta_2,
+                     checkpoint=checkpoint, retry=False, want_final=False)
+    ok = (res.status & _lib.ST_OUT_OF_DOMAIN) == 0
+    if host_in:
+        W_out = res.W.cpu()
+        if isinstance(W, np.ndarray):
+            W[...] = W_out.numpy()
+            W_out = W
+        return W_out, ok.cpu().numpy(), res.stage_stats.cpu().numpy()
+    return res.W, ok, res.stage_stats
+
+
+def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1.0, mu_factor=0.1,
+              s=(1.0, .9, .8, .7, .6), warm_iter=3e4, max_iter=6e4, lr=0.0003, checkpoint=1000,
+              beta_1=0.99, beta_2=0.999, tol=1e-6, device=None, return_info=False):
+    """``DagmaLinear('l2').fit`` (linear.py:335-462) for a batch of independent problems.
+
+    ``X``: [batch, n, d] (centred on device, the caller's array is not modified) or
+    ``cov``: [batch, d, d].  ``lambda1``: scalar or [batch].  Each problem follows the
+    reference schedule independently (own convergence checks, retries, back-tracking);
+    problems are pulled from a device-side work queue by persistent CTAs.
+    Returns thresholded ``W_est`` [batch, d, d] as numpy (+ info dict)."""
+    device = torch.device(device or "cuda")
+    if cov is None:
+        Xd = _as_dev(X, device)
+        if Xd.data_ptr() == (X.data_ptr() if isinstance(X, torch.Tensor) else 0):
+            Xd = Xd.clone()
+        covd = center_cov(Xd, center=True)
+        del Xd
+    else:
+        covd = _as_dev(cov, device)
+    batch, d, _ = covd.shape
+    assert d <= _lib.SMALL_MAX_D, "fit_batch uses the on-chip path (d <= 64)"
+    lam = _as_dev(np.broadcast_to(np.asarray(lambda1, dtype=np.float64), (batch,)), device)
+    T = int(T)
+    ss = list(s) if isinstance(s, (list, tuple)) else T * [s]
+    if len(ss) < T:
+        ss = ss + (T - len(ss)) * [ss[-1]]
+    mus = _mu_schedule(mu_init, mu_factor, T)
+    iters = [int(max_iter) if i == T - 1 else int(warm_iter) for i in range(T)]
+    Wd = torch.zeros(batch, d, d, dtype=torch.float64, device=device)
+    res = _run_small(covd, Wd, lam, mus, ss[:T], iters, lr=lr, tol=tol, beta1=beta_1, beta2=beta_2,
+                     checkpoint=checkpoint, retry=True)
+    W_raw = res.W.cpu().numpy()
+    W_est = W_raw.copy()
+    W_est[np.abs(W_est) < w_threshold] = 0
+    if not return_info:
+        return W_est
+    stats = res.stage_stats.cpu().numpy()
+    fin = res.final.cpu().numpy()
+    info = {"W_raw": W_raw, "status": res.status.cpu().numpy(), "stage_iters": stats[:, :, 0].astype(np.int64),
+            "stage_stats": stats, "h_final": fin[:, 0], "score_final": fin[:, 1],
+            "total_iters": int(stats[:, :, 0].sum())}
+    return W_est, info
+
+
+# =============================================================================
+# the drop-in class
+# =============================================================================
+class DagmaLinear:
+    """DAGMA for linear SEMs on B200 (same surface as the reference class, linear.py:20)."""
+
+    def __init__(self, loss_type: str, verbose: bool = False, dtype: type = np.float64, *,
+                 trek_reg=None, logger=None, log_cfg=None) -> None:
+        losses = ['l2', 'logistic']
+        assert loss_type in losses, f"loss_type should be one of {losses}"     # linear.py:52-53
+        self.loss_type = loss_type
+        self.dtype = dtype
+        self.vprint = print if verbose else lambda *a, **k: None
+        if trek_reg is not None and getattr(trek_reg, "enabled", lambda: False)() \
+                and getattr(trek_reg, "mode", "off") == "opt":
+            raise NotImplementedError(
+                "trek regularisers in mode='opt' are outside the B200 hot path (SURVEY.md 8f3); "
+                "only the no-regulariser path of DagmaLinear is accelerated")
+        self.trek_reg = trek_reg
+        self._torch_dtype = torch.double
+        self._device = torch.device("cuda")
+        self._logger, self._log_cfg = logger, log_cfg
+        self._large = None
+        self.checkpoint_log = []            # rows (stage, iter, obj, score, h, lr) of the last calls
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self, x) -> torch.Tensor:
+        return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(self._device)
+
+    def _small_ok(self) -> bool:
+        return self.loss_type == 'l2' and self.d <= _lib.SMALL_MAX_D
+
+    def _large_engine(self):
+        from ._large import LargeLinearEngine
+        if self._large is None or self._large.stale(self):
+            self._large = LargeLinearEngine(self)
+        return self._large
+
+    # ------------------------------------------------------------------ _score (linear.py:70-94)
+    def _score(self, W: np.ndarray) -> typing.Tuple[float, np.ndarray]:
+        loss, G = self._large_engine().score(self._dev(W))
+        return loss, G.cpu().numpy()
+
+    # ------------------------------------------------------------------ _h (linear.py:97-116)
+    def _h(self, W: np.ndarray, s: float = 1.0) -> typing.Tuple[float, np.ndarray]:
+        out = logdet_inv(self._dev(W)[None], s=s, square_input=True, want_inv=False, want_grad=True)
+        return float(out["h"].item()), out["grad"][0].cpu().numpy()
+
+    # ------------------------------------------------------------------ _func (linear.py:118-135)
+    def _func(self, W: np.ndarray, mu: float, s: float = 1.0):
+        score, _ = self._score(W)
+        h, _ = self._h(W, s)
+        obj = mu * (score + self.lambda1 * np.abs(W).sum()) + h
+        return obj, score, h, 0.0
+
+    # ------------------------------------------------------------------ _adam_update (linear.py:138-163)
+    def _adam_update(self, grad: np.ndarray, iter: int, beta_1: float, beta_2: float) -> np.ndarray:
+        return self._large_engine().adam_direction(grad, iter, beta_1, beta_2)
+
+    # ------------------------------------------------------------------ minimize (linear.py:165-333)
+    def minimize(self, W: np.ndarray, mu: float, max_iter: int, s: float, lr: float, tol: float = 1e-6,
+                 beta_1: float = 0.99, beta_2: float = 0.999, pbar=None) -> typing.Tuple[np.ndarray, bool]:
+        self.vprint(f'\n\nMinimize with -- mu:{mu} -- lr: {lr} -- s: {s} -- l1: {self.lambda1} for {max_iter} max iterations')
+        if self._small_ok():
+            Wd = self._dev(W)[None].contiguous()
+            res = _run_small(self._cov_dev[None], Wd, self._lam_dev, [mu], [s], [int(max_iter)], lr=lr, tol=tol,
+                             beta1=beta_1, beta2=beta_2, checkpoint=self.checkpoint, retry=False,
+                             mask_exc=self._mask_exc, mask_inc=self._mask_inc,
+                             ckpt_log_cap=int(max_iter) // max(int(self.checkpoint), 1) + 2, want_final=False)
+            W[...] = res.W[0].cpu().numpy()
+            status = int(res.status.item())
+            iters_done = int(res.stage_stats[0, 0, 0].item())
+            self._record_log(res)
+        else:
+            status, iters_done = self._large_engine().minimize(W, mu, int(max_iter), s, lr, tol, beta_1, beta_2)
+        self.last_iters = iters_done
+        success = (status & _lib.ST_OUT_OF_DOMAIN) == 0
+        if not success:
+            self.vprint(f'W went out of domain for s={s} at iteration {iters_done + 1}')
+        if pbar is not None:
+            pbar.update(int(max_iter))
+        return W, success
+
+    def _record_log(self, res: SmallFitResult) -> None:
+        if res.ckpt_log is None:
+            return
+        n = int(res.ckpt_count[0].item())
+        rows = res.ckpt_log[0, :n].cpu().numpy()
+        self.checkpoint_log.extend(map(tuple, rows))
+        for st, it, obj, score, h, lr in rows:
+            self.vprint(f'\nInner iteration {int(it)}\n\th(W_est): {h:.4e}\n\tscore(W_est): {score:.4e}\n\tobj: {obj:.4e}')
+
+    # ------------------------------------------------------------------ fit (linear.py:335-462)
+    def fit(self, X: np.ndarray, lambda1: float = 0.03, w_threshold: float = 0.3, T: int = 5,
+            mu_init: float = 1.0, mu_factor: float = 0.1,
+            s: typing.Union[typing.List[float], float] = [1.0, .9, .8, .7, .6],
+            warm_iter: int = 3e4, max_iter: int = 6e4, lr: float = 0.0003, checkpoint: int = 1000,
+            beta_1: float = 0.99, beta_2: float = 0.999,
+            exclude_edges: typing.Optional[typing.List[typing.Tuple[int, int]]] = None,
+            include_edges: typing.Optional[typing.List[typing.Tuple[int, int]]] = None) -> np.ndarray:
+        _lib.require_device()
+        t0 = time.time()
+        self.X, self.lambda1, self.checkpoint = X, lambda1, checkpoint
+        self.n, self.d = X.shape
+        self.Id = np.eye(self.d).astype(self.dtype)
+        self.checkpoint_log = []
+
+        # centring + covariance on device; the centred X is copied back into the caller's
+        # array to keep the reference's in-place side effect (linear.py:410-411, Q8)
+        Xd = self._dev(X)[None].contiguous()
+        cov = center_cov(Xd, center=(self.loss_type == 'l2'))
+        if self.loss_type == 'l2':
+            self.X[...] = Xd[0].cpu().numpy()
+        self._X_dev = Xd[0]
+        self._cov_dev = cov[0]
+        self.cov = cov[0].cpu().numpy()
+
+        self.exc_r, self.exc_c = None, None
+        self.inc_r, self.inc_c = None, None
+        if exclude_edges is not None:
+            if type(exclude_edges) is tuple and type(exclude_edges[0]) is tuple and \
+                    np.all(np.array([len(e) for e in exclude_edges]) == 2):
+                self.exc_r, self.exc_c = zip(*exclude_edges)
+            else:
+                ValueError("blacklist should be a tuple of edges, e.g., ((1,2), (2,3))")   # not raised (Q5)
+        if include_edges is not None:
+            if type(include_edges) is tuple and type(include_edges[0]) is tuple and \
+                    np.all(np.array([len(e) for e in include_edges]) == 2):
+                self.inc_r, self.inc_c = zip(*include_edges)
+            else:
+                ValueError("whitelist should be a tuple of edges, e.g., ((1,2), (2,3))")
+        self._mask_exc = _edge_mask(list(zip(self.exc_r, self.exc_c)) if self.exc_c is not None else None,
+                                    self.d, self._device)
+        self._mask_inc = _edge_mask(list(zip(self.inc_r, self.inc_c)) if self.inc_c is not None else None,
+                                    self.d, self._device)
+        self._lam_dev = torch.tensor([float(lambda1)], dtype=torch.float64, device=self._device)
+
+        self.W_est = np.zeros((self.d, self.d)).astype(self.dtype)
+        if type(s) == list:
+            if len(s) < T:
+                self.vprint(f"Length of s is {len(s)}, using last value in s for iteration t >= {len(s)}")
+                s = s + (T - len(s)) * [s[-1]]
+        elif type(s) in [int, float]:
+            s = T * [s]
+        else:
+            ValueError("s should be a list, int, or float.")
+        T = int(T)
+        mus = _mu_schedule(mu_init, mu_factor, T)
+        iters = [int(max_iter) if i == T - 1 else int(warm_iter) for i in range(T)]
+
+        if self._small_ok():
+            # the whole path-following loop (stages, retries, back-tracking) in one launch
+            Wd = torch.zeros(1, self.d, self.d, dtype=torch.float64, device=self._device)
+            cap = sum(it // max(int(checkpoint), 1) + 2 for it in iters)
+            res = _run_small(self._cov_dev[None], Wd, self._lam_dev, mus, s[:T], iters, lr=lr, tol=1e-6,
+                             beta1=beta_1, beta2=beta_2, checkpoint=checkpoint, retry=True,
+                             mask_exc=self._mask_exc, mask_inc=self._mask_inc, ckpt_log_cap=min(cap, 4096))
+            stats = res.stage_stats[0].cpu().numpy()
+            for i in range(T):
+                if stats[i, 6] > 0:
+                    s[i] = float(stats[i, 2])           # s[i] += 0.1 per retry mutates the list (Q9)
+            self.stage_iters = [int(x) for x in stats[:, 0]]
+            self.stage_stats = stats
+            self.status = int(res.status.item())
+            self._record_log(res)
+            self.W_est = res.W[0].cpu().numpy().astype(self.dtype)
+            fin = res.final[0].cpu().numpy()
+            self.h_final, self.score_final = float(fin[0]), float(fin[1])
+        else:
+            eng = self._large_engine()
+            self.stage_iters = []
+            mu = mu_init
+            for i in range(T):
+                self.vprint(f'\nIteration -- {i+1}:')
+                lr_adam, success = lr, False
+                while success is False:
+                    W_temp, success = self.minimize(self.W_est.copy(), mu, iters[i], s[i], lr=lr_adam,
+                                                    beta_1=beta_1, beta_2=beta_2)
+                    if success is False:
+                        self.vprint('Retrying with larger s')
+                        lr_adam *= 0.5
+                        s[i] += 0.1
+                self.stage_iters.append(self.last_iters)
+                self.W_est = W_temp
+                mu *= mu_factor
+            self.h_final, _ = self._h(self.W_est)
+            self.score_final, _ = self._score(self.W_est)
+            del eng
+        self.W_raw = self.W_est.copy()
+        self.W_est[np.abs(self.W_est) < w_threshold] = 0
+        self.fit_seconds = time.time() - t0
+        return self.W_est
