@@ -23,21 +23,18 @@
 
 namespace dagma {
 
-template <int R>
-struct SmallSmem {
-    using T = Tile<R>;
-    static constexpr int DP = T::DP;
-    // doubles
+template <class C>
+struct FitSmem {
+    static constexpr int DP = C::DP;
+    static constexpr int XLD = DP + 1;
+    // offsets in doubles
     static constexpr size_t off_covT = 0;
     static constexpr size_t off_cov = off_covT + (size_t)DP * DP;
     static constexpr size_t off_W = off_cov + (size_t)DP * DP;
     static constexpr size_t off_xch = off_W + (size_t)DP * DP;
-    static constexpr size_t off_row = off_xch + (size_t)R * R * T::XLD;
-    static constexpr size_t off_col = off_row + 2 * DP;
-    static constexpr size_t off_pinv = off_col + 2 * DP;
-    static constexpr size_t off_piv = off_pinv + 2;
-    static constexpr size_t off_red = off_piv + DP;
-    static constexpr size_t total = off_red + 32;
+    static constexpr size_t off_line = ((off_xch + (size_t)DP * XLD + 1) / 2) * 2;
+    static constexpr size_t off_red = off_line + ((SweepSmem<C>::doubles + 1) / 2) * 2;
+    static constexpr size_t total = off_red + 96;
     static constexpr size_t bytes = total * sizeof(double);
 };
 
@@ -53,25 +50,23 @@ struct DD {   // double-double running power beta^k
     __device__ __forceinline__ double one_minus() const { return (1.0 - hi) - lo; }
 };
 
-template <int R>
-__global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_args P) {
-    using T = Tile<R>;
-    using S = SmallSmem<R>;
-    constexpr int DP = T::DP;
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1) fit_small_kernel(const dagma_small_fit_args P) {
+    using S = FitSmem<C>;
+    constexpr int DP = C::DP, RM = C::RM, RN = C::RN, NT = C::NT, XLD = S::XLD;
     extern __shared__ __align__(16) double smem[];
     double* covT = smem + S::off_covT;
     double* covS = smem + S::off_cov;
     double* Ws = smem + S::off_W;
     double* xch = smem + S::off_xch;
-    double* rowbuf = smem + S::off_row;
-    double* colbuf = smem + S::off_col;
-    double* pinvbuf = smem + S::off_pinv;
-    double* pivots = smem + S::off_piv;
+    double* linebuf = smem + S::off_line;
+    double* pivots = linebuf + SweepSmem<C>::piv_off;
     double* red = smem + S::off_red;
+    const uint32_t covT_a = smem_u32(covT), cov_a = smem_u32(covS), W_a = smem_u32(Ws), line_a = smem_u32(linebuf);
     __shared__ unsigned s_prob;
 
     const int tid = threadIdx.x;
-    const ThreadPos pos(tid);
+    const ThreadPos<C> pos(tid);
     const int ty = pos.ty, tx = pos.tx;
     const int d = P.d;
     const size_t dd = (size_t)d * d;
@@ -79,13 +74,13 @@ __global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_
     // exclusion / inclusion bit masks of this thread's tile (shared by the batch)
     unsigned excbits = 0, incbits = 0;
 #pragma unroll
-    for (int i = 0; i < R; ++i)
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-            const int r = T::g(ty, i), c = T::g(tx, j);
+        for (int j = 0; j < RN; ++j) {
+            const int r = C::grow(ty, i), c = C::gcol(tx, j);
             if (r < d && c < d) {
-                if (P.mask_exc_dev && P.mask_exc_dev[r * d + c]) excbits |= 1u << (i * R + j);
-                if (P.mask_inc_dev && P.mask_inc_dev[r * d + c]) incbits |= 1u << (i * R + j);
+                if (P.mask_exc_dev && P.mask_exc_dev[r * d + c]) excbits |= 1u << (i * RN + j);
+                if (P.mask_inc_dev && P.mask_inc_dev[r * d + c]) incbits |= 1u << (i * RN + j);
             }
         }
 
@@ -110,14 +105,13 @@ __global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_
         }
         __syncthreads();
 
-        double a[R][R], g[R][R], m[R][R], v[R][R];
+        double a[RM][RN], g[RM][RN], m[RM][RN], v[RM][RN];
         int status = 0;
         int n_ckpt = 0;
 
         // ---- state of the path-following loop ----
         int stage = 0;
         bool final_phase = (P.n_stages == 0);
-        // per-stage state (initialised by start_attempt)
         double mu = 0, s_cur = 1, lr = 0, lr_adam = P.lr, obj_prev = 1e16;
         double last_obj = 0, last_score = 0, last_h = 0;
         int iters_max = 0, it = 0, retries = 0, backtracks = 0;
@@ -133,9 +127,9 @@ __global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_
             p1 = DD{1.0, 0.0};
             p2 = DD{1.0, 0.0};
 #pragma unroll
-            for (int i = 0; i < R; ++i)
+            for (int i = 0; i < RM; ++i)
 #pragma unroll
-                for (int j = 0; j < R; ++j) m[i][j] = v[i][j] = 0.0;
+                for (int j = 0; j < RN; ++j) m[i][j] = v[i][j] = 0.0;
         };
         auto start_stage = [&]() {
             mu = P.mu[stage];
@@ -173,20 +167,20 @@ __global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_
                 st[7] = (double)backtracks;
             }
         };
-        // previous Adam direction from the moments (bias correction of iteration `it`)
-        auto apply_dir = [&](double scale) {   // Ws += scale * dir(m, v, it)
+        // Ws += scale * dir(m, v, it): the previous Adam direction rebuilt from the moments
+        auto apply_dir = [&](double scale) {
             const double c1 = 1.0 / p1.one_minus(), c2 = 1.0 / p2.one_minus();
 #pragma unroll
-            for (int i = 0; i < R; ++i) {
-                double wrow[R];
-                double* wp = Ws + T::g(ty, i) * DP;
-                load_frag<R>(wrow, wp, tx);
+            for (int i = 0; i < RM; ++i) {
+                double wrow[RN];
+                const uint32_t wp = W_a + C::grow(ty, i) * DP * 8;
+                load_rowfrag<C>(wrow, wp, tx);
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const double dir = (m[i][j] * c1) / (sqrt(v[i][j] * c2) + 1e-8);
+                for (int j = 0; j < RN; ++j) {
+                    const double dir = fast_div(m[i][j] * c1, fast_sqrt_nonneg(v[i][j] * c2) + 1e-8);
                     wrow[j] = __dadd_rn(wrow[j], __dmul_rn(scale, dir));
                 }
-                store_frag<R>(wrow, wp, tx);
+                store_rowfrag<C>(wrow, wp, tx);
             }
             __syncthreads();
         };
@@ -197,19 +191,19 @@ __global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_
             // ================= build M and run the fused sweep =================
             const double s_use = final_phase ? 1.0 : s_cur;
 #pragma unroll
-            for (int i = 0; i < R; ++i) {
-                double wrow[R], crow[R];
-                const int r = T::g(ty, i);
-                load_frag<R>(wrow, Ws + r * DP, tx);
-                load_frag<R>(crow, covS + r * DP, tx);
+            for (int i = 0; i < RM; ++i) {
+                double wrow[RN], crow[RN];
+                const int r = C::grow(ty, i);
+                load_rowfrag<C>(wrow, W_a + r * DP * 8, tx);
+                load_rowfrag<C>(crow, cov_a + r * DP * 8, tx);
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const int c = T::g(tx, j);
+                for (int j = 0; j < RN; ++j) {
+                    const int c = C::gcol(tx, j);
                     a[i][j] = ((r == c) ? s_use : 0.0) - wrow[j] * wrow[j];
                     g[i][j] = crow[j];
                 }
             }
-            gj_sweep<R, true>(a, g, covT, Ws, rowbuf, colbuf, pinvbuf, pivots, d, ty, tx);
+            gj_sweep<C, true>(a, g, covT_a, W_a, line_a, d, ty, tx);
             // now: a = M^{-1},  g = cov - cov W = cov (I - W),  pivots[0..d)
 
             // ================= objective pieces (checkpoint / final) =================
@@ -218,20 +212,20 @@ __global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_
             if (at_ckpt || final_phase) {
                 double sc = 0.0, l1 = 0.0, ld = 0.0;
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    double wrow[R];
-                    const int r = T::g(ty, i);
-                    load_frag<R>(wrow, Ws + r * DP, tx);
+                for (int i = 0; i < RM; ++i) {
+                    double wrow[RN];
+                    const int r = C::grow(ty, i);
+                    load_rowfrag<C>(wrow, W_a + r * DP * 8, tx);
 #pragma unroll
-                    for (int j = 0; j < R; ++j) {
-                        const int c = T::g(tx, j);
+                    for (int j = 0; j < RN; ++j) {
+                        const int c = C::gcol(tx, j);
                         const double dif = ((r == c && r < d) ? 1.0 : 0.0) - wrow[j];
                         sc = fma(dif, g[i][j], sc);
                         l1 += fabs(wrow[j]);
                     }
                 }
                 if (tid < d) ld = log(fabs(pivots[tid]));
-                block_sum3(sc, l1, ld, red, tid);
+                block_sum3<NT>(sc, l1, ld, red, tid);
                 const double score = 0.5 * sc;
                 const double h = -ld + (double)d * log(s_use);
                 if (final_phase) {
@@ -262,9 +256,9 @@ __global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_
                 bool bad = false;
                 if (tid < d) bad = !(pivots[tid] > 0.0);
 #pragma unroll
-                for (int i = 0; i < R; ++i)
+                for (int i = 0; i < RM; ++i)
 #pragma unroll
-                    for (int j = 0; j < R; ++j) bad |= (a[i][j] + 1e-16 < 0.0);
+                    for (int j = 0; j < RN; ++j) bad |= (a[i][j] + 1e-16 < 0.0);
                 bad = __syncthreads_or(bad);
                 if (bad) {
                     if (it == 0 || s_cur <= 0.9) {            // linear.py:231-233
@@ -303,28 +297,33 @@ __global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_
                 const double c1 = 1.0 / p1.one_minus(), c2 = 1.0 / p2.one_minus();
                 const double ob1 = 1.0 - P.beta1, ob2 = 1.0 - P.beta2;
                 const double l1c = mu * lambda1, incc = -2.0 * mu * lambda1;
-                double aT[R][R];
-                transpose_tile<R>(aT, a, xch, ty, tx);
+                // transpose M^{-1} through shared memory: aT[i][j] = Minv[col][row]
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    double wrow[R];
-                    double* wp = Ws + T::g(ty, i) * DP;
-                    load_frag<R>(wrow, wp, tx);
+                for (int i = 0; i < RM; ++i)
 #pragma unroll
-                    for (int j = 0; j < R; ++j) {
+                    for (int j = 0; j < RN; ++j) xch[C::grow(ty, i) * XLD + C::gcol(tx, j)] = a[i][j];
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < RM; ++i) {
+                    double wrow[RN];
+                    const uint32_t wp = W_a + C::grow(ty, i) * DP * 8;
+                    load_rowfrag<C>(wrow, wp, tx);
+#pragma unroll
+                    for (int j = 0; j < RN; ++j) {
                         const double w = wrow[j];
+                        const double minvT = xch[C::gcol(tx, j) * XLD + C::grow(ty, i)];
                         const double sg = (w > 0.0) ? 1.0 : ((w < 0.0) ? -1.0 : 0.0);
                         double go = fma(-mu, g[i][j], l1c * sg);
-                        go = fma(2.0 * w, aT[i][j] + 1e-16, go);
-                        if (incbits >> (i * R + j) & 1u) go = fma(incc, sg, go);
+                        go = fma(2.0 * w, minvT + 1e-16, go);
+                        if (incbits >> (i * RN + j) & 1u) go = fma(incc, sg, go);
                         m[i][j] = fma(m[i][j], P.beta1, ob1 * go);
                         v[i][j] = fma(v[i][j], P.beta2, ob2 * (go * go));
-                        const double dir = (m[i][j] * c1) / (sqrt(v[i][j] * c2) + 1e-8);
+                        const double dir = fast_div(m[i][j] * c1, fast_sqrt_nonneg(v[i][j] * c2) + 1e-8);
                         double wn = w - lr * dir;
-                        if (excbits >> (i * R + j) & 1u) wn = 0.0;
+                        if (excbits >> (i * RN + j) & 1u) wn = 0.0;
                         wrow[j] = wn;
                     }
-                    store_frag<R>(wrow, wp, tx);
+                    store_rowfrag<C>(wrow, wp, tx);
                 }
                 __syncthreads();
                 continue;
@@ -352,24 +351,41 @@ __global__ void __launch_bounds__(NT, 1) fit_small_kernel(const dagma_small_fit_
     }
 }
 
-template <int R>
-static int launch_fit(cudaStream_t stream, const dagma_small_fit_args& a, int ctas) {
-    constexpr size_t bytes = SmallSmem<R>::bytes;
-    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    fit_small_kernel<R><<<ctas, NT, bytes, stream>>>(a);
+using C16 = Cfg<1, 1, 16, 16>;     // d <= 16 : 256 threads, 1 element each
+using C32 = Cfg<2, 2, 16, 16>;     // d <= 32 : 256 threads, 2 x 2
+using C48 = Cfg<4, 2, 12, 24>;     // d <= 48 : 288 threads, 4 x 2
+using C64 = Cfg<4, 2, 16, 32>;     // d <= 64 : 512 threads, 4 x 2
+
+template <class C>
+static int fit_geometry(int batch, int sms, int* ctas, int* threads, size_t* smem_bytes) {
+    constexpr size_t bytes = FitSmem<C>::bytes;
+    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int per_sm = 0;
+    DAGMA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_small_kernel<C>, C::NT, bytes));
+    if (per_sm < 1) return set_error(-5, "fit kernel does not fit on an SM");
+    long n = (long)sms * per_sm;
+    if (n > batch) n = batch;
+    if (ctas) *ctas = (int)n;
+    if (threads) *threads = C::NT;
+    if (smem_bytes) *smem_bytes = bytes;
+    return 0;
+}
+
+template <class C>
+static int launch_fit(cudaStream_t stream, const dagma_small_fit_args& a, int sms) {
+    int ctas = 0;
+    int rc = fit_geometry<C>(a.batch, sms, &ctas, nullptr, nullptr);
+    if (rc) return rc;
+    fit_small_kernel<C><<<ctas, C::NT, FitSmem<C>::bytes, stream>>>(a);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-static int tile_for(int d) { return (d + TG - 1) / TG; }
-
-static size_t smem_for(int R) {
-    switch (R) {
-        case 1: return SmallSmem<1>::bytes;
-        case 2: return SmallSmem<2>::bytes;
-        case 3: return SmallSmem<3>::bytes;
-        default: return SmallSmem<4>::bytes;
-    }
+static int sm_count(int* sms) {
+    int dev = 0;
+    DAGMA_CUDA_OK(cudaGetDevice(&dev));
+    DAGMA_CUDA_OK(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+    return 0;
 }
 
 }  // namespace dagma
@@ -378,20 +394,13 @@ using namespace dagma;
 
 extern "C" int dagma_linear_fit_small_geometry(int d, int batch, int* ctas, int* threads, size_t* smem_bytes) {
     DAGMA_REQUIRE(d >= 1 && d <= DAGMA_SMALL_MAX_D, "d out of range for the on-chip fit path");
-    int dev = 0, sms = 0;
-    DAGMA_CUDA_OK(cudaGetDevice(&dev));
-    DAGMA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int R = tile_for(d);
-    const size_t bytes = smem_for(R);
-    int per_sm = (int)((227u * 1024u) / (bytes + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 1) per_sm = 1;   // 255-register tiles: one CTA per SM
-    int n = sms * per_sm;
-    if (n > batch) n = batch;
-    if (ctas) *ctas = n;
-    if (threads) *threads = NT;
-    if (smem_bytes) *smem_bytes = bytes;
-    return 0;
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc) return rc;
+    if (d <= 16) return fit_geometry<C16>(batch, sms, ctas, threads, smem_bytes);
+    if (d <= 32) return fit_geometry<C32>(batch, sms, ctas, threads, smem_bytes);
+    if (d <= 48) return fit_geometry<C48>(batch, sms, ctas, threads, smem_bytes);
+    return fit_geometry<C64>(batch, sms, ctas, threads, smem_bytes);
 }
 
 extern "C" int dagma_linear_fit_small_f64(dagma_stream_t stream_, const dagma_small_fit_args* args) {
@@ -404,13 +413,11 @@ extern "C" int dagma_linear_fit_small_f64(dagma_stream_t stream_, const dagma_sm
     DAGMA_REQUIRE(a.cov_dev && a.w_dev && a.lambda1_dev && a.work_counter_dev, "null device pointer");
     cudaStream_t stream = (cudaStream_t)stream_;
     DAGMA_CUDA_OK(cudaMemsetAsync(a.work_counter_dev, 0, sizeof(uint32_t), stream));
-    int ctas = 0;
-    int rc = dagma_linear_fit_small_geometry(a.d, a.batch, &ctas, nullptr, nullptr);
+    int sms = 0;
+    int rc = sm_count(&sms);
     if (rc) return rc;
-    switch (tile_for(a.d)) {
-        case 1: return launch_fit<1>(stream, a, ctas);
-        case 2: return launch_fit<2>(stream, a, ctas);
-        case 3: return launch_fit<3>(stream, a, ctas);
-        default: return launch_fit<4>(stream, a, ctas);
-    }
+    if (a.d <= 16) return launch_fit<C16>(stream, a, sms);
+    if (a.d <= 32) return launch_fit<C32>(stream, a, sms);
+    if (a.d <= 48) return launch_fit<C48>(stream, a, sms);
+    return launch_fit<C64>(stream, a, sms);
 }

@@ -1,200 +1,277 @@
-// On-chip Gauss-Jordan sweep for one d x d FP64 problem held by one 256-thread CTA.
+// On-chip Gauss-Jordan sweep for one d x d FP64 problem held by one CTA.
 //
-// Layout.  The CTA is a 16 x 16 thread grid; thread (ty, tx) owns an R x R register
-// tile of the (padded, DP = 16 R) matrix.  Rows and columns use the same interleaved
-// map  g(t, i) = (i / CW) * 16 CW + CW t + i % CW  (CW = 2 for even R), so a thread's
-// row/column fragments are 16-byte chunks that a warp reads from shared memory
-// without bank conflicts, and the transpose of thread (ty, tx)'s tile is exactly the
-// tile of thread (tx, ty).  Warps are 4 (ty) x 8 (tx) patches so that the row and
-// column fragments broadcast inside a warp.
+// Layout.  The CTA is a TY x TX thread grid; thread (ty, tx) owns an RM x RN register
+// tile of the padded matrix (DP = TY*RM = TX*RN).  Rows use the interleaved map
+// grow(ty, i) = (i / CW) * TY*CW + CW*ty + i % CW and columns the same with TX (CW = 2
+// doubles = one 16-byte chunk), so the row / column fragments a thread needs in every
+// step are 16-byte shared-memory chunks read without bank conflicts.  Warps are
+// 4 (ty) x 8 (tx) patches so fragments broadcast inside a warp.
 //
 // Sweep.  In-place Gauss-Jordan without pivoting (stable for the M-matrices
-// sI - W o W of DAGMA: every off-diagonal update adds numbers of one sign), pivots in
+// sI - W o W of DAGMA: off-diagonal updates add numbers of one sign), pivots in
 // natural order.  Step k: the owners publish row k, column k and 1/pivot through a
-// double-buffered shared-memory line (one __syncthreads per step), zero their copies,
-// and every thread applies  a_ij += (-a_ik / p) * a_kj  to its whole tile; publishing
-// row[k] = 1, col[k] = -1 makes the same FMA produce the scaled pivot row, the
-// negated pivot column and 1/p, so there is no per-element special case.  The next
-// pivot's reciprocal is started one step early by its owner to take the FP64
-// reciprocal off the serial chain.  With GEMM = true the k-th rank-1 update of
-// G -= cov[:, k] W[k, :] is interleaved into the same step: it is independent of the
-// sweep, has the same shape, and fills the latency of the publish/barrier/read chain.
+// double-buffered shared-memory line (ONE __syncthreads per step) and every thread
+// applies  a_ij += (-a_ik / p) * a_kj  to its whole tile.  Publishing row[k] = 1 + p
+// and col[k] = p - 1 makes that same FMA turn the pivot row into a_kj / p, the pivot
+// column into -a_ik / p and the pivot into 1 / p, so no element is special-cased and
+// nothing is zeroed.  (The identity costs a relative error eps*max(1, p); p <= s,
+// which the callers keep <= 2 -- by a power-of-two pre-scale where s is arbitrary.)
+// The reciprocal of the NEXT pivot is started by its owner inside the current step,
+// which takes the FP64 reciprocal off the serial publish/barrier/read chain.
+// With GEMM = true the k-th rank-1 update of  G -= cov[:, k] W[k, :]  is interleaved
+// into the same step (operands prefetched one step ahead): it is independent of the
+// sweep, has the same shape, and fills the latency of the chain.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdint>
 
 namespace dagma {
 
-constexpr int TG = 16;        // thread grid side
-constexpr int NT = TG * TG;   // threads per CTA
+// ---------------------------------------------------------------- shared memory access
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ double lds64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lds128(uint32_t a, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, double x) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void sts64_if(bool p, uint32_t a, double x) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.shared.f64 [%1], %2;\n\t}"
+                 ::"r"((int)p), "r"(a), "d"(x) : "memory");
+}
+__device__ __forceinline__ void sts128_if(bool p, uint32_t a, double x, double y) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.shared.v2.f64 [%1], {%2, %3};\n\t}"
+                 ::"r"((int)p), "r"(a), "d"(x), "d"(y) : "memory");
+}
 
-template <int R>
-struct Tile {
-    static constexpr int CW = (R % 2 == 0) ? 2 : 1;   // chunk width (doubles)
-    static constexpr int NCH = R / CW;                // chunks per fragment
-    static constexpr int DP = TG * R;                 // padded dimension
-    static constexpr int XLD = TG * (TG + 1);         // exchange-buffer plane stride
-    __host__ __device__ static constexpr int g(int t, int i) {
-        return (i / CW) * (TG * CW) + CW * t + (i % CW);
+// full-precision reciprocal without the slow-path branch of 1.0/x (inputs are pivots:
+// finite, normal range; 0 gives inf, which the callers flag as "not an M-matrix")
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);      // 2^-20 -> 2^-40
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);             // -> 2^-80
+    r = fma(r, e, r);
+    return r;
+}
+
+// sqrt(x) for x >= 0 (0 allowed) to ~1 ulp, branch free
+__device__ __forceinline__ double fast_sqrt_nonneg(double x) {
+    const double xs = fmax(x, 1e-290);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
+    double g = xs * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double res = fma(-g, g, xs);
+    return fma(res, h, g);
+}
+
+// n / dn for dn in the normal range, ~1 ulp, branch free
+__device__ __forceinline__ double fast_div(double n, double dn) {
+    const double r = fast_rcp(dn);
+    const double q = n * r;
+    const double rem = fma(-q, dn, n);
+    return fma(rem, r, q);
+}
+
+// ---------------------------------------------------------------- tiling
+template <int RM_, int RN_, int TY_, int TX_>
+struct Cfg {
+    static constexpr int RM = RM_, RN = RN_, TY = TY_, TX = TX_;
+    static constexpr int DP = TY * RM;
+    static constexpr int NT = TY * TX;
+    static constexpr int CW = (RM % 2 == 0 && RN % 2 == 0) ? 2 : 1;
+    static constexpr int TMIN = TY < TX ? TY : TX;
+    static constexpr int NU = DP / (TMIN * CW);           // unrolled super-chunks
+    static_assert(TY * RM == TX * RN, "tile grid must be square in elements");
+    static_assert(TY % 4 == 0 && TX % 8 == 0, "warps are 4 x 8 thread patches");
+    static_assert(TY % TMIN == 0 && TX % TMIN == 0, "thread grid sides must nest");
+    static_assert(RM % CW == 0 && RN % CW == 0, "chunking");
+    static_assert(NT % 32 == 0 && NT <= 1024, "whole warps");
+    __host__ __device__ static constexpr int grow(int ty, int i) {
+        return (i / CW) * (TY * CW) + CW * ty + (i % CW);
+    }
+    __host__ __device__ static constexpr int gcol(int tx, int j) {
+        return (j / CW) * (TX * CW) + CW * tx + (j % CW);
     }
 };
 
+template <class C>
 struct ThreadPos {
     int ty, tx;
     __device__ __forceinline__ explicit ThreadPos(int tid) {
         const int w = tid >> 5, lane = tid & 31;
-        ty = (w >> 1) * 4 + (lane >> 3);
-        tx = (w & 1) * 8 + (lane & 7);
+        constexpr int WX = C::TX / 8;
+        ty = (w / WX) * 4 + (lane >> 3);
+        tx = (w % WX) * 8 + (lane & 7);
     }
 };
 
-// fragment = the R entries base[g(t, 0..R-1)] of one shared-memory line
-template <int R>
-__device__ __forceinline__ void load_frag(double (&f)[R], const double* base, int t) {
-    using T = Tile<R>;
+// row fragment: the RN entries line[gcol(tx, 0..RN-1)] of a shared-memory line (byte address)
+template <class C>
+__device__ __forceinline__ void load_rowfrag(double (&f)[C::RN], uint32_t line, int tx) {
 #pragma unroll
-    for (int ch = 0; ch < T::NCH; ++ch) {
-        if constexpr (T::CW == 2) {
-            const double2 v = *reinterpret_cast<const double2*>(base + ch * (TG * 2) + 2 * t);
-            f[2 * ch] = v.x;
-            f[2 * ch + 1] = v.y;
-        } else {
-            f[ch] = base[ch * TG + t];
-        }
+    for (int ch = 0; ch < C::RN / C::CW; ++ch) {
+        if constexpr (C::CW == 2)
+            lds128(line + (ch * C::TX * 2 + 2 * tx) * 8, f[2 * ch], f[2 * ch + 1]);
+        else
+            f[ch] = lds64(line + (ch * C::TX + tx) * 8);
     }
 }
-
-template <int R>
-__device__ __forceinline__ void store_frag(const double (&f)[R], double* base, int t) {
-    using T = Tile<R>;
+// column fragment: the RM entries line[grow(ty, 0..RM-1)]
+template <class C>
+__device__ __forceinline__ void load_colfrag(double (&f)[C::RM], uint32_t line, int ty) {
 #pragma unroll
-    for (int ch = 0; ch < T::NCH; ++ch) {
-        if constexpr (T::CW == 2) {
-            *reinterpret_cast<double2*>(base + ch * (TG * 2) + 2 * t) = make_double2(f[2 * ch], f[2 * ch + 1]);
-        } else {
-            base[ch * TG + t] = f[ch];
-        }
+    for (int ch = 0; ch < C::RM / C::CW; ++ch) {
+        if constexpr (C::CW == 2)
+            lds128(line + (ch * C::TY * 2 + 2 * ty) * 8, f[2 * ch], f[2 * ch + 1]);
+        else
+            f[ch] = lds64(line + (ch * C::TY + ty) * 8);
     }
 }
-
-// tile[i][j] = src[g(ty,i) * DP + g(tx,j)]
-template <int R>
-__device__ __forceinline__ void load_tile(double (&tile)[R][R], const double* src, int ty, int tx) {
-    using T = Tile<R>;
+template <class C>
+__device__ __forceinline__ void store_rowfrag(const double (&f)[C::RN], uint32_t line, int tx) {
 #pragma unroll
-    for (int i = 0; i < R; ++i) load_frag<R>(tile[i], src + T::g(ty, i) * T::DP, tx);
-}
-
-template <int R>
-__device__ __forceinline__ void store_tile(const double (&tile)[R][R], double* dst, int ty, int tx) {
-    using T = Tile<R>;
-#pragma unroll
-    for (int i = 0; i < R; ++i) store_frag<R>(tile[i], dst + T::g(ty, i) * T::DP, tx);
-}
-
-// out[i][j] = in_of_thread(tx,ty)[j][i]  (pairwise exchange through shared memory)
-template <int R>
-__device__ __forceinline__ void transpose_tile(double (&out)[R][R], const double (&in)[R][R],
-                                               double* xch, int ty, int tx) {
-    using T = Tile<R>;
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < R; ++j) xch[(i * R + j) * T::XLD + ty * (TG + 1) + tx] = in[i][j];
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < R; ++j) out[i][j] = xch[(j * R + i) * T::XLD + tx * (TG + 1) + ty];
+    for (int ch = 0; ch < C::RN / C::CW; ++ch) {
+        if constexpr (C::CW == 2)
+            sts128(line + (ch * C::TX * 2 + 2 * tx) * 8, f[2 * ch], f[2 * ch + 1]);
+        else
+            sts64(line + (ch * C::TX + tx) * 8, f[ch]);
+    }
 }
 
 // Gauss-Jordan sweep over pivots 0..d-1 of the register-resident matrix `a`
 // (on exit a = inverse on the leading d x d block; pivots[k] = k-th pivot).
+// Shared-memory operands are byte addresses in the shared window:
+//   line  : 2 x (DP row line, DP column line) doubles, then 2 reciprocals, then DP pivots
+//   covT  : cov transposed, [k][row] (GEMM only);   Ws : W, [k][col] (GEMM only)
 // GEMM: additionally g -= covT[k][rows] * Ws[k][cols] for k < d.
-template <int R, bool GEMM>
-__device__ __forceinline__ void gj_sweep(double (&a)[R][R], double (&g)[R][R],
-                                         const double* __restrict__ covT,
-                                         const double* __restrict__ Ws,
-                                         double* rowbuf, double* colbuf, double* pinvbuf,
-                                         double* pivots, int d, int ty, int tx) {
-    using T = Tile<R>;
-    constexpr int DP = T::DP, CW = T::CW;
-    double pinv_early = 0.0;
-    int cur = 0;
+template <class C>
+struct SweepSmem {
+    static constexpr int row_off = 0;                  // doubles
+    static constexpr int col_off = 2 * C::DP;
+    static constexpr int pinv_off = 4 * C::DP;
+    static constexpr int piv_off = 4 * C::DP + 2;
+    static constexpr int doubles = 5 * C::DP + 2;
+};
+
+template <class C, bool GEMM>
+__device__ __forceinline__ void gj_sweep(double (&a)[C::RM][C::RN], double (&g)[C::RM][C::RN],
+                                         uint32_t covT, uint32_t Ws, uint32_t line, int d, int ty, int tx) {
+    constexpr int RM = C::RM, RN = C::RN, DP = C::DP, CW = C::CW, TMIN = C::TMIN, NU = C::NU;
+    using SS = SweepSmem<C>;
+    const uint32_t rowbuf = line + SS::row_off * 8, colbuf = line + SS::col_off * 8;
+    const uint32_t pinvbuf = line + SS::pinv_off * 8, pivots = line + SS::piv_off * 8;
+
+    // reciprocal of pivot 0 (owner = thread (0,0), local (0,0))
+    double pinv_early = fast_rcp(a[0][0]);
+    double af[RM], bf[RN];
+    if constexpr (GEMM) {
+        load_colfrag<C>(af, covT, ty);
+        load_rowfrag<C>(bf, Ws, tx);
+    }
 #pragma unroll
-    for (int c = 0; c < T::NCH; ++c) {
-        const int kbase = c * TG * CW;
+    for (int u = 0; u < NU; ++u) {
+        const int kbase = u * TMIN * CW;
+        const int cr = (u * TMIN) / C::TY, cc = (u * TMIN) / C::TX;     // chunk of rows / cols
+        const int tr0 = (u * TMIN) % C::TY, tc0 = (u * TMIN) % C::TX;   // first owner in chunk
         int tmax = (d - kbase + CW - 1) / CW;
-        tmax = tmax < 0 ? 0 : (tmax > TG ? TG : tmax);
+        tmax = tmax < 0 ? 0 : (tmax > TMIN ? TMIN : tmax);
 #pragma unroll 1
         for (int t = 0; t < tmax; ++t) {
 #pragma unroll
             for (int e = 0; e < CW; ++e) {
-                const int IK = c * CW + e;          // local index of pivot k (compile time)
+                const int IK = cr * CW + e, JK = cc * CW + e;   // local indices (compile time)
                 const int k = kbase + t * CW + e;
                 if (k < d) {
-                    double* rb = rowbuf + cur * DP;
-                    double* cb = colbuf + cur * DP;
-                    const bool own_r = (ty == t), own_c = (tx == t);
+                    const int cur = (CW == 2) ? e : (t & 1);
+                    const uint32_t rb = rowbuf + cur * DP * 8, cb = colbuf + cur * DP * 8;
+                    const bool own_r = (ty == tr0 + t), own_c = (tx == tc0 + t);
                     // ---- publish pivot row / column / reciprocal ----
-                    if (own_r) store_frag<R>(a[IK], rb, tx);
-                    if (own_c) {
-                        double colv[R];
 #pragma unroll
-                        for (int i = 0; i < R; ++i) colv[i] = a[i][IK];
-                        store_frag<R>(colv, cb, ty);
+                    for (int ch = 0; ch < RN / CW; ++ch) {
+                        if constexpr (CW == 2)
+                            sts128_if(own_r, rb + (ch * C::TX * 2 + 2 * tx) * 8, a[IK][2 * ch], a[IK][2 * ch + 1]);
+                        else
+                            sts64_if(own_r, rb + (ch * C::TX + tx) * 8, a[IK][ch]);
                     }
-                    if (own_r && own_c) {
-                        const double p = a[IK][IK];
-                        const bool late = (e == 0) && (t == 0);
-                        const double pinv = late ? __drcp_rn(p) : pinv_early;
-                        pivots[k] = p;
-                        pinvbuf[cur] = pinv;
-                        rb[k] = 1.0;
-                        cb[k] = -1.0;
-                    }
-                    if (own_r) {
 #pragma unroll
-                        for (int j = 0; j < R; ++j) a[IK][j] = 0.0;
-                    }
-                    if (own_c) {
-#pragma unroll
-                        for (int i = 0; i < R; ++i) a[i][IK] = 0.0;
+                    for (int i = 0; i < RM; ++i) sts64_if(own_c, cb + C::grow(ty, i) * 8, a[i][JK]);
+                    {
+                        const bool own = own_r && own_c;
+                        const double p = a[IK][JK];
+                        sts64_if(own, pivots + k * 8, p);
+                        sts64_if(own, pinvbuf + cur * 8, pinv_early);
+                        sts64_if(own, rb + k * 8, 1.0 + p);
+                        sts64_if(own, cb + k * 8, p - 1.0);
                     }
                     __syncthreads();
                     // ---- read the published line ----
-                    const double pinv = pinvbuf[cur];
-                    double r[R], cs[R];
-                    load_frag<R>(r, rb, tx);
-                    load_frag<R>(cs, cb, ty);
+                    const double pinv = lds64(pinvbuf + cur * 8);
+                    double r[RN], cs[RM];
+                    load_rowfrag<C>(r, rb, tx);
+                    load_colfrag<C>(cs, cb, ty);
+                    // ---- GEMM rank-1 update with the operands fetched one step ago ----
+                    if constexpr (GEMM) {
 #pragma unroll
-                    for (int i = 0; i < R; ++i) cs[i] = -cs[i] * pinv;
-                    // ---- start the next pivot's reciprocal early ----
-                    if (k + 1 < d) {
+                        for (int i = 0; i < RM; ++i)
+#pragma unroll
+                            for (int j = 0; j < RN; ++j) g[i][j] = fma(-af[i], bf[j], g[i][j]);
+                        const int kn = (k + 1 < d) ? k + 1 : k;
+                        load_colfrag<C>(af, covT + kn * DP * 8, ty);
+                        load_rowfrag<C>(bf, Ws + kn * DP * 8, tx);
+                    }
+#pragma unroll
+                    for (int i = 0; i < RM; ++i) cs[i] = -cs[i] * pinv;
+                    // ---- reciprocal of the next pivot, by its owner ----
+                    {
+                        double cand;
+                        bool own_next;
                         if (e + 1 < CW) {
-                            const int IN = IK + 1 < R ? IK + 1 : IK;
-                            if (own_r && own_c)
-                                pinv_early = __drcp_rn(fma(cs[IN], r[IN], a[IN][IN]));
-                        } else if (t + 1 < TG) {
-                            const int IN = c * CW;
-                            if (ty == t + 1 && tx == t + 1)
-                                pinv_early = __drcp_rn(fma(cs[IN], r[IN], a[IN][IN]));
+                            const int IN = (IK + 1 < RM) ? IK + 1 : IK, JN = (JK + 1 < RN) ? JK + 1 : JK;
+                            cand = fma(cs[IN], r[JN], a[IN][JN]);
+                            own_next = own_r && own_c;
+                        } else {
+                            const int IA = cr * CW, JA = cc * CW;                     // next t, same chunk
+                            const double candA = fma(cs[IA], r[JA], a[IA][JA]);
+                            double candB = 1.0;
+                            bool ownB = false;
+                            if (u + 1 < NU) {                                         // first of next chunk
+                                const int crn = ((u + 1) * TMIN) / C::TY, ccn = ((u + 1) * TMIN) / C::TX;
+                                const int IB = crn * CW, JB = ccn * CW;
+                                candB = fma(cs[IB], r[JB], a[IB][JB]);
+                                ownB = (ty == ((u + 1) * TMIN) % C::TY) && (tx == ((u + 1) * TMIN) % C::TX);
+                            }
+                            const bool last = (t == TMIN - 1);
+                            cand = last ? candB : candA;
+                            own_next = last ? ownB : ((ty == tr0 + t + 1) && (tx == tc0 + t + 1));
+                        }
+                        // warp-uniform branch: only the owner's warp pays for the Newton chain
+                        if (__any_sync(0xffffffffu, own_next)) {
+                            if (own_next) pinv_early = fast_rcp(cand);
                         }
                     }
-                    // ---- rank-1 updates ----
-                    if constexpr (GEMM) {
-                        double af[R], bf[R];
-                        load_frag<R>(af, covT + k * DP, ty);
-                        load_frag<R>(bf, Ws + k * DP, tx);
+                    // ---- Gauss-Jordan rank-1 update ----
 #pragma unroll
-                        for (int i = 0; i < R; ++i)
+                    for (int i = 0; i < RM; ++i)
 #pragma unroll
-                            for (int j = 0; j < R; ++j) g[i][j] = fma(-af[i], bf[j], g[i][j]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < R; ++i)
-#pragma unroll
-                        for (int j = 0; j < R; ++j) a[i][j] = fma(cs[i], r[j], a[i][j]);
-                    cur ^= 1;
+                        for (int j = 0; j < RN; ++j) a[i][j] = fma(cs[i], r[j], a[i][j]);
                 }
             }
         }
@@ -202,8 +279,10 @@ __device__ __forceinline__ void gj_sweep(double (&a)[R][R], double (&g)[R][R],
     __syncthreads();
 }
 
-// deterministic block-wide sum of up to 3 values (all threads get the totals)
+// deterministic block-wide sum of 3 values (all threads get the totals); red: 3*32 doubles
+template <int NTHREADS>
 __device__ __forceinline__ void block_sum3(double& x, double& y, double& z, double* red, int tid) {
+    constexpr int NW = NTHREADS / 32;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         x += __shfl_xor_sync(0xffffffffu, x, off);
@@ -213,16 +292,16 @@ __device__ __forceinline__ void block_sum3(double& x, double& y, double& z, doub
     const int w = tid >> 5;
     if ((tid & 31) == 0) {
         red[w] = x;
-        red[8 + w] = y;
-        red[16 + w] = z;
+        red[32 + w] = y;
+        red[64 + w] = z;
     }
     __syncthreads();
     double sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll
-    for (int i = 0; i < NT / 32; ++i) {
+    for (int i = 0; i < NW; ++i) {
         sx += red[i];
-        sy += red[8 + i];
-        sz += red[16 + i];
+        sy += red[32 + i];
+        sz += red[64 + i];
     }
     __syncthreads();
     x = sx;
@@ -230,7 +309,9 @@ __device__ __forceinline__ void block_sum3(double& x, double& y, double& z, doub
     z = sz;
 }
 
+template <int NTHREADS>
 __device__ __forceinline__ double block_min(double x, double* red, int tid) {
+    constexpr int NW = NTHREADS / 32;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, off));
     const int w = tid >> 5;
@@ -238,7 +319,7 @@ __device__ __forceinline__ double block_min(double x, double* red, int tid) {
     __syncthreads();
     double m = red[0];
 #pragma unroll
-    for (int i = 1; i < NT / 32; ++i) m = fmin(m, red[i]);
+    for (int i = 1; i < NW; ++i) m = fmin(m, red[i]);
     __syncthreads();
     return m;
 }

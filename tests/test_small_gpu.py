@@ -167,10 +167,10 @@ def test_backtracking_matches_oracle():
     from midagma_b200 import minimize_batch
     d = 10
     X, _ = simulate.make_linear_problem(d, 2, 300, "ER", "gauss", 4)
-    o = OracleLinear("l2").prepare(X, 0.01, checkpoint=50)
-    W_ref, ok_ref = o.minimize(np.zeros((d, d)), 1.0, 200, 1.0, 0.25)
+    o = OracleLinear("l2").prepare(X, 0.0, checkpoint=50)
+    W_ref, ok_ref = o.minimize(np.zeros((d, d)), 1.0, 40, 1.0, 1.0)
     n_halved = sum(1 for e in o.events if e[0] == "lr_halved")
-    W, ok, st = minimize_batch(np.zeros((1, d, d)), o.cov[None], 0.01, 1.0, 200, 1.0, 0.25, checkpoint=50)
+    W, ok, st = minimize_batch(np.zeros((1, d, d)), o.cov[None], 0.0, 1.0, 40, 1.0, 1.0, checkpoint=50)
     print("halvings oracle", n_halved, "gpu", st[0, 0, 7], "lr", o.last_lr if ok_ref else None, st[0, 0, 1])
     assert n_halved > 0, "test input must exercise back-tracking"
     assert bool(ok[0]) == ok_ref
@@ -184,7 +184,7 @@ def test_fit_retry_path():
     d = 10
     X, _ = simulate.make_linear_problem(d, 2, 300, "ER", "gauss", 4)
     o = OracleLinear("l2")
-    kw = dict(lambda1=0.01, T=2, warm_iter=300, max_iter=300, lr=0.2, checkpoint=100)
+    kw = dict(lambda1=0.01, T=2, warm_iter=300, max_iter=300, lr=0.01, checkpoint=100)
     W_ref = o.fit(X.copy(), s=[1.0, 0.3], **kw)
     fails = [e for e in o.events if e[0] == "out_of_domain"]
     assert fails, "test input must exercise the retry path"
