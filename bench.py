@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- DagmaLinear inner Adam iterations/second on the batched d=64 sweep.
+
+Workload (BASELINE.json configs[3], "C4"): independent DagmaLinear l2 problems, ER4 graphs,
+d=64, n=1000, 1024 seeds x lambda1 in {0.01, 0.02, 0.03, 0.05}; 4096 problems per GPU
+(weak scaling: every rank owns its own 4096 problems, no data-path collective).
+
+A "step" is one pass of the hot path over the batch: one `DagmaLinear.minimize` call of
+`checkpoint` = 1000 inner iterations (mu=1, s=1, lr=3e-4; tol=0 so no problem stops early)
+for every problem, i.e. 4096 x 1000 inner Adam iterations per GPU per step.
+
+    value  : problem-iterations / s, inputs resident in HBM (CUDA events, max over ranks)
+    e2e    : same metric through the public host API `minimize_batch` on pinned host
+             buffers (H2D of W and cov, kernel, D2H of W inside the timed region)
+    roofline: 4 d^3 flop per iteration (inverse 2d^3 + cov@(I-W) 2d^3) against the FP64
+             pipe peak measured live with the DFMA/DMMA yardstick kernels
+    cpu_baseline / --impl reference: the numpy restatement of the reference
+             (oracle/linear_ref.py, bit-identical to it in the build container) on the
+             host cores, one single-threaded-BLAS process per core, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, N_SAMPLES, K_EDGES = 64, 1000, 4
+LAMBDAS = (0.01, 0.02, 0.03, 0.05)
+ITERS_PER_STEP = 1000
+FLOP_PER_ITER = 4.0 * D ** 3
+
+
+# --------------------------------------------------------------------------- data
+def make_covs(n_seeds: int, seed0: int):
+    """[n_seeds, n, d] synthetic ER4 gaussian SEM data (oracle/simulate.py is only a data generator here)."""
+    import numpy as np
+    from oracle import simulate
+    X = np.empty((n_seeds, N_SAMPLES, D))
+    for i in range(n_seeds):
+        X[i], _ = simulate.make_linear_problem(D, K_EDGES, N_SAMPLES, "ER", "gauss", seed0 + i)
+    return X
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    seed, lam, iters = args
+    import numpy as np
+    from threadpoolctl import threadpool_limits
+    from oracle import simulate
+    from oracle.linear_ref import OracleLinear
+    with threadpool_limits(limits=1):
+        X, _ = simulate.make_linear_problem(D, K_EDGES, N_SAMPLES, "ER", "gauss", seed)
+        o = OracleLinear("l2").prepare(X, lam, checkpoint=ITERS_PER_STEP)
+        t0 = time.perf_counter()
+        o.minimize(np.zeros((D, D)), 1.0, iters, 1.0, 3e-4, tol=0.0)
+        return o.last_iters, time.perf_counter() - t0
+
+
+def cpu_rate(iters: int, rounds: int = 1):
+    """problem-iterations/s of the oracle port with one single-thread process per host core."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    jobs = [(1000 + i, LAMBDAS[i % 4], iters) for i in range(cores * rounds)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(1000, 0.02, 5)] * cores)          # spawn + import warm-up
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    done = sum(r[0] for r in res)
+    return done / wall, cores, done, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    iters = 300
+    for _ in range(args.warmup):
+        pass   # process-pool warm-up happens inside cpu_rate
+    rates = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rate, cores, done, wall = cpu_rate(iters)
+        rates.append((rate, done, wall))
+    total_wall = sum(r[2] for r in rates)
+    total_done = sum(r[1] for r in rates)
+    value = total_done / total_wall
+    sample = f"{cores} problems (one per core) x {iters} inner iterations per step, single-thread BLAS per process"
+    line = {
+        "impl": "reference", "metric": "DagmaLinear inner Adam iters/sec (batched d=64)", "value": value,
+        "unit": "problem-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4: DagmaLinear l2 minimize, ER4 d=64 n=1000, mu=1 s=1 lr=3e-4", "d": D,
+                   "n": N_SAMPLES, "iters_per_problem_per_step": iters},
+        "cpu_baseline": {"value": value, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "problem-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        rows = [r.strip().split(", ") for r in self.f.read().splitlines() if r.count(",") >= 5]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = sorted(int(float(r[0])) for r in rows)
+        out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_max_mhz"] = int(float(rows[0][1]))
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, nme in enumerate(names):
+            if any(r[2 + i].strip().lower().startswith("active") for r in rows):
+                out["reasons"].append(nme)
+        out["samples"] = len(rows)
+        return out
+
+
+# --------------------------------------------------------------------------- GPU arm
+def fp64_peak_tflops(torch, _lib, sms):
+    """FP64 pipe peak measured live (DFMA and DMMA.8x8x4 yardsticks; the larger is the denominator)."""
+    lib = _lib.load()
+    sink = torch.zeros(8, dtype=torch.float64, device="cuda")
+    best = {}
+    for name, fn, flops in (("dfma", lib.dagma_bench_fp64_fma, lambda c, t, i: c * t * i * 32.0),
+                            ("dmma", lib.dagma_bench_fp64_dmma, lambda c, t, i: c * (t // 32) * i * 8 * 512.0)):
+        ctas, threads, iters = sms * 4, 512, 4000 if name == "dfma" else 500
+        fn(_lib.stream_ptr(), ctas, threads, iters, sink.data_ptr())
+        torch.cuda.synchronize()
+        tbest = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(_lib.stream_ptr(), ctas, threads, iters, sink.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            tbest = min(tbest, e0.elapsed_time(e1) * 1e-3)
+        best[name] = flops(ctas, threads, iters) / tbest / 1e12
+    return best
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from midagma_b200 import _lib, fit_batch
+    from midagma_b200.linear import _run_small, center_cov
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sms = _lib.require_device()
+    dev = torch.device("cuda", local)
+
+    nprob = args.problems
+    n_seeds = max(nprob // len(LAMBDAS), 1)
+    seed0 = 1000 + rank * n_seeds                       # every rank owns different problems
+    t_gen = time.perf_counter()
+    X = make_covs(n_seeds, seed0)
+    Xd = torch.from_numpy(X).to(dev)
+    cov_seed = center_cov(Xd, center=True)
+    del Xd, X
+    cov = cov_seed.repeat_interleave(len(LAMBDAS), dim=0)[:nprob].contiguous()
+    lam = torch.tensor([LAMBDAS[i % 4] for i in range(nprob)], dtype=torch.float64, device=dev)
+    t_gen = time.perf_counter() - t_gen
+
+    W = torch.zeros(nprob, D, D, dtype=torch.float64, device=dev)
+
+    def step():
+        return _run_small(cov, W, lam, [1.0], [1.0], [ITERS_PER_STEP], lr=3e-4, tol=0.0, beta1=0.99, beta2=0.999,
+                          checkpoint=ITERS_PER_STEP, retry=False, want_final=False)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    done = 0
+    ev[0].record()
+    results = []
+    for k in range(args.steps):
+        results.append(step())
+        ev[k + 1].record()
+    sync()
+    clocks = sampler.stop() if sampler else None
+    dt = ev[0].elapsed_time(ev[-1]) * 1e-3
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    done = sum(int(r.stage_stats[:, 0, 0].sum().item()) for r in results)
+    assert done == nprob * ITERS_PER_STEP * args.steps, "a problem stopped early inside the timed region"
+
+    # ---- e2e: public host API, pinned host buffers, copies inside the timed region
+    from midagma_b200 import minimize_batch
+    W_host = torch.zeros(nprob, D, D, dtype=torch.float64).pin_memory()
+    cov_host = cov.cpu().pin_memory()
+    lam_host = lam.cpu().numpy()
+    minimize_batch(W_host, cov_host, lam_host, 1.0, ITERS_PER_STEP, 1.0, 3e-4, tol=0.0,
+                   checkpoint=ITERS_PER_STEP, device=dev)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t_e2e = time.perf_counter()
+    for _ in range(args.steps):
+        W_host, ok, st = minimize_batch(W_host, cov_host, lam_host, 1.0, ITERS_PER_STEP, 1.0, 3e-4,
+                                        tol=0.0, checkpoint=ITERS_PER_STEP, device=dev)
+    e1.record()
+    sync()
+    dt_e2e = max(e0.elapsed_time(e1) * 1e-3, 0.0)
+    dt_e2e_wall = time.perf_counter() - t_e2e
+
+    # ---- max over ranks
+    def rmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dt, dt_e2e = rmax(dt), rmax(max(dt_e2e, dt_e2e_wall))
+    total_iters = float(nprob) * ITERS_PER_STEP * args.steps * world
+    value = total_iters / dt
+    e2e_value = total_iters / dt_e2e
+
+    extra = {}
+    if rank == 0:
+        peaks = fp64_peak_tflops(torch, _lib, sms)
+        peak = max(peaks.values())
+        per_gpu_rate = nprob * ITERS_PER_STEP / (sum(kernel_ms) / len(kernel_ms) * 1e-3)
+        achieved = per_gpu_rate * FLOP_PER_ITER / 1e12
+        extra["roofline"] = {
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "fit_small_kernel (one launch per step)",
+            "peak_source": "measured live: FP64 pipe yardsticks " + json.dumps({k: round(v, 2) for k, v in peaks.items()})
+                           + " TFLOP/s (MEASURED_PEAKS.json has no FP64 entry; FP64 tensor = FP64 FMA rate on B200)",
+            "flop_per_unit": FLOP_PER_ITER, "units_per_launch": nprob * ITERS_PER_STEP,
+        }
+        if args.cpu_baseline:
+            rate, cores, cdone, cwall = cpu_rate(args.cpu_iters)
+            extra["cpu_baseline"] = {
+                "value": rate, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
+                "sample": f"{cores} problems (one per core) x {args.cpu_iters} iterations, {cwall:.1f} s wall, "
+                          "oracle/linear_ref.py (numpy/scipy restatement of the reference), 1 BLAS thread per process"}
+        if args.full_fit and world == 1:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            W_est, info = fit_batch(cov=cov, lambda1=lam, return_info=True, device=dev)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            extra["full_fit"] = {"problems": nprob, "wall_s": wall, "total_inner_iters": info["total_iters"],
+                                 "iters_per_s": info["total_iters"] / wall,
+                                 "status_nonzero": int((info["status"] != 0).sum()),
+                                 "mean_edges": float((W_est != 0).sum(axis=(1, 2)).mean())}
+
+    if rank == 0:
+        line = {
+            "metric": "DagmaLinear inner Adam iters/sec (batched d=64)", "value": value,
+            "unit": "problem-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4: batched DagmaLinear l2 minimize, ER4 d=64 n=1000, 1024 seeds x 4 lambda1",
+                       "problems_per_gpu": nprob, "d": D, "n": N_SAMPLES, "iters_per_step": ITERS_PER_STEP,
+                       "mu": 1.0, "s": 1.0, "lr": 3e-4, "l2_policy": "inputs exceed L2 (cov+W = 268 MB per GPU)",
+                       "data_gen_s": round(t_gen, 1)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "problem-iterations/s",
+                    "h2d_bytes_per_step": 2 * nprob * D * D * 8 + nprob * 8, "d2h_bytes_per_step": nprob * D * D * 8},
+            "gpu_launches": args.steps,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--problems", type=int, default=4096, help="problems per GPU")
+    ap.add_argument("--cpu-iters", type=int, default=1500)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-full-fit", dest="full_fit", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,49 @@ int dagma_linear_fit_small_geometry(int d, int batch, int* ctas, int* threads, s
  * H2D, the fit and D2H on `stream`, then synchronises.  w_host in/out [batch][d][d].  */
 int dagma_linear_fit_small_host_f64(dagma_stream_t stream, const dagma_small_fit_args* args_host_ptrs);
 
+/* ---- large-d / logistic building blocks (one inner iteration = a fixed launch sequence) ---
+ * FP64 tensor-core (DMMA) GEMM, row-major:  C = alpha * op(A) * B + beta * C, optional
+ * sigmoid epilogue (epilogue = 1).  Replaces the BLAS calls of the score:
+ *   cov @ (I - W)                       src/dagma/linear.py:86, 244
+ *   X @ W, (X^T / n) @ sigmoid(X @ W)   src/dagma/linear.py:90-92, 246
+ * ws_dev: optional split-K workspace (deterministic two-pass reduction).              */
+int dagma_gemm_f64(dagma_stream_t stream, int trans_a, int M, int N, int K, double alpha,
+                   const double* a_dev, int lda, const double* b_dev, int ldb, double beta,
+                   double* c_dev, int ldc, int epilogue, double* ws_dev, size_t ws_bytes);
+
+/* single-problem fused slogdet+inverse with caller-provided workspace (graph capturable);
+ * d <= 128 on chip, larger d blocked Gauss-Jordan with DMMA trailing updates.           */
+size_t dagma_large_workspace_bytes(int d);
+int dagma_logdet_inv_ws_f64(dagma_stream_t stream, int d, double s, const double* a_dev, int lda,
+                            int square_input, double* logabsdet_dev, double* h_dev, double* minv_dev,
+                            double* grad_dev, int ldo, double* min_entry_dev, int* info_dev,
+                            double* ws_dev, size_t ws_bytes);
+
+/* device-resident iteration state (19 doubles): mu, s, lr, lambda1, beta1, beta2,
+ * beta1^it (hi, lo), beta2^it (hi, lo), logabsdet, h, min_entry, score_acc, l1_acc,
+ * loss_acc, gscale, then int32 it, halted, info, pad.                                   */
+#define DAGMA_LIN_STATE_DOUBLES 19
+/* Gobj + Adam + step + masks + iteration counter; no-op (latching `halted`) if the
+ * inverse of this iteration was infeasible.   src/dagma/linear.py:248, 158-162, 275-276  */
+int dagma_linear_update_f64(dagma_stream_t stream, int d, void* state_dev, double* w_dev,
+                            const double* minv_dev, const double* t_dev, const double* cov_dev,
+                            double* m_dev, double* v_dev, const uint8_t* mask_exc_dev,
+                            const uint8_t* mask_inc_dev);
+/* W += sign * lr * (previous Adam direction)     src/dagma/linear.py:235, 239           */
+int dagma_linear_apply_dir_f64(dagma_stream_t stream, int d, const void* state_dev, double* w_dev,
+                               const double* m_dev, const double* v_dev, double sign);
+/* checkpoint reductions: l2 score 1/2 tr((I-W)^T cov (I-W)) and sum|W|   linear.py:85-87, 129 */
+int dagma_linear_objective_f64(dagma_stream_t stream, int d, void* state_dev, const double* w_dev,
+                               const double* t_dev, const double* cov_dev, int l2);
+/* out = scale * sum(logaddexp(0, R) - X o R)      src/dagma/linear.py:91                 */
+int dagma_logistic_loss_f64(dagma_stream_t stream, int n, int d, const double* x_dev, const double* r_dev,
+                            double scale, double* partial_dev, int n_partial, double* out_dev);
+
+/* Replaces: DagmaLinear._adam_update   src/dagma/linear.py:158-163 (bias1 = 1 - beta1^iter) */
+int dagma_adam_direction_f64(dagma_stream_t stream, size_t n, const double* grad_dev, double* m_dev,
+                             double* v_dev, double beta1, double beta2, double bias1, double bias2,
+                             double* out_dev);
+
 /* ---- data staging in front of the path ---------------------------------------------
  * Replaces: X -= X.mean(0) (in place) and cov = X^T X / n   src/dagma/linear.py:410-411, 428
  * x_dev [batch][n][d] (centred in place when center != 0), cov_dev [batch][d][d].     */

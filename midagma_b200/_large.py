@@ -1,0 +1,265 @@
+"""Multi-CTA engine behind ``DagmaLinear`` for d > 64 and for the logistic loss.
+
+One inner iteration of ``DagmaLinear.minimize`` (src/dagma/linear.py:224-276) is a fixed
+sequence of kernel launches from libdagma_b200.so working on a 19-double device state
+block (mu, s, lr, bias-correction powers, iteration counter, feasibility latch):
+
+    fused slogdet+inverse  ->  score GEMM(s)  [-> all-reduce when rows are sharded]
+    ->  fused Gobj/Adam/step/mask/feasibility
+
+captured once as a CUDA graph and replayed; the host only synchronises at the
+convergence checkpoints (every ``checkpoint`` iterations), exactly where the reference
+evaluates the objective (linear.py:279-331).  Infeasible inverses latch ``halted`` on
+the device; the (rare) undo / halve-lr / redo logic of linear.py:230-241 then runs on
+the host with the same kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ST_DOUBLES = 19
+(F_MU, F_S, F_LR, F_LAM, F_B1, F_B2, F_P1H, F_P1L, F_P2H, F_P2L, F_LAD, F_H, F_MIN, F_SCORE, F_L1, F_LOSS,
+ F_GSCALE) = range(17)
+I_IT, I_HALTED, I_INFO = 0, 1, 2          # int32 slots inside doubles 17..18
+
+
+def gemm(A, B, C, *, trans_a=False, alpha=1.0, beta=0.0, epilogue=0, ws=None):
+    """C = alpha * op(A) @ B + beta * C on device (FP64 DMMA kernel); 2-D contiguous tensors."""
+    K, N = B.shape
+    M = A.shape[1] if trans_a else A.shape[0]
+    assert (A.shape[0] if trans_a else A.shape[1]) == K and C.shape == (M, N)
+    assert A.is_contiguous() and B.is_contiguous() and C.is_contiguous()
+    _lib.check(_lib.load().dagma_gemm_f64(
+        _lib.stream_ptr(), int(trans_a), M, N, K, float(alpha), A.data_ptr(), A.shape[1], B.data_ptr(), N,
+        float(beta), C.data_ptr(), N, int(epilogue), ws.data_ptr() if ws is not None else None,
+        ws.numel() * 8 if ws is not None else 0), "dagma_gemm_f64")
+    return C
+
+
+class LargeLinearEngine:
+    def __init__(self, model, group=None):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.loss_type = model.loss_type
+        self.d, self.n = model.d, model.n
+        self.dev = model._device
+        self.cov = model._cov_dev.contiguous()
+        self.X = model._X_dev.contiguous() if self.loss_type == "logistic" else None
+        self.mask_exc, self.mask_inc = model._mask_exc, model._mask_inc
+        self.group = group                       # torch.distributed group when rows of X are sharded
+        self.n_total = getattr(model, "_n_total", self.n)
+        d = self.d
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.W = torch.zeros(d, d, **f64)
+        self.Minv = torch.empty(d, d, **f64)
+        self.T = torch.empty(d, d, **f64)
+        self.m = torch.zeros(d, d, **f64)
+        self.v = torch.zeros(d, d, **f64)
+        self.state = torch.zeros(ST_DOUBLES, **f64)
+        self.state_host = torch.zeros(ST_DOUBLES, dtype=torch.float64).pin_memory()
+        ws_bytes = self.lib.dagma_large_workspace_bytes(d)
+        self.ws = torch.empty(ws_bytes // 8 + 8, **f64)
+        self.kws = torch.empty(148 * d * d + 8, **f64) if self.loss_type == "logistic" else None
+        if self.X is not None:
+            self.R = torch.empty(self.n, d, **f64)
+            self.partial = torch.empty(1024, **f64)
+        self._graph = None
+        self._model_cov_ptr = model._cov_dev.data_ptr()
+        self.launches_per_iter = None
+
+    def stale(self, model) -> bool:
+        return model._cov_dev.data_ptr() != self._model_cov_ptr or model.d != self.d
+
+    # ------------------------------------------------------------------ state block
+    def _sptr(self, field: int) -> int:
+        return self.state.data_ptr() + 8 * field
+
+    def _iptr(self, slot: int) -> int:
+        return self.state.data_ptr() + 8 * 17 + 4 * slot
+
+    def _push(self, **kw):
+        self.state_host.copy_(self.state)
+        ints = self.state_host[17:].view(torch.int32)
+        for k, val in kw.items():
+            if k in ("it", "halted", "info"):
+                ints[{"it": I_IT, "halted": I_HALTED, "info": I_INFO}[k]] = int(val)
+            else:
+                self.state_host[k] = float(val)
+        self.state.copy_(self.state_host, non_blocking=True)
+
+    def _pull(self):
+        self.state_host.copy_(self.state)
+        ints = self.state_host[17:].view(torch.int32)
+        return self.state_host, int(ints[I_IT]), int(ints[I_HALTED]), int(ints[I_INFO])
+
+    # ------------------------------------------------------------------ launch sequences
+    def _inverse(self, s: float, W=None, want_grad=None):
+        W = self.W if W is None else W
+        _lib.check(self.lib.dagma_logdet_inv_ws_f64(
+            _lib.stream_ptr(), self.d, float(s), W.data_ptr(), self.d, 1, self._sptr(F_LAD), self._sptr(F_H),
+            self.Minv.data_ptr(), want_grad.data_ptr() if want_grad is not None else None, self.d,
+            self._sptr(F_MIN), self._iptr(I_INFO), self.ws.data_ptr(), self.ws.numel() * 8), "dagma_logdet_inv_ws_f64")
+
+    def _score_T(self, W=None, sigmoid=True):
+        """l2: T = cov @ W.  logistic: T = X^T sigmoid(X W) (partial over the local rows, then all-reduced)."""
+        W = self.W if W is None else W
+        if self.loss_type == "l2":
+            gemm(self.cov, W, self.T)
+        else:
+            gemm(self.X, W, self.R, epilogue=1 if sigmoid else 0)
+            if sigmoid:
+                gemm(self.X, self.R, self.T, trans_a=True, ws=self.kws)
+                if self.group is not None:
+                    torch.distributed.all_reduce(self.T, group=self.group)
+
+    def _update(self):
+        ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        _lib.check(self.lib.dagma_linear_update_f64(
+            _lib.stream_ptr(), self.d, self.state.data_ptr(), self.W.data_ptr(), self.Minv.data_ptr(),
+            self.T.data_ptr(), self.cov.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), ptr(self.mask_exc),
+            ptr(self.mask_inc)), "dagma_linear_update_f64")
+
+    def _iteration(self, s: float):
+        self._inverse(s)
+        self._score_T()
+        self._update()
+
+    def _replay(self, s: float, n: int):
+        if self.group is not None:               # NCCL inside the sequence: launch eagerly
+            for _ in range(n):
+                self._iteration(s)
+            return
+        if self._graph is None or self._graph_s != s:
+            self._iteration(s)                   # warm-up on the current stream (also sets kernel attributes)
+            torch.cuda.synchronize()
+            # the warm-up advanced the state: it is re-initialised by the caller before counting
+            self._graph = torch.cuda.CUDAGraph()
+            self._graph_s = s
+            self._restore_after_warmup()
+            with torch.cuda.graph(self._graph):
+                self._iteration(s)
+        for _ in range(n):
+            self._graph.replay()
+
+    def _snapshot(self):
+        self._snap = (self.W.clone(), self.m.clone(), self.v.clone(), self.state.clone())
+
+    def _restore_after_warmup(self):
+        W, m, v, st = self._snap
+        self.W.copy_(W)
+        self.m.copy_(m)
+        self.v.copy_(v)
+        self.state.copy_(st)
+
+    def _apply_dir(self, sign: float):
+        _lib.check(self.lib.dagma_linear_apply_dir_f64(_lib.stream_ptr(), self.d, self.state.data_ptr(),
+                                                       self.W.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                                       float(sign)), "dagma_linear_apply_dir_f64")
+
+    # ------------------------------------------------------------------ objective (linear.py:118-135)
+    def _objective(self, mu: float, s: float, lambda1: float):
+        self._inverse(s)
+        if self.loss_type == "l2":
+            self._score_T()
+            _lib.check(self.lib.dagma_linear_objective_f64(_lib.stream_ptr(), self.d, self.state.data_ptr(),
+                                                           self.W.data_ptr(), self.T.data_ptr(), self.cov.data_ptr(), 1),
+                       "dagma_linear_objective_f64")
+            st, *_ = self._pull()
+            score = float(st[F_SCORE])
+        else:
+            score = self._logistic_loss(self.W)
+            _lib.check(self.lib.dagma_linear_objective_f64(_lib.stream_ptr(), self.d, self.state.data_ptr(),
+                                                           self.W.data_ptr(), None, None, 0), "dagma_linear_objective_f64")
+            st, *_ = self._pull()
+        h, l1 = float(st[F_H]), float(st[F_L1])
+        obj = mu * (score + lambda1 * l1) + h
+        return obj, score, h
+
+    def _logistic_loss(self, W) -> float:
+        gemm(self.X, W, self.R)
+        _lib.check(self.lib.dagma_logistic_loss_f64(_lib.stream_ptr(), self.n, self.d, self.X.data_ptr(),
+                                                    self.R.data_ptr(), 1.0 / self.n_total, self.partial.data_ptr(), 592,
+                                                    self._sptr(F_LOSS)), "dagma_logistic_loss_f64")
+        if self.group is not None:
+            torch.distributed.all_reduce(self.state[F_LOSS:F_LOSS + 1], group=self.group)
+        st, *_ = self._pull()
+        return float(st[F_LOSS])
+
+    # ------------------------------------------------------------------ public pieces
+    def score(self, W: torch.Tensor):
+        """``_score`` (linear.py:70-94): (loss, gradient) at W."""
+        W = W.contiguous()
+        G = self.cov.clone()
+        if self.loss_type == "l2":
+            gemm(self.cov, W, G, alpha=1.0, beta=-1.0)                 # cov W - cov = -cov (I - W)
+            gemm(self.cov, W, self.T)
+            _lib.check(self.lib.dagma_linear_objective_f64(_lib.stream_ptr(), self.d, self.state.data_ptr(),
+                                                           W.data_ptr(), self.T.data_ptr(), self.cov.data_ptr(), 1),
+                       "dagma_linear_objective_f64")
+            st, *_ = self._pull()
+            return float(st[F_SCORE]), G
+        loss = self._logistic_loss(W)
+        gemm(self.X, W, self.R, epilogue=1)
+        if self.group is None:
+            gemm(self.X, self.R, G, trans_a=True, alpha=1.0 / self.n_total, beta=-1.0, ws=self.kws)
+        else:
+            gemm(self.X, self.R, self.T, trans_a=True, ws=self.kws)
+            torch.distributed.all_reduce(self.T, group=self.group)
+            G = self.T / self.n_total - self.cov
+        return loss, G
+
+    def minimize(self, W_np: np.ndarray, mu, max_iter, s, lr, tol, beta_1, beta_2, lambda1, checkpoint, log=None):
+        """linear.py:165-333 on device; returns (status, iterations done).  ``W_np`` is updated in place."""
+        self.W.copy_(torch.from_numpy(np.ascontiguousarray(W_np)))
+        self.m.zero_()
+        self.v.zero_()
+        self.state.zero_()
+        gscale = 1.0 if self.loss_type == "l2" else 1.0 / self.n_total
+        self.state_host.zero_()
+        for f, val in ((F_MU, mu), (F_S, s), (F_LR, lr), (F_LAM, lambda1), (F_B1, beta_1), (F_B2, beta_2),
+                       (F_P1H, 1.0), (F_P2H, 1.0), (F_GSCALE, gscale)):
+            self.state_host[f] = float(val)
+        self.state.copy_(self.state_host)
+        self._snapshot()
+        status, it_done, obj_prev = _lib.ST_OK, 0, 1e16
+        max_iter = int(max_iter)
+        while it_done < max_iter:
+            chunk_end = min((it_done // checkpoint + 1) * checkpoint, max_iter)
+            self._replay(s, chunk_end - it_done)
+            st, it_dev, halted, info = self._pull()
+            if halted:
+                it_done = it_dev
+                if it_done == 0 or s <= 0.9:                      # linear.py:231-233
+                    status |= _lib.ST_OUT_OF_DOMAIN
+                    break
+                stop = False
+                while True:                                      # linear.py:235-241
+                    self._apply_dir(+1.0)
+                    lr *= 0.5
+                    self.state[F_LR:F_LR + 1].fill_(lr)
+                    if lr <= 1e-16:
+                        status |= _lib.ST_LR_UNDERFLOW
+                        stop = True
+                        break
+                    self._apply_dir(-1.0)
+                    self._inverse(s)
+                    _, _, _, info = self._pull()
+                    if info == 0:
+                        break
+                self.state[17:].view(torch.int32)[I_HALTED:I_INFO + 1].zero_()
+                if stop:
+                    break
+                continue
+            it_done = chunk_end
+            obj, score, h = self._objective(mu, s, lambda1)      # linear.py:279-280
+            if log is not None:
+                log.append((0, it_done, obj, score, h, lr))
+            if np.abs((obj_prev - obj) / obj_prev) <= tol:       # linear.py:328
+                break
+            obj_prev = obj
+        W_np[...] = self.W.cpu().numpy()
+        self.last_lr = lr
+        return status, it_done

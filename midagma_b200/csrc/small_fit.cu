@@ -19,6 +19,7 @@
 // update (log-det from the pivots, score from cov @ (I - W)) and the next iteration.
 #include "common.cuh"
 #include "small_gj.cuh"
+#include <cstdlib>
 #include "../../include/dagma_b200.h"
 
 namespace dagma {
@@ -355,6 +356,17 @@ using C16 = Cfg<1, 1, 16, 16>;     // d <= 16 : 256 threads, 1 element each
 using C32 = Cfg<2, 2, 16, 16>;     // d <= 32 : 256 threads, 2 x 2
 using C48 = Cfg<4, 2, 12, 24>;     // d <= 48 : 288 threads, 4 x 2
 using C64 = Cfg<4, 2, 16, 32>;     // d <= 64 : 512 threads, 4 x 2
+using C64B = Cfg<4, 4, 16, 16>;    // d <= 64 : 256 threads, 4 x 4 (fewer shared-memory loads per FMA)
+using C64C = Cfg<2, 4, 32, 16>;    // d <= 64 : 512 threads, 2 x 4
+
+static int c64_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_SMALL_CFG");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
 
 template <class C>
 static int fit_geometry(int batch, int sms, int* ctas, int* threads, size_t* smem_bytes) {
@@ -400,6 +412,8 @@ extern "C" int dagma_linear_fit_small_geometry(int d, int batch, int* ctas, int*
     if (d <= 16) return fit_geometry<C16>(batch, sms, ctas, threads, smem_bytes);
     if (d <= 32) return fit_geometry<C32>(batch, sms, ctas, threads, smem_bytes);
     if (d <= 48) return fit_geometry<C48>(batch, sms, ctas, threads, smem_bytes);
+    if (c64_variant() == 1) return fit_geometry<C64B>(batch, sms, ctas, threads, smem_bytes);
+    if (c64_variant() == 2) return fit_geometry<C64C>(batch, sms, ctas, threads, smem_bytes);
     return fit_geometry<C64>(batch, sms, ctas, threads, smem_bytes);
 }
 
@@ -419,5 +433,7 @@ extern "C" int dagma_linear_fit_small_f64(dagma_stream_t stream_, const dagma_sm
     if (a.d <= 16) return launch_fit<C16>(stream, a, sms);
     if (a.d <= 32) return launch_fit<C32>(stream, a, sms);
     if (a.d <= 48) return launch_fit<C48>(stream, a, sms);
+    if (c64_variant() == 1) return launch_fit<C64B>(stream, a, sms);
+    if (c64_variant() == 2) return launch_fit<C64C>(stream, a, sms);
     return launch_fit<C64>(stream, a, sms);
 }

@@ -137,31 +137,38 @@ def _as_dev(x, device, dtype=torch.float64) -> torch.Tensor:
     return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device)
 
 
+def _lam_dev(lambda1, batch: int, device) -> torch.Tensor:
+    if isinstance(lambda1, torch.Tensor):
+        lam = lambda1.to(device=device, dtype=torch.float64).reshape(-1)
+        return (lam.expand(batch) if lam.numel() == 1 else lam).contiguous()
+    return _as_dev(np.broadcast_to(np.asarray(lambda1, dtype=np.float64), (batch,)), device)
+
+
 def minimize_batch(W, cov, lambda1, mu, max_iter, s, lr, *, tol=1e-6, beta_1=0.99, beta_2=0.999,
                    checkpoint=1000, device=None):
     """One ``DagmaLinear.minimize`` call (linear.py:165-333, l2 loss) for a batch of
-    independent problems.  ``W``/``cov``: [batch, d, d] numpy (pinned or not) or torch
-    tensors on host or device; results come back in the same kind of container.
-    Returns ``(W, success[batch], stats)``."""
+    independent problems.  ``W``/``cov``: [batch, d, d] numpy arrays or torch tensors on
+    host (pinned or not) or device.  Like the reference, ``W`` is updated in place and
+    returned.  Returns ``(W, success[batch], stage_stats[batch, 1, 8])``."""
     device = torch.device(device or "cuda")
-    host_in = not (isinstance(W, torch.Tensor) and W.is_cuda)
-    Wd = _as_dev(W, device)
-    if Wd.data_ptr() == (W.data_ptr() if isinstance(W, torch.Tensor) else 0) and not host_in:
-        pass   # in place on the caller's device tensor, like the reference's in-place W
+    on_device = isinstance(W, torch.Tensor) and W.is_cuda
+    Wd = W if on_device and W.dtype == torch.float64 and W.is_contiguous() else _as_dev(W, device)
     covd = _as_dev(cov, device)
     batch, d, _ = covd.shape
     assert d <= _lib.SMALL_MAX_D, "minimize_batch uses the on-chip path (d <= 64)"
-    lam = _as_dev(np.broadcast_to(np.asarray(lambda1, dtype=np.float64), (batch,)), device)
-    res = _run_small(covd, Wd, lam, [mu], [s], [max_iter], lr=lr, tol=tol, beta1=beta_1, beta2=beta_2,
+    lam = _lam_dev(lambda1, batch, device)
+    res = _run_small(covd, Wd, lam, [mu], [s], [int(max_iter)], lr=lr, tol=tol, beta1=beta_1, beta2=beta_2,
                      checkpoint=checkpoint, retry=False, want_final=False)
     ok = (res.status & _lib.ST_OUT_OF_DOMAIN) == 0
-    if host_in:
-        W_out = res.W.cpu()
-        if isinstance(W, np.ndarray):
-            W[...] = W_out.numpy()
-            W_out = W
-        return W_out, ok.cpu().numpy(), res.stage_stats.cpu().numpy()
-    return res.W, ok, res.stage_stats
+    if on_device:
+        if Wd is not W:
+            W.copy_(Wd)
+        return W, ok, res.stage_stats
+    if isinstance(W, torch.Tensor):
+        W.copy_(res.W)                       # D2H into the caller's (possibly pinned) buffer
+    else:
+        W[...] = res.W.cpu().numpy()
+    return W, ok.cpu().numpy(), res.stage_stats.cpu().numpy()
 
 
 def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1.0, mu_factor=0.1,
@@ -185,7 +192,7 @@ def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1
         covd = _as_dev(cov, device)
     batch, d, _ = covd.shape
     assert d <= _lib.SMALL_MAX_D, "fit_batch uses the on-chip path (d <= 64)"
-    lam = _as_dev(np.broadcast_to(np.asarray(lambda1, dtype=np.float64), (batch,)), device)
+    lam = _lam_dev(lambda1, batch, device)
     T = int(T)
     ss = list(s) if isinstance(s, (list, tuple)) else T * [s]
     if len(ss) < T:
@@ -265,7 +272,15 @@ class DagmaLinear:
 
     # ------------------------------------------------------------------ _adam_update (linear.py:138-163)
     def _adam_update(self, grad: np.ndarray, iter: int, beta_1: float, beta_2: float) -> np.ndarray:
-        return self._large_engine().adam_direction(grad, iter, beta_1, beta_2)
+        g = self._dev(grad)
+        if not isinstance(getattr(self, "opt_m", 0), torch.Tensor):      # reference resets to scalar 0 (:215)
+            self.opt_m, self.opt_v = torch.zeros_like(g), torch.zeros_like(g)
+        out = torch.empty_like(g)
+        _lib.check(_lib.load().dagma_adam_direction_f64(
+            _lib.stream_ptr(), g.numel(), g.data_ptr(), self.opt_m.data_ptr(), self.opt_v.data_ptr(),
+            float(beta_1), float(beta_2), 1 - beta_1 ** iter, 1 - beta_2 ** iter, out.data_ptr()),
+            "dagma_adam_direction_f64")
+        return out.cpu().numpy()
 
     # ------------------------------------------------------------------ minimize (linear.py:165-333)
     def minimize(self, W: np.ndarray, mu: float, max_iter: int, s: float, lr: float, tol: float = 1e-6,
@@ -282,7 +297,10 @@ class DagmaLinear:
             iters_done = int(res.stage_stats[0, 0, 0].item())
             self._record_log(res)
         else:
-            status, iters_done = self._large_engine().minimize(W, mu, int(max_iter), s, lr, tol, beta_1, beta_2)
+            log = []
+            status, iters_done = self._large_engine().minimize(W, mu, int(max_iter), s, lr, tol, beta_1, beta_2,
+                                                               self.lambda1, int(self.checkpoint), log)
+            self.checkpoint_log.extend(log)
         self.last_iters = iters_done
         success = (status & _lib.ST_OUT_OF_DOMAIN) == 0
         if not success:
