@@ -147,6 +147,42 @@ int dagma_adam_direction_f64(dagma_stream_t stream, size_t n, const double* grad
                              double* v_dev, double beta1, double beta2, double bias1, double bias2,
                              double* out_dev);
 
+/* ---- (iv) DagmaMLP / DagmaNonlinear, dims = [d, m1, 1] --------------------------------------
+ * theta = [W1 (P x d) | b1 (P) | W2 (P) | b2 (d)], P = d*m1 (fc1.weight, fc1.bias, fc2.0.weight,
+ * fc2.0.bias of the reference state_dict, src/dagma/nonlinear.py:36-43).  Activations are
+ * [P][n] (transposed).  Device state block (17 doubles): mu, s, lr, lambda1, lambda2, beta1,
+ * beta2, logabsdet, h, min_entry, S, l1, obj, score, lr_gamma, then int32 step, halted, info.
+ * One iteration of DagmaNonlinear.minimize (nonlinear.py:212-225) is:
+ *   dagma_mlp_adj  -> dagma_logdet_inv_ws (square_input = 0)  -> dagma_gemm (Zt = W1 Xt)
+ *   -> dagma_mlp_forward -> [all-reduce S] -> dagma_mlp_objective -> dagma_mlp_backward
+ *   -> dagma_gemm (gW1 = dZt X) -> [all-reduce grads] -> dagma_mlp_adam                        */
+#define DAGMA_MLP_STATE_DOUBLES 17
+/* A[i][j] = sum_k fc1[j,k,i]^2 and partial sums of |fc1|        nonlinear.py:82-84, 97          */
+int dagma_mlp_adj_f64(dagma_stream_t stream, int d, int m1, const double* theta_dev, double* a_dev,
+                      double* l1_partial_dev);
+/* sigmoid + locally-connected layer + residual + partial sum of squares   nonlinear.py:60-65,
+ * locally_connected.py:70-74; writes S and l1 into the state block                              */
+int dagma_mlp_forward_f64(dagma_stream_t stream, int n, int d, int m1, double* zt_dev,
+                          const double* theta_dev, const double* xt_dev, double* res_dev,
+                          double* out_opt_dev, double* s_partial_dev, const double* l1_partial_dev,
+                          void* state_dev);
+/* score = d/2 log(S / n), obj = mu (score + lambda1 l1) + h; latches halted if h < 0
+ *                                                               nonlinear.py:158, 215-221        */
+int dagma_mlp_objective_f64(dagma_stream_t stream, void* state_dev, int n_total, int d);
+/* closed-form backward of the two-layer MLP (un-scaled sums)     autograd of nonlinear.py:218-222 */
+int dagma_mlp_backward_f64(dagma_stream_t stream, int n, int d, int m1, double* ht_dev,
+                           const double* theta_dev, const double* res_dev, double* part_dev,
+                           double* grads_tail_dev);
+/* torch.optim.Adam(betas, weight_decay = mu lambda2) over theta + ExponentialLR   nonlinear.py:208-225 */
+int dagma_mlp_adam_f64(dagma_stream_t stream, int d, int m1, void* state_dev, double* theta_dev,
+                       const double* grads_dev, double* m_dev, double* v_dev, const double* minv_dev);
+/* LocallyConnected.forward                                       locally_connected.py:55-75     */
+int dagma_locally_connected_f64(dagma_stream_t stream, int n, int d, int m1, int m2, const double* in_dev,
+                                const double* w_dev, const double* b_dev, double* out_dev);
+/* out = sum (a - b)^2  (log_mse_loss, nonlinear.py:158)                                           */
+int dagma_sumsq_diff_f64(dagma_stream_t stream, size_t total, const double* a_dev, const double* b_dev,
+                         double* partial_dev, int n_partial, double* out_dev);
+
 /* ---- data staging in front of the path ---------------------------------------------
  * Replaces: X -= X.mean(0) (in place) and cov = X^T X / n   src/dagma/linear.py:410-411, 428
  * x_dev [batch][n][d] (centred in place when center != 0), cov_dev [batch][d][d].     */

@@ -1,0 +1,294 @@
+// DagmaMLP / DagmaNonlinear inner iteration for dims = [d, m1, 1] (reference:
+// src/dagma/nonlinear.py:45-97, 139-159, 208-225; src/dagma/locally_connected.py:55-75).
+//
+// Parameters live in one flat FP64 buffer  theta = [W1 (P x d) | b1 (P) | W2 (P) | b2 (d)],
+// P = d*m1, row p = j*m1 + k of W1 is hidden unit k of node j (fc1.weight layout).
+// Activations are kept TRANSPOSED ([P][n], sample index fastest) so that both GEMMs are
+// plain row-major products on the DMMA kernel and every element-wise pass is coalesced:
+//     Zt = W1 Xt            (P x n,  K = d)
+//     gW1 = dZt X           (P x d,  K = n, split-K)
+// The log couples all samples only through S = sum res^2, so all sums are accumulated
+// un-scaled (d/S is applied in the Adam kernel): with rows of X sharded over GPUs one
+// all-reduce of [grads | S] per iteration is enough.
+#include "common.cuh"
+#include "small_gj.cuh"
+#include "../../include/dagma_b200.h"
+
+namespace dagma {
+
+struct MlpState {            // mirrored by midagma_b200/nonlinear.py
+    double mu, s, lr, lambda1, lambda2, beta1, beta2;
+    double logabsdet, h, min_entry;       // written by the logdet kernel
+    double S, l1, obj, score;             // S = sum res^2 (this rank, then global), l1 = sum |W1|
+    double lr_gamma;                      // ExponentialLR factor applied every 1000 steps (1 = off)
+    int32_t step, halted, info, pad;
+};
+
+// A[i][j] = sum_k W1[(j*m1+k)][i]^2  (nonlinear.py:82-84)  + partial sums of |W1|
+__global__ void mlp_adj_kernel(const double* __restrict__ W1, int d, int m1, double* __restrict__ A,
+                               double* __restrict__ l1_partial) {
+    __shared__ double red[96];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;      // e = j*d + i  (coalesced over i)
+    double a = 0.0, l1 = 0.0, z = 0.0;
+    if (e < d * d) {
+        const int j = e / d, i = e - j * d;
+        for (int k = 0; k < m1; ++k) {
+            const double w = W1[(size_t)(j * m1 + k) * d + i];
+            a = fma(w, w, a);
+            l1 += fabs(w);
+        }
+        A[(size_t)i * d + j] = a;
+    }
+    double dummy = 0.0;
+    block_sum3<256>(l1, z, dummy, red, threadIdx.x);
+    if (threadIdx.x == 0) l1_partial[blockIdx.x] = l1;
+}
+
+// forward tail: H = sigmoid(Zt + b1) (in place), out = sum_k H W2 + b2, res = out - Xt, partial S
+__global__ void __launch_bounds__(256) mlp_forward_kernel(double* __restrict__ Zt, const double* __restrict__ theta,
+                                                          const double* __restrict__ Xt, int n, int d, int m1,
+                                                          double* __restrict__ res, double* __restrict__ out_opt,
+                                                          double* __restrict__ S_partial) {
+    __shared__ double red[96];
+    const int P = d * m1;
+    const double* b1 = theta + (size_t)P * d;
+    const double* W2 = b1 + P;
+    const double* b2 = W2 + P;
+    const int j = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    double sq = 0.0, z1 = 0.0, z2 = 0.0;
+    if (s < n) {
+        double o = b2[j];
+        for (int k = 0; k < m1; ++k) {
+            const int p = j * m1 + k;
+            const double zz = Zt[(size_t)p * n + s] + b1[p];
+            const double hh = 1.0 / (1.0 + exp(-zz));
+            Zt[(size_t)p * n + s] = hh;
+            o = fma(hh, W2[p], o);
+        }
+        const double r = o - Xt[(size_t)j * n + s];
+        res[(size_t)j * n + s] = r;
+        if (out_opt) out_opt[(size_t)s * d + j] = o;
+        sq = r * r;
+    }
+    block_sum3<256>(sq, z1, z2, red, threadIdx.x);
+    if (threadIdx.x == 0) S_partial[blockIdx.y * gridDim.x + blockIdx.x] = sq;
+}
+
+// S, l1 -> state; score, obj; latch `halted` when h < 0 (nonlinear.py:215-221)
+__global__ void mlp_finish_forward_kernel(MlpState* st, const double* S_partial, int nS, const double* l1_partial,
+                                          int nl1, int n_total, int d) {
+    if (threadIdx.x != 0) return;
+    double S = 0.0, l1 = 0.0;
+    for (int i = 0; i < nS; ++i) S += S_partial[i];
+    for (int i = 0; i < nl1; ++i) l1 += l1_partial[i];
+    st->S = S;
+    st->l1 = l1;
+    (void)n_total; (void)d;
+}
+// after the (optional) all-reduce of S
+__global__ void mlp_objective_kernel(MlpState* st, int n_total, int d) {
+    if (threadIdx.x != 0) return;
+    const double score = 0.5 * (double)d * log(st->S / (double)n_total);
+    st->score = score;
+    st->obj = st->mu * (score + st->lambda1 * st->l1) + st->h;
+    if (st->halted == 0 && st->h < 0.0) st->halted = 1;
+}
+
+// backward tail: dZt (un-scaled, overwrites H) and the partial sums over this block's samples of
+//   gW2[p] = sum res H, gb1[p] = sum dZ, gb2[j] = sum res      (SURVEY.md "validated restatements")
+__global__ void __launch_bounds__(256) mlp_backward_kernel(double* __restrict__ Ht, const double* __restrict__ theta,
+                                                           const double* __restrict__ res, int n, int d, int m1,
+                                                           double* __restrict__ part) {   // [chunks][2P + d]
+    __shared__ double red[96];
+    const int P = d * m1;
+    const double* W2 = theta + (size_t)P * d + P;
+    const int j = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = s < n;
+    const double r = ok ? res[(size_t)j * n + s] : 0.0;
+    double* row = part + (size_t)blockIdx.x * (2 * P + d);
+    for (int k = 0; k < m1; ++k) {
+        const int p = j * m1 + k;
+        double gw2 = 0.0, gb1 = 0.0, z = 0.0;
+        if (ok) {
+            const double hh = Ht[(size_t)p * n + s];
+            const double dz = r * W2[p] * hh * (1.0 - hh);
+            Ht[(size_t)p * n + s] = dz;
+            gw2 = r * hh;
+            gb1 = dz;
+        }
+        block_sum3<256>(gw2, gb1, z, red, threadIdx.x);
+        if (threadIdx.x == 0) {
+            row[P + p] = gw2;          // layout of `part` row: [gb1 (P) | gW2 (P) | gb2 (d)]
+            row[p] = gb1;
+        }
+    }
+    double rr = r, z1 = 0.0, z2 = 0.0;
+    block_sum3<256>(rr, z1, z2, red, threadIdx.x);
+    if (threadIdx.x == 0) row[2 * P + j] = rr;
+}
+// grads[P*d ...] = sum over chunks (fixed order)
+__global__ void mlp_reduce_parts_kernel(const double* __restrict__ part, int chunks, int width, double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= width) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; ++c) s += part[(size_t)c * width + e];
+    out[e] = s;
+}
+
+// torch.optim.Adam step (single-tensor form, weight decay added to the gradient) over theta.
+// grads hold UN-SCALED score sums; the factor d/S and mu are applied here; fc1.weight also gets
+// mu*lambda1*sign(w) and dh/dw = 2 w Minv[j][i]   (nonlinear.py:208, 220-223).
+__global__ void __launch_bounds__(256) mlp_adam_kernel(const MlpState* st, double* __restrict__ theta,
+                                                       const double* __restrict__ grads, double* __restrict__ m,
+                                                       double* __restrict__ v, const double* __restrict__ Minv,
+                                                       int d, int m1, size_t total) {
+    if (st->halted != 0) return;
+    const double mu = st->mu, lr = st->lr, b1 = st->beta1, b2 = st->beta2;
+    const double wd = mu * st->lambda2, l1c = mu * st->lambda1;
+    const double gs = mu * (double)d / st->S;
+    const int step = st->step + 1;
+    const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+    const double step_size = lr / bc1, bc2s = sqrt(bc2);
+    const size_t nW1 = (size_t)d * m1 * d;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const double p = theta[e];
+        double g = gs * grads[e];
+        if (e < nW1) {
+            const int row = (int)(e / d), i = (int)(e - (size_t)row * d), j = row / m1;
+            const double sg = (p > 0.0) ? 1.0 : ((p < 0.0) ? -1.0 : 0.0);
+            g = fma(l1c, sg, g);
+            g = fma(2.0 * p, Minv[(size_t)j * d + i], g);
+        }
+        g = fma(wd, p, g);
+        const double mn = m[e] + (g - m[e]) * (1.0 - b1);            // exp_avg.lerp_(grad, 1 - beta1)
+        const double vn = fma(v[e], b2, (1.0 - b2) * g * g);
+        m[e] = mn;
+        v[e] = vn;
+        const double denom = sqrt(vn) / bc2s + 1e-8;
+        theta[e] = p - step_size * (mn / denom);
+    }
+}
+__global__ void mlp_advance_kernel(MlpState* st) {
+    if (st->halted != 0) return;
+    st->step += 1;
+    if (st->lr_gamma != 1.0 && (st->step % 1000) == 0) st->lr *= st->lr_gamma;   // ExponentialLR, nonlinear.py:224-225
+}
+
+}  // namespace dagma
+
+using namespace dagma;
+
+extern "C" int dagma_mlp_adj_f64(dagma_stream_t stream, int d, int m1, const double* theta_dev, double* a_dev,
+                                 double* l1_partial_dev) {
+    DAGMA_REQUIRE(theta_dev && a_dev && l1_partial_dev, "null pointer");
+    mlp_adj_kernel<<<(d * d + 255) / 256, 256, 0, (cudaStream_t)stream>>>(theta_dev, d, m1, a_dev, l1_partial_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dagma_mlp_forward_f64(dagma_stream_t stream, int n, int d, int m1, double* zt_dev,
+                                     const double* theta_dev, const double* xt_dev, double* res_dev,
+                                     double* out_opt_dev, double* s_partial_dev, const double* l1_partial_dev,
+                                     void* state_dev) {
+    DAGMA_REQUIRE(zt_dev && theta_dev && xt_dev && res_dev && s_partial_dev && state_dev, "null pointer");
+    dim3 grid((n + 255) / 256, d);
+    mlp_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(zt_dev, theta_dev, xt_dev, n, d, m1, res_dev, out_opt_dev,
+                                                              s_partial_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    mlp_finish_forward_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((MlpState*)state_dev, s_partial_dev, grid.x * grid.y,
+                                                                 l1_partial_dev, l1_partial_dev ? (d * d + 255) / 256 : 0, 0, d);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dagma_mlp_objective_f64(dagma_stream_t stream, void* state_dev, int n_total, int d) {
+    mlp_objective_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((MlpState*)state_dev, n_total, d);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dagma_mlp_backward_f64(dagma_stream_t stream, int n, int d, int m1, double* ht_dev,
+                                      const double* theta_dev, const double* res_dev, double* part_dev,
+                                      double* grads_tail_dev) {
+    DAGMA_REQUIRE(ht_dev && theta_dev && res_dev && part_dev && grads_tail_dev, "null pointer");
+    const int chunks = (n + 255) / 256, width = 2 * d * m1 + d;
+    dim3 grid(chunks, d);
+    mlp_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ht_dev, theta_dev, res_dev, n, d, m1, part_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    mlp_reduce_parts_kernel<<<(width + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part_dev, chunks, width, grads_tail_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dagma_mlp_adam_f64(dagma_stream_t stream, int d, int m1, void* state_dev, double* theta_dev,
+                                  const double* grads_dev, double* m_dev, double* v_dev, const double* minv_dev) {
+    DAGMA_REQUIRE(state_dev && theta_dev && grads_dev && m_dev && v_dev && minv_dev, "null pointer");
+    const size_t total = (size_t)d * m1 * d + 2 * (size_t)d * m1 + d;
+    const int blocks = (int)((total + 255) / 256);
+    mlp_adam_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, (cudaStream_t)stream>>>((const MlpState*)state_dev, theta_dev,
+                                                                                     grads_dev, m_dev, v_dev, minv_dev, d, m1, total);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    mlp_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((MlpState*)state_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- stand-alone helpers of the public surface -------------------------------------------
+namespace dagma {
+// LocallyConnected.forward (locally_connected.py:70-74): out[n,j,:] = in[n,j,:] @ W[j] + b[j]
+__global__ void locally_connected_kernel(const double* __restrict__ in, const double* __restrict__ W,
+                                         const double* __restrict__ b, double* __restrict__ out, int n, int d,
+                                         int m1, int m2) {
+    const size_t total = (size_t)n * d * m2;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(e % m2);
+        const int j = (int)((e / m2) % d);
+        const size_t s = e / ((size_t)m2 * d);
+        double acc = b ? b[(size_t)j * m2 + o] : 0.0;
+        const double* x = in + (s * d + j) * m1;
+        const double* w = W + (size_t)j * m1 * m2 + o;
+        for (int k = 0; k < m1; ++k) acc = fma(x[k], w[(size_t)k * m2], acc);
+        out[e] = acc;
+    }
+}
+__global__ void __launch_bounds__(256) sumsq_diff_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                         size_t total, double* partial) {
+    __shared__ double red[96];
+    double acc = 0.0, z1 = 0.0, z2 = 0.0;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const double dlt = a[e] - b[e];
+        acc = fma(dlt, dlt, acc);
+    }
+    block_sum3<256>(acc, z1, z2, red, threadIdx.x);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void sum_small_kernel(const double* partial, int n, double* out) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += partial[i];
+    *out = s;
+}
+}  // namespace dagma
+
+extern "C" int dagma_locally_connected_f64(dagma_stream_t stream, int n, int d, int m1, int m2, const double* in_dev,
+                                           const double* w_dev, const double* b_dev, double* out_dev) {
+    DAGMA_REQUIRE(in_dev && w_dev && out_dev, "null pointer");
+    const size_t total = (size_t)n * d * m2;
+    const int blocks = (int)((total + 255) / 256);
+    dagma::locally_connected_kernel<<<blocks < 2368 ? blocks : 2368, 256, 0, (cudaStream_t)stream>>>(in_dev, w_dev, b_dev,
+                                                                                                   out_dev, n, d, m1, m2);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dagma_sumsq_diff_f64(dagma_stream_t stream, size_t total, const double* a_dev, const double* b_dev,
+                                    double* partial_dev, int n_partial, double* out_dev) {
+    DAGMA_REQUIRE(a_dev && b_dev && partial_dev && out_dev && n_partial >= 1, "bad arguments");
+    const int blocks = n_partial < 592 ? n_partial : 592;
+    dagma::sumsq_diff_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a_dev, b_dev, total, partial_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    dagma::sum_small_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(partial_dev, blocks, out_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}

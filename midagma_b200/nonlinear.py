@@ -1,0 +1,371 @@
+"""Drop-in ``DagmaMLP`` / ``DagmaNonlinear`` / ``LocallyConnected`` on the B200 kernels
+(reference: src/dagma/nonlinear.py, src/dagma/locally_connected.py).
+
+Same class names, constructor arguments, parameter names and shapes (``fc1.weight
+[d*m1, d]``, ``fc1.bias``, ``fc2.0.weight [d, m1, 1]``, ``fc2.0.bias``) so ``state_dict``s
+interchange with the reference; same defaults and failure behaviour (``minimize`` returns
+``False`` when ``h < 0``; ``fit`` restores the stage-start parameters, halves ``lr``, turns on
+the exponential decay and retries with ``s = 1``).  The reference differentiates with torch
+autograd on the CPU; here one inner iteration is a fixed sequence of hand-written kernels
+(closed-form backward, see csrc/mlp.cu) replayed as a CUDA graph, and the host only
+synchronises at the convergence checkpoints.  ``dims = [d, m1, 1]`` (the reference's and
+BASELINE.json's configuration) is the supported architecture.
+"""
+from __future__ import annotations
+
+import copy
+import typing
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._large import gemm
+
+__all__ = ["DagmaMLP", "DagmaNonlinear", "LocallyConnected"]
+
+ST_DOUBLES = 17
+(F_MU, F_S, F_LR, F_LAM1, F_LAM2, F_B1, F_B2, F_LAD, F_H, F_MIN, F_SS, F_L1, F_OBJ, F_SCORE, F_GAMMA) = range(15)
+I_STEP, I_HALTED, I_INFO = 0, 1, 2
+
+
+def _cuda64(x) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    return x.detach().to(device="cuda", dtype=torch.float64).contiguous()
+
+
+class LocallyConnected(nn.Module):
+    """d independent ``m1 -> m2`` linear maps (locally_connected.py:6); forward runs on the GPU."""
+
+    def __init__(self, num_linear: int, input_features: int, output_features: int, bias: bool = True):
+        super().__init__()
+        self.num_linear, self.input_features, self.output_features = num_linear, input_features, output_features
+        self.weight = nn.Parameter(torch.Tensor(num_linear, input_features, output_features))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(num_linear, output_features))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    @torch.no_grad()
+    def reset_parameters(self):
+        bound = (1.0 / self.input_features) ** 0.5            # locally_connected.py:49-53
+        nn.init.uniform_(self.weight, -bound, bound)
+        if self.bias is not None:
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    @torch.no_grad()
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        _lib.require_device()
+        x = _cuda64(input)
+        n, d, m1 = x.shape
+        out = torch.empty(n, d, self.output_features, dtype=torch.float64, device="cuda")
+        b = _cuda64(self.bias) if self.bias is not None else None
+        _lib.check(_lib.load().dagma_locally_connected_f64(
+            _lib.stream_ptr(), n, d, m1, self.output_features, x.data_ptr(), _cuda64(self.weight).data_ptr(),
+            b.data_ptr() if b is not None else None, out.data_ptr()), "dagma_locally_connected_f64")
+        return out.to(input.device)
+
+    def extra_repr(self) -> str:
+        return 'num_linear={}, in_features={}, out_features={}, bias={}'.format(
+            self.num_linear, self.input_features, self.output_features, self.bias is not None)
+
+
+class DagmaMLP(nn.Module):
+    """Structural equations as MLPs (nonlinear.py:14)."""
+
+    def __init__(self, dims: typing.List[int], bias: bool = True, dtype: torch.dtype = torch.double):
+        torch.set_default_dtype(dtype)                          # global side effect kept (Q13)
+        super().__init__()
+        assert len(dims) >= 2
+        assert dims[-1] == 1
+        self.dims, self.d = dims, dims[0]
+        self.I = torch.eye(self.d)
+        self.fc1 = nn.Linear(self.d, self.d * dims[1], bias=bias)
+        nn.init.zeros_(self.fc1.weight)
+        nn.init.zeros_(self.fc1.bias)
+        layers = []
+        for l in range(len(dims) - 2):
+            layers.append(LocallyConnected(self.d, dims[l + 1], dims[l + 2], bias=bias))
+        self.fc2 = nn.ModuleList(layers)
+
+    # ---- flat parameter vector  theta = [W1 | b1 | W2 | b2]
+    def _check_arch(self):
+        if len(self.dims) != 3:
+            raise NotImplementedError("the B200 path implements dims = [d, m1, 1] (SURVEY.md 8a row a8)")
+
+    def pack(self) -> torch.Tensor:
+        self._check_arch()
+        parts = [self.fc1.weight, self.fc1.bias, self.fc2[0].weight, self.fc2[0].bias]
+        return torch.cat([_cuda64(p).reshape(-1) for p in parts])
+
+    @torch.no_grad()
+    def unpack(self, theta: torch.Tensor) -> None:
+        off = 0
+        for p in (self.fc1.weight, self.fc1.bias, self.fc2[0].weight, self.fc2[0].bias):
+            k = p.numel()
+            p.copy_(theta[off:off + k].reshape(p.shape).to(p.device, p.dtype))
+            off += k
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:       # [n, d] -> [n, d]
+        eng = _MlpEngine(self, _cuda64(x))
+        return eng.forward().to(x.device)
+
+    @torch.no_grad()
+    def h_func(self, s: float = 1.0) -> torch.Tensor:
+        eng = _MlpEngine(self, None)
+        eng.h(s)
+        st = eng.pull()[0]
+        return torch.tensor(float(st[F_H]), dtype=torch.float64)
+
+    @torch.no_grad()
+    def fc1_l1_reg(self) -> torch.Tensor:
+        eng = _MlpEngine(self, None)
+        return torch.tensor(eng.l1(), dtype=torch.float64)
+
+    @torch.no_grad()
+    def fc1_to_adj(self) -> np.ndarray:                        # [j * m1, i] -> [i, j]
+        eng = _MlpEngine(self, None)
+        eng.adj()
+        return np.sqrt(eng.A.cpu().numpy())
+
+
+class _MlpEngine:
+    """Device buffers + launch sequences for one (model, X) pair."""
+
+    def __init__(self, model: DagmaMLP, X: typing.Optional[torch.Tensor], group=None, n_total=None):
+        _lib.require_device()
+        model._check_arch()
+        self.lib = _lib.load()
+        self.model = model
+        self.d, self.m1 = model.d, model.dims[1]
+        d, P = self.d, self.d * self.m1
+        self.P = P
+        f64 = dict(dtype=torch.float64, device="cuda")
+        self.theta = model.pack()
+        self.total = self.theta.numel()
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        self.grads = torch.zeros_like(self.theta)
+        self.A = torch.empty(d, d, **f64)
+        self.Minv = torch.empty(d, d, **f64)
+        self.l1_partial = torch.zeros((d * d + 255) // 256, **f64)
+        self.state = torch.zeros(ST_DOUBLES, **f64)
+        self.state_host = torch.zeros(ST_DOUBLES, dtype=torch.float64).pin_memory()
+        self.ws = torch.empty(self.lib.dagma_large_workspace_bytes(d) // 8 + 8, **f64)
+        self.group, self.graph = group, None
+        if X is not None:
+            self.X = X
+            self.n = X.shape[0]
+            self.n_total = n_total or self.n
+            self.Xt = X.t().contiguous()
+            self.Zt = torch.empty(P, self.n, **f64)
+            self.res = torch.empty(d, self.n, **f64)
+            chunks = (self.n + 255) // 256
+            self.S_partial = torch.empty(chunks * d, **f64)
+            self.part = torch.empty(chunks * (2 * P + d), **f64)
+            self.kws = torch.empty(148 * P * d + 8, **f64)
+
+    def _sptr(self, f):
+        return self.state.data_ptr() + 8 * f
+
+    def _iptr(self, slot):
+        return self.state.data_ptr() + 8 * 15 + 4 * slot
+
+    def pull(self):
+        self.state_host.copy_(self.state)
+        ints = self.state_host[15:].view(torch.int32)
+        return self.state_host, int(ints[I_STEP]), int(ints[I_HALTED])
+
+    # ---- pieces
+    def adj(self):
+        _lib.check(self.lib.dagma_mlp_adj_f64(_lib.stream_ptr(), self.d, self.m1, self.theta.data_ptr(),
+                                              self.A.data_ptr(), self.l1_partial.data_ptr()), "dagma_mlp_adj_f64")
+
+    def l1(self) -> float:
+        self.adj()
+        return float(self.l1_partial.sum().item())
+
+    def h(self, s: float):
+        self.adj()
+        _lib.check(self.lib.dagma_logdet_inv_ws_f64(
+            _lib.stream_ptr(), self.d, float(s), self.A.data_ptr(), self.d, 0, self._sptr(F_LAD), self._sptr(F_H),
+            self.Minv.data_ptr(), None, self.d, self._sptr(F_MIN), self._iptr(I_INFO), self.ws.data_ptr(),
+            self.ws.numel() * 8), "dagma_logdet_inv_ws_f64")
+
+    def _forward(self, out=None):
+        W1 = self.theta[:self.P * self.d].view(self.P, self.d)
+        gemm(W1, self.Xt, self.Zt)
+        _lib.check(self.lib.dagma_mlp_forward_f64(
+            _lib.stream_ptr(), self.n, self.d, self.m1, self.Zt.data_ptr(), self.theta.data_ptr(), self.Xt.data_ptr(),
+            self.res.data_ptr(), out.data_ptr() if out is not None else None, self.S_partial.data_ptr(),
+            self.l1_partial.data_ptr(), self.state.data_ptr()), "dagma_mlp_forward_f64")
+
+    def forward(self) -> torch.Tensor:
+        out = torch.empty(self.n, self.d, dtype=torch.float64, device="cuda")
+        self.adj()
+        self._forward(out)
+        return out
+
+    def iteration(self, s: float):
+        self.evaluate(s)
+        _lib.check(self.lib.dagma_mlp_adam_f64(
+            _lib.stream_ptr(), self.d, self.m1, self.state.data_ptr(), self.theta.data_ptr(), self.grads.data_ptr(),
+            self.m.data_ptr(), self.v.data_ptr(), self.Minv.data_ptr()), "dagma_mlp_adam_f64")
+
+    def evaluate(self, s: float):
+        """h, forward, objective and the (un-scaled) gradient sums at the current parameters."""
+        self.h(s)
+        self._forward()
+        if self.group is not None:
+            torch.distributed.all_reduce(self.state[F_SS:F_SS + 1], group=self.group)
+        _lib.check(self.lib.dagma_mlp_objective_f64(_lib.stream_ptr(), self.state.data_ptr(), self.n_total, self.d),
+                   "dagma_mlp_objective_f64")
+        _lib.check(self.lib.dagma_mlp_backward_f64(
+            _lib.stream_ptr(), self.n, self.d, self.m1, self.Zt.data_ptr(), self.theta.data_ptr(), self.res.data_ptr(),
+            self.part.data_ptr(), self.grads.data_ptr() + 8 * self.P * self.d), "dagma_mlp_backward_f64")
+        gW1 = self.grads[:self.P * self.d].view(self.P, self.d)
+        gemm(self.Zt, self.X, gW1, ws=self.kws)
+        if self.group is not None:
+            torch.distributed.all_reduce(self.grads, group=self.group)
+
+    def replay(self, s: float, n: int):
+        if self.group is not None:
+            for _ in range(n):
+                self.iteration(s)
+            return
+        if self.graph is None:
+            snap = (self.theta.clone(), self.m.clone(), self.v.clone(), self.state.clone())
+            self.iteration(s)                                  # warm-up
+            torch.cuda.synchronize()
+            for dst, src in zip((self.theta, self.m, self.v, self.state), snap):
+                dst.copy_(src)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.iteration(s)
+        for _ in range(n):
+            self.graph.replay()
+
+    def grads_scaled(self) -> dict:
+        """Gradients of mu*(score + lambda1 |fc1|) + h as the reference's autograd returns them
+        (before weight decay): used by the parity tests."""
+        st, _, _ = self.pull()
+        mu, lam1 = float(st[F_MU]), float(st[F_LAM1])
+        gs = mu * self.d / float(st[F_SS])
+        g = (gs * self.grads).clone()
+        P, d, m1 = self.P, self.d, self.m1
+        w1 = self.theta[:P * d].view(d, m1, d)
+        g[:P * d] += (mu * lam1 * torch.sign(w1) + 2.0 * w1 * self.Minv[:, None, :]).reshape(-1)
+        names = ("fc1.weight", "fc1.bias", "fc2.0.weight", "fc2.0.bias")
+        sizes = (P * d, P, P, d)
+        out, off = {}, 0
+        for nme, k in zip(names, sizes):
+            out[nme] = g[off:off + k].cpu().numpy()
+            off += k
+        return out
+
+
+class DagmaNonlinear:
+    """DAGMA with MLP structural equations (nonlinear.py:118)."""
+
+    def __init__(self, model: nn.Module, verbose: bool = False, dtype: torch.dtype = torch.double):
+        self.vprint = print if verbose else lambda *a, **k: None
+        self.model = model
+        self.dtype = dtype
+        self.group = None            # torch.distributed group when the rows of X are sharded across ranks
+        self.n_total = None
+        self.n_iters = 0
+
+    @torch.no_grad()
+    def log_mse_loss(self, output: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        _lib.require_device()
+        n, d = target.shape
+        a, b = _cuda64(output), _cuda64(target)
+        partial = torch.empty(592, dtype=torch.float64, device="cuda")
+        out = torch.empty(1, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().dagma_sumsq_diff_f64(_lib.stream_ptr(), a.numel(), a.data_ptr(), b.data_ptr(),
+                                                    partial.data_ptr(), 592, out.data_ptr()), "dagma_sumsq_diff_f64")
+        return (0.5 * d * torch.log(out[0] / n)).cpu()
+
+    def minimize(self, max_iter: float, lr: float, lambda1: float, lambda2: float, mu: float, s: float,
+                 lr_decay: float = False, tol: float = 1e-6, pbar=None) -> bool:
+        self.vprint(f'\nMinimize s={s} -- lr={lr}')
+        eng = _MlpEngine(self.model, self.X, self.group, self.n_total)     # optimizer re-created (Q13)
+        sh = eng.state_host
+        sh.zero_()
+        for f, val in ((F_MU, mu), (F_S, s), (F_LR, lr), (F_LAM1, lambda1), (F_LAM2, lambda2), (F_B1, 0.99),
+                       (F_B2, 0.999), (F_GAMMA, 0.8 if lr_decay is True else 1.0)):
+            sh[f] = float(val)
+        eng.state.copy_(sh)
+        self._engine = eng
+        max_iter = int(max_iter)
+        obj_prev, i_next, ok = 1e16, 0, True
+        while i_next < max_iter:
+            # run up to and including the next checkpoint iteration (i % checkpoint == 0 or the last one)
+            i_ck = i_next if i_next % self.checkpoint == 0 else min((i_next // self.checkpoint + 1) * self.checkpoint,
+                                                                    max_iter - 1)
+            i_ck = min(i_ck, max_iter - 1)
+            eng.replay(s, i_ck - i_next + 1)
+            st, step, halted = eng.pull()
+            self.n_iters += step - i_next
+            if halted:                                         # nonlinear.py:215-217
+                self.vprint(f'Found h negative {float(st[F_H])} at iter {step}')
+                ok = False
+                break
+            i_next = i_ck + 1
+            obj_new = float(st[F_OBJ])
+            self.vprint(f"\nInner iteration {i_ck}\n\th(W(model)): {float(st[F_H])}\n\tscore(model): {obj_new}")
+            if np.abs((obj_prev - obj_new) / obj_prev) <= tol:  # nonlinear.py:231
+                break
+            obj_prev = obj_new
+        self.model.unpack(eng.theta)
+        if pbar is not None:
+            pbar.update(max_iter)
+        return ok
+
+    def fit(self, X: typing.Union[torch.Tensor, np.ndarray], lambda1: float = .02, lambda2: float = .005,
+            T: int = 4, mu_init: float = .1, mu_factor: float = .1, s: float = 1.0, warm_iter: int = 5e4,
+            max_iter: int = 8e4, lr: float = .0002, w_threshold: float = 0.3, checkpoint: int = 1000) -> np.ndarray:
+        _lib.require_device()
+        torch.set_default_dtype(self.dtype)
+        if type(X) == torch.Tensor:
+            self.X = _cuda64(X)
+        elif type(X) == np.ndarray:
+            self.X = _cuda64(torch.from_numpy(X))
+        else:
+            ValueError("X should be numpy array or torch Tensor.")
+        self.checkpoint = checkpoint
+        mu = mu_init
+        if type(s) == list:
+            if len(s) < T:
+                self.vprint(f"Length of s is {len(s)}, using last value in s for iteration t >= {len(s)}")
+                s = s + (T - len(s)) * [s[-1]]
+        elif type(s) in [int, float]:
+            s = T * [s]
+        else:
+            ValueError("s should be a list, int, or float.")
+        self.stage_iters = []
+        for i in range(int(T)):
+            self.vprint(f'\nDagma iter t={i+1} -- mu: {mu}', 30 * '-')
+            success, s_cur = False, s[i]
+            inner_iter = int(max_iter) if i == T - 1 else int(warm_iter)
+            model_copy = copy.deepcopy(self.model)
+            lr_decay = False
+            while success is False:
+                before = self.n_iters
+                success = self.minimize(inner_iter, lr, lambda1, lambda2, mu, s_cur, lr_decay)
+                if success is False:
+                    self.model.load_state_dict(model_copy.state_dict().copy())
+                    lr *= 0.5
+                    lr_decay = True
+                    if lr < 1e-10:
+                        break
+                    s_cur = 1
+            self.stage_iters.append(self.n_iters - before)
+            mu *= mu_factor
+        W_est = self.model.fc1_to_adj()
+        W_est[np.abs(W_est) < w_threshold] = 0
+        return W_est
