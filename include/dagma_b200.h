@@ -183,6 +183,15 @@ int dagma_locally_connected_f64(dagma_stream_t stream, int n, int d, int m1, int
 int dagma_sumsq_diff_f64(dagma_stream_t stream, size_t total, const double* a_dev, const double* b_dev,
                          double* partial_dev, int n_partial, double* out_dev);
 
+/* ---- the fork's log-det trek-cycle-coupling constraint -----------------------------------
+ * A = [[W o W, w S], [I, (W o W)^T]] (2d x 2d; with_s = 0: baseline B)   src/notreks/notreks.py:319-337
+ * fold: out (+)= sign * 2 W o (G11 + G22^T)                              src/notreks/notreks.py:285-287, 384
+ * The value/gradient themselves come from dagma_logdet_inv_f64(square_input = 0).             */
+int dagma_tcc_assemble_f64(dagma_stream_t stream, int d, const double* w_dev, const double* s_dev,
+                           double w, int with_s, double* a_dev);
+int dagma_tcc_fold_f64(dagma_stream_t stream, int d, const double* w_dev, const double* g_dev, double sign,
+                       int accumulate, double* out_dev);
+
 /* ---- data staging in front of the path ---------------------------------------------
  * Replaces: X -= X.mean(0) (in place) and cov = X^T X / n   src/dagma/linear.py:410-411, 428
  * x_dev [batch][n][d] (centred in place when center != 0), cov_dev [batch][d][d].     */

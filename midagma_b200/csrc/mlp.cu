@@ -292,3 +292,47 @@ extern "C" int dagma_sumsq_diff_f64(dagma_stream_t stream, size_t total, const d
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+// ---- fork's TCC log-det constraint: block assembly and fold-back (src/notreks/notreks.py) ----
+namespace dagma {
+// A = [[W o W, w S], [I, (W o W)^T]]  (n = 2d);  with_S = 0 builds the baseline B (zero block)
+__global__ void tcc_assemble_kernel(const double* __restrict__ W, const double* __restrict__ S, double w, int d,
+                                    int with_S, double* __restrict__ A) {
+    const int n = 2 * d;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * n) return;
+    const int r = e / n, c = e - r * n;
+    double val;
+    if (r < d && c < d) { const double x = W[(size_t)r * d + c]; val = x * x; }
+    else if (r < d) val = with_S ? w * S[(size_t)r * d + (c - d)] : 0.0;
+    else if (c < d) val = (r - d == c) ? 1.0 : 0.0;
+    else { const double x = W[(size_t)(c - d) * d + (r - d)]; val = x * x; }
+    A[e] = val;
+}
+// out (+)= sign * 2 W o (G11 + G22^T)    (notreks.py:285-287, 384)
+__global__ void tcc_fold_kernel(const double* __restrict__ W, const double* __restrict__ G, int d, double sign,
+                                int accumulate, double* __restrict__ out) {
+    const int n = 2 * d;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d * d) return;
+    const int r = e / d, c = e - r * d;
+    const double g = G[(size_t)r * n + c] + G[(size_t)(d + c) * n + (d + r)];
+    const double val = sign * 2.0 * W[e] * g;
+    out[e] = accumulate ? out[e] + val : val;
+}
+}  // namespace dagma
+
+extern "C" int dagma_tcc_assemble_f64(dagma_stream_t stream, int d, const double* w_dev, const double* s_dev,
+                                      double w, int with_s, double* a_dev) {
+    DAGMA_REQUIRE(w_dev && a_dev && (s_dev || !with_s), "null pointer");
+    dagma::tcc_assemble_kernel<<<(4 * d * d + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_dev, s_dev, w, d, with_s, a_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int dagma_tcc_fold_f64(dagma_stream_t stream, int d, const double* w_dev, const double* g_dev, double sign,
+                                  int accumulate, double* out_dev) {
+    DAGMA_REQUIRE(w_dev && g_dev && out_dev, "null pointer");
+    dagma::tcc_fold_kernel<<<(d * d + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_dev, g_dev, d, sign, accumulate, out_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}

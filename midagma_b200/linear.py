@@ -150,6 +150,7 @@ def minimize_batch(W, cov, lambda1, mu, max_iter, s, lr, *, tol=1e-6, beta_1=0.9
     independent problems.  ``W``/``cov``: [batch, d, d] numpy arrays or torch tensors on
     host (pinned or not) or device.  Like the reference, ``W`` is updated in place and
     returned.  Returns ``(W, success[batch], stage_stats[batch, 1, 8])``."""
+    _lib.require_device()
     device = torch.device(device or "cuda")
     on_device = isinstance(W, torch.Tensor) and W.is_cuda
     Wd = W if on_device and W.dtype == torch.float64 and W.is_contiguous() else _as_dev(W, device)
@@ -181,6 +182,7 @@ def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1
     reference schedule independently (own convergence checks, retries, back-tracking);
     problems are pulled from a device-side work queue by persistent CTAs.
     Returns thresholded ``W_est`` [batch, d, d] as numpy (+ info dict)."""
+    _lib.require_device()
     device = torch.device(device or "cuda")
     if cov is None:
         Xd = _as_dev(X, device)
@@ -238,19 +240,28 @@ class DagmaLinear:
         self._device = torch.device("cuda")
         self._logger, self._log_cfg = logger, log_cfg
         self._large = None
+        self._group = None                  # torch.distributed group when the rows of X are sharded
         self.checkpoint_log = []            # rows (stage, iter, obj, score, h, lr) of the last calls
+
+    def shard_rows(self, group=None) -> "DagmaLinear":
+        """Declare that the ``X`` given to ``fit`` is this rank's contiguous row shard of the data
+        (SURVEY.md 8e2): cov, the column means and the score gradient are then sum all-reduced over
+        ``group``; every rank holds identical parameters and returns the identical ``W_est``."""
+        import torch.distributed as dist
+        self._group = group if group is not None else dist.group.WORLD
+        return self
 
     # ------------------------------------------------------------------ helpers
     def _dev(self, x) -> torch.Tensor:
         return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(self._device)
 
     def _small_ok(self) -> bool:
-        return self.loss_type == 'l2' and self.d <= _lib.SMALL_MAX_D
+        return self.loss_type == 'l2' and self.d <= _lib.SMALL_MAX_D and self._group is None
 
     def _large_engine(self):
         from ._large import LargeLinearEngine
         if self._large is None or self._large.stale(self):
-            self._large = LargeLinearEngine(self)
+            self._large = LargeLinearEngine(self, group=self._group)
         return self._large
 
     # ------------------------------------------------------------------ _score (linear.py:70-94)
@@ -336,7 +347,19 @@ class DagmaLinear:
         # centring + covariance on device; the centred X is copied back into the caller's
         # array to keep the reference's in-place side effect (linear.py:410-411, Q8)
         Xd = self._dev(X)[None].contiguous()
-        cov = center_cov(Xd, center=(self.loss_type == 'l2'))
+        self._n_total = self.n
+        if self._group is None:
+            cov = center_cov(Xd, center=(self.loss_type == 'l2'))
+        else:                                   # row-sharded: global n, global column means, summed cov
+            from .parallel import allreduce_sum_
+            nt = allreduce_sum_(torch.tensor([float(self.n)], dtype=torch.float64, device=self._device), self._group)
+            self._n_total = int(nt.item())
+            if self.loss_type == 'l2':
+                mean = allreduce_sum_(Xd[0].sum(dim=0), self._group) / self._n_total
+                Xd[0] -= mean
+            cov = center_cov(Xd, center=False)
+            cov *= self.n / self._n_total
+            allreduce_sum_(cov, self._group)
         if self.loss_type == 'l2':
             self.X[...] = Xd[0].cpu().numpy()
         self._X_dev = Xd[0]

@@ -31,6 +31,7 @@ I_STEP, I_HALTED, I_INFO = 0, 1, 2
 
 
 def _cuda64(x) -> torch.Tensor:
+    _lib.require_device()
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(x)
     return x.detach().to(device="cuda", dtype=torch.float64).contiguous()

@@ -1,0 +1,64 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol the
+header declares, the ctypes mirror matches the C struct, and the product fails loudly (no
+fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "dagma_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dagma_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    if not os.path.exists(__graft_entry__.LIB):
+        __graft_entry__.build()
+    from midagma_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dagma_b200.h but not exported"
+    for n in _lib.EXPORTS:
+        assert n in names, f"{n} bound in _lib.py but not declared in the header"
+    assert lib.dagma_version() >= 100
+    assert lib.dagma_last_error() is not None
+
+
+def test_struct_mirror_layout():
+    from midagma_b200 import _lib
+    a = _lib.SmallFitArgs
+    # 6 int32 (24 B), 4 doubles, 2 x 16 doubles, 16 int32, 11 pointers
+    assert C.sizeof(a) == 24 + 4 * 8 + 2 * 16 * 8 + 16 * 4 + 11 * 8
+    assert a.mu.offset == 56 and a.iters.offset == 56 + 256 and a.cov.offset == 56 + 256 + 64
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    from midagma_b200 import DagmaLinear, fit_batch, _lib
+    from midagma_b200.nonlinear import DagmaMLP
+    X = np.random.default_rng(0).normal(size=(50, 5))
+    with pytest.raises(_lib.DagmaB200Error):
+        DagmaLinear("l2").fit(X)
+    with pytest.raises(_lib.DagmaB200Error):
+        fit_batch(X[None])
+    with pytest.raises((_lib.DagmaB200Error, AssertionError, RuntimeError)):
+        DagmaMLP([5, 3, 1]).h_func()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "midagma_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
