@@ -19,6 +19,7 @@
 // update (log-det from the pivots, score from cov @ (I - W)) and the next iteration.
 #include "common.cuh"
 #include "small_gj.cuh"
+#include "small_fit_internal.h"
 #include <cstdlib>
 #include "../../include/dagma_b200.h"
 
@@ -37,18 +38,6 @@ struct FitSmem {
     static constexpr size_t off_red = off_line + ((SweepSmem<C>::doubles + 1) / 2) * 2;
     static constexpr size_t total = off_red + 96;
     static constexpr size_t bytes = total * sizeof(double);
-};
-
-struct DD {   // double-double running power beta^k
-    double hi, lo;
-    __device__ __forceinline__ void mul(double b) {
-        const double ph = hi * b;
-        const double pl = fma(hi, b, -ph) + lo * b;
-        const double s = ph + pl;
-        lo = pl - (s - ph);
-        hi = s;
-    }
-    __device__ __forceinline__ double one_minus() const { return (1.0 - hi) - lo; }
 };
 
 template <class C>
@@ -359,6 +348,8 @@ using C64 = Cfg<4, 2, 16, 32>;     // d <= 64 : 512 threads, 4 x 2
 using C64B = Cfg<4, 4, 16, 16>;    // d <= 64 : 256 threads, 4 x 4 (fewer shared-memory loads per FMA)
 using C64C = Cfg<2, 4, 32, 16>;    // d <= 64 : 512 threads, 2 x 4
 
+// DAGMA_SMALL_CFG (debug / A-B timing only): unset or 0 = DMMA kernel for 32 < d <= 64;
+// 10 / 11 / 12 = scalar rank-1 kernels C64 / C64B / C64C
 static int c64_variant() {
     static int v = -1;
     if (v < 0) {
@@ -411,9 +402,10 @@ extern "C" int dagma_linear_fit_small_geometry(int d, int batch, int* ctas, int*
     if (rc) return rc;
     if (d <= 16) return fit_geometry<C16>(batch, sms, ctas, threads, smem_bytes);
     if (d <= 32) return fit_geometry<C32>(batch, sms, ctas, threads, smem_bytes);
+    if (c64_variant() == 0) return fit_dmma_geometry(batch, sms, ctas, threads, smem_bytes);
     if (d <= 48) return fit_geometry<C48>(batch, sms, ctas, threads, smem_bytes);
-    if (c64_variant() == 1) return fit_geometry<C64B>(batch, sms, ctas, threads, smem_bytes);
-    if (c64_variant() == 2) return fit_geometry<C64C>(batch, sms, ctas, threads, smem_bytes);
+    if (c64_variant() == 11) return fit_geometry<C64B>(batch, sms, ctas, threads, smem_bytes);
+    if (c64_variant() == 12) return fit_geometry<C64C>(batch, sms, ctas, threads, smem_bytes);
     return fit_geometry<C64>(batch, sms, ctas, threads, smem_bytes);
 }
 
@@ -432,8 +424,9 @@ extern "C" int dagma_linear_fit_small_f64(dagma_stream_t stream_, const dagma_sm
     if (rc) return rc;
     if (a.d <= 16) return launch_fit<C16>(stream, a, sms);
     if (a.d <= 32) return launch_fit<C32>(stream, a, sms);
+    if (c64_variant() == 0) return launch_fit_dmma(stream, a, sms);
     if (a.d <= 48) return launch_fit<C48>(stream, a, sms);
-    if (c64_variant() == 1) return launch_fit<C64B>(stream, a, sms);
-    if (c64_variant() == 2) return launch_fit<C64C>(stream, a, sms);
+    if (c64_variant() == 11) return launch_fit<C64B>(stream, a, sms);
+    if (c64_variant() == 12) return launch_fit<C64C>(stream, a, sms);
     return launch_fit<C64>(stream, a, sms);
 }

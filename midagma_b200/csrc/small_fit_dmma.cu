@@ -1,0 +1,382 @@
+// Tensor-core (DMMA) variant of the on-chip batched DAGMA-linear fit for 32 < d <= 64.
+//
+// Same contract and reference semantics as fit_small_kernel (small_fit.cu; quirks Q1-Q7 of
+// SURVEY.md 8, src/dagma/linear.py:165-333 and :441-457); what changes is the machine mapping:
+//   * one 256-thread CTA per problem, TWO CTAs per SM, so the serial publish / barrier /
+//     pivot-block chain of one problem is hidden behind the DMMA work of the other;
+//   * the sweep is the block-4 Gauss-Jordan of small_dmma.cuh: inverse and cov @ W both run
+//     on the FP64 tensor pipe (DMMA.8x8x4);
+//   * the kernel inverts M^T = sI - (W o W)^T, so the accumulator tile already holds the
+//     entries of M^{-T} that the gradient 2 W o M^{-T} needs (linear.py:248) -- no transpose;
+//   * Adam moments live in tensor memory (tcgen05.ld/st), W and -cov in shared memory,
+//     M^{-T} and cov (I - W) in registers.
+#include "common.cuh"
+#include "small_dmma.cuh"
+#include "small_fit_internal.h"
+#include "../../include/dagma_b200.h"
+
+namespace dagma {
+
+__global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_small_fit_args P) {
+    using S = DmmaSmem;
+    constexpr int NT = DM_NT, LD = DM_LD;
+    extern __shared__ __align__(16) double smem[];
+    double* ncov = smem + S::ncov;
+    double* Ws = smem + S::W;
+    double* pinfo = smem + S::pinfo;
+    double* red = smem + S::red;
+    __shared__ unsigned s_prob;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x;
+    const DmmaPos ps(tid);
+    const int d = P.d;
+    const int np = 4 * ((d + 3) >> 2);          // pivots swept (d rounded up to the block size)
+    const size_t dd = (size_t)d * d;
+
+    // ---- step barrier of the sweep: one arrival per warp
+    SweepSync sy{smem_u32(smem + S::mbar), 0u, 0};
+    if (tid == 0) mbar_init(sy.bar, NT / 32);
+
+    // ---- tensor-memory scratch for the Adam moments (thread-private, 64 columns per thread)
+    if (ps.warp == 0) tmem_alloc(smem_u32(&s_tmem));
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const uint32_t tm = tmem_base + ((uint32_t)(32 * (ps.warp & 3)) << 16) + (uint32_t)((ps.warp >> 2) * 64);
+    // columns: [m(ti=0) 16 | v(ti=0) 16 | m(ti=1) 16 | v(ti=1) 16]
+
+    // exclusion / inclusion bit masks of this thread's 16 entries (shared by the batch)
+    unsigned excbits = 0, incbits = 0;
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = ps.row(ti), c = ps.col(tj) + e;
+                if (r < d && c < d) {
+                    if (P.mask_exc_dev && P.mask_exc_dev[r * d + c]) excbits |= 1u << (ti * 8 + tj * 2 + e);
+                    if (P.mask_inc_dev && P.mask_inc_dev[r * d + c]) incbits |= 1u << (ti * 8 + tj * 2 + e);
+                }
+            }
+
+    for (;;) {
+        if (tid == 0) s_prob = atomicAdd(P.work_counter_dev, 1u);
+        __syncthreads();
+        const unsigned b = s_prob;
+        __syncthreads();
+        if (b >= (unsigned)P.batch) break;
+
+        const double* cov_g = P.cov_dev + (size_t)b * dd;
+        double* W_g = P.w_dev + (size_t)b * dd;
+        const double lambda1 = P.lambda1_dev[b];
+
+        for (int idx = tid; idx < DM_DP * DM_DP; idx += NT) {
+            const int r = idx >> 6, c = idx & 63;
+            const bool in = (r < d) && (c < d);
+            ncov[r * LD + c] = in ? -cov_g[r * d + c] : 0.0;
+            Ws[r * LD + c] = in ? W_g[r * d + c] : 0.0;
+        }
+        __syncthreads();
+
+        double a[2][4][2], g[2][4][2];
+        int status = 0;
+        int n_ckpt = 0;
+
+        // ---- state of the path-following loop ----
+        int stage = 0;
+        bool final_phase = (P.n_stages == 0);
+        double mu = 0, s_cur = 1, lr = 0, lr_adam = P.lr, obj_prev = 1e16;
+        double last_obj = 0, last_score = 0, last_h = 0;
+        int iters_max = 0, it = 0, retries = 0, backtracks = 0;
+        bool in_backtrack = false;
+        DD p1{1.0, 0.0}, p2{1.0, 0.0};
+
+        auto start_attempt = [&]() {
+            it = 0;
+            lr = lr_adam;
+            obj_prev = 1e16;
+            in_backtrack = false;
+            backtracks = 0;
+            p1 = DD{1.0, 0.0};
+            p2 = DD{1.0, 0.0};
+            const double z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tmem_st8(tm + 16 * q, z);
+            tmem_wait_st();
+        };
+        auto start_stage = [&]() {
+            mu = P.mu[stage];
+            s_cur = P.s[stage];
+            iters_max = P.iters[stage];
+            lr_adam = P.lr;
+            retries = 0;
+            start_attempt();
+        };
+        auto write_W = [&]() {   // Ws -> global (stage result / restart point)
+            __syncthreads();
+            for (int idx = tid; idx < d * d; idx += NT) {
+                const int r = idx / d, c = idx - r * d;
+                W_g[idx] = Ws[r * LD + c];
+            }
+        };
+        auto read_W = [&]() {
+            __syncthreads();
+            for (int idx = tid; idx < d * d; idx += NT) {
+                const int r = idx / d, c = idx - r * d;
+                Ws[r * LD + c] = W_g[idx];
+            }
+            __syncthreads();
+        };
+        auto write_stage_stats = [&]() {
+            if (tid == 0 && P.stage_stats_dev) {
+                double* st = P.stage_stats_dev + ((size_t)b * P.n_stages + stage) * 8;
+                st[0] = (double)it;
+                st[1] = lr;
+                st[2] = s_cur;
+                st[3] = last_obj;
+                st[4] = last_score;
+                st[5] = last_h;
+                st[6] = (double)retries;
+                st[7] = (double)backtracks;
+            }
+        };
+        // Ws += scale * dir(m, v, it): the previous Adam direction rebuilt from the moments
+        auto apply_dir = [&](double scale) {
+            const double c1 = 1.0 / p1.one_minus(), c2 = 1.0 / p2.one_minus();
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti) {
+                TmemLoad8 lm, lv;
+                lm.issue(tm + 32 * ti);
+                lv.issue(tm + 32 * ti + 16);
+                lm.finish();
+                lv.finish();
+                double* wp = Ws + ps.row(ti) * LD;
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) {
+                    double2 w = *reinterpret_cast<double2*>(wp + ps.col(tj));
+                    const double d0 = fast_div(lm.get(2 * tj) * c1, fast_sqrt_nonneg(lv.get(2 * tj) * c2) + 1e-8);
+                    const double d1 = fast_div(lm.get(2 * tj + 1) * c1, fast_sqrt_nonneg(lv.get(2 * tj + 1) * c2) + 1e-8);
+                    w.x = __dadd_rn(w.x, __dmul_rn(scale, d0));
+                    w.y = __dadd_rn(w.y, __dmul_rn(scale, d1));
+                    *reinterpret_cast<double2*>(wp + ps.col(tj)) = w;
+                }
+            }
+            __syncthreads();
+        };
+
+        if (!final_phase) start_stage();
+
+        for (;;) {
+            // ================= build M^T and run the fused sweep =================
+            const double s_use = final_phase ? 1.0 : s_cur;
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti) {
+                const int r = ps.row(ti);
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) {
+                    const int c = ps.col(tj);
+                    const double w0 = Ws[c * LD + r], w1 = Ws[(c + 1) * LD + r];     // W^T
+                    const double dg = (r < d) ? s_use : 1.0;
+                    a[ti][tj][0] = ((r == c) ? dg : 0.0) - w0 * w0;
+                    a[ti][tj][1] = ((r == c + 1) ? dg : 0.0) - w1 * w1;
+                    const double2 nc = *reinterpret_cast<const double2*>(ncov + r * LD + c);
+                    g[ti][tj][0] = -nc.x;
+                    g[ti][tj][1] = -nc.y;
+                }
+            }
+            dmma_sweep<true>(a, g, ps, smem, d, sy);
+            // now: a = M^{-T},  g = cov - cov W = cov (I - W),  pinfo[0..np) = pivots
+
+            // ================= objective pieces (checkpoint / final) =================
+            const bool at_ckpt = !final_phase && !in_backtrack && it >= 1 &&
+                                 (it % P.checkpoint == 0 || it == iters_max);
+            if (at_ckpt || final_phase) {
+                double sc = 0.0, l1 = 0.0, ld = 0.0;
+#pragma unroll
+                for (int ti = 0; ti < 2; ++ti) {
+                    const int r = ps.row(ti);
+#pragma unroll
+                    for (int tj = 0; tj < 4; ++tj) {
+                        const int c = ps.col(tj);
+                        const double2 w = *reinterpret_cast<const double2*>(Ws + r * LD + c);
+                        const double dif0 = ((r == c && r < d) ? 1.0 : 0.0) - w.x;
+                        const double dif1 = ((r == c + 1 && r < d) ? 1.0 : 0.0) - w.y;
+                        sc = fma(dif0, g[ti][tj][0], sc);
+                        sc = fma(dif1, g[ti][tj][1], sc);
+                        l1 += fabs(w.x) + fabs(w.y);
+                    }
+                }
+                if (tid < np) ld = (double)((tid & 3) - 2) * log(fabs(pinfo[tid]));   // fraction-free pivots
+                block_sum3<NT>(sc, l1, ld, red, tid);
+                const double score = 0.5 * sc;
+                const double h = -ld + (double)d * log(s_use);
+                if (final_phase) {
+                    if (tid == 0 && P.final_dev) {
+                        P.final_dev[2 * (size_t)b] = h;
+                        P.final_dev[2 * (size_t)b + 1] = score;
+                    }
+                    break;
+                }
+                const double obj = mu * (score + lambda1 * l1) + h;
+                last_obj = obj;
+                last_score = score;
+                last_h = h;
+                if (tid == 0 && P.ckpt_log_dev && n_ckpt < P.ckpt_log_cap) {
+                    double* row = P.ckpt_log_dev + ((size_t)b * P.ckpt_log_cap + n_ckpt) * 6;
+                    row[0] = stage; row[1] = it; row[2] = obj; row[3] = score; row[4] = h; row[5] = lr;
+                }
+                ++n_ckpt;
+                const bool converged = fabs((obj_prev - obj) / obj_prev) <= P.tol;
+                obj_prev = obj;
+                if (converged || it == iters_max) goto stage_done;
+            } else if (!final_phase && !in_backtrack && it == iters_max) {
+                goto stage_done;   // only reachable for iters_max == 0
+            }
+
+            {
+                // ================= feasibility of iteration it + 1 =================
+                bool bad = false;
+                if (tid < np) bad = !(pinfo[tid] > 0.0);
+#pragma unroll
+                for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                    for (int tj = 0; tj < 4; ++tj)
+                        bad |= (a[ti][tj][0] + 1e-16 < 0.0) | (a[ti][tj][1] + 1e-16 < 0.0);
+                bad = __syncthreads_or(bad);
+                if (bad) {
+                    if (it == 0 || s_cur <= 0.9) {            // linear.py:231-233
+                        if (P.retry_on_fail) {
+                            if (++retries > 64) { status |= DAGMA_ST_RETRY_LIMIT; write_W(); goto problem_done; }
+                            lr_adam *= 0.5;                    // linear.py:450-451
+                            s_cur += 0.1;
+                            read_W();
+                            start_attempt();
+                            continue;
+                        }
+                        status |= DAGMA_ST_OUT_OF_DOMAIN;
+                        write_W();
+                        write_stage_stats();
+                        goto problem_done;
+                    }
+                    apply_dir(lr);                             // W += lr * grad   :235
+                    lr *= 0.5;                                 //                  :236
+                    if (lr <= 1e-16) {                         //                  :237-238
+                        status |= DAGMA_ST_LR_UNDERFLOW;
+                        goto stage_done;
+                    }
+                    apply_dir(-lr);                            // W -= lr * grad   :239
+                    ++backtracks;
+                    in_backtrack = true;
+                    continue;                                  // re-invert        :240
+                }
+                in_backtrack = false;
+            }
+
+            {
+                // ================= gradient, Adam, step (iteration it + 1) =================
+                ++it;
+                p1.mul(P.beta1);
+                p2.mul(P.beta2);
+                const double c1 = 1.0 / p1.one_minus(), c2 = 1.0 / p2.one_minus();
+                const double ob1 = 1.0 - P.beta1, ob2 = 1.0 - P.beta2;
+                const double l1c = mu * lambda1, incc = -2.0 * mu * lambda1;
+#pragma unroll
+                for (int ti = 0; ti < 2; ++ti) {
+                    TmemLoad8 lm, lv;
+                    lm.issue(tm + 32 * ti);
+                    lv.issue(tm + 32 * ti + 16);
+                    double* wp = Ws + ps.row(ti) * LD;
+                    double2 w2[4];
+#pragma unroll
+                    for (int tj = 0; tj < 4; ++tj) w2[tj] = *reinterpret_cast<const double2*>(wp + ps.col(tj));
+                    lm.finish();
+                    lv.finish();
+                    double mn[8], vn[8];
+#pragma unroll
+                    for (int tj = 0; tj < 4; ++tj) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int q = 2 * tj + e, bit = ti * 8 + q;
+                            const double w = e ? w2[tj].y : w2[tj].x;
+                            const double sg = (w > 0.0) ? 1.0 : ((w < 0.0) ? -1.0 : 0.0);
+                            double go = fma(-mu, g[ti][tj][e], l1c * sg);
+                            go = fma(2.0 * w, a[ti][tj][e] + 1e-16, go);
+                            if (incbits >> bit & 1u) go = fma(incc, sg, go);
+                            mn[q] = fma(lm.get(q), P.beta1, ob1 * go);
+                            vn[q] = fma(lv.get(q), P.beta2, ob2 * (go * go));
+                            const double dir = fast_div(mn[q] * c1, fast_sqrt_nonneg(vn[q] * c2) + 1e-8);
+                            double wn = w - lr * dir;
+                            if (excbits >> bit & 1u) wn = 0.0;
+                            if (e) w2[tj].y = wn; else w2[tj].x = wn;
+                        }
+                        *reinterpret_cast<double2*>(wp + ps.col(tj)) = w2[tj];
+                    }
+                    tmem_st8(tm + 32 * ti, mn);
+                    tmem_st8(tm + 32 * ti + 16, vn);
+                }
+                tmem_wait_st();
+                __syncthreads();
+                continue;
+            }
+
+        stage_done:
+            write_stage_stats();
+            write_W();
+            ++stage;
+            if (stage < P.n_stages) {
+                start_stage();
+                __syncthreads();
+                continue;
+            }
+            if (!P.final_dev) goto problem_done;
+            final_phase = true;
+            __syncthreads();
+        }
+    problem_done:
+        if (tid == 0) {
+            if (P.status_dev) P.status_dev[b] = status;
+            if (P.ckpt_count_dev) P.ckpt_count_dev[b] = n_ckpt < P.ckpt_log_cap ? n_ckpt : P.ckpt_log_cap;
+        }
+        __syncthreads();
+    }
+
+    tmem_fence_before();
+    __syncthreads();
+    if (ps.warp == 0) tmem_free(tmem_base);
+}
+
+int fit_dmma_geometry(int batch, int sms, int* ctas, int* threads, size_t* smem_bytes) {
+    constexpr size_t bytes = DmmaSmem::bytes;
+    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_dmma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
+    // Two CTAs per SM by construction: __launch_bounds__(256, 2) caps registers at 128 (2 x 256 x 128
+    // = the whole file), 2 x 80.8 KB of shared memory fit the 228 KB carve-out and 2 x 128 TMEM columns
+    // fit the 512 of an SM.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for this kernel on
+    // driver 580 although two are resident -- ncu: sm__warps_active 25 % = 16 warps; if only one fitted,
+    // the work-queue loop would still be correct, the surplus CTAs just start late.)
+    int per_sm = 0;
+    DAGMA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_small_dmma_kernel, DM_NT, bytes));
+    if (per_sm < 1) return set_error(-5, "DMMA fit kernel does not fit on an SM");
+    per_sm = 2;
+    long n = (long)sms * per_sm;
+    if (n > batch) n = batch;
+    if (ctas) *ctas = (int)n;
+    if (threads) *threads = DM_NT;
+    if (smem_bytes) *smem_bytes = bytes;
+    return 0;
+}
+
+int launch_fit_dmma(cudaStream_t stream, const dagma_small_fit_args& a, int sms) {
+    int ctas = 0;
+    int rc = fit_dmma_geometry(a.batch, sms, &ctas, nullptr, nullptr);
+    if (rc) return rc;
+    fit_small_dmma_kernel<<<ctas, DM_NT, DmmaSmem::bytes, stream>>>(a);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dagma

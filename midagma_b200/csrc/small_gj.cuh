@@ -324,4 +324,16 @@ __device__ __forceinline__ double block_min(double x, double* red, int tid) {
     return m;
 }
 
+struct DD {   // double-double running power beta^k
+    double hi, lo;
+    __device__ __forceinline__ void mul(double b) {
+        const double ph = hi * b;
+        const double pl = fma(hi, b, -ph) + lo * b;
+        const double s = ph + pl;
+        lo = pl - (s - ph);
+        hi = s;
+    }
+    __device__ __forceinline__ double one_minus() const { return (1.0 - hi) - lo; }
+};
+
 }  // namespace dagma

@@ -53,3 +53,104 @@ extern "C" int dagma_bench_fp64_dmma(dagma_stream_t stream, int ctas, int thread
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+// ---- dependent-issue latencies of the instructions on the serial chain of the on-chip sweep
+// (one warp, clock64 around a chain of N dependent operations); out[i] = cycles per operation.
+namespace dagma {
+__global__ void latency_probe(double* out, double seed) {
+    constexpr int N = 256;
+    __shared__ double sh[64];
+    const int lane = threadIdx.x;
+    sh[lane] = seed + lane;
+    sh[32 + lane] = 0.0;
+    __syncthreads();
+    double x = seed, y = 1.0 + 1e-9 * lane;
+    long long t0, t1;
+    // 0: DFMA chain
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) x = fma(x, y, 1e-12);
+    t1 = clock64();
+    if (lane == 0) out[0] = double(t1 - t0) / N;
+    // 1: DMMA chain through the accumulator
+    double c0 = x, c1 = y;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(y), "d"(y));
+    t1 = clock64();
+    if (lane == 0) out[1] = double(t1 - t0) / N;
+    // 2: DMMA chain through the A operand (CS -> update dependency)
+    double a0 = c0;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) {
+        double d0 = 0.0, d1 = 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(d0), "+d"(d1) : "d"(a0), "d"(y));
+        a0 = d0;
+    }
+    t1 = clock64();
+    if (lane == 0) out[2] = double(t1 - t0) / N;
+    // 3: 64-bit shuffle chain
+    double s = a0 + c1;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) s = __shfl_sync(0xffffffffu, s, (lane + 1) & 31);
+    t1 = clock64();
+    if (lane == 0) out[3] = double(t1 - t0) / N;
+    // 4: MUFU.RCP64H + one DFMA (dependent)
+    double r = s + 3.0;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) {
+        double q;
+        asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(r));
+        r = fma(q, 1e-3, 2.0);
+    }
+    t1 = clock64();
+    if (lane == 0) out[4] = double(t1 - t0) / N;
+    // 5: shared-memory pointer chase (LDS.64 -> address)
+    int idx = lane;
+    double acc = r;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) {
+        const double v = sh[32 + (idx & 31)];
+        idx = idx + (int)v + 1;
+        acc += v;
+    }
+    t1 = clock64();
+    if (lane == 0) out[5] = double(t1 - t0) / N;
+    // 6: STS -> __syncwarp -> LDS round trip (publish / read back)
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) {
+        sh[lane] = acc;
+        __syncwarp();
+        acc = sh[(lane + 1) & 31] + 1.0;
+        __syncwarp();
+    }
+    t1 = clock64();
+    if (lane == 0) out[6] = double(t1 - t0) / N;
+    // 7: DADD chain, 8: DMUL chain
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) acc = acc + y;
+    t1 = clock64();
+    if (lane == 0) out[7] = double(t1 - t0) / N;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) acc = acc * y;
+    t1 = clock64();
+    if (lane == 0) out[8] = double(t1 - t0) / N;
+    if (acc + idx == 123.456) out[15] = acc;
+}
+}  // namespace dagma
+
+extern "C" int dagma_bench_latency(dagma_stream_t stream, double* out_dev) {
+    dagma::latency_probe<<<1, 32, 0, (cudaStream_t)stream>>>(out_dev, 1.5);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
