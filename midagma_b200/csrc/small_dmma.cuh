@@ -52,8 +52,8 @@ static_assert(DmmaSmem::rbuf % 2 == 0 && DmmaSmem::cbuf % 2 == 0 && DmmaSmem::qb
               DmmaSmem::pinfo % 2 == 0 && DmmaSmem::W % 2 == 0, "16-byte alignment of vector accesses");
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 struct DmmaPos {
@@ -72,11 +72,9 @@ __device__ __forceinline__ void mbar_init(uint32_t addr, int count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
 }
-__device__ __forceinline__ bool mbar_test(uint32_t addr, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    return ok != 0;
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {   // try_wait suspends the warp in hardware
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 ::"r"(addr), "r"(parity) : "memory");
 }
 
 // The diagonal warp of block `b` inverts the pivot block P = A[K,K] (it sits in tile (TI,TJ),
@@ -96,51 +94,52 @@ __device__ __forceinline__ void stage_pivot_block(const double (&a)[2][4][2], co
     const int src = ((4 * HALF + i) << 2) | (2 * HALF + (j >> 1));
     const double v0 = __shfl_sync(FULL, a[TI][TJ][0], src), v1 = __shfl_sync(FULL, a[TI][TJ][1], src);
     double x = (j & 1) ? v1 : v0;
-    double piv[4], D = 1.0, E = 1.0;          // E = prod_{m<k} p_m: scale of a row not yet pivoted
+    double D = 1.0, E = 1.0;                  // E = prod_{m<k} p_m: scale of a row not yet pivoted
+    double* pi = sm + DmmaSmem::pinfo + b * 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const double p = __shfl_sync(FULL, x, 5 * k);
         const double r = __shfl_sync(FULL, x, 4 * k + j), c = __shfl_sync(FULL, x, 4 * i + k);
-        piv[k] = p;
+        if (ps.lane == 0) pi[k] = p;
+        const bool ik = (i == k), jk = (j == k);
+        // off the chain: what the pivot row / pivot column lanes become
+        const double alt = ik ? (jk ? E : x) : (-c * E);
         const double Dp = D * p;
-        D = (i == k) ? p : ((k > i) ? Dp : D);
-        const double xm = (j == k) ? 0.0 : x, rm = (j == k) ? E : r;
-        const double t = fma(-c, rm, p * xm);
-        x = (i == k) ? ((j == k) ? E : x) : t;
+        D = (k >= i) ? Dp : D;                // D_i = prod_{m >= i} p_m
         E *= p;
+        // on the chain: one multiply, one fma, one select
+        const double t = fma(-c, r, p * x);
+        x = (ik || jk) ? alt : t;
     }
     const double q = x * fast_rcp(D);
     if (ps.lane < 16) sm[DmmaSmem::qbuf + qslot * 16 + L] = -q;
-    if (ps.lane == 0) {
-        double* pi = sm + DmmaSmem::pinfo + b * 4;
-        *reinterpret_cast<double2*>(pi) = make_double2(piv[0], piv[1]);
-        *reinterpret_cast<double2*>(pi + 2) = make_double2(piv[2], piv[3]);
-    }
 }
 
-// publish the pivot rows (+I) / pivot columns (-I) of block b = 8 bo + BQ into line buffer BQ & 1
+// publish the pivot rows (+I) / pivot columns (-I) of block b = 8 bo + BQ into line buffer BQ & 1;
+// the +-I touches only the pivot block itself, i.e. tile (TI, TJ) of the diagonal warp
 template <int BQ>
 __device__ __forceinline__ void publish_block(const double (&a)[2][4][2], const DmmaPos& ps, double* sm, int b) {
     constexpr int TI = (BQ & 3) >> 1, TJ = BQ >> 1, HALF = BQ & 1, CUR = BQ & 1;
     double* rb = sm + DmmaSmem::rbuf + CUR * 4 * DM_LD;
     double* cb = sm + DmmaSmem::cbuf + CUR * DM_DP * 4;
-    if (ps.wr == (b >> 2) && (ps.qr >> 2) == HALF) {
-        const int r = ps.row(TI), kk = ps.qr & 3;
-#pragma unroll
-        for (int tj = 0; tj < 4; ++tj) {
-            const int c = ps.col(tj);
-            const double v0 = a[TI][tj][0] + ((r == c) ? 1.0 : 0.0), v1 = a[TI][tj][1] + ((r == c + 1) ? 1.0 : 0.0);
-            *reinterpret_cast<double2*>(rb + kk * DM_LD + c) = make_double2(v0, v1);
-        }
+    const bool rown = ps.wr == (b >> 2), cown = ps.wc == (b >> 3);
+    double p0 = a[TI][TJ][0], p1 = a[TI][TJ][1], m0 = p0, m1 = p1;      // pivot-block tile: row / column copy
+    if (rown && cown) {
+        const int dlt = ps.row(TI) - ps.col(TJ);
+        const double i0 = (dlt == 0) ? 1.0 : 0.0, i1 = (dlt == 1) ? 1.0 : 0.0;
+        p0 += i0; p1 += i1; m0 -= i0; m1 -= i1;
     }
-    if (ps.wc == (b >> 3) && (ps.qc >> 1) == HALF) {
-        const int c = ps.col(TJ), kk = 2 * (ps.qc & 1);
+    if (rown && (ps.qr >> 2) == HALF) {
+        double* dst = rb + (ps.qr & 3) * DM_LD + ps.col(0);
 #pragma unroll
-        for (int ti = 0; ti < 2; ++ti) {
-            const int r = ps.row(ti);
-            const double v0 = a[ti][TJ][0] - ((r == c) ? 1.0 : 0.0), v1 = a[ti][TJ][1] - ((r == c + 1) ? 1.0 : 0.0);
-            *reinterpret_cast<double2*>(cb + r * 4 + kk) = make_double2(v0, v1);
-        }
+        for (int tj = 0; tj < 4; ++tj)
+            *reinterpret_cast<double2*>(dst + 8 * tj) = (tj == TJ) ? make_double2(p0, p1) : make_double2(a[TI][tj][0], a[TI][tj][1]);
+    }
+    if (cown && (ps.qc >> 1) == HALF) {
+        double* dst = cb + ps.row(0) * 4 + 2 * (ps.qc & 1);
+#pragma unroll
+        for (int ti = 0; ti < 2; ++ti)
+            *reinterpret_cast<double2*>(dst + 32 * ti) = (ti == TI) ? make_double2(m0, m1) : make_double2(a[ti][TJ][0], a[ti][TJ][1]);
     }
 }
 
@@ -160,15 +159,14 @@ __device__ __forceinline__ void gemm_chunk(double (&g)[2][4][2], const DmmaPos& 
         for (int tj = 0; tj < 4; ++tj) dmma(g[ti][tj][0], g[ti][tj][1], an[ti], bw[tj]);
 }
 
-struct SweepSync {        // per-thread view of the step barrier and of the GEMM backlog
+struct SweepSync {        // per-thread view of the step barrier
     uint32_t bar;         // shared address of the mbarrier (count = warps)
     uint32_t phase;       // parity to wait for next
-    int gk;               // next k-block of the score GEMM this warp still owes
 };
 
 // One block step; BQ = b % 8 is compile time, bo = b / 8.  On entry the lines of block b are
 // published and every warp has arrived on the step barrier; the step
-//   waits for it (doing owed GEMM chunks instead of idling),
+//   waits for it,
 //   forms CS, updates FIRST the five tiles that hold the pivot rows / columns of block b + 1,
 //   lets the diagonal warp invert the next pivot block, publishes the lines of block b + 1 and
 //   arrives -- and only then updates its remaining three tiles, off the serial chain.
@@ -182,11 +180,7 @@ __device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], double (&g
     const double* rb = sm + DmmaSmem::rbuf + CUR * 4 * DM_LD;
     const double* cb = sm + DmmaSmem::cbuf + CUR * DM_DP * 4;
     const double* qb = sm + DmmaSmem::qbuf + CUR * 16;
-    while (!mbar_test(sy.bar, sy.phase)) {
-        if constexpr (GEMM) {
-            if (sy.gk < nb) gemm_chunk(g, ps, sm, sy.gk++);
-        }
-    }
+    mbar_wait(sy.bar, sy.phase);
     sy.phase ^= 1u;
     // ---- CS = Cpub (-Q) as ONE DMMA per 8 rows: B[k][n] = -Q[k][n/2] on even n, so the C
     //      fragment element c0 of lane (qr, qc) is CS[row qr][qc] = exactly its A fragment.
@@ -229,7 +223,12 @@ template <bool GEMM>
 __device__ __forceinline__ void dmma_sweep(double (&a)[2][4][2], double (&g)[2][4][2], const DmmaPos& ps, double* sm,
                                            int d, SweepSync& sy) {
     const int nb = (d + 3) >> 2;
-    sy.gk = 0;
+    // the score GEMM first: 16 independent DMMA per k-block and warp, no serial chain -- this is
+    // the phase that keeps the FP64 pipe busy while the other CTA of the SM is inside its sweep
+    if constexpr (GEMM) {
+#pragma unroll 1
+        for (int kb = 0; kb < nb; ++kb) gemm_chunk(g, ps, sm, kb);
+    }
     if (ps.wr == 0 && ps.wc == 0) stage_pivot_block<0, 0, 0>(a, ps, sm, 0, 0);
     publish_block<0>(a, ps, sm, 0);
     __syncwarp();
@@ -246,10 +245,6 @@ __device__ __forceinline__ void dmma_sweep(double (&a)[2][4][2], double (&g)[2][
         if (left > 5) dmma_block_step<5, GEMM>(a, g, ps, sm, bo, nb, sy);
         if (left > 6) dmma_block_step<6, GEMM>(a, g, ps, sm, bo, nb, sy);
         if (left > 7) dmma_block_step<7, GEMM>(a, g, ps, sm, bo, nb, sy);
-    }
-    if constexpr (GEMM) {
-#pragma unroll 1
-        while (sy.gk < nb) gemm_chunk(g, ps, sm, sy.gk++);
     }
     __syncthreads();
 }

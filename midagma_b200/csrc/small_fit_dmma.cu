@@ -17,6 +17,59 @@
 
 namespace dagma {
 
+// c with the sign of w, 0 for w == +-0: c * sign(w) without touching the FP64 pipe
+__device__ __forceinline__ double signed_const(double w, double c) {
+    const int hi = __double2hiint(w), lo = __double2loint(w);
+    const bool zero = ((hi & 0x7fffffff) | lo) == 0;
+    const int chi = __double2hiint(c) ^ (hi & (int)0x80000000);
+    return zero ? 0.0 : __hiloint2double(chi, __double2loint(c));
+}
+
+// w -= lr * mhat / (sqrt(vhat) + 1e-8) for N independent entries   (linear.py:160-162, 275), written
+// stage by stage so the N Newton chains interleave.  MUFU seeds are good to 2^-20 or better
+// (measured, scripts/latency.py): rsqrt seed + two coupled iterations, reciprocal seed + one iteration
+// + one division-residual step leave errors far below 1 ulp of the quotient.
+template <int N>
+__device__ __forceinline__ void adam_step(double* __restrict__ w, const double* __restrict__ m,
+                                          const double* __restrict__ v, double c1, double c2, double lr) {
+    double x[N], gq[N], hq[N], dn[N], r[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        x[q] = v[q] * c2;
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x[q]));
+        if (__double2hiint(x[q]) < 0x00200000) y = 0.0;       // vhat == 0 (or denormal): sqrt -> 0, not NaN
+        gq[q] = x[q] * y;
+        hq[q] = 0.5 * y;
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const double e = fma(-gq[q], hq[q], 0.5);
+        gq[q] = fma(gq[q], e, gq[q]);
+        hq[q] = fma(hq[q], e, hq[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const double e = fma(-gq[q], hq[q], 0.5);
+        gq[q] = fma(gq[q], e, gq[q]);
+        dn[q] = gq[q] + 1e-8;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[q]) : "d"(dn[q]));
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const double e = fma(-dn[q], r[q], 1.0);
+        r[q] = fma(r[q], e, r[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const double mh = m[q] * c1;
+        const double qv = mh * r[q];
+        const double rem = fma(-qv, dn[q], mh);
+        const double dir = fma(rem, r[q], qv);
+        w[q] = fma(-lr, dir, w[q]);
+    }
+}
+
 __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_small_fit_args P) {
     using S = DmmaSmem;
     constexpr int NT = DM_NT, LD = DM_LD;
@@ -35,7 +88,7 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
     const size_t dd = (size_t)d * d;
 
     // ---- step barrier of the sweep: one arrival per warp
-    SweepSync sy{smem_u32(smem + S::mbar), 0u, 0};
+    SweepSync sy{smem_u32(smem + S::mbar), 0u};
     if (tid == 0) mbar_init(sy.bar, NT / 32);
 
     // ---- tensor-memory scratch for the Adam moments (thread-private, 64 columns per thread)
@@ -280,7 +333,7 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                 ++it;
                 p1.mul(P.beta1);
                 p2.mul(P.beta2);
-                const double c1 = 1.0 / p1.one_minus(), c2 = 1.0 / p2.one_minus();
+                const double c1 = fast_rcp(p1.one_minus()), c2 = fast_rcp(p2.one_minus());
                 const double ob1 = 1.0 - P.beta1, ob2 = 1.0 - P.beta2;
                 const double l1c = mu * lambda1, incc = -2.0 * mu * lambda1;
 #pragma unroll
@@ -289,33 +342,38 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                     lm.issue(tm + 32 * ti);
                     lv.issue(tm + 32 * ti + 16);
                     double* wp = Ws + ps.row(ti) * LD;
-                    double2 w2[4];
-#pragma unroll
-                    for (int tj = 0; tj < 4; ++tj) w2[tj] = *reinterpret_cast<const double2*>(wp + ps.col(tj));
-                    lm.finish();
-                    lv.finish();
-                    double mn[8], vn[8];
+                    double w[8], go[8], mn[8], vn[8];
 #pragma unroll
                     for (int tj = 0; tj < 4; ++tj) {
+                        const double2 t = *reinterpret_cast<const double2*>(wp + ps.col(tj));
+                        w[2 * tj] = t.x;
+                        w[2 * tj + 1] = t.y;
+                    }
+                    // Gobj = -mu cov (I - W) + mu l1 sign(W) + 2 W o (M^{-T} + 1e-16)   linear.py:248
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int q = 2 * tj + e, bit = ti * 8 + q;
-                            const double w = e ? w2[tj].y : w2[tj].x;
-                            const double sg = (w > 0.0) ? 1.0 : ((w < 0.0) ? -1.0 : 0.0);
-                            double go = fma(-mu, g[ti][tj][e], l1c * sg);
-                            go = fma(2.0 * w, a[ti][tj][e] + 1e-16, go);
-                            if (incbits >> bit & 1u) go = fma(incc, sg, go);
-                            mn[q] = fma(lm.get(q), P.beta1, ob1 * go);
-                            vn[q] = fma(lv.get(q), P.beta2, ob2 * (go * go));
-                            const double dir = fast_div(mn[q] * c1, fast_sqrt_nonneg(vn[q] * c2) + 1e-8);
-                            double wn = w - lr * dir;
-                            if (excbits >> bit & 1u) wn = 0.0;
-                            if (e) w2[tj].y = wn; else w2[tj].x = wn;
-                        }
-                        *reinterpret_cast<double2*>(wp + ps.col(tj)) = w2[tj];
+                    for (int q = 0; q < 8; ++q) {
+                        go[q] = fma(-mu, g[ti][q >> 1][q & 1], signed_const(w[q], l1c));
+                        go[q] = fma(w[q] + w[q], a[ti][q >> 1][q & 1] + 1e-16, go[q]);
+                        if (incbits >> (ti * 8 + q) & 1u) go[q] += signed_const(w[q], incc);
+                    }
+                    lm.finish();
+                    lv.finish();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        mn[q] = fma(lm.get(q), P.beta1, ob1 * go[q]);
+                        vn[q] = fma(lv.get(q), P.beta2, ob2 * (go[q] * go[q]));
                     }
                     tmem_st8(tm + 32 * ti, mn);
                     tmem_st8(tm + 32 * ti + 16, vn);
+                    adam_step<4>(w, mn, vn, c1, c2, lr);
+                    adam_step<4>(w + 4, mn + 4, vn + 4, c1, c2, lr);
+#pragma unroll
+                    for (int tj = 0; tj < 4; ++tj) {
+                        double2 t = make_double2(w[2 * tj], w[2 * tj + 1]);
+                        if (excbits >> (ti * 8 + 2 * tj) & 1u) t.x = 0.0;
+                        if (excbits >> (ti * 8 + 2 * tj + 1) & 1u) t.y = 0.0;
+                        *reinterpret_cast<double2*>(wp + ps.col(tj)) = t;
+                    }
                 }
                 tmem_wait_st();
                 __syncthreads();

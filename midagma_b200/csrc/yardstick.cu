@@ -145,6 +145,21 @@ __global__ void latency_probe(double* out, double seed) {
     for (int i = 0; i < N; ++i) acc = acc * y;
     t1 = clock64();
     if (lane == 0) out[8] = double(t1 - t0) / N;
+    // 9, 10: worst relative error of the MUFU seeds rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64
+    double e_rcp = 0.0, e_rsq = 0.0;
+    for (int i = 0; i < 20000; ++i) {
+        const double xx = (1.0 + (lane * 20000 + i) * (3.0 / 640000.0)) * ((i & 1) ? 1e-7 : 37.0);
+        double q, z;
+        asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(xx));
+        asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(z) : "d"(xx));
+        e_rcp = fmax(e_rcp, fabs(q * xx - 1.0));
+        e_rsq = fmax(e_rsq, fabs(z * z * xx - 1.0) * 0.5);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        e_rcp = fmax(e_rcp, __shfl_xor_sync(0xffffffffu, e_rcp, off));
+        e_rsq = fmax(e_rsq, __shfl_xor_sync(0xffffffffu, e_rsq, off));
+    }
+    if (lane == 0) { out[9] = e_rcp; out[10] = e_rsq; }
     if (acc + idx == 123.456) out[15] = acc;
 }
 }  // namespace dagma

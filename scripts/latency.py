@@ -10,3 +10,4 @@ for _ in range(2):
 names = ["DFMA", "DMMA (acc chain)", "DMMA (A-operand chain)", "SHFL.64", "MUFU.RCP64H+DFMA", "LDS chase",
          "STS+syncwarp+LDS+syncwarp", "DADD", "DMUL"]
 for n, v in zip(names, out.tolist()): print(f"{n:28s} {v:7.1f} clk")
+print(f"rcp.approx.ftz.f64 max rel err {out[9].item():.3e}   rsqrt.approx.ftz.f64 max rel err {out[10].item():.3e}")
