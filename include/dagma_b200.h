@@ -201,6 +201,9 @@ int dagma_center_cov_f64(dagma_stream_t stream, int batch, int n, int d, double*
 /* ---- FP64 pipe yardsticks used by bench.py for the roofline denominator ---------- */
 int dagma_bench_fp64_fma(dagma_stream_t stream, int ctas, int threads, int iters, double* sink_dev);
 int dagma_bench_fp64_dmma(dagma_stream_t stream, int ctas, int threads, int iters, double* sink_dev);
+/* 4 x 4 accumulator tiles from 4 A / 4 B fragments (mode 1: fragments reloaded from shared memory) */
+int dagma_bench_fp64_dmma_tiles(dagma_stream_t stream, int ctas, int threads, int iters, int mode,
+                                double* sink_dev);
 /* dependent-issue latencies (cycles / op, one warp): out_dev[0..8] = DFMA, DMMA via C, DMMA via A,
  * 64-bit SHFL, MUFU.RCP64H + DFMA, LDS chase, STS/sync/LDS round trip, DADD, DMUL (16 doubles) */
 int dagma_bench_latency(dagma_stream_t stream, double* out_dev);

@@ -4,17 +4,21 @@
 // block so that a whole inner iteration is a fixed launch sequence (CUDA-graph
 // replayable, no host synchronisation until the next convergence checkpoint).
 //
-// Blocked inverse (d > 128), block size 64, in place, no pivoting (M-matrix):
-//   step kb:  P = A[K,K];  Q = P^{-1} (on-chip sweep, redundantly in every panel CTA);
-//             CS = -Cpub Q  (d x 64)  with Cpub = A[:,K] and its K block replaced by P - I;
+// Blocked inverse (d > 128), in place, no pivoting (M-matrix).  Single level (d <= 256), block 64:
+//   step kb:  P = A[K,K];  Q = P^{-1} (tensor-core sweep of small_dmma.cuh, redundantly in every
+//             panel CTA);  CS = -Cpub Q (d x 64) with Cpub = A[:,K] and its K block replaced by P - I;
 //             Rpub = A[K,:]           with its K block replaced by I + P;
 //             A += CS * Rpub          (one d x d x 64 DMMA GEMM, no special tiles).
 // The two replacements make the single GEMM produce Q in the pivot block, Q A[K,:] in
 // the pivot rows and -A[:,K] Q in the pivot columns (block form of the identity used
-// by the on-chip sweep, see small_gj.cuh).  log|det| = sum of the logs of all pivots.
+// by the on-chip sweep, see small_gj.cuh).  Two levels (d > 256): the same step with 256-wide
+// blocks whose pivot block is inverted by the single-level sweep, so that the d x d updates are
+// rank-256 GEMMs.  log|det| comes from the pivots of all 4 x 4 pivot blocks.
 #include "common.cuh"
 #include "gemm_f64.cuh"
 #include "small_gj.cuh"
+#include "small_dmma.cuh"
+#include <cstdlib>
 #include "../../include/dagma_b200.h"
 
 namespace dagma {
@@ -23,24 +27,27 @@ int logdet_inv_small(cudaStream_t, int, int, double, const double*, int, int, do
                      double*, double*, int, double*, int*);
 
 // ------------------------------------------------------------------ GEMM host side
-static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, double alpha, const double* A, int lda,
-                       const double* B, int ldb, double beta, double* C, int ldc, int epi, double* ws,
-                       size_t ws_bytes) {
-    if (M <= 0 || N <= 0) return 0;
+template <int BM, int BN, int WM, int WN>
+static int gemm_launch_tile(cudaStream_t stream, int transA, int M, int N, int K, double alpha, const double* A,
+                            int lda, const double* B, int ldb, double beta, double* C, int ldc, int epi, double* ws,
+                            size_t ws_bytes) {
+    using T = GemmTile<BM, BN, WM, WN>;
+    constexpr int GTHREADS = T::THREADS;
     static bool attr_done = false;
     if (!attr_done) {
-        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_f64_kernel<false, EPI_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
-        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_f64_kernel<false, EPI_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
-        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_f64_kernel<true, EPI_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
-        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_f64_kernel<true, EPI_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_f64_kernel<false, EPI_NONE, BM, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_f64_kernel<false, EPI_SIGMOID, BM, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_f64_kernel<true, EPI_NONE, BM, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_f64_kernel<true, EPI_SIGMOID, BM, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
         attr_done = true;
     }
-    const int tm = (M + GBM - 1) / GBM, tn = (N + GBN - 1) / GBN;
+    const int tm = (M + BM - 1) / BM, tn = (N + BN - 1) / BN;
     const int ktiles = (K + GBK - 1) / GBK;
     // split K when the output grid cannot fill the machine and K is long
     int splits = 1;
-    if (tm * tn < 74 && ktiles >= 8 && ws != nullptr) {
-        splits = 148 / (tm * tn);
+    const int slots = 148 * T::MINB * BM * BN / (128 * 64);   // in units that keep the old heuristic
+    if (tm * tn < slots / 2 && ktiles >= 8 && ws != nullptr) {
+        splits = slots / (tm * tn);
         if (splits > ktiles / 4) splits = ktiles / 4;
         while (splits > 1 && (size_t)splits * M * N * sizeof(double) > ws_bytes) --splits;
         if (splits < 1) splits = 1;
@@ -49,9 +56,10 @@ static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, dou
     splits = (ktiles + kchunk_tiles - 1) / kchunk_tiles;
     GemmArgs P{M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kchunk_tiles * GBK, splits > 1 ? ws : nullptr};
     dim3 grid(tn, tm, splits);
+    const size_t sm = T::SMEM_BYTES;
     if (splits > 1) {   // epilogue is applied by the reduce kernel
-        if (transA) gemm_f64_kernel<true, EPI_NONE><<<grid, GTHREADS, GEMM_SMEM_BYTES, stream>>>(P);
-        else gemm_f64_kernel<false, EPI_NONE><<<grid, GTHREADS, GEMM_SMEM_BYTES, stream>>>(P);
+        if (transA) gemm_f64_kernel<true, EPI_NONE, BM, BN, WM, WN><<<grid, GTHREADS, sm, stream>>>(P);
+        else gemm_f64_kernel<false, EPI_NONE, BM, BN, WM, WN><<<grid, GTHREADS, sm, stream>>>(P);
         DAGMA_CUDA_OK(cudaGetLastError());
         const int blocks = (int)(((size_t)M * N + 255) / 256);
         if (epi == EPI_SIGMOID)
@@ -59,19 +67,40 @@ static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, dou
         else
             splitk_reduce_kernel<EPI_NONE><<<blocks < 1184 ? blocks : 1184, 256, 0, stream>>>(ws, splits, M, N, C, ldc, alpha, beta);
     } else if (epi == EPI_SIGMOID) {
-        if (transA) gemm_f64_kernel<true, EPI_SIGMOID><<<grid, GTHREADS, GEMM_SMEM_BYTES, stream>>>(P);
-        else gemm_f64_kernel<false, EPI_SIGMOID><<<grid, GTHREADS, GEMM_SMEM_BYTES, stream>>>(P);
+        if (transA) gemm_f64_kernel<true, EPI_SIGMOID, BM, BN, WM, WN><<<grid, GTHREADS, sm, stream>>>(P);
+        else gemm_f64_kernel<false, EPI_SIGMOID, BM, BN, WM, WN><<<grid, GTHREADS, sm, stream>>>(P);
     } else {
-        if (transA) gemm_f64_kernel<true, EPI_NONE><<<grid, GTHREADS, GEMM_SMEM_BYTES, stream>>>(P);
-        else gemm_f64_kernel<false, EPI_NONE><<<grid, GTHREADS, GEMM_SMEM_BYTES, stream>>>(P);
+        if (transA) gemm_f64_kernel<true, EPI_NONE, BM, BN, WM, WN><<<grid, GTHREADS, sm, stream>>>(P);
+        else gemm_f64_kernel<false, EPI_NONE, BM, BN, WM, WN><<<grid, GTHREADS, sm, stream>>>(P);
     }
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
+// DAGMA_GEMM_TILE (debug / A-B timing): 0 = 128 x 64 tile, two CTAs per SM (default); 1 = 128 x 128, one CTA;
+// 2 = 64 x 64 tile, 128 threads, four CTAs per SM
+static int gemm_tile_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_GEMM_TILE");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, double alpha, const double* A, int lda,
+                       const double* B, int ldb, double beta, double* C, int ldc, int epi, double* ws,
+                       size_t ws_bytes) {
+    if (M <= 0 || N <= 0) return 0;
+    if (gemm_tile_variant() == 1)
+        return gemm_launch_tile<128, 128, 4, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
+    if (gemm_tile_variant() == 2)
+        return gemm_launch_tile<64, 64, 2, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
+    return gemm_launch_tile<128, 64, 4, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
+}
+
 // ------------------------------------------------------------------ blocked inverse
 constexpr int NB = 64;
-using CP = Cfg<4, 2, 16, 32>;     // panel CTA: 512 threads, 64 x 64 on chip
 
 // build M = s I - (square ? A o A : A), scaled by inv_scale, into out (d x d, ld = d)
 __global__ void build_m_kernel(const double* __restrict__ A, int lda, double* __restrict__ out, int d, double s,
@@ -85,121 +114,127 @@ __global__ void build_m_kernel(const double* __restrict__ A, int lda, double* __
     }
 }
 
-constexpr int PANEL_LINE = ((SweepSmem<CP>::doubles + 3) / 2) * 2;
-constexpr size_t PANEL_SMEM_BYTES = (size_t)(PANEL_LINE + 2 * NB * (NB + 2)) * sizeof(double);
-
 struct PanelArgs {
     double* A;      // d x d in place (ld = d)
     int d, kb;
     double* CS;     // d x NB  (ld = NB)
     double* Rbuf;   // NB x d  (ld = d)
-    double* pivots; // d
+    double* pivots; // fraction-free pivots (see stage_pivot_block), 4*ceil(d/4) entries
 };
 
-__global__ void __launch_bounds__(CP::NT, 1) inv_panel_kernel(const PanelArgs P) {
-    constexpr int RM = CP::RM, RN = CP::RN, NT = CP::NT, LQ = NB + 2;
+// Panel of block step kb, one 256-thread CTA per 64-row block `blk`:
+//   Q = P^{-1} by the tensor-core block Gauss-Jordan sweep of small_dmma.cuh (every CTA redundantly:
+//       P is 32 KB and L2 resident, and a broadcast would cost a grid-wide synchronisation),
+//   CS[blk rows, :] = -Cpub Q   (64 x 64 x 64 DMMA, Cpub = A[rows, K], K block: P - I),
+//   Rbuf[:, blk cols] = A[K, cols]                  (K block: P + I).
+constexpr size_t PANEL_SMEM_BYTES = DmmaSmem::bytes;      // ncov / W slots hold Cpub / Q
+
+__global__ void __launch_bounds__(DM_NT, 2) inv_panel_kernel(const PanelArgs P) {
+    using S = DmmaSmem;
+    constexpr int LD = DM_LD;
     extern __shared__ __align__(16) double psm[];
-    double* linebuf = psm;
-    double* Qs = psm + PANEL_LINE;
-    double* Cs = Qs + NB * LQ;
+    double* Cs = psm + S::ncov;     // [64][68]  Cpub rows of this block
+    double* Qs = psm + S::W;        // [64][68]  Q
     const int tid = threadIdx.x;
-    const ThreadPos<CP> pos(tid);
-    const int ty = pos.ty, tx = pos.tx;
+    const DmmaPos ps(tid);
     const int d = P.d, k0 = P.kb * NB;
     const int kn = min(NB, d - k0);
     const int blk = blockIdx.x;                 // row block (for CS) and column block (for Rbuf)
-    const double* pivots_s = linebuf + SweepSmem<CP>::piv_off;
-
-    // ---- Q = P^{-1} on chip (every CTA redundantly; P is 32 KB and L2 resident)
-    double a[RM][RN], dummy[RM][RN];
-#pragma unroll
-    for (int i = 0; i < RM; ++i)
-#pragma unroll
-        for (int j = 0; j < RN; ++j) {
-            const int r = CP::grow(ty, i), c = CP::gcol(tx, j);
-            a[i][j] = (r < kn && c < kn) ? P.A[(size_t)(k0 + r) * d + k0 + c] : ((r == c) ? 1.0 : 0.0);
-            dummy[i][j] = 0.0;
-        }
-    // stash P - I (for Cpub) before the sweep destroys it
-    if (blk == P.kb) {
-#pragma unroll
-        for (int i = 0; i < RM; ++i)
-#pragma unroll
-            for (int j = 0; j < RN; ++j) {
-                const int r = CP::grow(ty, i), c = CP::gcol(tx, j);
-                Cs[r * LQ + c] = (r < kn && c < kn) ? a[i][j] - ((r == c) ? 1.0 : 0.0) : 0.0;
-            }
-    }
-    gj_sweep<CP, false>(a, dummy, 0u, 0u, smem_u32(linebuf), kn, ty, tx);
-    if (blk == 0 && tid < kn) P.pivots[k0 + tid] = pivots_s[tid];
-#pragma unroll
-    for (int i = 0; i < RM; ++i)
-#pragma unroll
-        for (int j = 0; j < RN; ++j) {
-            const int r = CP::grow(ty, i), c = CP::gcol(tx, j);
-            Qs[r * LQ + c] = (r < kn && c < kn) ? a[i][j] : 0.0;
-        }
-
-    // ---- Cpub rows of this block: A[I, K]  (K block: P - I, stashed above)
     const int r0 = blk * NB;
-    if (blk != P.kb) {
-        for (int e = tid; e < NB * NB; e += NT) {
-            const int r = e / NB, c = e - r * NB;
-            Cs[r * LQ + c] = (r0 + r < d && c < kn) ? P.A[(size_t)(r0 + r) * d + k0 + c] : 0.0;
-        }
-    }
-    // ---- Rpub columns of this block: A[K, J]  (K block: I + P)
-    for (int e = tid; e < NB * NB; e += NT) {
-        const int r = e / NB, c = e - r * NB;
+    SweepSync sy{smem_u32(psm + S::mbar), 0u};
+    if (tid == 0) mbar_init(sy.bar, DM_NT / 32);
+
+    // ---- P into the accumulator layout (identity padding), Cpub rows / Rpub columns of this block
+    double a[2][4][2], dummy[2][4][2];
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = ps.row(ti), c = ps.col(tj) + e;
+                a[ti][tj][e] = (r < kn && c < kn) ? P.A[(size_t)(k0 + r) * d + k0 + c] : ((r == c) ? 1.0 : 0.0);
+                dummy[ti][tj][e] = 0.0;
+            }
+    for (int e = tid; e < NB * NB; e += DM_NT) {
+        const int r = e >> 6, c = e & 63;
+        double v = (r0 + r < d && c < kn) ? P.A[(size_t)(r0 + r) * d + k0 + c] : 0.0;
+        if (blk == P.kb && r == c && r < kn) v -= 1.0;
+        Cs[r * LD + c] = v;
         if (r < kn && r0 + c < d) {
-            double v = P.A[(size_t)(k0 + r) * d + r0 + c];
-            if (blk == P.kb && r == c) v += 1.0;
-            P.Rbuf[(size_t)r * d + r0 + c] = v;
+            double w = P.A[(size_t)(k0 + r) * d + r0 + c];
+            if (blk == P.kb && r == c) w += 1.0;
+            P.Rbuf[(size_t)r * d + r0 + c] = w;
         }
     }
     __syncthreads();
-    // ---- CS[I, :] = -Cpub Q   (64 x 64 x kn on chip)
-    double acc[RM][RN];
+    dmma_sweep<false>(a, dummy, ps, psm, kn, sy);
+    if (blk == 0 && tid < 4 * ((kn + 3) >> 2)) P.pivots[k0 + tid] = psm[S::pinfo + tid];
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
-        for (int j = 0; j < RN; ++j) acc[i][j] = 0.0;
-    for (int k = 0; k < kn; ++k) {
-        double cv[RM], qv[RN];
+        for (int tj = 0; tj < 4; ++tj) {
+            const int r = ps.row(ti), c = ps.col(tj);
+            const bool in0 = (r < kn && c < kn), in1 = (r < kn && c + 1 < kn);
+            *reinterpret_cast<double2*>(Qs + r * LD + c) = make_double2(in0 ? a[ti][tj][0] : 0.0, in1 ? a[ti][tj][1] : 0.0);
+        }
+    __syncthreads();
+    // ---- CS[rows, :] = -Cpub Q  (warp tile 16 x 32, 16 k-blocks of 4)
+    double acc[2][4][2];
 #pragma unroll
-        for (int i = 0; i < RM; ++i) cv[i] = Cs[CP::grow(ty, i) * LQ + k];
+    for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
-        for (int j = 0; j < RN; ++j) qv[j] = Qs[k * LQ + CP::gcol(tx, j)];
+        for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < NB; kk += 4) {
+        double an[2], bw[4];
 #pragma unroll
-        for (int i = 0; i < RM; ++i)
+        for (int ti = 0; ti < 2; ++ti) an[ti] = -Cs[ps.row(ti) * LD + kk + ps.qc];
 #pragma unroll
-            for (int j = 0; j < RN; ++j) acc[i][j] = fma(-cv[i], qv[j], acc[i][j]);
+        for (int tj = 0; tj < 4; ++tj) bw[tj] = Qs[(kk + ps.qc) * LD + 32 * ps.wc + 8 * tj + ps.qr];
+#pragma unroll
+        for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < 4; ++tj) dmma(acc[ti][tj][0], acc[ti][tj][1], an[ti], bw[tj]);
     }
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
-        for (int j = 0; j < RN; ++j) {
-            const int r = r0 + CP::grow(ty, i), c = CP::gcol(tx, j);
-            if (r < d && c < kn) P.CS[(size_t)r * NB + c] = acc[i][j];
+        for (int tj = 0; tj < 4; ++tj) {
+            const int r = r0 + ps.row(ti), c = ps.col(tj);
+            if (r < d) *reinterpret_cast<double2*>(P.CS + (size_t)r * NB + c) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
         }
 }
 
-// after the sweep: log|det|, min entry, info; optional outputs (scaled back)
-__global__ void inv_finish_kernel(const double* __restrict__ Minv, const double* __restrict__ pivots, int d,
+// per-block partial minima of the inverse (grid-stride; finished by inv_finish_kernel)
+__global__ void __launch_bounds__(256) min_partial_kernel(const double* __restrict__ Minv, size_t total,
+                                                          double* __restrict__ partial) {
+    __shared__ double red[32];
+    double mn = INFINITY;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+        mn = fmin(mn, Minv[e]);
+    mn = block_min<256>(mn, red, threadIdx.x);
+    if (threadIdx.x == 0) partial[blockIdx.x] = mn;
+}
+
+// after the sweep: log|det| from the fraction-free pivots (weights k mod 4 - 2, see stage_pivot_block),
+// min entry from the per-block partial minima, info; optional outputs (scaled back)
+constexpr int MIN_PARTIALS = 592;
+__global__ void inv_finish_kernel(const double* __restrict__ partial_min, const double* __restrict__ pivots, int d,
                                   double s, double inv_scale, double log_scale, double* logabsdet, double* h,
                                   double* min_entry, int* info) {
     __shared__ double red[96];
     const int tid = threadIdx.x;
     double ld = 0.0, z1 = 0.0, z2 = 0.0;
     bool bad = false;
-    for (int k = tid; k < d; k += blockDim.x) {
+    const int np = (d + 3) & ~3;
+    for (int k = tid; k < np; k += blockDim.x) {
         const double p = pivots[k];
-        ld += log(fabs(p));
+        ld += (double)((k & 3) - 2) * log(fabs(p));
         bad |= !(p > 0.0);
     }
     double mn = INFINITY;
-    const size_t total = (size_t)d * d;
-    for (size_t e = tid; e < total; e += blockDim.x) mn = fmin(mn, Minv[e]);
+    for (int e = tid; e < MIN_PARTIALS; e += blockDim.x) mn = fmin(mn, partial_min[e]);
     block_sum3<1024>(ld, z1, z2, red, tid);
     mn = block_min<1024>(mn, red, tid) * inv_scale;
     const int anybad = __syncthreads_or(bad);
@@ -236,11 +271,101 @@ __global__ void inv_outputs_kernel(const double* __restrict__ Minv, const double
     }
 }
 
-static size_t large_ws_bytes(int d) {
-    return ((size_t)d * d + (size_t)d * NB + (size_t)NB * d + d + 64) * sizeof(double);
+constexpr int OB = 256;            // outer block of the two-level blocked inverse (d > OB)
+
+struct LargeWs {                   // offsets in doubles into the caller's workspace
+    size_t M, CS, Rbuf, piv, Pbuf, CSin, Rin, pmin, total;
+    explicit LargeWs(int d) {
+        const size_t dd = ((size_t)d * d + 1) & ~(size_t)1;        // keep every buffer 16-byte aligned
+        const size_t strip = ((size_t)d * OB + 1) & ~(size_t)1;
+        M = 0;
+        CS = M + dd;
+        Rbuf = CS + strip;
+        piv = Rbuf + strip;
+        Pbuf = piv + (((size_t)d + 64 + 1) & ~(size_t)1);
+        CSin = Pbuf + (size_t)OB * OB;
+        Rin = CSin + (size_t)OB * NB;
+        pmin = Rin + (size_t)NB * OB;
+        total = pmin + MIN_PARTIALS + 64;
+    }
+};
+static size_t large_ws_bytes(int d) { return LargeWs(d).total * sizeof(double); }
+
+// ---- small helpers of the two-level algorithm
+// dst (rows x cols, ld = ldd) = src (ld = lds) [+ identity on the diagonal starting at column diag_col]
+__global__ void copy_block_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd,
+                                  int rows, int cols, int diag_col, double diag_add) {
+    const size_t total = (size_t)rows * cols;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cols), c = (int)(e - (size_t)r * cols);
+        double v = src[(size_t)r * lds + c];
+        if (c - diag_col == r) v += diag_add;
+        dst[(size_t)r * ldd + c] = v;
+    }
+}
+// dst (n x n, ld = ldd) += src (ld = lds)
+__global__ void add_block_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int n) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int r = e / n, c = e - r * n;
+        dst[(size_t)r * ldd + c] += src[(size_t)r * lds + c];
+    }
 }
 
-// one problem; ws holds: Mwork (d*d) | CS (d*NB) | Rbuf (NB*d) | pivots (d)
+static int ensure_panel_attr() {
+    static bool panel_attr = false;
+    if (!panel_attr) {
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(inv_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_BYTES));
+        panel_attr = true;
+    }
+    return 0;
+}
+
+// single-level block Gauss-Jordan (block NB = 64) of the dense n x n matrix Mw (ld = n), in place;
+// CS: n x NB, Rbuf: NB x n, piv: n scalar pivots
+static int gj_inplace_nb64(cudaStream_t stream, double* Mw, int n, double* CS, double* Rbuf, double* piv) {
+    int rc = ensure_panel_attr();
+    if (rc) return rc;
+    const int nblk = (n + NB - 1) / NB;
+    for (int kb = 0; kb < nblk; ++kb) {
+        PanelArgs P{Mw, n, kb, CS, Rbuf, piv};
+        inv_panel_kernel<<<nblk, DM_NT, PANEL_SMEM_BYTES, stream>>>(P);
+        DAGMA_CUDA_OK(cudaGetLastError());
+        const int kn = (n - kb * NB) < NB ? (n - kb * NB) : NB;
+        rc = gemm_launch(stream, 0, n, n, kn, 1.0, CS, NB, Rbuf, n, 1.0, Mw, n, EPI_NONE, nullptr, 0);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// two-level block Gauss-Jordan, outer block OB = 256: per outer block K
+//   Q  = P^{-1}, P = A[K,K]          (copy + single-level sweep on the 256 x 256 block)
+//   CS = -A[:,K] Q, CS[K,:] += Q      (= -(A[:,K] - E_K) Q : the "- I" of the publish identity)
+//   R  = A[K,:] + E_K^T               (row copy: the GEMM below overwrites those rows)
+//   A += CS R                         (one d x d x 256 DMMA GEMM, accumulators initialised from A)
+static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* ws) {
+    const LargeWs L(d);
+    double *CS = ws + L.CS, *Rbuf = ws + L.Rbuf, *piv = ws + L.piv, *Pbuf = ws + L.Pbuf, *CSin = ws + L.CSin,
+           *Rin = ws + L.Rin;
+    const int nob = (d + OB - 1) / OB;
+    for (int ob = 0; ob < nob; ++ob) {
+        const int k0 = ob * OB, kn = (d - k0) < OB ? (d - k0) : OB;
+        copy_block_kernel<<<64, 256, 0, stream>>>(Mw + (size_t)k0 * d + k0, d, Pbuf, kn, kn, kn, 0, 0.0);
+        DAGMA_CUDA_OK(cudaGetLastError());
+        int rc = gj_inplace_nb64(stream, Pbuf, kn, CSin, Rin, piv + k0);
+        if (rc) return rc;
+        rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw + k0, d, Pbuf, kn, 0.0, CS, kn, EPI_NONE, nullptr, 0);
+        if (rc) return rc;
+        add_block_kernel<<<64, 256, 0, stream>>>(Pbuf, kn, CS + (size_t)k0 * kn, kn, kn);
+        DAGMA_CUDA_OK(cudaGetLastError());
+        copy_block_kernel<<<296, 256, 0, stream>>>(Mw + (size_t)k0 * d, d, Rbuf, d, kn, d, k0, 1.0);
+        DAGMA_CUDA_OK(cudaGetLastError());
+        rc = gemm_launch(stream, 0, d, d, kn, 1.0, CS, kn, Rbuf, d, 1.0, Mw, d, EPI_NONE, nullptr, 0);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// one problem; ws layout: see large_ws_bytes
 static int logdet_inv_blocked(cudaStream_t stream, int d, double s, const double* a_dev, int lda, int square,
                               double* logabsdet, double* h, double* minv, double* grad, int ldo,
                               double* min_entry, int* info, double* ws) {
@@ -253,27 +378,16 @@ static int logdet_inv_blocked(cudaStream_t stream, int d, double s, const double
     }
     const double inv_scale = 1.0 / scale;
     // work in place in the caller's minv buffer when it is dense (ldo == d), else in ws
-    double* Mw = (minv != nullptr && ldo == d) ? minv : ws;
-    double* CS = ws + (size_t)d * d;
-    double* Rbuf = CS + (size_t)d * NB;
-    double* piv = Rbuf + (size_t)NB * d;
-    static bool panel_attr = false;
-    if (!panel_attr) {
-        DAGMA_CUDA_OK(cudaFuncSetAttribute(inv_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_BYTES));
-        panel_attr = true;
-    }
+    const LargeWs L(d);
+    double* Mw = (minv != nullptr && ldo == d) ? minv : ws + L.M;
+    double* piv = ws + L.piv;
     build_m_kernel<<<592, 256, 0, stream>>>(a_dev, lda, Mw, d, s, inv_scale, square);
     DAGMA_CUDA_OK(cudaGetLastError());
-    const int nblk = (d + NB - 1) / NB;
-    for (int kb = 0; kb < nblk; ++kb) {
-        PanelArgs P{Mw, d, kb, CS, Rbuf, piv};
-        inv_panel_kernel<<<nblk, CP::NT, PANEL_SMEM_BYTES, stream>>>(P);
-        DAGMA_CUDA_OK(cudaGetLastError());
-        const int kn = (d - kb * NB) < NB ? (d - kb * NB) : NB;
-        int rc = gemm_launch(stream, 0, d, d, kn, 1.0, CS, NB, Rbuf, d, 1.0, Mw, d, EPI_NONE, nullptr, 0);
-        if (rc) return rc;
-    }
-    inv_finish_kernel<<<1, 1024, 0, stream>>>(Mw, piv, d, s, inv_scale, log(scale), logabsdet, h, min_entry, info);
+    int rc = (d > OB) ? gj_inplace_two_level(stream, Mw, d, ws) : gj_inplace_nb64(stream, Mw, d, ws + L.CS, ws + L.Rbuf, piv);
+    if (rc) return rc;
+    min_partial_kernel<<<MIN_PARTIALS, 256, 0, stream>>>(Mw, (size_t)d * d, ws + L.pmin);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    inv_finish_kernel<<<1, 1024, 0, stream>>>(ws + L.pmin, piv, d, s, inv_scale, log(scale), logabsdet, h, min_entry, info);
     DAGMA_CUDA_OK(cudaGetLastError());
     if (grad != nullptr || (minv != nullptr && (minv != Mw || inv_scale != 1.0))) {
         dim3 grid((d + 31) / 32, (d + 31) / 32);

@@ -37,9 +37,55 @@ __global__ void dmma_yardstick(int iters, double* sink) {
     if (s == 123.456) sink[0] = s;
 }
 
+// the GEMM's register pattern: 4 x 4 accumulator tiles fed by 4 A and 4 B fragments, optionally
+// reloaded from shared memory every step (mode 1) as in the k-loop of gemm_f64_kernel
+__global__ void dmma_yardstick_tiles(int iters, double* sink, int mode) {
+    __shared__ double sh[2][8][36];
+    double c[4][4][2], a[4], b[4];
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 2 * 8 * 36; i += blockDim.x) (&sh[0][0][0])[i] = 1.0 + 1e-9 * i;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+        b[i] = 1e-12 * (blockIdx.x + 1 + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = i + j;
+    }
+    for (int it = 0; it < iters; ++it) {
+        if (mode == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = sh[it & 1][i][lane];
+                b[i] = sh[it & 1][4 + i][lane];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += c[i][j][0] + c[i][j][1];
+    if (s == 123.456) sink[0] = s;
+}
+
 }  // namespace dagma
 
 using namespace dagma;
+
+// flops per launch: ctas*(threads/32)*iters*16*512
+extern "C" int dagma_bench_fp64_dmma_tiles(dagma_stream_t stream, int ctas, int threads, int iters, int mode,
+                                           double* sink_dev) {
+    dmma_yardstick_tiles<<<ctas, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev, mode);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 // flops per launch: ctas*threads*iters*16*2 (fma); ctas*(threads/32)*iters*8*512 (dmma)
 extern "C" int dagma_bench_fp64_fma(dagma_stream_t stream, int ctas, int threads, int iters, double* sink_dev) {

@@ -20,3 +20,9 @@ for threads in (32, 64, 128, 256, 512, 1024):
     t2 = timed(lambda: lib.dagma_bench_fp64_fma(_lib.stream_ptr(), sms, threads, iters, sink.data_ptr()))
     tf2 = sms * threads * iters * 16 * 2 / t2 / 1e12
     print(f"warps/SM={threads//32:2d}: DMMA {tf:6.2f} TF/s ({clk_per_dmma_per_smsp:5.1f} clk per DMMA per SMSP-warp-slot)  DFMA {tf2:6.2f} TF/s")
+
+for mode in (0, 1):
+    for threads in (128, 256, 512):
+        iters = 10000
+        t = timed(lambda: lib.dagma_bench_fp64_dmma_tiles(_lib.stream_ptr(), sms, threads, iters, mode, sink.data_ptr()))
+        print(f"tiles mode={mode} warps/SM={threads//32:2d}: {sms * (threads // 32) * iters * 16 * 512 / t / 1e12:6.2f} TF/s")

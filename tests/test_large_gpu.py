@@ -35,7 +35,7 @@ def test_gemm_vs_numpy(M, N, K, trans):
     assert np.abs(C2.cpu().numpy() - ref2).max() <= 1e-14
 
 
-@pytest.mark.parametrize("d", [129, 192, 200, 257, 500])
+@pytest.mark.parametrize("d", [129, 192, 200, 256, 257, 500, 513, 1000])
 @pytest.mark.parametrize("square", [True, False])
 def test_blocked_logdet_inv_vs_numpy(d, square):
     from midagma_b200.linear import logdet_inv
