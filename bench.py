@@ -82,7 +82,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    iters = 300
+    iters = 20000      # ~3 s of CPU work per core and step: the whole --steps 5 run stays well under a minute
     for _ in range(args.warmup):
         pass   # process-pool warm-up happens inside cpu_rate
     rates = []
@@ -170,6 +170,65 @@ def fp64_peak_tflops(torch, _lib, sms):
             tbest = min(tbest, e0.elapsed_time(e1) * 1e-3)
         best[name] = flops(ctas, threads, iters) / tbest / 1e12
     return best
+
+
+def bench_c5(torch, _lib, peak_tflops, with_cpu):
+    """BASELINE.json configs[4]: one DagmaLinear l2 problem, SF4 d=2000 n=20000 -- inner iterations / s of the
+    multi-CTA path (blocked DMMA inverse + cov@W DGEMM + fused update), each replayed as a CUDA graph and
+    timed with CUDA events; the numpy restatement of the reference is timed beside it on a few iterations."""
+    import numpy as np
+    from oracle import simulate
+    from midagma_b200 import DagmaLinear
+    d, n = 2000, 20000
+    X, _ = simulate.make_linear_problem(d, 4, n, "SF", "gauss", 0)
+    model = DagmaLinear("l2")
+    model.fit(X.copy(), lambda1=0.02, T=1, warm_iter=0, max_iter=0)        # centring + covariance on the GPU
+    eng = model._large_engine()
+    W = np.zeros((d, d))
+    model.minimize(W, 1.0, 30, 1.0, lr=3e-4)                               # captures the iteration graph
+    torch.cuda.synchronize()
+
+    def graph_of(fn):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def timed(g, reps=20):
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    t_it = timed(eng._graph)
+    t_inv = timed(graph_of(lambda: eng._inverse(1.0)))
+    t_gemm = timed(graph_of(lambda: eng._score_T()))
+    out = {"workload": "C5: single DagmaLinear l2 problem, SF4 d=2000 n=20000, mu=1 s=1 lr=3e-4 (graph-replayed inner iteration)",
+           "ms_per_iter": t_it * 1e3, "iters_per_s": 1.0 / t_it, "flop_per_iter": 4.0 * d ** 3,
+           "tflops": 4.0 * d ** 3 / t_it / 1e12, "frac_of_fp64_peak": 4.0 * d ** 3 / t_it / 1e12 / peak_tflops,
+           "inverse_ms": t_inv * 1e3, "inverse_tflops": 2.0 * d ** 3 / t_inv / 1e12,
+           "inverse_frac_of_fp64_peak": 2.0 * d ** 3 / t_inv / 1e12 / peak_tflops,
+           "score_gemm_ms": t_gemm * 1e3, "score_gemm_tflops": 2.0 * d ** 3 / t_gemm / 1e12}
+    if with_cpu:
+        from oracle.linear_ref import OracleLinear
+        o = OracleLinear("l2").prepare(X, 0.02, checkpoint=1000)
+        Wc = W.copy()
+        o.minimize(Wc, 1.0, 1, 1.0, 3e-4, tol=0.0)
+        t0 = time.perf_counter()
+        o.minimize(Wc, 1.0, 8, 1.0, 3e-4, tol=0.0)
+        cpu = (time.perf_counter() - t0) / 8
+        out["cpu_ms_per_iter"] = cpu * 1e3
+        out["cpu_sample"] = f"8 iterations of oracle/linear_ref.py with all host BLAS threads ({len(os.sched_getaffinity(0))} cores)"
+        out["speedup_vs_cpu"] = cpu / t_it
+    return out
 
 
 def run_b200(args):
@@ -271,7 +330,7 @@ def run_b200(args):
         achieved = per_gpu_rate * FLOP_PER_ITER / 1e12
         extra["roofline"] = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "fit_small_kernel (one launch per step)",
+            "traffic": None, "kernel": "fit_small_dmma_kernel (one launch per step)",
             "peak_source": "measured live: FP64 pipe yardsticks " + json.dumps({k: round(v, 2) for k, v in peaks.items()})
                            + " TFLOP/s (MEASURED_PEAKS.json has no FP64 entry; FP64 tensor = FP64 FMA rate on B200)",
             "flop_per_unit": FLOP_PER_ITER, "units_per_launch": nprob * ITERS_PER_STEP,
@@ -292,6 +351,10 @@ def run_b200(args):
                                  "iters_per_s": info["total_iters"] / wall,
                                  "status_nonzero": int((info["status"] != 0).sum()),
                                  "mean_edges": float((W_est != 0).sum(axis=(1, 2)).mean())}
+
+        if args.c5 and world == 1:
+            del W_host, cov_host
+            extra["c5"] = bench_c5(torch, _lib, peak, args.cpu_baseline)
 
     if rank == 0:
         line = {
@@ -322,9 +385,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--problems", type=int, default=4096, help="problems per GPU")
-    ap.add_argument("--cpu-iters", type=int, default=1500)
+    ap.add_argument("--cpu-iters", type=int, default=100000, help="oracle iterations per core (~15 s)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-full-fit", dest="full_fit", action="store_false")
+    ap.add_argument("--no-c5", dest="c5", action="store_false", help="skip the single d=2000 problem (C5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -77,8 +77,8 @@ static int gemm_launch_tile(cudaStream_t stream, int transA, int M, int N, int K
     return 0;
 }
 
-// DAGMA_GEMM_TILE (debug / A-B timing): 0 = 128 x 64 tile, two CTAs per SM (default); 1 = 128 x 128, one CTA;
-// 2 = 64 x 64 tile, 128 threads, four CTAs per SM
+// DAGMA_GEMM_TILE (debug / A-B timing): 0 = 64 x 64 tile, 128 threads, four CTAs per SM (default: the finest
+// granularity wins at the 2000-wide outputs of this path); 1 = 128 x 128, one CTA; 2 = 128 x 64, two CTAs
 static int gemm_tile_variant() {
     static int v = -1;
     if (v < 0) {
@@ -95,8 +95,8 @@ static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, dou
     if (gemm_tile_variant() == 1)
         return gemm_launch_tile<128, 128, 4, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
     if (gemm_tile_variant() == 2)
-        return gemm_launch_tile<64, 64, 2, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
-    return gemm_launch_tile<128, 64, 4, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
+        return gemm_launch_tile<128, 64, 4, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
+    return gemm_launch_tile<64, 64, 2, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
 }
 
 // ------------------------------------------------------------------ blocked inverse
@@ -271,11 +271,21 @@ __global__ void inv_outputs_kernel(const double* __restrict__ Minv, const double
     }
 }
 
-constexpr int OB = 256;            // outer block of the two-level blocked inverse (d > OB)
+// outer block of the two-level blocked inverse (d > OB); DAGMA_OUTER_BLOCK = 256 | 512 for A-B timing
+static int outer_block() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_OUTER_BLOCK");
+        v = e ? atoi(e) : 256;
+        if (v != 256 && v != 512) v = 256;
+    }
+    return v;
+}
 
 struct LargeWs {                   // offsets in doubles into the caller's workspace
     size_t M, CS, Rbuf, piv, Pbuf, CSin, Rin, pmin, total;
     explicit LargeWs(int d) {
+        const int OB = outer_block();
         const size_t dd = ((size_t)d * d + 1) & ~(size_t)1;        // keep every buffer 16-byte aligned
         const size_t strip = ((size_t)d * OB + 1) & ~(size_t)1;
         M = 0;
@@ -311,6 +321,23 @@ __global__ void add_block_kernel(const double* __restrict__ src, int lds, double
     }
 }
 
+// one launch for the two small fix-ups of an outer step:  CS[K,:] += Q  and  R = A[K,:] + E_K^T
+__global__ void outer_prep_kernel(const double* __restrict__ Q, double* __restrict__ CSk, int kn,
+                                  const double* __restrict__ Arows, int d, int k0, double* __restrict__ R) {
+    const size_t nq = (size_t)kn * kn, total = nq + (size_t)kn * d;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        if (e < nq) {
+            CSk[e] += Q[e];
+        } else {
+            const size_t f = e - nq;
+            const int r = (int)(f / d), c = (int)(f - (size_t)r * d);
+            double v = Arows[f];
+            if (c - k0 == r) v += 1.0;
+            R[f] = v;
+        }
+    }
+}
+
 static int ensure_panel_attr() {
     static bool panel_attr = false;
     if (!panel_attr) {
@@ -337,30 +364,75 @@ static int gj_inplace_nb64(cudaStream_t stream, double* Mw, int n, double* CS, d
     return 0;
 }
 
+// side stream + events for the look-ahead of the two-level algorithm (one set per process: the library
+// drives one GPU stream per process; capturable -- the fork / join pattern below is what
+// CUDA-graph stream capture records as parallel branches)
+struct LookAhead {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int lookahead_get(LookAhead** out) {
+    static LookAhead la;
+    if (!la.side) {
+        // highest priority: the panel chain is short and serial, the d x d update it overlaps is wide
+        int lo = 0, hi = 0;
+        DAGMA_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        DAGMA_CUDA_OK(cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, hi));
+        DAGMA_CUDA_OK(cudaEventCreateWithFlags(&la.fork, cudaEventDisableTiming));
+        DAGMA_CUDA_OK(cudaEventCreateWithFlags(&la.join, cudaEventDisableTiming));
+    }
+    *out = &la;
+    return 0;
+}
+
 // two-level block Gauss-Jordan, outer block OB = 256: per outer block K
-//   Q  = P^{-1}, P = A[K,K]          (copy + single-level sweep on the 256 x 256 block)
+//   Q  = P^{-1}, P = A[K,K]          (single-level sweep on a copy of the 256 x 256 block)
 //   CS = -A[:,K] Q, CS[K,:] += Q      (= -(A[:,K] - E_K) Q : the "- I" of the publish identity)
 //   R  = A[K,:] + E_K^T               (row copy: the GEMM below overwrites those rows)
 //   A += CS R                         (one d x d x 256 DMMA GEMM, accumulators initialised from A)
+// Look-ahead: the next pivot block P' = A[K',K'] + CS[K',:] R[:,K'] is formed first (a 256^3 GEMM) and
+// inverted on a side stream while the main stream runs the d x d update, so the serial panel chain
+// (4 sweeps + 4 small GEMMs) is off the critical path.
 static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* ws) {
+    const int OB = outer_block();
     const LargeWs L(d);
     double *CS = ws + L.CS, *Rbuf = ws + L.Rbuf, *piv = ws + L.piv, *Pbuf = ws + L.Pbuf, *CSin = ws + L.CSin,
            *Rin = ws + L.Rin;
+    LookAhead* la = nullptr;
+    int rc = lookahead_get(&la);
+    if (rc) return rc;
     const int nob = (d + OB - 1) / OB;
+    {   // first pivot block
+        const int kn = d < OB ? d : OB;
+        copy_block_kernel<<<64, 256, 0, stream>>>(Mw, d, Pbuf, kn, kn, kn, 0, 0.0);
+        DAGMA_CUDA_OK(cudaGetLastError());
+        rc = gj_inplace_nb64(stream, Pbuf, kn, CSin, Rin, piv);
+        if (rc) return rc;
+    }
     for (int ob = 0; ob < nob; ++ob) {
         const int k0 = ob * OB, kn = (d - k0) < OB ? (d - k0) : OB;
-        copy_block_kernel<<<64, 256, 0, stream>>>(Mw + (size_t)k0 * d + k0, d, Pbuf, kn, kn, kn, 0, 0.0);
-        DAGMA_CUDA_OK(cudaGetLastError());
-        int rc = gj_inplace_nb64(stream, Pbuf, kn, CSin, Rin, piv + k0);
-        if (rc) return rc;
         rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw + k0, d, Pbuf, kn, 0.0, CS, kn, EPI_NONE, nullptr, 0);
         if (rc) return rc;
-        add_block_kernel<<<64, 256, 0, stream>>>(Pbuf, kn, CS + (size_t)k0 * kn, kn, kn);
+        outer_prep_kernel<<<296, 256, 0, stream>>>(Pbuf, CS + (size_t)k0 * kn, kn, Mw + (size_t)k0 * d, d, k0, Rbuf);
         DAGMA_CUDA_OK(cudaGetLastError());
-        copy_block_kernel<<<296, 256, 0, stream>>>(Mw + (size_t)k0 * d, d, Rbuf, d, kn, d, k0, 1.0);
-        DAGMA_CUDA_OK(cudaGetLastError());
+        const bool more = ob + 1 < nob;
+        if (more) {   // side stream: next pivot block P' = A[K',K'] + CS[K',:] R[:,K'], then its inversion
+            const int k1 = k0 + OB, kn1 = (d - k1) < OB ? (d - k1) : OB;
+            // (the copy stays on the main stream: the d x d update below overwrites A[K',K'] in place)
+            copy_block_kernel<<<64, 256, 0, stream>>>(Mw + (size_t)k1 * d + k1, d, Pbuf, kn1, kn1, kn1, 0, 0.0);
+            DAGMA_CUDA_OK(cudaGetLastError());
+            DAGMA_CUDA_OK(cudaEventRecord(la->fork, stream));
+            DAGMA_CUDA_OK(cudaStreamWaitEvent(la->side, la->fork, 0));
+            rc = gemm_launch(la->side, 0, kn1, kn1, kn, 1.0, CS + (size_t)k1 * kn, kn, Rbuf + k1, d, 1.0, Pbuf, kn1,
+                             EPI_NONE, nullptr, 0);
+            if (rc) return rc;
+            rc = gj_inplace_nb64(la->side, Pbuf, kn1, CSin, Rin, piv + k1);
+            if (rc) return rc;
+            DAGMA_CUDA_OK(cudaEventRecord(la->join, la->side));
+        }
         rc = gemm_launch(stream, 0, d, d, kn, 1.0, CS, kn, Rbuf, d, 1.0, Mw, d, EPI_NONE, nullptr, 0);
         if (rc) return rc;
+        if (more) DAGMA_CUDA_OK(cudaStreamWaitEvent(stream, la->join, 0));
     }
     return 0;
 }
@@ -383,7 +455,7 @@ static int logdet_inv_blocked(cudaStream_t stream, int d, double s, const double
     double* piv = ws + L.piv;
     build_m_kernel<<<592, 256, 0, stream>>>(a_dev, lda, Mw, d, s, inv_scale, square);
     DAGMA_CUDA_OK(cudaGetLastError());
-    int rc = (d > OB) ? gj_inplace_two_level(stream, Mw, d, ws) : gj_inplace_nb64(stream, Mw, d, ws + L.CS, ws + L.Rbuf, piv);
+    int rc = (d > outer_block()) ? gj_inplace_two_level(stream, Mw, d, ws) : gj_inplace_nb64(stream, Mw, d, ws + L.CS, ws + L.Rbuf, piv);
     if (rc) return rc;
     min_partial_kernel<<<MIN_PARTIALS, 256, 0, stream>>>(Mw, (size_t)d * d, ws + L.pmin);
     DAGMA_CUDA_OK(cudaGetLastError());
