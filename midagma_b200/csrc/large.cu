@@ -114,38 +114,38 @@ __global__ void build_m_kernel(const double* __restrict__ A, int lda, double* __
     }
 }
 
-struct PanelArgs {
-    double* A;      // d x d in place (ld = d)
-    int d, kb;
-    double* CS;     // d x NB  (ld = NB)
-    double* Rbuf;   // NB x d  (ld = d)
-    double* pivots; // fraction-free pivots (see stage_pivot_block), 4*ceil(d/4) entries
+struct TileStepArgs {
+    const double* Ain;   // n x n (ld = n), state before block step kb
+    double* Aout;        // n x n (ld = n), state after it (a different buffer: tiles are owned, not synchronised)
+    int n, kb;
+    double* pivots;      // fraction-free pivots (see stage_pivot_block), 4*ceil(n/4) entries
 };
 
-// Panel of block step kb, one 256-thread CTA per 64-row block `blk`:
-//   Q = P^{-1} by the tensor-core block Gauss-Jordan sweep of small_dmma.cuh (every CTA redundantly:
-//       P is 32 KB and L2 resident, and a broadcast would cost a grid-wide synchronisation),
-//   CS[blk rows, :] = -Cpub Q   (64 x 64 x 64 DMMA, Cpub = A[rows, K], K block: P - I),
-//   Rbuf[:, blk cols] = A[K, cols]                  (K block: P + I).
-constexpr size_t PANEL_SMEM_BYTES = DmmaSmem::bytes;      // ncov / W slots hold Cpub / Q
+// One block step (block 64) of the single-level Gauss-Jordan as ONE launch without any inter-CTA
+// synchronisation: CTA (bi, bj) owns the 64 x 64 tile (bi, bj) and recomputes what it needs --
+//   Q = P^{-1} by the tensor-core sweep of small_dmma.cuh (P = A[K,K], 32 KB, L2 resident),
+//   CS_i = -(A[I,K] - [bi == kb] I) Q,   R_j = A[K,J] + [bj == kb] I,
+//   tile_out = tile_in + CS_i R_j        (two 64^3 DMMA products).
+// Reading the old state from Ain and writing the new one to Aout (ping-pong) removes every hazard;
+// the redundancy (nblk^2 sweeps, nblk CS products) runs in parallel on otherwise idle SMs.
+constexpr size_t TILE_STEP_SMEM_BYTES = (size_t)(DmmaSmem::total + DM_DP * DM_LD) * sizeof(double);
 
-__global__ void __launch_bounds__(DM_NT, 2) inv_panel_kernel(const PanelArgs P) {
+__device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }   // L2: written by other CTAs
+
+__device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj, double* psm, SweepSync& sy) {
     using S = DmmaSmem;
     constexpr int LD = DM_LD;
-    extern __shared__ __align__(16) double psm[];
-    double* Cs = psm + S::ncov;     // [64][68]  Cpub rows of this block
+        double* Cs = psm + S::ncov;     // [64][68]  Cpub rows of this tile, later CS
     double* Qs = psm + S::W;        // [64][68]  Q
+    double* Rs = psm + S::total;    // [64][68]  Rpub columns of this tile
     const int tid = threadIdx.x;
     const DmmaPos ps(tid);
-    const int d = P.d, k0 = P.kb * NB;
-    const int kn = min(NB, d - k0);
-    const int blk = blockIdx.x;                 // row block (for CS) and column block (for Rbuf)
-    const int r0 = blk * NB;
-    SweepSync sy{smem_u32(psm + S::mbar), 0u};
-    if (tid == 0) mbar_init(sy.bar, DM_NT / 32);
+    const int n = P.n, k0 = P.kb * NB;
+    const int kn = min(NB, n - k0);
+    const int r0 = bi * NB, c0 = bj * NB;
 
-    // ---- P into the accumulator layout (identity padding), Cpub rows / Rpub columns of this block
-    double a[2][4][2], dummy[2][4][2];
+    // ---- P into the accumulator layout (identity padding); Cpub rows and Rpub columns into shared memory
+    double a[2][4][2], acc[2][4][2];
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
@@ -153,23 +153,20 @@ __global__ void __launch_bounds__(DM_NT, 2) inv_panel_kernel(const PanelArgs P) 
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int r = ps.row(ti), c = ps.col(tj) + e;
-                a[ti][tj][e] = (r < kn && c < kn) ? P.A[(size_t)(k0 + r) * d + k0 + c] : ((r == c) ? 1.0 : 0.0);
-                dummy[ti][tj][e] = 0.0;
+                a[ti][tj][e] = (r < kn && c < kn) ? ldcg(&P.Ain[(size_t)(k0 + r) * n + k0 + c]) : ((r == c) ? 1.0 : 0.0);
             }
     for (int e = tid; e < NB * NB; e += DM_NT) {
         const int r = e >> 6, c = e & 63;
-        double v = (r0 + r < d && c < kn) ? P.A[(size_t)(r0 + r) * d + k0 + c] : 0.0;
-        if (blk == P.kb && r == c && r < kn) v -= 1.0;
-        Cs[r * LD + c] = v;
-        if (r < kn && r0 + c < d) {
-            double w = P.A[(size_t)(k0 + r) * d + r0 + c];
-            if (blk == P.kb && r == c) w += 1.0;
-            P.Rbuf[(size_t)r * d + r0 + c] = w;
-        }
+        double v = (r0 + r < n && c < kn) ? ldcg(&P.Ain[(size_t)(r0 + r) * n + k0 + c]) : 0.0;
+        if (bi == P.kb && r == c && r < kn) v -= 1.0;
+        Cs[r * LD + c] = -v;
+        double w = (r < kn && c0 + c < n) ? ldcg(&P.Ain[(size_t)(k0 + r) * n + c0 + c]) : 0.0;
+        if (bj == P.kb && r == c && r < kn) w += 1.0;
+        Rs[r * LD + c] = w;
     }
     __syncthreads();
-    dmma_sweep<false>(a, dummy, ps, psm, kn, sy);
-    if (blk == 0 && tid < 4 * ((kn + 3) >> 2)) P.pivots[k0 + tid] = psm[S::pinfo + tid];
+    dmma_sweep<false>(a, acc, ps, psm, kn, sy);
+    if (bi == 0 && bj == 0 && tid < 4 * ((kn + 3) >> 2)) P.pivots[k0 + tid] = psm[S::pinfo + tid];
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
@@ -179,31 +176,155 @@ __global__ void __launch_bounds__(DM_NT, 2) inv_panel_kernel(const PanelArgs P) 
             *reinterpret_cast<double2*>(Qs + r * LD + c) = make_double2(in0 ? a[ti][tj][0] : 0.0, in1 ? a[ti][tj][1] : 0.0);
         }
     __syncthreads();
-    // ---- CS[rows, :] = -Cpub Q  (warp tile 16 x 32, 16 k-blocks of 4)
-    double acc[2][4][2];
+    // ---- CS = (-Cpub) Q   (warp tile 16 x 32, 16 k-blocks of 4)
+    auto product = [&](const double* Am, const double* Bm) {
+#pragma unroll 4
+        for (int kk = 0; kk < NB; kk += 4) {
+            double an[2], bw[4];
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti) an[ti] = Am[ps.row(ti) * LD + kk + ps.qc];
+#pragma unroll
+            for (int tj = 0; tj < 4; ++tj) bw[tj] = Bm[(kk + ps.qc) * LD + 32 * ps.wc + 8 * tj + ps.qr];
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) dmma(acc[ti][tj][0], acc[ti][tj][1], an[ti], bw[tj]);
+        }
+    };
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
         for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
+    product(Cs, Qs);
+    __syncthreads();                 // every warp is done reading Cpub
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) {
+            *reinterpret_cast<double2*>(Cs + ps.row(ti) * LD + ps.col(tj)) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+            const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);          // accumulators restart from the old tile
+            acc[ti][tj][0] = (r < n && c < n) ? ldcg(&P.Ain[(size_t)r * n + c]) : 0.0;
+            acc[ti][tj][1] = (r < n && c + 1 < n) ? ldcg(&P.Ain[(size_t)r * n + c + 1]) : 0.0;
+        }
+    __syncthreads();
+    // ---- tile_out = tile_in + CS R
+    product(Cs, Rs);
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) {
+            const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
+            if (r < n && c < n) P.Aout[(size_t)r * n + c] = acc[ti][tj][0];
+            if (r < n && c + 1 < n) P.Aout[(size_t)r * n + c + 1] = acc[ti][tj][1];
+        }
+}
+
+
+__global__ void __launch_bounds__(DM_NT, 1) inv_tile_step_kernel(const TileStepArgs P) {
+    extern __shared__ __align__(16) double psm[];
+    SweepSync sy{smem_u32(psm + DmmaSmem::mbar), 0u};
+    if (threadIdx.x == 0) mbar_init(sy.bar, DM_NT / 32);
+    tile_step(P, blockIdx.y, blockIdx.x, psm, sy);
+}
+
+// ---- look-ahead "panel server": the whole inversion of the NEXT 256-wide pivot block as one kernel that
+// runs beside the d x d update.  One CTA per 64 x 64 tile of the block (<= 16 CTAs); each asks for the
+// whole shared memory of an SM, so it shares its SM with nobody and the update kernel simply runs on the
+// remaining SMs.  Phase 0: tile of P' = A[K',K'] + CS[K',:] R[:,K'] (the update restricted to the pivot
+// block); then nblk tile steps, separated by a counter barrier in global memory.  The CTAs of ONE launch
+// wait for each other, never for another kernel: if some are scheduled late the early ones spin, nothing
+// else is blocked, and the spin is bounded (err flag) -- progress never depends on co-residency.
+struct ServerArgs {
+    double *buf0, *buf1;     // ping-pong n x n (ld = n); buf0 holds a copy of A[K',K'] on entry
+    int n, nblk;
+    const double* CSk;       // CS rows K' (n x kprev, ld = kprev)
+    const double* Rk;        // R columns K' (kprev x n, ld = ldr)
+    int kprev, ldr;
+    double* pivots;
+    unsigned* counter;       // zeroed before the launch
+    int* err;
+};
+constexpr size_t SERVER_SMEM_BYTES = 227 * 1024;
+
+__device__ __forceinline__ void server_barrier(unsigned* counter, unsigned target, int* err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned spins = 0;
+        while (*((volatile unsigned*)counter) < target) {
+            if (++spins > (1u << 28)) { *err = 1; break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(DM_NT, 1) inv_block_server_kernel(const ServerArgs P) {
+    using S = DmmaSmem;
+    constexpr int LD = DM_LD;
+    extern __shared__ __align__(16) double psm[];
+    double* Cs = psm + S::ncov;
+    double* Rs = psm + S::total;
+    const int tid = threadIdx.x;
+    const DmmaPos ps(tid);
+    const int bi = blockIdx.x / P.nblk, bj = blockIdx.x % P.nblk;
+    const int n = P.n, r0 = bi * NB, c0 = bj * NB;
+    SweepSync sy{smem_u32(psm + S::mbar), 0u};
+    if (tid == 0) mbar_init(sy.bar, DM_NT / 32);
+    const unsigned nctas = gridDim.x;
+
+    // ---- phase 0: own tile of P' += CS[K'_i, :] R[:, K'_j], staged through shared memory 64 k at a time
+    double acc[2][4][2];
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) {
+            const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
+            acc[ti][tj][0] = (r < n && c < n) ? P.buf0[(size_t)r * n + c] : 0.0;
+            acc[ti][tj][1] = (r < n && c + 1 < n) ? P.buf0[(size_t)r * n + c + 1] : 0.0;
+        }
+    for (int kc = 0; kc < P.kprev; kc += NB) {
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += DM_NT) {
+            const int r = e >> 6, c = e & 63;
+            Cs[r * LD + c] = (r0 + r < n && kc + c < P.kprev) ? P.CSk[(size_t)(r0 + r) * P.kprev + kc + c] : 0.0;
+            Rs[r * LD + c] = (kc + r < P.kprev && c0 + c < n) ? P.Rk[(size_t)(kc + r) * P.ldr + c0 + c] : 0.0;
+        }
+        __syncthreads();
 #pragma unroll 4
-    for (int kk = 0; kk < NB; kk += 4) {
-        double an[2], bw[4];
+        for (int kk = 0; kk < NB; kk += 4) {
+            double an[2], bw[4];
 #pragma unroll
-        for (int ti = 0; ti < 2; ++ti) an[ti] = -Cs[ps.row(ti) * LD + kk + ps.qc];
+            for (int ti = 0; ti < 2; ++ti) an[ti] = Cs[ps.row(ti) * LD + kk + ps.qc];
 #pragma unroll
-        for (int tj = 0; tj < 4; ++tj) bw[tj] = Qs[(kk + ps.qc) * LD + 32 * ps.wc + 8 * tj + ps.qr];
+            for (int tj = 0; tj < 4; ++tj) bw[tj] = Rs[(kk + ps.qc) * LD + 32 * ps.wc + 8 * tj + ps.qr];
 #pragma unroll
-        for (int ti = 0; ti < 2; ++ti)
+            for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
-            for (int tj = 0; tj < 4; ++tj) dmma(acc[ti][tj][0], acc[ti][tj][1], an[ti], bw[tj]);
+                for (int tj = 0; tj < 4; ++tj) dmma(acc[ti][tj][0], acc[ti][tj][1], an[ti], bw[tj]);
+        }
     }
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
         for (int tj = 0; tj < 4; ++tj) {
-            const int r = r0 + ps.row(ti), c = ps.col(tj);
-            if (r < d) *reinterpret_cast<double2*>(P.CS + (size_t)r * NB + c) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+            const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
+            if (r < n && c < n) P.buf0[(size_t)r * n + c] = acc[ti][tj][0];
+            if (r < n && c + 1 < n) P.buf0[(size_t)r * n + c + 1] = acc[ti][tj][1];
         }
+    server_barrier(P.counter, nctas, P.err);
+
+    // ---- the block steps
+    double *in = P.buf0, *out = P.buf1;
+    for (int kb = 0; kb < P.nblk; ++kb) {
+        TileStepArgs T{in, out, n, kb, P.pivots};
+        tile_step(T, bi, bj, psm, sy);
+        if (kb + 1 < P.nblk) server_barrier(P.counter, nctas * (unsigned)(kb + 2), P.err);
+        double* t = in;
+        in = out;
+        out = t;
+    }
 }
 
 // per-block partial minima of the inverse (grid-stride; finished by inv_finish_kernel)
@@ -283,7 +404,7 @@ static int outer_block() {
 }
 
 struct LargeWs {                   // offsets in doubles into the caller's workspace
-    size_t M, CS, Rbuf, piv, Pbuf, CSin, Rin, pmin, total;
+    size_t M, CS, Rbuf, piv, Pbuf, Pbuf2, pmin, sync, total;
     explicit LargeWs(int d) {
         const int OB = outer_block();
         const size_t dd = ((size_t)d * d + 1) & ~(size_t)1;        // keep every buffer 16-byte aligned
@@ -293,10 +414,10 @@ struct LargeWs {                   // offsets in doubles into the caller's works
         Rbuf = CS + strip;
         piv = Rbuf + strip;
         Pbuf = piv + (((size_t)d + 64 + 1) & ~(size_t)1);
-        CSin = Pbuf + (size_t)OB * OB;
-        Rin = CSin + (size_t)OB * NB;
-        pmin = Rin + (size_t)NB * OB;
-        total = pmin + MIN_PARTIALS + 64;
+        Pbuf2 = Pbuf + (size_t)OB * OB;
+        pmin = Pbuf2 + (size_t)OB * OB;
+        sync = pmin + MIN_PARTIALS + 8;          // barrier counter + error flag of the panel server
+        total = sync + 64;
     }
 };
 static size_t large_ws_bytes(int d) { return LargeWs(d).total * sizeof(double); }
@@ -313,14 +434,6 @@ __global__ void copy_block_kernel(const double* __restrict__ src, int lds, doubl
         dst[(size_t)r * ldd + c] = v;
     }
 }
-// dst (n x n, ld = ldd) += src (ld = lds)
-__global__ void add_block_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int n) {
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
-        const int r = e / n, c = e - r * n;
-        dst[(size_t)r * ldd + c] += src[(size_t)r * lds + c];
-    }
-}
-
 // one launch for the two small fix-ups of an outer step:  CS[K,:] += Q  and  R = A[K,:] + E_K^T
 __global__ void outer_prep_kernel(const double* __restrict__ Q, double* __restrict__ CSk, int kn,
                                   const double* __restrict__ Arows, int d, int k0, double* __restrict__ R) {
@@ -338,29 +451,26 @@ __global__ void outer_prep_kernel(const double* __restrict__ Q, double* __restri
     }
 }
 
-static int ensure_panel_attr() {
-    static bool panel_attr = false;
-    if (!panel_attr) {
-        DAGMA_CUDA_OK(cudaFuncSetAttribute(inv_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_BYTES));
-        panel_attr = true;
+// single-level block Gauss-Jordan (block 64) of the dense n x n matrix in `buf0` (ld = n); `buf1` is the
+// ping-pong partner.  Returns (through *result) the buffer that holds the inverse; piv: n (+3) pivots.
+static int gj_nb64(cudaStream_t stream, double* buf0, double* buf1, int n, double* piv, double** result) {
+    static bool attr = false;
+    if (!attr) {
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(inv_tile_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)TILE_STEP_SMEM_BYTES));
+        attr = true;
     }
-    return 0;
-}
-
-// single-level block Gauss-Jordan (block NB = 64) of the dense n x n matrix Mw (ld = n), in place;
-// CS: n x NB, Rbuf: NB x n, piv: n scalar pivots
-static int gj_inplace_nb64(cudaStream_t stream, double* Mw, int n, double* CS, double* Rbuf, double* piv) {
-    int rc = ensure_panel_attr();
-    if (rc) return rc;
     const int nblk = (n + NB - 1) / NB;
+    double *in = buf0, *out = buf1;
     for (int kb = 0; kb < nblk; ++kb) {
-        PanelArgs P{Mw, n, kb, CS, Rbuf, piv};
-        inv_panel_kernel<<<nblk, DM_NT, PANEL_SMEM_BYTES, stream>>>(P);
+        TileStepArgs P{in, out, n, kb, piv};
+        inv_tile_step_kernel<<<dim3(nblk, nblk), DM_NT, TILE_STEP_SMEM_BYTES, stream>>>(P);
         DAGMA_CUDA_OK(cudaGetLastError());
-        const int kn = (n - kb * NB) < NB ? (n - kb * NB) : NB;
-        rc = gemm_launch(stream, 0, n, n, kn, 1.0, CS, NB, Rbuf, n, 1.0, Mw, n, EPI_NONE, nullptr, 0);
-        if (rc) return rc;
+        double* t = in;
+        in = out;
+        out = t;
     }
+    *result = in;
     return 0;
 }
 
@@ -385,6 +495,16 @@ static int lookahead_get(LookAhead** out) {
     return 0;
 }
 
+// DAGMA_LOOKAHEAD (A-B timing): 1 = panel-server kernel (default), 0 = chain of small kernels
+static int lookahead_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_LOOKAHEAD");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 // two-level block Gauss-Jordan, outer block OB = 256: per outer block K
 //   Q  = P^{-1}, P = A[K,K]          (single-level sweep on a copy of the 256 x 256 block)
 //   CS = -A[:,K] Q, CS[K,:] += Q      (= -(A[:,K] - E_K) Q : the "- I" of the publish identity)
@@ -396,8 +516,8 @@ static int lookahead_get(LookAhead** out) {
 static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* ws) {
     const int OB = outer_block();
     const LargeWs L(d);
-    double *CS = ws + L.CS, *Rbuf = ws + L.Rbuf, *piv = ws + L.piv, *Pbuf = ws + L.Pbuf, *CSin = ws + L.CSin,
-           *Rin = ws + L.Rin;
+    double *CS = ws + L.CS, *Rbuf = ws + L.Rbuf, *piv = ws + L.piv, *Pbuf = ws + L.Pbuf, *Pbuf2 = ws + L.Pbuf2;
+    double* Q = nullptr;             // where the inverse of the current pivot block lives (Pbuf or Pbuf2)
     LookAhead* la = nullptr;
     int rc = lookahead_get(&la);
     if (rc) return rc;
@@ -406,14 +526,14 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         const int kn = d < OB ? d : OB;
         copy_block_kernel<<<64, 256, 0, stream>>>(Mw, d, Pbuf, kn, kn, kn, 0, 0.0);
         DAGMA_CUDA_OK(cudaGetLastError());
-        rc = gj_inplace_nb64(stream, Pbuf, kn, CSin, Rin, piv);
+        rc = gj_nb64(stream, Pbuf, Pbuf2, kn, piv, &Q);
         if (rc) return rc;
     }
     for (int ob = 0; ob < nob; ++ob) {
         const int k0 = ob * OB, kn = (d - k0) < OB ? (d - k0) : OB;
-        rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw + k0, d, Pbuf, kn, 0.0, CS, kn, EPI_NONE, nullptr, 0);
+        rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw + k0, d, Q, kn, 0.0, CS, kn, EPI_NONE, nullptr, 0);
         if (rc) return rc;
-        outer_prep_kernel<<<296, 256, 0, stream>>>(Pbuf, CS + (size_t)k0 * kn, kn, Mw + (size_t)k0 * d, d, k0, Rbuf);
+        outer_prep_kernel<<<296, 256, 0, stream>>>(Q, CS + (size_t)k0 * kn, kn, Mw + (size_t)k0 * d, d, k0, Rbuf);
         DAGMA_CUDA_OK(cudaGetLastError());
         const bool more = ob + 1 < nob;
         if (more) {   // side stream: next pivot block P' = A[K',K'] + CS[K',:] R[:,K'], then its inversion
@@ -423,11 +543,28 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
             DAGMA_CUDA_OK(cudaGetLastError());
             DAGMA_CUDA_OK(cudaEventRecord(la->fork, stream));
             DAGMA_CUDA_OK(cudaStreamWaitEvent(la->side, la->fork, 0));
-            rc = gemm_launch(la->side, 0, kn1, kn1, kn, 1.0, CS + (size_t)k1 * kn, kn, Rbuf + k1, d, 1.0, Pbuf, kn1,
-                             EPI_NONE, nullptr, 0);
-            if (rc) return rc;
-            rc = gj_inplace_nb64(la->side, Pbuf, kn1, CSin, Rin, piv + k1);
-            if (rc) return rc;
+            if (lookahead_mode() == 1) {           // one self-synchronising kernel on SMs of its own
+                static bool attr = false;
+                if (!attr) {
+                    DAGMA_CUDA_OK(cudaFuncSetAttribute(inv_block_server_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       (int)SERVER_SMEM_BYTES));
+                    attr = true;
+                }
+                unsigned* counter = reinterpret_cast<unsigned*>(ws + L.sync);
+                DAGMA_CUDA_OK(cudaMemsetAsync(counter, 0, 16, la->side));
+                const int nblk1 = (kn1 + NB - 1) / NB;
+                ServerArgs SA{Pbuf, Pbuf2, kn1, nblk1, CS + (size_t)k1 * kn, Rbuf + k1, kn, d, piv + k1, counter,
+                              reinterpret_cast<int*>(counter + 2)};
+                inv_block_server_kernel<<<nblk1 * nblk1, DM_NT, SERVER_SMEM_BYTES, la->side>>>(SA);
+                DAGMA_CUDA_OK(cudaGetLastError());
+                Q = (nblk1 & 1) ? Pbuf2 : Pbuf;
+            } else {                               // chain of small kernels (P' GEMM, then the tile steps)
+                rc = gemm_launch(la->side, 0, kn1, kn1, kn, 1.0, CS + (size_t)k1 * kn, kn, Rbuf + k1, d, 1.0, Pbuf, kn1,
+                                 EPI_NONE, nullptr, 0);
+                if (rc) return rc;
+                rc = gj_nb64(la->side, Pbuf, Pbuf2, kn1, piv + k1, &Q);
+                if (rc) return rc;
+            }
             DAGMA_CUDA_OK(cudaEventRecord(la->join, la->side));
         }
         rc = gemm_launch(stream, 0, d, d, kn, 1.0, CS, kn, Rbuf, d, 1.0, Mw, d, EPI_NONE, nullptr, 0);
@@ -455,7 +592,15 @@ static int logdet_inv_blocked(cudaStream_t stream, int d, double s, const double
     double* piv = ws + L.piv;
     build_m_kernel<<<592, 256, 0, stream>>>(a_dev, lda, Mw, d, s, inv_scale, square);
     DAGMA_CUDA_OK(cudaGetLastError());
-    int rc = (d > outer_block()) ? gj_inplace_two_level(stream, Mw, d, ws) : gj_inplace_nb64(stream, Mw, d, ws + L.CS, ws + L.Rbuf, piv);
+    int rc = 0;
+    if (d > outer_block()) {
+        rc = gj_inplace_two_level(stream, Mw, d, ws);
+    } else {                                   // ping-pong between Mw and the CS strip (d * OB >= d * d here)
+        double* res = nullptr;
+        rc = gj_nb64(stream, Mw, ws + L.CS, d, piv, &res);
+        if (rc == 0 && res != Mw)
+            DAGMA_CUDA_OK(cudaMemcpyAsync(Mw, res, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    }
     if (rc) return rc;
     min_partial_kernel<<<MIN_PARTIALS, 256, 0, stream>>>(Mw, (size_t)d * d, ws + L.pmin);
     DAGMA_CUDA_OK(cudaGetLastError());
