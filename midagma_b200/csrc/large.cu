@@ -126,18 +126,17 @@ struct TileStepArgs {
 //   Q = P^{-1} by the tensor-core sweep of small_dmma.cuh (P = A[K,K], 32 KB, L2 resident),
 //   CS_i = -(A[I,K] - [bi == kb] I) Q,   R_j = A[K,J] + [bj == kb] I,
 //   tile_out = tile_in + CS_i R_j        (two 64^3 DMMA products).
-// Reading the old state from Ain and writing the new one to Aout (ping-pong) removes every hazard;
+// Reading the old state from Ain (through L2) and writing the new one to Aout (ping-pong) removes every hazard;
 // the redundancy (nblk^2 sweeps, nblk CS products) runs in parallel on otherwise idle SMs.
-constexpr size_t TILE_STEP_SMEM_BYTES = (size_t)(DmmaSmem::total + DM_DP * DM_LD) * sizeof(double);
+constexpr size_t TILE_STEP_SMEM_BYTES = DmmaSmem::bytes;
 
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }   // L2: written by other CTAs
 
 __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj, double* psm, SweepSync& sy) {
     using S = DmmaSmem;
     constexpr int LD = DM_LD;
-        double* Cs = psm + S::ncov;     // [64][68]  Cpub rows of this tile, later CS
-    double* Qs = psm + S::W;        // [64][68]  Q
-    double* Rs = psm + S::total;    // [64][68]  Rpub columns of this tile
+    double* Cs = psm + S::ncov;     // [64][68]  Cpub rows of this tile, later CS
+    double* Qs = psm + S::W;        // [64][68]  Q, later the Rpub columns of this tile
     const int tid = threadIdx.x;
     const DmmaPos ps(tid);
     const int n = P.n, k0 = P.kb * NB;
@@ -155,14 +154,19 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
                 const int r = ps.row(ti), c = ps.col(tj) + e;
                 a[ti][tj][e] = (r < kn && c < kn) ? ldcg(&P.Ain[(size_t)(k0 + r) * n + k0 + c]) : ((r == c) ? 1.0 : 0.0);
             }
-    for (int e = tid; e < NB * NB; e += DM_NT) {
-        const int r = e >> 6, c = e & 63;
-        double v = (r0 + r < n && c < kn) ? ldcg(&P.Ain[(size_t)(r0 + r) * n + k0 + c]) : 0.0;
-        if (bi == P.kb && r == c && r < kn) v -= 1.0;
-        Cs[r * LD + c] = -v;
-        double w = (r < kn && c0 + c < n) ? ldcg(&P.Ain[(size_t)(k0 + r) * n + c0 + c]) : 0.0;
-        if (bj == P.kb && r == c && r < kn) w += 1.0;
-        Rs[r * LD + c] = w;
+    {   // all 16 loads of a thread in flight before the first use
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
+            v[q] = (r0 + r < n && c < kn) ? ldcg(&P.Ain[(size_t)(r0 + r) * n + k0 + c]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
+            if (bi == P.kb && r == c && r < kn) v[q] -= 1.0;
+            Cs[r * LD + c] = -v[q];
+        }
     }
     __syncthreads();
     dmma_sweep<false>(a, acc, ps, psm, kn, sy);
@@ -196,7 +200,21 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
 #pragma unroll
         for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
     product(Cs, Qs);
-    __syncthreads();                 // every warp is done reading Cpub
+    __syncthreads();                 // every warp is done reading Cpub and Q
+    {
+        double w[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
+            w[q] = (r < kn && c0 + c < n) ? ldcg(&P.Ain[(size_t)(k0 + r) * n + c0 + c]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
+            if (bj == P.kb && r == c && r < kn) w[q] += 1.0;
+            Qs[r * LD + c] = w[q];
+        }
+    }
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
@@ -208,7 +226,7 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
         }
     __syncthreads();
     // ---- tile_out = tile_in + CS R
-    product(Cs, Rs);
+    product(Cs, Qs);
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
@@ -244,8 +262,6 @@ struct ServerArgs {
     unsigned* counter;       // zeroed before the launch
     int* err;
 };
-constexpr size_t SERVER_SMEM_BYTES = 227 * 1024;
-
 __device__ __forceinline__ void server_barrier(unsigned* counter, unsigned target, int* err) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -260,19 +276,18 @@ __device__ __forceinline__ void server_barrier(unsigned* counter, unsigned targe
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(DM_NT, 1) inv_block_server_kernel(const ServerArgs P) {
+// server CTA `rank` of `nctas`: owns tile (rank / nblk, rank % nblk) of the next pivot block
+__device__ __forceinline__ void server_role(const ServerArgs& P, int rank, unsigned nctas, double* psm) {
     using S = DmmaSmem;
     constexpr int LD = DM_LD;
-    extern __shared__ __align__(16) double psm[];
     double* Cs = psm + S::ncov;
-    double* Rs = psm + S::total;
+    double* Rs = psm + S::W;
     const int tid = threadIdx.x;
     const DmmaPos ps(tid);
-    const int bi = blockIdx.x / P.nblk, bj = blockIdx.x % P.nblk;
+    const int bi = rank / P.nblk, bj = rank % P.nblk;
     const int n = P.n, r0 = bi * NB, c0 = bj * NB;
     SweepSync sy{smem_u32(psm + S::mbar), 0u};
     if (tid == 0) mbar_init(sy.bar, DM_NT / 32);
-    const unsigned nctas = gridDim.x;
 
     // ---- phase 0: own tile of P' += CS[K'_i, :] R[:, K'_j], staged through shared memory 64 k at a time
     double acc[2][4][2];
@@ -286,10 +301,20 @@ __global__ void __launch_bounds__(DM_NT, 1) inv_block_server_kernel(const Server
         }
     for (int kc = 0; kc < P.kprev; kc += NB) {
         __syncthreads();
-        for (int e = tid; e < NB * NB; e += DM_NT) {
-            const int r = e >> 6, c = e & 63;
-            Cs[r * LD + c] = (r0 + r < n && kc + c < P.kprev) ? P.CSk[(size_t)(r0 + r) * P.kprev + kc + c] : 0.0;
-            Rs[r * LD + c] = (kc + r < P.kprev && c0 + c < n) ? P.Rk[(size_t)(kc + r) * P.ldr + c0 + c] : 0.0;
+        {
+            double u[16], w[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
+                u[q] = (r0 + r < n && kc + c < P.kprev) ? P.CSk[(size_t)(r0 + r) * P.kprev + kc + c] : 0.0;
+                w[q] = (kc + r < P.kprev && c0 + c < n) ? P.Rk[(size_t)(kc + r) * P.ldr + c0 + c] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
+                Cs[r * LD + c] = u[q];
+                Rs[r * LD + c] = w[q];
+            }
         }
         __syncthreads();
 #pragma unroll 4
@@ -324,6 +349,125 @@ __global__ void __launch_bounds__(DM_NT, 1) inv_block_server_kernel(const Server
         double* t = in;
         in = out;
         out = t;
+    }
+    __syncthreads();
+}
+
+// ---- one outer step of the two-level algorithm as ONE persistent kernel (two CTAs per SM):
+//   CTAs [0, nserver): first the look-ahead -- the inversion of the next pivot block (server_role) --,
+//   all CTAs: 64 x 64 tiles of  A += CS R  pulled from an atomic queue (accumulators start as A, operands
+//   staged 32 k at a time by a double-buffered cp.async pipeline, warp tile 16 x 32).
+// The server CTAs are the lowest block indices of a grid that fits the machine in one wave, so they are
+// resident together; they wait only for each other and the wait is bounded.
+struct OuterArgs {
+    double* A; int d;            // d x d in place (ld = d, d even)
+    const double* CS; int kn;    // d x kn (ld = kn)
+    const double* R;             // kn x d (ld = d)
+    unsigned* queue;             // tile counter, zeroed before the launch
+    int* sm_busy;                // [SM id] 1 while a server CTA runs there (zeroed before the launch)
+    int nserver;
+    ServerArgs srv;
+};
+constexpr int SM_SLOTS = 256;
+
+__device__ __forceinline__ unsigned smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+constexpr int OU_LDA = 36, OU_LDB = 68, OU_KC = 32;
+constexpr int OU_STAGE = NB * OU_LDA + OU_KC * OU_LDB;                  // doubles per pipeline stage
+static_assert(2 * OU_STAGE <= DmmaSmem::total, "the worker pipeline reuses the server's shared memory");
+constexpr size_t OUTER_SMEM_BYTES = DmmaSmem::bytes;
+
+__global__ void __launch_bounds__(DM_NT, 2) outer_update_kernel(const OuterArgs P) {
+    extern __shared__ __align__(16) double psm[];
+    __shared__ unsigned s_tile;
+    const int tid = threadIdx.x;
+    // The look-ahead chain is serial, so its CTAs get their SM to themselves: a worker CTA that shares
+    // an SM with a running server CTA sleeps (no issue slots, no FP64 pipe) until the server is done.
+    volatile int* busy = P.sm_busy + (smid() % SM_SLOTS);
+    if ((int)blockIdx.x < P.nserver) {
+        if (tid == 0) *busy = 1;
+        server_role(P.srv, blockIdx.x, (unsigned)P.nserver, psm);
+        if (tid == 0) *busy = 0;
+    }
+
+    const DmmaPos ps(tid);
+    const uint32_t sbase = smem_u32(psm);
+    const int d = P.d, kn = P.kn;
+    const int tn = (d + NB - 1) / NB, ntiles = tn * tn;
+    const int nchunk = (kn + OU_KC - 1) / OU_KC;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            while (*busy) __nanosleep(2000);
+            s_tile = atomicAdd(P.queue, 1u);
+        }
+        __syncthreads();
+        const int t = (int)s_tile;
+        if (t >= ntiles) break;
+        const int r0 = (t / tn) * NB, c0 = (t % tn) * NB;
+        auto issue = [&](int ch) {
+            const int kc = ch * OU_KC;
+            const uint32_t sa = sbase + (uint32_t)((ch & 1) * OU_STAGE) * 8, sb = sa + (uint32_t)(NB * OU_LDA) * 8;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {          // A chunk: 64 rows x 32 k = 1024 16-byte copies
+                const int e = tid + q * DM_NT, r = e >> 4, c = (e & 15) * 2;
+                const bool ok = (r0 + r < d) && (kc + c < kn);
+                cp_async16(sa + (r * OU_LDA + c) * 8, ok ? P.CS + (size_t)(r0 + r) * kn + kc + c : P.CS, ok);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {          // B chunk: 32 k x 64 cols
+                const int e = tid + q * DM_NT, r = e >> 5, c = (e & 31) * 2;
+                const bool ok = (kc + r < kn) && (c0 + c < d);
+                cp_async16(sb + (r * OU_LDB + c) * 8, ok ? P.R + (size_t)(kc + r) * d + c0 + c : P.R, ok);
+            }
+            cp_async_commit();
+        };
+        issue(0);
+        double acc[2][4][2];
+#pragma unroll
+        for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < 4; ++tj) {
+                const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
+                double2 v = make_double2(0.0, 0.0);
+                if (r < d && c < d) v = *reinterpret_cast<const double2*>(P.A + (size_t)r * d + c);
+                acc[ti][tj][0] = v.x;
+                acc[ti][tj][1] = v.y;
+            }
+        for (int ch = 0; ch < nchunk; ++ch) {
+            if (ch + 1 < nchunk) {
+                issue(ch + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            const double* As = psm + (ch & 1) * OU_STAGE;
+            const double* Bs = As + NB * OU_LDA;
+#pragma unroll
+            for (int kk = 0; kk < OU_KC; kk += 4) {
+                double an[2], bw[4];
+#pragma unroll
+                for (int ti = 0; ti < 2; ++ti) an[ti] = As[ps.row(ti) * OU_LDA + kk + ps.qc];
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) bw[tj] = Bs[(kk + ps.qc) * OU_LDB + 32 * ps.wc + 8 * tj + ps.qr];
+#pragma unroll
+                for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                    for (int tj = 0; tj < 4; ++tj) dmma(acc[ti][tj][0], acc[ti][tj][1], an[ti], bw[tj]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < 4; ++tj) {
+                const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
+                if (r < d && c < d) *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+            }
     }
 }
 
@@ -416,8 +560,8 @@ struct LargeWs {                   // offsets in doubles into the caller's works
         Pbuf = piv + (((size_t)d + 64 + 1) & ~(size_t)1);
         Pbuf2 = Pbuf + (size_t)OB * OB;
         pmin = Pbuf2 + (size_t)OB * OB;
-        sync = pmin + MIN_PARTIALS + 8;          // barrier counter + error flag of the panel server
-        total = sync + 64;
+        sync = pmin + MIN_PARTIALS + 8;          // barrier counter, tile queue, error flag, per-SM busy flags
+        total = sync + 64 + 160;
     }
 };
 static size_t large_ws_bytes(int d) { return LargeWs(d).total * sizeof(double); }
@@ -495,7 +639,8 @@ static int lookahead_get(LookAhead** out) {
     return 0;
 }
 
-// DAGMA_LOOKAHEAD (A-B timing): 1 = panel-server kernel (default), 0 = chain of small kernels
+// DAGMA_LOOKAHEAD (A-B timing): 1 = persistent update kernel with the look-ahead inside (default, even d),
+// 0 = plain GEMM update + chain of small kernels on a high-priority side stream
 static int lookahead_mode() {
     static int v = -1;
     if (v < 0) {
@@ -529,6 +674,21 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         rc = gj_nb64(stream, Pbuf, Pbuf2, kn, piv, &Q);
         if (rc) return rc;
     }
+    const bool fused = (lookahead_mode() == 1) && (d % 2 == 0);
+    if (fused) {
+        static bool attr = false;
+        if (!attr) {
+            DAGMA_CUDA_OK(cudaFuncSetAttribute(outer_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)OUTER_SMEM_BYTES));
+            DAGMA_CUDA_OK(cudaFuncSetAttribute(outer_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               cudaSharedmemCarveoutMaxShared));
+            attr = true;
+        }
+    }
+    int sms = 0, dev = 0;
+    DAGMA_CUDA_OK(cudaGetDevice(&dev));
+    DAGMA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    unsigned* sync_words = reinterpret_cast<unsigned*>(ws + L.sync);     // [0] barrier, [1] tile queue, [2] err
     for (int ob = 0; ob < nob; ++ob) {
         const int k0 = ob * OB, kn = (d - k0) < OB ? (d - k0) : OB;
         rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw + k0, d, Q, kn, 0.0, CS, kn, EPI_NONE, nullptr, 0);
@@ -536,35 +696,30 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         outer_prep_kernel<<<296, 256, 0, stream>>>(Q, CS + (size_t)k0 * kn, kn, Mw + (size_t)k0 * d, d, k0, Rbuf);
         DAGMA_CUDA_OK(cudaGetLastError());
         const bool more = ob + 1 < nob;
-        if (more) {   // side stream: next pivot block P' = A[K',K'] + CS[K',:] R[:,K'], then its inversion
-            const int k1 = k0 + OB, kn1 = (d - k1) < OB ? (d - k1) : OB;
-            // (the copy stays on the main stream: the d x d update below overwrites A[K',K'] in place)
+        const int k1 = k0 + OB, kn1 = more ? ((d - k1) < OB ? (d - k1) : OB) : 0;
+        if (more) {   // copy of the next pivot block: the d x d update below overwrites A[K',K'] in place
             copy_block_kernel<<<64, 256, 0, stream>>>(Mw + (size_t)k1 * d + k1, d, Pbuf, kn1, kn1, kn1, 0, 0.0);
             DAGMA_CUDA_OK(cudaGetLastError());
+        }
+        if (fused) {  // update + look-ahead in one persistent kernel
+            DAGMA_CUDA_OK(cudaMemsetAsync(sync_words, 0, 16 + SM_SLOTS * sizeof(int), stream));
+            const int nblk1 = (kn1 + NB - 1) / NB;
+            OuterArgs OA{Mw, d, CS, kn, Rbuf, sync_words + 1, reinterpret_cast<int*>(sync_words + 4), nblk1 * nblk1,
+                         ServerArgs{Pbuf, Pbuf2, kn1, nblk1, CS + (size_t)k1 * kn, Rbuf + k1, kn, d, piv + k1, sync_words,
+                                    reinterpret_cast<int*>(sync_words + 2)}};
+            outer_update_kernel<<<2 * sms, DM_NT, OUTER_SMEM_BYTES, stream>>>(OA);
+            DAGMA_CUDA_OK(cudaGetLastError());
+            if (more) Q = (nblk1 & 1) ? Pbuf2 : Pbuf;
+            continue;
+        }
+        if (more) {   // side stream: next pivot block P' = A[K',K'] + CS[K',:] R[:,K'], then its inversion
             DAGMA_CUDA_OK(cudaEventRecord(la->fork, stream));
             DAGMA_CUDA_OK(cudaStreamWaitEvent(la->side, la->fork, 0));
-            if (lookahead_mode() == 1) {           // one self-synchronising kernel on SMs of its own
-                static bool attr = false;
-                if (!attr) {
-                    DAGMA_CUDA_OK(cudaFuncSetAttribute(inv_block_server_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                       (int)SERVER_SMEM_BYTES));
-                    attr = true;
-                }
-                unsigned* counter = reinterpret_cast<unsigned*>(ws + L.sync);
-                DAGMA_CUDA_OK(cudaMemsetAsync(counter, 0, 16, la->side));
-                const int nblk1 = (kn1 + NB - 1) / NB;
-                ServerArgs SA{Pbuf, Pbuf2, kn1, nblk1, CS + (size_t)k1 * kn, Rbuf + k1, kn, d, piv + k1, counter,
-                              reinterpret_cast<int*>(counter + 2)};
-                inv_block_server_kernel<<<nblk1 * nblk1, DM_NT, SERVER_SMEM_BYTES, la->side>>>(SA);
-                DAGMA_CUDA_OK(cudaGetLastError());
-                Q = (nblk1 & 1) ? Pbuf2 : Pbuf;
-            } else {                               // chain of small kernels (P' GEMM, then the tile steps)
-                rc = gemm_launch(la->side, 0, kn1, kn1, kn, 1.0, CS + (size_t)k1 * kn, kn, Rbuf + k1, d, 1.0, Pbuf, kn1,
-                                 EPI_NONE, nullptr, 0);
-                if (rc) return rc;
-                rc = gj_nb64(la->side, Pbuf, Pbuf2, kn1, piv + k1, &Q);
-                if (rc) return rc;
-            }
+            rc = gemm_launch(la->side, 0, kn1, kn1, kn, 1.0, CS + (size_t)k1 * kn, kn, Rbuf + k1, d, 1.0, Pbuf, kn1,
+                             EPI_NONE, nullptr, 0);
+            if (rc) return rc;
+            rc = gj_nb64(la->side, Pbuf, Pbuf2, kn1, piv + k1, &Q);
+            if (rc) return rc;
             DAGMA_CUDA_OK(cudaEventRecord(la->join, la->side));
         }
         rc = gemm_launch(stream, 0, d, d, kn, 1.0, CS, kn, Rbuf, d, 1.0, Mw, d, EPI_NONE, nullptr, 0);
