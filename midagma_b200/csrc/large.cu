@@ -253,11 +253,8 @@ __global__ void __launch_bounds__(DM_NT, 1) inv_tile_step_kernel(const TileStepA
 // wait for each other, never for another kernel: if some are scheduled late the early ones spin, nothing
 // else is blocked, and the spin is bounded (err flag) -- progress never depends on co-residency.
 struct ServerArgs {
-    double *buf0, *buf1;     // ping-pong n x n (ld = n); buf0 holds a copy of A[K',K'] on entry
+    double *buf0, *buf1;     // ping-pong n x n (ld = n)
     int n, nblk;
-    const double* CSk;       // CS rows K' (n x kprev, ld = kprev)
-    const double* Rk;        // R columns K' (kprev x n, ld = ldr)
-    int kprev, ldr;
     double* pivots;
     unsigned* counter;       // zeroed before the launch
     int* err;
@@ -276,68 +273,16 @@ __device__ __forceinline__ void server_barrier(unsigned* counter, unsigned targe
     __syncthreads();
 }
 
-// server CTA `rank` of `nctas`: owns tile (rank / nblk, rank % nblk) of the next pivot block
+// server CTA `rank` of `nctas`: owns tile (rank / nblk, rank % nblk) of the next pivot block, whose
+// current value the CTAs have just written to buf0
 __device__ __forceinline__ void server_role(const ServerArgs& P, int rank, unsigned nctas, double* psm) {
     using S = DmmaSmem;
-    constexpr int LD = DM_LD;
-    double* Cs = psm + S::ncov;
-    double* Rs = psm + S::W;
     const int tid = threadIdx.x;
-    const DmmaPos ps(tid);
     const int bi = rank / P.nblk, bj = rank % P.nblk;
-    const int n = P.n, r0 = bi * NB, c0 = bj * NB;
+    const int n = P.n;
     SweepSync sy{smem_u32(psm + S::mbar), 0u};
     if (tid == 0) mbar_init(sy.bar, DM_NT / 32);
 
-    // ---- phase 0: own tile of P' += CS[K'_i, :] R[:, K'_j], staged through shared memory 64 k at a time
-    double acc[2][4][2];
-#pragma unroll
-    for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-        for (int tj = 0; tj < 4; ++tj) {
-            const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
-            acc[ti][tj][0] = (r < n && c < n) ? P.buf0[(size_t)r * n + c] : 0.0;
-            acc[ti][tj][1] = (r < n && c + 1 < n) ? P.buf0[(size_t)r * n + c + 1] : 0.0;
-        }
-    for (int kc = 0; kc < P.kprev; kc += NB) {
-        __syncthreads();
-        {
-            double u[16], w[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
-                u[q] = (r0 + r < n && kc + c < P.kprev) ? P.CSk[(size_t)(r0 + r) * P.kprev + kc + c] : 0.0;
-                w[q] = (kc + r < P.kprev && c0 + c < n) ? P.Rk[(size_t)(kc + r) * P.ldr + c0 + c] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
-                Cs[r * LD + c] = u[q];
-                Rs[r * LD + c] = w[q];
-            }
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int kk = 0; kk < NB; kk += 4) {
-            double an[2], bw[4];
-#pragma unroll
-            for (int ti = 0; ti < 2; ++ti) an[ti] = Cs[ps.row(ti) * LD + kk + ps.qc];
-#pragma unroll
-            for (int tj = 0; tj < 4; ++tj) bw[tj] = Rs[(kk + ps.qc) * LD + 32 * ps.wc + 8 * tj + ps.qr];
-#pragma unroll
-            for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-                for (int tj = 0; tj < 4; ++tj) dmma(acc[ti][tj][0], acc[ti][tj][1], an[ti], bw[tj]);
-        }
-    }
-#pragma unroll
-    for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-        for (int tj = 0; tj < 4; ++tj) {
-            const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
-            if (r < n && c < n) P.buf0[(size_t)r * n + c] = acc[ti][tj][0];
-            if (r < n && c + 1 < n) P.buf0[(size_t)r * n + c + 1] = acc[ti][tj][1];
-        }
     server_barrier(P.counter, nctas, P.err);
 
     // ---- the block steps
@@ -353,121 +298,245 @@ __device__ __forceinline__ void server_role(const ServerArgs& P, int rank, unsig
     __syncthreads();
 }
 
-// ---- one outer step of the two-level algorithm as ONE persistent kernel (two CTAs per SM):
-//   CTAs [0, nserver): first the look-ahead -- the inversion of the next pivot block (server_role) --,
-//   all CTAs: 64 x 64 tiles of  A += CS R  pulled from an atomic queue (accumulators start as A, operands
-//   staged 32 k at a time by a double-buffered cp.async pipeline, warp tile 16 x 32).
-// The server CTAs are the lowest block indices of a grid that fits the machine in one wave, so they are
-// resident together; they wait only for each other and the wait is bounded.
+// ---- one outer step of the two-level algorithm as ONE persistent kernel (two CTAs per SM).
+// Work items are pulled from an atomic queue, in this order (K = current 256-block, K' = next one):
+//   [server CTAs only]  tile (i, j) of the pivot block: A[K'_i,K'_j] += CS[K'_i,:] R[:,K'_j], then the
+//                       inversion of that block (tile steps + counter barrier)  -> Q'
+//   update tiles         A[I,J] += CS[I,:] R[:,J]: column strip K' first, then row strip K', then the rest
+//   CS' tiles            CS'[I,:] = -(A[I,K'] - [I in K'] I) Q'    -- wait for: column strip done, Q' done
+//   R' tiles             R'[:,J]  =   A[K',J] + [J in K'] I        -- wait for: row strip done
+// so the next outer step needs no other kernel: CS / R are double buffered across steps.  Waiting items sit
+// at the end of the queue behind items that never wait, every wait is bounded, and the CTAs of the serial
+// look-ahead chain get their SM to themselves (the co-resident worker CTA sleeps meanwhile).
 struct OuterArgs {
-    double* A; int d;            // d x d in place (ld = d, d even)
-    const double* CS; int kn;    // d x kn (ld = kn)
-    const double* R;             // kn x d (ld = d)
-    unsigned* queue;             // tile counter, zeroed before the launch
-    int* sm_busy;                // [SM id] 1 while a server CTA runs there (zeroed before the launch)
+    double* A; int d;                       // d x d in place (ld = d, d even)
+    const double* CS; const double* R;      // current: d x kn (ld = kn), kn x d (ld = d)
+    int kn;
+    double* CSn; double* Rn;                // next:    d x kn1 (ld = kn1), kn1 x d (ld = d)
+    int k1, kn1;                            // first column and width of the next block (kn1 = 0: last step)
+    const double* Qn;                       // where the server leaves Q' (kn1 x kn1, ld = kn1)
+    unsigned* sync;                         // [0] server barrier [1] queue [2] err [3] col strip [4] row strip [5] server done
+    int* sm_busy;                           // [SM id] 1 while a server CTA runs there
     int nserver;
     ServerArgs srv;
 };
 constexpr int SM_SLOTS = 256;
+constexpr int OU_LDA = 36, OU_LDB = 68, OU_KC = 32;
+constexpr int OU_STAGE = NB * OU_LDA + OU_KC * OU_LDB;                  // doubles per pipeline stage
+static_assert(2 * OU_STAGE <= DmmaSmem::total, "the worker pipeline reuses the server's shared memory");
+constexpr size_t OUTER_SMEM_BYTES = DmmaSmem::bytes;
 
 __device__ __forceinline__ unsigned smid() {
     unsigned r;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
     return r;
 }
-constexpr int OU_LDA = 36, OU_LDB = 68, OU_KC = 32;
-constexpr int OU_STAGE = NB * OU_LDA + OU_KC * OU_LDB;                  // doubles per pipeline stage
-static_assert(2 * OU_STAGE <= DmmaSmem::total, "the worker pipeline reuses the server's shared memory");
-constexpr size_t OUTER_SMEM_BYTES = DmmaSmem::bytes;
+__device__ __forceinline__ bool wait_count(volatile unsigned* c, unsigned target, int* err) {
+    unsigned spins = 0;
+    while (*c < target) {
+        __nanosleep(500);
+        if (++spins > (1u << 22)) { *err = 2; return false; }
+    }
+    __threadfence();
+    return true;
+}
 
-__global__ void __launch_bounds__(DM_NT, 2) outer_update_kernel(const OuterArgs P) {
+// acc += Am[r0.., 0..kdim) * Bm[0..kdim, c0..)  for one 64 x 64 tile (warp tile 16 x 32); operands come
+// through L2 (cp.async.cg) 32 k at a time, double buffered.  rmax / cmax: valid rows of Am / columns of Bm.
+__device__ __forceinline__ void tile_gemm(double (&acc)[2][4][2], const double* Am, int lda, const double* Bm, int ldb,
+                                          int r0, int c0, int rmax, int cmax, int kdim, double* psm, uint32_t sbase,
+                                          const DmmaPos& ps, int tid) {
+    const int nchunk = (kdim + OU_KC - 1) / OU_KC;
+    auto issue = [&](int ch) {
+        const int kc = ch * OU_KC;
+        const uint32_t sa = sbase + (uint32_t)((ch & 1) * OU_STAGE) * 8, sb = sa + (uint32_t)(NB * OU_LDA) * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {          // A chunk: 64 rows x 32 k = 1024 16-byte copies
+            const int e = tid + q * DM_NT, r = e >> 4, c = (e & 15) * 2;
+            const bool ok = (r0 + r < rmax) && (kc + c < kdim);
+            cp_async16(sa + (r * OU_LDA + c) * 8, ok ? Am + (size_t)(r0 + r) * lda + kc + c : Am, ok);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {          // B chunk: 32 k x 64 cols
+            const int e = tid + q * DM_NT, r = e >> 5, c = (e & 31) * 2;
+            const bool ok = (kc + r < kdim) && (c0 + c < cmax);
+            cp_async16(sb + (r * OU_LDB + c) * 8, ok ? Bm + (size_t)(kc + r) * ldb + c0 + c : Bm, ok);
+        }
+        cp_async_commit();
+    };
+    __syncthreads();                           // the stage buffers may still be read by the previous item
+    issue(0);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        if (ch + 1 < nchunk) {
+            issue(ch + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double* As = psm + (ch & 1) * OU_STAGE;
+        const double* Bs = As + NB * OU_LDA;
+#pragma unroll
+        for (int kk = 0; kk < OU_KC; kk += 4) {
+            double an[2], bw[4];
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti) an[ti] = As[ps.row(ti) * OU_LDA + kk + ps.qc];
+#pragma unroll
+            for (int tj = 0; tj < 4; ++tj) bw[tj] = Bs[(kk + ps.qc) * OU_LDB + 32 * ps.wc + 8 * tj + ps.qr];
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) dmma(acc[ti][tj][0], acc[ti][tj][1], an[ti], bw[tj]);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P) {
     extern __shared__ __align__(16) double psm[];
     __shared__ unsigned s_tile;
     const int tid = threadIdx.x;
-    // The look-ahead chain is serial, so its CTAs get their SM to themselves: a worker CTA that shares
-    // an SM with a running server CTA sleeps (no issue slots, no FP64 pipe) until the server is done.
-    volatile int* busy = P.sm_busy + (smid() % SM_SLOTS);
-    if ((int)blockIdx.x < P.nserver) {
-        if (tid == 0) *busy = 1;
-        server_role(P.srv, blockIdx.x, (unsigned)P.nserver, psm);
-        if (tid == 0) *busy = 0;
-    }
-
     const DmmaPos ps(tid);
     const uint32_t sbase = smem_u32(psm);
-    const int d = P.d, kn = P.kn;
-    const int tn = (d + NB - 1) / NB, ntiles = tn * tn;
-    const int nchunk = (kn + OU_KC - 1) / OU_KC;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            while (*busy) __nanosleep(2000);
-            s_tile = atomicAdd(P.queue, 1u);
-        }
-        __syncthreads();
-        const int t = (int)s_tile;
-        if (t >= ntiles) break;
-        const int r0 = (t / tn) * NB, c0 = (t % tn) * NB;
-        auto issue = [&](int ch) {
-            const int kc = ch * OU_KC;
-            const uint32_t sa = sbase + (uint32_t)((ch & 1) * OU_STAGE) * 8, sb = sa + (uint32_t)(NB * OU_LDA) * 8;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {          // A chunk: 64 rows x 32 k = 1024 16-byte copies
-                const int e = tid + q * DM_NT, r = e >> 4, c = (e & 15) * 2;
-                const bool ok = (r0 + r < d) && (kc + c < kn);
-                cp_async16(sa + (r * OU_LDA + c) * 8, ok ? P.CS + (size_t)(r0 + r) * kn + kc + c : P.CS, ok);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {          // B chunk: 32 k x 64 cols
-                const int e = tid + q * DM_NT, r = e >> 5, c = (e & 31) * 2;
-                const bool ok = (kc + r < kn) && (c0 + c < d);
-                cp_async16(sb + (r * OU_LDB + c) * 8, ok ? P.R + (size_t)(kc + r) * d + c0 + c : P.R, ok);
-            }
-            cp_async_commit();
-        };
-        issue(0);
-        double acc[2][4][2];
+    const int d = P.d, kn = P.kn, k1 = P.k1, kn1 = P.kn1;
+    int* err = reinterpret_cast<int*>(P.sync + 2);
+    volatile int* busy = P.sm_busy + (smid() % SM_SLOTS);
+    double acc[2][4][2];
+
+    auto load_acc = [&](const double* M, int ld, int r0, int c0, int rmax, int cmax) {
 #pragma unroll
         for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
             for (int tj = 0; tj < 4; ++tj) {
                 const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
                 double2 v = make_double2(0.0, 0.0);
-                if (r < d && c < d) v = *reinterpret_cast<const double2*>(P.A + (size_t)r * d + c);
+                if (r < rmax && c < cmax) v = __ldcg(reinterpret_cast<const double2*>(M + (size_t)r * ld + c));
                 acc[ti][tj][0] = v.x;
                 acc[ti][tj][1] = v.y;
             }
-        for (int ch = 0; ch < nchunk; ++ch) {
-            if (ch + 1 < nchunk) {
-                issue(ch + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncthreads();
-            const double* As = psm + (ch & 1) * OU_STAGE;
-            const double* Bs = As + NB * OU_LDA;
-#pragma unroll
-            for (int kk = 0; kk < OU_KC; kk += 4) {
-                double an[2], bw[4];
-#pragma unroll
-                for (int ti = 0; ti < 2; ++ti) an[ti] = As[ps.row(ti) * OU_LDA + kk + ps.qc];
-#pragma unroll
-                for (int tj = 0; tj < 4; ++tj) bw[tj] = Bs[(kk + ps.qc) * OU_LDB + 32 * ps.wc + 8 * tj + ps.qr];
-#pragma unroll
-                for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-                    for (int tj = 0; tj < 4; ++tj) dmma(acc[ti][tj][0], acc[ti][tj][1], an[ti], bw[tj]);
-            }
-            __syncthreads();
-        }
+    };
+
+    // ================= look-ahead: the CTAs of the next pivot block =================
+    if ((int)blockIdx.x < P.nserver) {
+        if (tid == 0) *busy = 1;
+        const int nb1 = P.srv.nblk, bi = blockIdx.x / nb1, bj = blockIdx.x % nb1;
+        const int r0 = k1 + bi * NB, c0 = k1 + bj * NB;
+        // the pivot-block tile of the update itself; its result is both the new A tile and the server's input
+        load_acc(P.A, d, r0, c0, d, d);
+        tile_gemm(acc, P.CS, kn, P.R, d, r0, c0, d, d, kn, psm, sbase, ps, tid);
 #pragma unroll
         for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
             for (int tj = 0; tj < 4; ++tj) {
                 const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
-                if (r < d && c < d) *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+                if (r < d && c < d) {
+                    const double2 v = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+                    *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = v;
+                    *reinterpret_cast<double2*>(P.srv.buf0 + (size_t)(r - k1) * kn1 + (c - k1)) = v;
+                }
             }
+        __syncthreads();
+        if (tid == 0) {                           // this tile belongs to the column strip and to the row strip
+            __threadfence();
+            atomicAdd(P.sync + 3, 1u);
+            atomicAdd(P.sync + 4, 1u);
+        }
+        server_role(P.srv, blockIdx.x, (unsigned)P.nserver, psm);
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(P.sync + 5, 1u);
+            *busy = 0;
+        }
+    }
+
+    // ================= the queue =================
+    const int tn = (d + NB - 1) / NB;
+    const int cb1 = k1 / NB, nk1 = (kn1 + NB - 1) / NB;          // block-column range of K'
+    const int n_cs = tn * nk1 - nk1 * nk1;                       // column strip without the pivot block
+    const int n_rs = nk1 * (tn - nk1);                           // row strip without the pivot block
+    const int n_rest = (tn - nk1) * (tn - nk1);
+    const int n_upd = n_cs + n_rs + n_rest;
+    const int n_csn = tn * nk1, n_rn = nk1 * tn;
+    const int n_items = n_upd + n_csn + n_rn;
+    auto outside = [&](int u) { return u < cb1 ? u : u + nk1; };  // u-th block index not in K'
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            while (*busy) __nanosleep(2000);
+            s_tile = atomicAdd(P.sync + 1, 1u);
+        }
+        __syncthreads();
+        int t = (int)s_tile;
+        if (t >= n_items) break;
+        if (t < n_upd) {
+            // ---- update tile
+            int bi, bj, strip = 0;
+            if (t < n_cs) { bi = outside(t / nk1); bj = cb1 + t % nk1; strip = 1; }
+            else if (t < n_cs + n_rs) { const int u = t - n_cs; bi = cb1 + u / (tn - nk1); bj = outside(u % (tn - nk1)); strip = 2; }
+            else { const int u = t - n_cs - n_rs; bi = outside(u / (tn - nk1)); bj = outside(u % (tn - nk1)); }
+            const int r0 = bi * NB, c0 = bj * NB;
+            load_acc(P.A, d, r0, c0, d, d);
+            tile_gemm(acc, P.CS, kn, P.R, d, r0, c0, d, d, kn, psm, sbase, ps, tid);
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) {
+                    const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
+                    if (r < d && c < d) *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+                }
+            if (strip) {
+                __syncthreads();
+                if (tid == 0) {
+                    __threadfence();
+                    atomicAdd(P.sync + 2 + strip, 1u);
+                }
+            }
+        } else if (t < n_upd + n_csn) {
+            // ---- CS' tile: rows of block bi, columns 64 jb.. of the next strip
+            const int u = t - n_upd, bi = u / nk1, jb = u % nk1;
+            if (tid == 0) (void)(wait_count(P.sync + 3, (unsigned)(tn * nk1), err) && wait_count(P.sync + 5, (unsigned)P.nserver, err));
+            __syncthreads();
+            const int r0 = bi * NB, c0 = jb * NB;
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
+            tile_gemm(acc, P.A + k1, d, P.Qn, kn1, r0, c0, d, kn1, kn1, psm, sbase, ps, tid);
+            const bool inK = (bi >= cb1) && (bi < cb1 + nk1);
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) {
+                    const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
+                    if (r < d && c < kn1) {
+                        double2 v = make_double2(-acc[ti][tj][0], -acc[ti][tj][1]);
+                        if (inK) {
+                            const double2 q = __ldcg(reinterpret_cast<const double2*>(P.Qn + (size_t)(r - k1) * kn1 + c));
+                            v.x += q.x;
+                            v.y += q.y;
+                        }
+                        *reinterpret_cast<double2*>(P.CSn + (size_t)r * kn1 + c) = v;
+                    }
+                }
+        } else {
+            // ---- R' tile: rows 64 ib.. of the next row strip, columns of block bj
+            const int u = t - n_upd - n_csn, ib = u / tn, bj = u % tn;
+            if (tid == 0) (void)wait_count(P.sync + 4, (unsigned)(tn * nk1), err);
+            __syncthreads();
+            const int c0 = bj * NB;
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) {
+                    const int rr = ib * NB + ps.row(ti), c = c0 + ps.col(tj);     // rr: row inside the strip
+                    if (rr < kn1 && c < d) {
+                        double2 v = __ldcg(reinterpret_cast<const double2*>(P.A + (size_t)(k1 + rr) * d + c));
+                        if (c == k1 + rr) v.x += 1.0;
+                        if (c + 1 == k1 + rr) v.y += 1.0;
+                        *reinterpret_cast<double2*>(P.Rn + (size_t)rr * d + c) = v;
+                    }
+                }
+        }
     }
 }
 
@@ -548,7 +617,7 @@ static int outer_block() {
 }
 
 struct LargeWs {                   // offsets in doubles into the caller's workspace
-    size_t M, CS, Rbuf, piv, Pbuf, Pbuf2, pmin, sync, total;
+    size_t M, CS, Rbuf, CS2, Rbuf2, piv, Pbuf, Pbuf2, pmin, sync, total;
     explicit LargeWs(int d) {
         const int OB = outer_block();
         const size_t dd = ((size_t)d * d + 1) & ~(size_t)1;        // keep every buffer 16-byte aligned
@@ -556,12 +625,14 @@ struct LargeWs {                   // offsets in doubles into the caller's works
         M = 0;
         CS = M + dd;
         Rbuf = CS + strip;
-        piv = Rbuf + strip;
+        CS2 = Rbuf + strip;                      // second set: the fused outer step writes the next CS / R
+        Rbuf2 = CS2 + strip;
+        piv = Rbuf2 + strip;
         Pbuf = piv + (((size_t)d + 64 + 1) & ~(size_t)1);
         Pbuf2 = Pbuf + (size_t)OB * OB;
         pmin = Pbuf2 + (size_t)OB * OB;
         sync = pmin + MIN_PARTIALS + 8;          // barrier counter, tile queue, error flag, per-SM busy flags
-        total = sync + 64 + 160;
+        total = sync + 64 + SM_SLOTS / 2;
     }
 };
 static size_t large_ws_bytes(int d) { return LargeWs(d).total * sizeof(double); }
@@ -675,20 +746,45 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         if (rc) return rc;
     }
     const bool fused = (lookahead_mode() == 1) && (d % 2 == 0);
+    unsigned* sync_words = reinterpret_cast<unsigned*>(ws + L.sync);
     if (fused) {
         static bool attr = false;
         if (!attr) {
-            DAGMA_CUDA_OK(cudaFuncSetAttribute(outer_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            DAGMA_CUDA_OK(cudaFuncSetAttribute(outer_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)OUTER_SMEM_BYTES));
-            DAGMA_CUDA_OK(cudaFuncSetAttribute(outer_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+            DAGMA_CUDA_OK(cudaFuncSetAttribute(outer_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                cudaSharedmemCarveoutMaxShared));
             attr = true;
         }
+        int sms = 0, dev = 0;
+        DAGMA_CUDA_OK(cudaGetDevice(&dev));
+        DAGMA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        // CS / R of the first block by the plain kernels; every later pair is produced by the previous fused step
+        double *CSa = CS, *Ra = Rbuf, *CSb = ws + L.CS2, *Rb = ws + L.Rbuf2;
+        {
+            const int kn = d < OB ? d : OB;
+            rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw, d, Q, kn, 0.0, CSa, kn, EPI_NONE, nullptr, 0);
+            if (rc) return rc;
+            outer_prep_kernel<<<296, 256, 0, stream>>>(Q, CSa, kn, Mw, d, 0, Ra);
+            DAGMA_CUDA_OK(cudaGetLastError());
+        }
+        for (int ob = 0; ob < nob; ++ob) {
+            const int k0 = ob * OB, kn = (d - k0) < OB ? (d - k0) : OB;
+            const bool more = ob + 1 < nob;
+            const int k1 = k0 + OB, kn1 = more ? ((d - k1) < OB ? (d - k1) : OB) : 0;
+            const int nblk1 = (kn1 + NB - 1) / NB;
+            double* Qn = (nblk1 & 1) ? Pbuf2 : Pbuf;
+            DAGMA_CUDA_OK(cudaMemsetAsync(sync_words, 0, 32 + SM_SLOTS * sizeof(int), stream));
+            OuterArgs OA{Mw, d, CSa, Ra, kn, CSb, Rb, k1, kn1, Qn, sync_words, reinterpret_cast<int*>(sync_words + 8),
+                         nblk1 * nblk1,
+                         ServerArgs{Pbuf, Pbuf2, kn1, nblk1, piv + k1, sync_words, reinterpret_cast<int*>(sync_words + 2)}};
+            outer_step_kernel<<<2 * sms, DM_NT, OUTER_SMEM_BYTES, stream>>>(OA);
+            DAGMA_CUDA_OK(cudaGetLastError());
+            double* t = CSa; CSa = CSb; CSb = t;
+            t = Ra; Ra = Rb; Rb = t;
+        }
+        return 0;
     }
-    int sms = 0, dev = 0;
-    DAGMA_CUDA_OK(cudaGetDevice(&dev));
-    DAGMA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    unsigned* sync_words = reinterpret_cast<unsigned*>(ws + L.sync);     // [0] barrier, [1] tile queue, [2] err
     for (int ob = 0; ob < nob; ++ob) {
         const int k0 = ob * OB, kn = (d - k0) < OB ? (d - k0) : OB;
         rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw + k0, d, Q, kn, 0.0, CS, kn, EPI_NONE, nullptr, 0);
@@ -700,17 +796,6 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         if (more) {   // copy of the next pivot block: the d x d update below overwrites A[K',K'] in place
             copy_block_kernel<<<64, 256, 0, stream>>>(Mw + (size_t)k1 * d + k1, d, Pbuf, kn1, kn1, kn1, 0, 0.0);
             DAGMA_CUDA_OK(cudaGetLastError());
-        }
-        if (fused) {  // update + look-ahead in one persistent kernel
-            DAGMA_CUDA_OK(cudaMemsetAsync(sync_words, 0, 16 + SM_SLOTS * sizeof(int), stream));
-            const int nblk1 = (kn1 + NB - 1) / NB;
-            OuterArgs OA{Mw, d, CS, kn, Rbuf, sync_words + 1, reinterpret_cast<int*>(sync_words + 4), nblk1 * nblk1,
-                         ServerArgs{Pbuf, Pbuf2, kn1, nblk1, CS + (size_t)k1 * kn, Rbuf + k1, kn, d, piv + k1, sync_words,
-                                    reinterpret_cast<int*>(sync_words + 2)}};
-            outer_update_kernel<<<2 * sms, DM_NT, OUTER_SMEM_BYTES, stream>>>(OA);
-            DAGMA_CUDA_OK(cudaGetLastError());
-            if (more) Q = (nblk1 & 1) ? Pbuf2 : Pbuf;
-            continue;
         }
         if (more) {   // side stream: next pivot block P' = A[K',K'] + CS[K',:] R[:,K'], then its inversion
             DAGMA_CUDA_OK(cudaEventRecord(la->fork, stream));
