@@ -134,7 +134,10 @@ def logdet_inv(A: torch.Tensor, s: float = 1.0, square_input: bool = True, want_
 def _as_dev(x, device, dtype=torch.float64) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=dtype).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device)
+    a = np.ascontiguousarray(x)
+    if not a.flags.writeable:            # e.g. a broadcast view: torch refuses to alias read-only memory quietly
+        a = a.copy()
+    return torch.as_tensor(a, dtype=dtype).to(device)
 
 
 def _lam_dev(lambda1, batch: int, device) -> torch.Tensor:
