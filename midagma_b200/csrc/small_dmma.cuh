@@ -10,8 +10,9 @@
 // Adam moments parked in tensor memory (TMEM) -- the 256 KB per SM that tcgen05 kernels
 // use for accumulators and that is otherwise idle here (FP64 has no tcgen05 kind).
 //
-// Layout.  256 threads = 8 warps in a 4 (wr) x 2 (wc) grid (wr = warp % 4 so that every SM
-// sub-partition hosts one warp of each column half); warp (wr, wc) owns rows
+// Layout.  256 threads = 8 warps in a 4 (wr) x 2 (wc) grid (wr = warp / 2: the two warps that
+// own the pivot rows of a step sit on different SM sub-partitions, and the diagonal warp shares
+// its FP64 pipe with a warp that has little to do before the publish); warp (wr, wc) owns rows
 // 16wr.., columns 32wc.. of the 64 x 64 padded matrix as 2 x 4 DMMA accumulator tiles:
 //   a[ti][tj][e] = A[16wr + 8ti + lane/4][32wc + 8tj + 2(lane%4) + e].
 // The score accumulator g and the Adam moments use the same ownership.
@@ -59,7 +60,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 struct DmmaPos {
     int warp, lane, wr, wc, qr, qc;
     __device__ __forceinline__ explicit DmmaPos(int tid) {
-        warp = tid >> 5; lane = tid & 31; wr = warp & 3; wc = warp >> 2; qr = lane >> 2; qc = lane & 3;
+        warp = tid >> 5; lane = tid & 31; wr = warp >> 1; wc = warp & 1; qr = lane >> 2; qc = lane & 3;
     }
     __device__ __forceinline__ int row(int ti) const { return 16 * wr + 8 * ti + qr; }
     __device__ __forceinline__ int col(int tj) const { return 32 * wc + 8 * tj + 2 * qc; }   // + e
@@ -72,8 +73,11 @@ __device__ __forceinline__ void mbar_init(uint32_t addr, int count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {   // try_wait suspends the warp in hardware
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+    // one cheap test first (the last arriver of a phase is usually the warp on the serial chain),
+    // then try_wait, which suspends the warp in hardware
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\t"
+                 "WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\tDONE_%=:\n\t}"
                  ::"r"(addr), "r"(parity) : "memory");
 }
 
@@ -86,9 +90,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {   //
 // add numbers of one sign, exactly as in the scaled elimination.
 // Writes -Q for the next block step and the four fraction-free pivots p_k (all > 0 <=> all
 // scalar pivots > 0; log|det P| = sum_k (k - 2) log|p_k|).
-template <int TI, int TJ, int HALF>
+// `extra(k)` is issued right after the shuffles of pivot k: independent tensor work of the same warp that
+// fits in the shuffle latency (the chain is latency bound, the warp's issue slots are mostly free).
+template <int TI, int TJ, int HALF, class Extra>
 __device__ __forceinline__ void stage_pivot_block(const double (&a)[2][4][2], const DmmaPos& ps, double* sm, int b,
-                                                  int qslot) {
+                                                  int qslot, Extra&& extra) {
     constexpr unsigned FULL = 0xffffffffu;
     const int L = ps.lane & 15, i = L >> 2, j = L & 3;
     const int src = ((4 * HALF + i) << 2) | (2 * HALF + (j >> 1));
@@ -100,6 +106,7 @@ __device__ __forceinline__ void stage_pivot_block(const double (&a)[2][4][2], co
     for (int k = 0; k < 4; ++k) {
         const double p = __shfl_sync(FULL, x, 5 * k);
         const double r = __shfl_sync(FULL, x, 4 * k + j), c = __shfl_sync(FULL, x, 4 * i + k);
+        extra(k);
         if (ps.lane == 0) pi[k] = p;
         const bool ik = (i == k), jk = (j == k);
         // off the chain: what the pivot row / pivot column lanes become
@@ -159,9 +166,21 @@ __device__ __forceinline__ void gemm_chunk(double (&g)[2][4][2], const DmmaPos& 
         for (int tj = 0; tj < 4; ++tj) dmma(g[ti][tj][0], g[ti][tj][1], an[ti], bw[tj]);
 }
 
+#ifdef DAGMA_SWEEP_TRACE
+// debug build only: cycle stamps of the serial chain (CTA 0, first 64 block steps after reset)
+__device__ long long g_sweep_trace[64 * 8];
+__device__ int g_sweep_trace_n;
+#define SWEEP_STAMP(slot, cond) do { if (blockIdx.x == 0 && (cond) && ps.lane == 0 && sy.trace >= 0 && sy.trace < 64) g_sweep_trace[sy.trace * 8 + (slot)] = clock64(); } while (0)
+#else
+#define SWEEP_STAMP(slot, cond) do { } while (0)
+#endif
+
 struct SweepSync {        // per-thread view of the step barrier
     uint32_t bar;         // shared address of the mbarrier (count = warps)
     uint32_t phase;       // parity to wait for next
+#ifdef DAGMA_SWEEP_TRACE
+    int trace = -1;
+#endif
 };
 
 // One block step; BQ = b % 8 is compile time, bo = b / 8.  On entry the lines of block b are
@@ -180,39 +199,63 @@ __device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], double (&g
     const double* rb = sm + DmmaSmem::rbuf + CUR * 4 * DM_LD;
     const double* cb = sm + DmmaSmem::cbuf + CUR * DM_DP * 4;
     const double* qb = sm + DmmaSmem::qbuf + CUR * 16;
+#ifdef DAGMA_SWEEP_TRACE
+    const bool trc_diag = (b + 1 < nb) && (ps.wr == ((b + 1) >> 2)) && (ps.wc == ((b + 1) >> 3));
+    const bool trc_other = (ps.warp == ((((b + 1) >> 2) + 2) & 3) + 4 * (1 - ((b + 1) >> 3)));   // a warp far from the diagonal
+#endif
+    SWEEP_STAMP(0, trc_diag);
+    SWEEP_STAMP(5, trc_other);
     mbar_wait(sy.bar, sy.phase);
     sy.phase ^= 1u;
+    SWEEP_STAMP(1, trc_diag);
+    SWEEP_STAMP(6, trc_other);
     // ---- CS = Cpub (-Q) as ONE DMMA per 8 rows: B[k][n] = -Q[k][n/2] on even n, so the C
     //      fragment element c0 of lane (qr, qc) is CS[row qr][qc] = exactly its A fragment.
     const double bq = (ps.qr & 1) ? 0.0 : qb[ps.qc * 4 + (ps.qr >> 1)];
-    double acs[2], br[4];
+    double acs[2], ac[2], br[4];
 #pragma unroll
-    for (int ti = 0; ti < 2; ++ti) {
-        const double ac = cb[ps.row(ti) * 4 + ps.qc];
-        double c0 = 0.0, c1 = 0.0;
-        dmma(c0, c1, ac, bq);
-        acs[ti] = c0;
-    }
+    for (int ti = 0; ti < 2; ++ti) ac[ti] = cb[ps.row(ti) * 4 + ps.qc];
 #pragma unroll
     for (int tj = 0; tj < 4; ++tj) br[tj] = rb[ps.qc * DM_LD + 32 * ps.wc + 8 * tj + ps.qr];
-    // ---- A += CS Rpub: next pivot block, then the rest of the next pivot rows / columns
+    auto form_cs = [&](int ti) {
+        double c0 = 0.0, c1 = 0.0;
+        dmma(c0, c1, ac[ti], bq);
+        acs[ti] = c0;
+    };
+    // ---- the serial chain first: CS of the next pivot rows, the next pivot block itself
+    form_cs(TIN);
     dmma(a[TIN][TJN][0], a[TIN][TJN][1], acs[TIN], br[TJN]);
     const bool has_next = b + 1 < nb;
+    SWEEP_STAMP(2, trc_diag);
+    // the rest of the next pivot rows / columns (what the publish needs), in four portions
+    constexpr int O0 = (TJN == 0) ? 1 : 0, O1 = (TJN <= 1) ? 2 : 1, O2 = (TJN <= 2) ? 3 : 2;   // tj != TJN
+    auto portion = [&](int k) {
+        if (k == 0) form_cs(TIN ^ 1);
+        else if (k == 1) {
+            dmma(a[TIN][O0][0], a[TIN][O0][1], acs[TIN], br[O0]);
+            dmma(a[TIN][O1][0], a[TIN][O1][1], acs[TIN], br[O1]);
+        } else if (k == 2) dmma(a[TIN][O2][0], a[TIN][O2][1], acs[TIN], br[O2]);
+        else dmma(a[TIN ^ 1][TJN][0], a[TIN ^ 1][TJN][1], acs[TIN ^ 1], br[TJN]);
+    };
     if (has_next && (ps.wr == ((b + 1) >> 2)) && (ps.wc == ((b + 1) >> 3)))
-        stage_pivot_block<TIN, TJN, HALFN>(a, ps, sm, b + 1, CUR ^ 1);
+        stage_pivot_block<TIN, TJN, HALFN>(a, ps, sm, b + 1, CUR ^ 1, [](int) {});
 #pragma unroll
-    for (int tj = 0; tj < 4; ++tj)
-        if (tj != TJN) dmma(a[TIN][tj][0], a[TIN][tj][1], acs[TIN], br[tj]);
-    dmma(a[TIN ^ 1][TJN][0], a[TIN ^ 1][TJN][1], acs[TIN ^ 1], br[TJN]);
+    for (int k = 0; k < 4; ++k) portion(k);
+    SWEEP_STAMP(3, trc_diag);
     if (has_next) {
         publish_block<BN>(a, ps, sm, b + 1);
         __syncwarp();
         if (ps.lane == 0) mbar_arrive(sy.bar);
     }
+    SWEEP_STAMP(4, trc_diag);
     // ---- the three tiles nobody is waiting for
 #pragma unroll
     for (int tj = 0; tj < 4; ++tj)
         if (tj != TJN) dmma(a[TIN ^ 1][tj][0], a[TIN ^ 1][tj][1], acs[TIN ^ 1], br[tj]);
+    SWEEP_STAMP(7, trc_other);
+#ifdef DAGMA_SWEEP_TRACE
+    if (sy.trace >= 0) ++sy.trace;
+#endif
 }
 
 // a := a^{-1} on the leading 4*ceil(d/4) block (padding inside the last pivot block must
@@ -229,7 +272,7 @@ __device__ __forceinline__ void dmma_sweep(double (&a)[2][4][2], double (&g)[2][
 #pragma unroll 1
         for (int kb = 0; kb < nb; ++kb) gemm_chunk(g, ps, sm, kb);
     }
-    if (ps.wr == 0 && ps.wc == 0) stage_pivot_block<0, 0, 0>(a, ps, sm, 0, 0);
+    if (ps.wr == 0 && ps.wc == 0) stage_pivot_block<0, 0, 0>(a, ps, sm, 0, 0, [](int) {});
     publish_block<0>(a, ps, sm, 0);
     __syncwarp();
     if (ps.lane == 0) mbar_arrive(sy.bar);

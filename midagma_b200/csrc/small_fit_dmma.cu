@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                     g[ti][tj][1] = -nc.y;
                 }
             }
+#ifdef DAGMA_SWEEP_TRACE
+            sy.trace = (it == 50) ? 0 : -1;          // trace the sweep of iteration 51
+#endif
             dmma_sweep<true>(a, g, ps, smem, d, sy);
             // now: a = M^{-T},  g = cov - cov W = cov (I - W),  pinfo[0..np) = pivots
 
@@ -405,6 +408,14 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
     __syncthreads();
     if (ps.warp == 0) tmem_free(tmem_base);
 }
+
+#ifdef DAGMA_SWEEP_TRACE
+}  // namespace dagma
+extern "C" int dagma_debug_sweep_trace(long long* out_host) {
+    return (int)cudaMemcpyFromSymbol(out_host, dagma::g_sweep_trace, sizeof(long long) * 64 * 8);
+}
+namespace dagma {
+#endif
 
 int fit_dmma_geometry(int batch, int sms, int* ctas, int* threads, size_t* smem_bytes) {
     constexpr size_t bytes = DmmaSmem::bytes;
