@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdagma_b200.so")
+# DAGMA_B200_LIB: another build of the same sources (A/B timing and debug builds, scripts/build_variant.py)
+LIB_PATH = os.environ.get("DAGMA_B200_LIB") or os.path.join(_HERE, "lib", "libdagma_b200.so")
 
 MAX_STAGES = 16
 SMALL_MAX_D = 64

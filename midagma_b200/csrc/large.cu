@@ -169,7 +169,7 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
         }
     }
     __syncthreads();
-    dmma_sweep<false>(a, acc, ps, psm, kn, sy);
+    dmma_sweep(a, ps, psm, kn, sy);
     if (bi == 0 && bj == 0 && tid < 4 * ((kn + 3) >> 2)) P.pivots[k0 + tid] = psm[S::pinfo + tid];
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)

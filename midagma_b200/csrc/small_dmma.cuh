@@ -1,30 +1,30 @@
 // Tensor-core version of the on-chip sweep for 32 < d <= 64: block Gauss-Jordan with
-// 4 x 4 pivot blocks whose rank-4 updates are DMMA.8x8x4 (mma.sync.m8n8k4.f64).
+// 8 x 8 pivot blocks whose rank-8 updates are pairs of DMMA.8x8x4 (mma.sync.m8n8k4.f64).
 //
 // Why.  The scalar rank-1 sweep (small_gj.cuh) is bound by shared->register bandwidth
 // (16 doubles/clk/SM; a 4 x 2 register tile gets 1.2 FMA per loaded double, the FP64 pipe
 // needs 4) and by one barrier per pivot.  A 16 x 32 warp tile updated by DMMA gets
-// 10.7 FMA per loaded double and needs ONE barrier per 4 pivots.  The remaining serial
-// chain (publish -> barrier -> 4 x 4 pivot-block inverse) is hidden by running TWO
+// 10.7 FMA per loaded double and needs ONE barrier per 8 pivots.  The remaining serial
+// chain (publish -> barrier -> 8 x 8 pivot-block inverse) is hidden by running TWO
 // independent problems (CTAs) per SM: 256 threads and <= 128 registers each, with the
 // Adam moments parked in tensor memory (TMEM) -- the 256 KB per SM that tcgen05 kernels
 // use for accumulators and that is otherwise idle here (FP64 has no tcgen05 kind).
 //
-// Layout.  256 threads = 8 warps in a 4 (wr) x 2 (wc) grid (wr = warp / 2: the two warps that
-// own the pivot rows of a step sit on different SM sub-partitions, and the diagonal warp shares
-// its FP64 pipe with a warp that has little to do before the publish); warp (wr, wc) owns rows
+// Layout.  256 threads = 8 warps in a 4 (wr) x 2 (wc) grid (wr = warp / 2); warp (wr, wc) owns rows
 // 16wr.., columns 32wc.. of the 64 x 64 padded matrix as 2 x 4 DMMA accumulator tiles:
 //   a[ti][tj][e] = A[16wr + 8ti + lane/4][32wc + 8tj + 2(lane%4) + e].
-// The score accumulator g and the Adam moments use the same ownership.
+// The score accumulator g and the Adam moments use the same ownership.  A pivot block is exactly
+// ONE accumulator tile: block b (pivots K = 8b..8b+7) is tile (ti, tj) = (b & 1, b & 3) of warp
+// (wr, wc) = (b >> 1, b >> 2), the "diagonal warp" of the step.
 //
-// Block step b (pivots K = 4b..4b+3) -- block form of the publish identity of small_gj.cuh:
+// Block step b -- block form of the publish identity of small_gj.cuh:
 //   publish  Rpub = A[K, :] + [I at the K block],  Cpub = A[:, K] - [I at the K block];
 //            -Q = -(A[K,K])^{-1} was computed one step EARLY by the diagonal warp,
-//   barrier, then every warp:  CS = Cpub (-Q)      (one DMMA per 8 rows, see cs_fragment),
-//            A += CS Rpub  (8 DMMA),   G += (-cov)[:, K] W[K, :]   (8 DMMA).
+//   barrier, then every warp:  CS = Cpub (-Q)      (two DMMA per 8 rows, see dmma_block_step),
+//            A += CS Rpub  (16 DMMA).
 // With the two I's the same product turns the pivot block into Q, the pivot rows into
 // Q A[K,:] and the pivot columns into -A[:,K] Q: no tile is special and nothing is zeroed.
-// The 4 x 4 pivot blocks are themselves inverted by scalar Gauss-Jordan in natural order,
+// The 8 x 8 pivot blocks are themselves inverted by scalar Gauss-Jordan in natural order,
 // so the sweep yields the same d scalar pivots as small_gj.cuh: log|det| = sum log|pivot|,
 // and "M-matrix" = all pivots > 0.
 #pragma once
@@ -35,15 +35,16 @@ namespace dagma {
 constexpr int DM_DP = 64;          // padded dimension
 constexpr int DM_NT = 256;         // threads per CTA
 constexpr int DM_LD = 68;          // row stride (doubles) of the padded smem matrices / row lines
+constexpr int DM_PB = 8;           // pivot block
 constexpr int DM_TMEM_COLS = 128;  // 32-bit TMEM columns per CTA: 2 warps per lane quarter x 64
 
 struct DmmaSmem {                  // offsets in doubles
     static constexpr int ncov = 0;                         // -cov, [64][68]
     static constexpr int W = ncov + DM_DP * DM_LD;         // W,    [64][68]
-    static constexpr int rbuf = W + DM_DP * DM_LD;         // 2 x [4][68]   published pivot rows
-    static constexpr int cbuf = rbuf + 2 * 4 * DM_LD;      // 2 x [64][4]   published pivot columns
-    static constexpr int qbuf = cbuf + 2 * DM_DP * 4;      // 2 x 16        -Q, row-major
-    static constexpr int pinfo = qbuf + 32;                // 64            scalar pivots in natural order
+    static constexpr int rbuf = W + DM_DP * DM_LD;         // 2 x [8][68]      published pivot rows
+    static constexpr int cbuf = rbuf + 2 * DM_PB * DM_LD;  // 2 x 2 x [64][4]  published pivot columns (two 4-column planes)
+    static constexpr int qbuf = cbuf + 2 * DM_DP * DM_PB;  // 2 x 64           -Q in B-fragment order
+    static constexpr int pinfo = qbuf + 2 * 64;            // 64               fraction-free pivots in natural order
     static constexpr int red = pinfo + 64;                 // 96
     static constexpr int mbar = red + 96;                  // 1 (the step barrier, 8 bytes)
     static constexpr int total = mbar + 2;
@@ -81,76 +82,92 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
                  ::"r"(addr), "r"(parity) : "memory");
 }
 
-// The diagonal warp of block `b` inverts the pivot block P = A[K,K] (it sits in tile (TI,TJ),
-// lanes with qr/4 == HALF and qc/2 == HALF), one element per lane, by a FRACTION-FREE 4 x 4
-// Gauss-Jordan in natural pivot order: rows i != k become p_k row_i - x_ik row_k, so no
-// reciprocal sits between two pivots; the row scales D_i = p_i prod_{m>i} p_m are divided out
-// once at the end (one reciprocal chain instead of four on the serial path of the sweep).
-// Broadcasts are warp shuffles.  For the Z-matrices of DAGMA the off-diagonal updates still
-// add numbers of one sign, exactly as in the scaled elimination.
-// Writes -Q for the next block step and the four fraction-free pivots p_k (all > 0 <=> all
-// scalar pivots > 0; log|det P| = sum_k (k - 2) log|p_k|).
+// The diagonal warp of block `b` inverts the pivot block P = A[K,K] = its accumulator tile (TI, TJ):
+// lane (qr, qc) holds P[qr][2qc], P[qr][2qc+1].  Two phases of four pivots, each a FRACTION-FREE
+// Gauss-Jordan in natural pivot order over all 8 rows: rows i != k become p_k row_i - x_ik row_k, so no
+// reciprocal sits between two pivots; the row scales (D_i = prod_{m>=i} p_m for the rows of the phase,
+// the product of its four pivots for the other rows) are divided out once per phase.  Four pivots per
+// phase keep the scale products inside 8th powers of the true pivots.  Broadcasts are warp shuffles.
+// For the Z-matrices of DAGMA the off-diagonal updates still add numbers of one sign, exactly as in the
+// scaled elimination.
+// Writes -Q (in the order the B fragments of the next block step read it) and the eight fraction-free
+// pivots p_k (all > 0 <=> all scalar pivots > 0; log|det P| = sum_k ((k & 3) - 2) log|p_k|).
 // `extra(k)` is issued right after the shuffles of pivot k: independent tensor work of the same warp that
 // fits in the shuffle latency (the chain is latency bound, the warp's issue slots are mostly free).
-template <int TI, int TJ, int HALF, class Extra>
+template <int TI, int TJ, class Extra>
 __device__ __forceinline__ void stage_pivot_block(const double (&a)[2][4][2], const DmmaPos& ps, double* sm, int b,
                                                   int qslot, Extra&& extra) {
     constexpr unsigned FULL = 0xffffffffu;
-    const int L = ps.lane & 15, i = L >> 2, j = L & 3;
-    const int src = ((4 * HALF + i) << 2) | (2 * HALF + (j >> 1));
-    const double v0 = __shfl_sync(FULL, a[TI][TJ][0], src), v1 = __shfl_sync(FULL, a[TI][TJ][1], src);
-    double x = (j & 1) ? v1 : v0;
-    double D = 1.0, E = 1.0;                  // E = prod_{m<k} p_m: scale of a row not yet pivoted
-    double* pi = sm + DmmaSmem::pinfo + b * 4;
+    const int i = ps.qr, jq = ps.qc;
+    double x0 = a[TI][TJ][0], x1 = a[TI][TJ][1];
+    double* pi = sm + DmmaSmem::pinfo + b * DM_PB;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double p = __shfl_sync(FULL, x, 5 * k);
-        const double r = __shfl_sync(FULL, x, 4 * k + j), c = __shfl_sync(FULL, x, 4 * i + k);
-        extra(k);
-        if (ps.lane == 0) pi[k] = p;
-        const bool ik = (i == k), jk = (j == k);
-        // off the chain: what the pivot row / pivot column lanes become
-        const double alt = ik ? (jk ? E : x) : (-c * E);
-        const double Dp = D * p;
-        D = (k >= i) ? Dp : D;                // D_i = prod_{m >= i} p_m
-        E *= p;
-        // on the chain: one multiply, one fma, one select
-        const double t = fma(-c, r, p * x);
-        x = (ik || jk) ? alt : t;
+    for (int ph = 0; ph < 2; ++ph) {
+        double D = 1.0, E = 1.0;                  // E = prod of the phase's earlier pivots: scale of its rows not yet pivoted
+        const int irel = i - 4 * ph;              // rows outside the phase collect all four pivots
+        const int ie = (irel > 3) ? -1 : irel;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = 4 * ph + kk, kl = k >> 1;
+            const double xs = (k & 1) ? x1 : x0;  // column k, in the lanes qc == kl
+            const double p = __shfl_sync(FULL, xs, 4 * k + kl);
+            const double c = __shfl_sync(FULL, xs, 4 * i + kl);
+            const double r0 = __shfl_sync(FULL, x0, 4 * k + jq), r1 = __shfl_sync(FULL, x1, 4 * k + jq);
+            extra(k);
+            if (ps.lane == 0) pi[k] = p;
+            const bool ik = (i == k), j0k = (2 * jq == k), j1k = (2 * jq + 1 == k);
+            // off the chain: what the pivot row / pivot column lanes become
+            const double nce = -c * E;
+            const double alt0 = ik ? (j0k ? E : x0) : nce, alt1 = ik ? (j1k ? E : x1) : nce;
+            const double Dp = D * p;
+            D = (kk >= ie) ? Dp : D;
+            E *= p;
+            // on the chain: one multiply, one fma, one select per element
+            const double t0 = fma(-c, r0, p * x0), t1 = fma(-c, r1, p * x1);
+            x0 = (ik || j0k) ? alt0 : t0;
+            x1 = (ik || j1k) ? alt1 : t1;
+        }
+        const double rd = fast_rcp(D);
+        x0 *= rd;
+        x1 *= rd;
     }
-    const double q = x * fast_rcp(D);
-    if (ps.lane < 16) sm[DmmaSmem::qbuf + qslot * 16 + L] = -q;
+    // -Q[k][n] goes where lane (qr, qc) of k-slab kk = k / 4 finds its B fragment:
+    //   B[qc][qr] = -Q[4kk + qc][(qr >> 1) + 4 (qr & 1)]   <=>   index 32 (k / 4) + 4 (2 (n & 3) + n / 4) + (k & 3)
+    double* qd = sm + DmmaSmem::qbuf + qslot * 64 + 32 * (i >> 2) + (i & 3);
+    const int n0 = 2 * jq, n1 = 2 * jq + 1;
+    qd[4 * (2 * (n0 & 3) + (n0 >> 2))] = -x0;
+    qd[4 * (2 * (n1 & 3) + (n1 >> 2))] = -x1;
 }
 
-// publish the pivot rows (+I) / pivot columns (-I) of block b = 8 bo + BQ into line buffer BQ & 1;
+// publish the pivot rows (+I) / pivot columns (-I) of block B into line buffer B & 1;
 // the +-I touches only the pivot block itself, i.e. tile (TI, TJ) of the diagonal warp
-template <int BQ>
-__device__ __forceinline__ void publish_block(const double (&a)[2][4][2], const DmmaPos& ps, double* sm, int b) {
-    constexpr int TI = (BQ & 3) >> 1, TJ = BQ >> 1, HALF = BQ & 1, CUR = BQ & 1;
-    double* rb = sm + DmmaSmem::rbuf + CUR * 4 * DM_LD;
-    double* cb = sm + DmmaSmem::cbuf + CUR * DM_DP * 4;
-    const bool rown = ps.wr == (b >> 2), cown = ps.wc == (b >> 3);
+template <int B>
+__device__ __forceinline__ void publish_block(const double (&a)[2][4][2], const DmmaPos& ps, double* sm) {
+    constexpr int TI = B & 1, TJ = B & 3, CUR = B & 1;
+    double* rb = sm + DmmaSmem::rbuf + CUR * DM_PB * DM_LD;
+    double* cb = sm + DmmaSmem::cbuf + CUR * DM_DP * DM_PB;
+    const bool rown = ps.wr == (B >> 1), cown = ps.wc == (B >> 2);
     double p0 = a[TI][TJ][0], p1 = a[TI][TJ][1], m0 = p0, m1 = p1;      // pivot-block tile: row / column copy
     if (rown && cown) {
-        const int dlt = ps.row(TI) - ps.col(TJ);
+        const int dlt = ps.qr - 2 * ps.qc;
         const double i0 = (dlt == 0) ? 1.0 : 0.0, i1 = (dlt == 1) ? 1.0 : 0.0;
         p0 += i0; p1 += i1; m0 -= i0; m1 -= i1;
     }
-    if (rown && (ps.qr >> 2) == HALF) {
-        double* dst = rb + (ps.qr & 3) * DM_LD + ps.col(0);
+    if (rown) {
+        double* dst = rb + ps.qr * DM_LD + ps.col(0);
 #pragma unroll
         for (int tj = 0; tj < 4; ++tj)
             *reinterpret_cast<double2*>(dst + 8 * tj) = (tj == TJ) ? make_double2(p0, p1) : make_double2(a[TI][tj][0], a[TI][tj][1]);
     }
-    if (cown && (ps.qc >> 1) == HALF) {
-        double* dst = cb + ps.row(0) * 4 + 2 * (ps.qc & 1);
+    if (cown) {
+        double* dst = cb + (ps.qc >> 1) * (DM_DP * 4) + ps.row(0) * 4 + 2 * (ps.qc & 1);
 #pragma unroll
         for (int ti = 0; ti < 2; ++ti)
             *reinterpret_cast<double2*>(dst + 32 * ti) = (ti == TI) ? make_double2(m0, m1) : make_double2(a[ti][TJ][0], a[ti][TJ][1]);
     }
 }
 
-// G += (-cov)[:, K] W[K, :] for the k-block kb (8 DMMA); independent of the elimination
+// G += (-cov)[:, K] W[K, :] for the k-block kb of 4 (8 DMMA); independent of the elimination
 __device__ __forceinline__ void gemm_chunk(double (&g)[2][4][2], const DmmaPos& ps, const double* sm, int kb) {
     const double* nc = sm + DmmaSmem::ncov;
     const double* Ws = sm + DmmaSmem::W;
@@ -167,12 +184,15 @@ __device__ __forceinline__ void gemm_chunk(double (&g)[2][4][2], const DmmaPos& 
 }
 
 #ifdef DAGMA_SWEEP_TRACE
-// debug build only: cycle stamps of the serial chain (CTA 0, first 64 block steps after reset)
+// debug build only: cycle stamps of the serial chain (CTA 0, the block steps of one sweep)
 __device__ long long g_sweep_trace[64 * 8];
-__device__ int g_sweep_trace_n;
 #define SWEEP_STAMP(slot, cond) do { if (blockIdx.x == 0 && (cond) && ps.lane == 0 && sy.trace >= 0 && sy.trace < 64) g_sweep_trace[sy.trace * 8 + (slot)] = clock64(); } while (0)
 #else
 #define SWEEP_STAMP(slot, cond) do { } while (0)
+#endif
+
+#ifndef DAGMA_STAGE_INTERLEAVE
+#define DAGMA_STAGE_INTERLEAVE 1     // 1: the diagonal warp issues its publish-critical DMMAs inside the pivot-block chain
 #endif
 
 struct SweepSync {        // per-thread view of the step barrier
@@ -183,25 +203,29 @@ struct SweepSync {        // per-thread view of the step barrier
 #endif
 };
 
-// One block step; BQ = b % 8 is compile time, bo = b / 8.  On entry the lines of block b are
-// published and every warp has arrived on the step barrier; the step
+// One block step, B compile time.  On entry the lines of block B are published and every warp has
+// arrived on the step barrier; the step
 //   waits for it,
-//   forms CS, updates FIRST the five tiles that hold the pivot rows / columns of block b + 1,
-//   lets the diagonal warp invert the next pivot block, publishes the lines of block b + 1 and
+//   forms CS, updates FIRST the five tiles that hold the pivot rows / columns of block B + 1,
+//   lets the diagonal warp invert the next pivot block, publishes the lines of block B + 1 and
 //   arrives -- and only then updates its remaining three tiles, off the serial chain.
-template <int BQ, bool GEMM>
-__device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], double (&g)[2][4][2], const DmmaPos& ps,
-                                                double* sm, int bo, int nb, SweepSync& sy) {
-    constexpr int CUR = BQ & 1;
-    constexpr int BN = (BQ + 1) & 7;                                   // next block (mod 8)
-    constexpr int TIN = (BN & 3) >> 1, TJN = BN >> 1, HALFN = BN & 1;
-    const int b = 8 * bo + BQ;
-    const double* rb = sm + DmmaSmem::rbuf + CUR * 4 * DM_LD;
-    const double* cb = sm + DmmaSmem::cbuf + CUR * DM_DP * 4;
-    const double* qb = sm + DmmaSmem::qbuf + CUR * 16;
+// CS = Cpub (-Q) for 8 rows is ONE accumulator tile: the B fragments carry -Q[:, n/2] in the even and
+// -Q[:, 4 + n/2] in the odd columns n, so that c0 / c1 of lane (qr, qc) are CS[qr][qc] / CS[qr][4 + qc]
+// = exactly its A fragments for the two k-slabs of the rank-8 update.
+template <int B>
+__device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], const DmmaPos& ps, double* sm, int nb,
+                                                SweepSync& sy) {
+    constexpr int CUR = B & 1;
+    constexpr int BN = (B + 1) & 7;                                   // next block
+    constexpr int TIN = BN & 1, TJN = BN & 3;
+    const double* rb = sm + DmmaSmem::rbuf + CUR * DM_PB * DM_LD;
+    const double* cb = sm + DmmaSmem::cbuf + CUR * DM_DP * DM_PB;
+    const double* qb = sm + DmmaSmem::qbuf + CUR * 64;
+    const bool has_next = B + 1 < nb;
+    const bool diag_next = has_next && (ps.wr == (BN >> 1)) && (ps.wc == (BN >> 2));
 #ifdef DAGMA_SWEEP_TRACE
-    const bool trc_diag = (b + 1 < nb) && (ps.wr == ((b + 1) >> 2)) && (ps.wc == ((b + 1) >> 3));
-    const bool trc_other = (ps.warp == ((((b + 1) >> 2) + 2) & 3) + 4 * (1 - ((b + 1) >> 3)));   // a warp far from the diagonal
+    const bool trc_diag = diag_next;
+    const bool trc_other = (ps.warp == ((((BN >> 1) + 2) & 3) * 2 + (1 - (BN >> 2))));   // a warp far from the diagonal
 #endif
     SWEEP_STAMP(0, trc_diag);
     SWEEP_STAMP(5, trc_other);
@@ -209,41 +233,53 @@ __device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], double (&g
     sy.phase ^= 1u;
     SWEEP_STAMP(1, trc_diag);
     SWEEP_STAMP(6, trc_other);
-    // ---- CS = Cpub (-Q) as ONE DMMA per 8 rows: B[k][n] = -Q[k][n/2] on even n, so the C
-    //      fragment element c0 of lane (qr, qc) is CS[row qr][qc] = exactly its A fragment.
-    const double bq = (ps.qr & 1) ? 0.0 : qb[ps.qc * 4 + (ps.qr >> 1)];
-    double acs[2], ac[2], br[4];
+    double bq[2], ac[2][2], br[2][4], acs[2][2];
 #pragma unroll
-    for (int ti = 0; ti < 2; ++ti) ac[ti] = cb[ps.row(ti) * 4 + ps.qc];
+    for (int kk = 0; kk < 2; ++kk) bq[kk] = qb[32 * kk + ps.lane];
 #pragma unroll
-    for (int tj = 0; tj < 4; ++tj) br[tj] = rb[ps.qc * DM_LD + 32 * ps.wc + 8 * tj + ps.qr];
-    auto form_cs = [&](int ti) {
-        double c0 = 0.0, c1 = 0.0;
-        dmma(c0, c1, ac[ti], bq);
-        acs[ti] = c0;
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) ac[ti][kk] = cb[kk * (DM_DP * 4) + ps.row(ti) * 4 + ps.qc];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) br[kk][tj] = rb[(4 * kk + ps.qc) * DM_LD + 32 * ps.wc + 8 * tj + ps.qr];
+    auto cs1 = [&](int ti) { acs[ti][0] = 0.0; acs[ti][1] = 0.0; dmma(acs[ti][0], acs[ti][1], ac[ti][0], bq[0]); };
+    auto cs2 = [&](int ti) { dmma(acs[ti][0], acs[ti][1], ac[ti][1], bq[1]); };
+    auto upd = [&](int ti, int tj) {
+        dmma(a[ti][tj][0], a[ti][tj][1], acs[ti][0], br[0][tj]);
+        dmma(a[ti][tj][0], a[ti][tj][1], acs[ti][1], br[1][tj]);
     };
     // ---- the serial chain first: CS of the next pivot rows, the next pivot block itself
-    form_cs(TIN);
-    dmma(a[TIN][TJN][0], a[TIN][TJN][1], acs[TIN], br[TJN]);
-    const bool has_next = b + 1 < nb;
+    cs1(TIN);
+    cs2(TIN);
+    upd(TIN, TJN);
     SWEEP_STAMP(2, trc_diag);
-    // the rest of the next pivot rows / columns (what the publish needs), in four portions
+    // the rest of the next pivot rows / columns (what the publish needs)
     constexpr int O0 = (TJN == 0) ? 1 : 0, O1 = (TJN <= 1) ? 2 : 1, O2 = (TJN <= 2) ? 3 : 2;   // tj != TJN
     auto portion = [&](int k) {
-        if (k == 0) form_cs(TIN ^ 1);
-        else if (k == 1) {
-            dmma(a[TIN][O0][0], a[TIN][O0][1], acs[TIN], br[O0]);
-            dmma(a[TIN][O1][0], a[TIN][O1][1], acs[TIN], br[O1]);
-        } else if (k == 2) dmma(a[TIN][O2][0], a[TIN][O2][1], acs[TIN], br[O2]);
-        else dmma(a[TIN ^ 1][TJN][0], a[TIN ^ 1][TJN][1], acs[TIN ^ 1], br[TJN]);
+        if (k == 0) cs1(TIN ^ 1);
+        else if (k == 1) cs2(TIN ^ 1);
+        else if (k == 2) upd(TIN, O0);
+        else if (k == 3) upd(TIN, O1);
+        else if (k == 4) upd(TIN, O2);
+        else if (k == 5) upd(TIN ^ 1, TJN);
     };
-    if (has_next && (ps.wr == ((b + 1) >> 2)) && (ps.wc == ((b + 1) >> 3)))
-        stage_pivot_block<TIN, TJN, HALFN>(a, ps, sm, b + 1, CUR ^ 1, [](int) {});
+    if (diag_next) {
+#if DAGMA_STAGE_INTERLEAVE
+        stage_pivot_block<TIN, TJN>(a, ps, sm, B + 1, CUR ^ 1, portion);
+#else
+        stage_pivot_block<TIN, TJN>(a, ps, sm, B + 1, CUR ^ 1, [](int) {});
 #pragma unroll
-    for (int k = 0; k < 4; ++k) portion(k);
+        for (int k = 0; k < 6; ++k) portion(k);
+#endif
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) portion(k);
+    }
     SWEEP_STAMP(3, trc_diag);
     if (has_next) {
-        publish_block<BN>(a, ps, sm, b + 1);
+        publish_block<BN>(a, ps, sm);
         __syncwarp();
         if (ps.lane == 0) mbar_arrive(sy.bar);
     }
@@ -251,45 +287,40 @@ __device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], double (&g
     // ---- the three tiles nobody is waiting for
 #pragma unroll
     for (int tj = 0; tj < 4; ++tj)
-        if (tj != TJN) dmma(a[TIN ^ 1][tj][0], a[TIN ^ 1][tj][1], acs[TIN ^ 1], br[tj]);
+        if (tj != TJN) upd(TIN ^ 1, tj);
     SWEEP_STAMP(7, trc_other);
 #ifdef DAGMA_SWEEP_TRACE
     if (sy.trace >= 0) ++sy.trace;
 #endif
 }
 
-// a := a^{-1} on the leading 4*ceil(d/4) block (padding inside the last pivot block must
-// carry a unit diagonal); GEMM: g += (-cov) W over the same k range.
-// pinfo[k] = fraction-free pivots (see stage_pivot_block), k < 4*ceil(d/4).
+// a := a^{-1} on the leading 8*ceil(d/8) block (padding inside the last pivot block must
+// carry a unit diagonal).  pinfo[k] = fraction-free pivots (see stage_pivot_block), k < 8*ceil(d/8).
 // All warps must have passed a __syncthreads since the last use of the line buffers.
-template <bool GEMM>
-__device__ __forceinline__ void dmma_sweep(double (&a)[2][4][2], double (&g)[2][4][2], const DmmaPos& ps, double* sm,
-                                           int d, SweepSync& sy) {
-    const int nb = (d + 3) >> 2;
-    // the score GEMM first: 16 independent DMMA per k-block and warp, no serial chain -- this is
-    // the phase that keeps the FP64 pipe busy while the other CTA of the SM is inside its sweep
-    if constexpr (GEMM) {
-#pragma unroll 1
-        for (int kb = 0; kb < nb; ++kb) gemm_chunk(g, ps, sm, kb);
-    }
-    if (ps.wr == 0 && ps.wc == 0) stage_pivot_block<0, 0, 0>(a, ps, sm, 0, 0, [](int) {});
-    publish_block<0>(a, ps, sm, 0);
+__device__ __forceinline__ void dmma_sweep(double (&a)[2][4][2], const DmmaPos& ps, double* sm, int d, SweepSync& sy) {
+    const int nb = (d + DM_PB - 1) / DM_PB;
+    if (ps.wr == 0 && ps.wc == 0) stage_pivot_block<0, 0>(a, ps, sm, 0, 0, [](int) {});
+    publish_block<0>(a, ps, sm);
     __syncwarp();
     if (ps.lane == 0) mbar_arrive(sy.bar);
-    const int nbo = (nb + 7) >> 3;
-#pragma unroll 1
-    for (int bo = 0; bo < nbo; ++bo) {
-        const int left = nb - 8 * bo;
-        dmma_block_step<0, GEMM>(a, g, ps, sm, bo, nb, sy);
-        if (left > 1) dmma_block_step<1, GEMM>(a, g, ps, sm, bo, nb, sy);
-        if (left > 2) dmma_block_step<2, GEMM>(a, g, ps, sm, bo, nb, sy);
-        if (left > 3) dmma_block_step<3, GEMM>(a, g, ps, sm, bo, nb, sy);
-        if (left > 4) dmma_block_step<4, GEMM>(a, g, ps, sm, bo, nb, sy);
-        if (left > 5) dmma_block_step<5, GEMM>(a, g, ps, sm, bo, nb, sy);
-        if (left > 6) dmma_block_step<6, GEMM>(a, g, ps, sm, bo, nb, sy);
-        if (left > 7) dmma_block_step<7, GEMM>(a, g, ps, sm, bo, nb, sy);
-    }
+    dmma_block_step<0>(a, ps, sm, nb, sy);
+    if (nb > 1) dmma_block_step<1>(a, ps, sm, nb, sy);
+    if (nb > 2) dmma_block_step<2>(a, ps, sm, nb, sy);
+    if (nb > 3) dmma_block_step<3>(a, ps, sm, nb, sy);
+    if (nb > 4) dmma_block_step<4>(a, ps, sm, nb, sy);
+    if (nb > 5) dmma_block_step<5>(a, ps, sm, nb, sy);
+    if (nb > 6) dmma_block_step<6>(a, ps, sm, nb, sy);
+    if (nb > 7) dmma_block_step<7>(a, ps, sm, nb, sy);
     __syncthreads();
+}
+
+// g += (-cov) W over the k range 4*ceil(d/4): 16 independent DMMA per k-block and warp, no serial chain --
+// the phase that keeps the FP64 pipe busy while the other CTA of the SM is inside its sweep.  Kept apart
+// from the sweep so that g is not live (32 registers) while the sweep holds its line fragments.
+__device__ __forceinline__ void dmma_score_gemm(double (&g)[2][4][2], const DmmaPos& ps, const double* sm, int d) {
+    const int nk = (d + 3) >> 2;
+#pragma unroll 1
+    for (int kb = 0; kb < nk; ++kb) gemm_chunk(g, ps, sm, kb);
 }
 
 // ---------------------------------------------------------------- tensor memory (TMEM) scratch

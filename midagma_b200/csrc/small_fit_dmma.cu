@@ -235,15 +235,21 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                     const double dg = (r < d) ? s_use : 1.0;
                     a[ti][tj][0] = ((r == c) ? dg : 0.0) - w0 * w0;
                     a[ti][tj][1] = ((r == c + 1) ? dg : 0.0) - w1 * w1;
-                    const double2 nc = *reinterpret_cast<const double2*>(ncov + r * LD + c);
-                    g[ti][tj][0] = -nc.x;
-                    g[ti][tj][1] = -nc.y;
                 }
             }
 #ifdef DAGMA_SWEEP_TRACE
             sy.trace = (it == 50) ? 0 : -1;          // trace the sweep of iteration 51
 #endif
-            dmma_sweep<true>(a, g, ps, smem, d, sy);
+            dmma_sweep(a, ps, smem, d, sy);
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) {
+                    const double2 nc = *reinterpret_cast<const double2*>(ncov + ps.row(ti) * LD + ps.col(tj));
+                    g[ti][tj][0] = -nc.x;
+                    g[ti][tj][1] = -nc.y;
+                }
+            dmma_score_gemm(g, ps, smem, d);
             // now: a = M^{-T},  g = cov - cov W = cov (I - W),  pinfo[0..np) = pivots
 
             // ================= objective pieces (checkpoint / final) =================

@@ -19,7 +19,7 @@ lib.dagma_debug_sweep_trace.argtypes = [C.c_void_p]
 print("rc", lib.dagma_debug_sweep_trace(buf))
 t = np.array(buf[:], dtype=np.int64).reshape(64, 8)
 print("step: diag[wait_enter->wait_exit | ->tile_dmma | ->inverse | ->publish+arrive]   other[wait | work]   step period (diag exit-to-exit)")
-for b in range(15):
+for b in range(7):
     r = t[b]
-    nxt = t[b + 1][1] if b + 1 < 16 else 0
+    nxt = t[b + 1][1] if b + 1 < 8 else 0
     print(f"{b:2d}: {r[1]-r[0]:5d} {r[2]-r[1]:5d} {r[3]-r[2]:5d} {r[4]-r[3]:5d}   other: {r[6]-r[5]:5d} {r[7]-r[6]:5d}   period {nxt - r[1] if nxt else 0:6d}")
