@@ -119,6 +119,9 @@ struct TileStepArgs {
     double* Aout;        // n x n (ld = n), state after it (a different buffer: tiles are owned, not synchronised)
     int n, kb;
     double* pivots;      // fraction-free pivots (see stage_pivot_block), 4*ceil(n/4) entries
+#ifdef DAGMA_OUTER_TRACE
+    int trace_kb = -1;
+#endif
 };
 
 // One block step (block 64) of the single-level Gauss-Jordan as ONE launch without any inter-CTA
@@ -131,6 +134,34 @@ struct TileStepArgs {
 constexpr size_t TILE_STEP_SMEM_BYTES = DmmaSmem::bytes;
 
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }   // L2: written by other CTAs
+
+#ifdef DAGMA_OUTER_TRACE
+// debug build only: %globaltimer stamps (ns) of one two-level inversion, [outer step][slot]
+//   0 first CTA in   1 server 0: pivot tile updated   2 server 0: past the first barrier
+//   3..6 server 0: tile step kb done   7 last server done   8 last update item done   9 first CS' item starts
+//   10 last CS' item done   11 last CTA out   12 first update item starts   13 last R' item done
+//   16 + 5 kb + {0 loads, 1 sweep, 2 CS product, 3 R loaded, 4 tile written}: inside tile step kb of server 0
+__device__ unsigned long long g_outer_trace[16 * 40];
+__device__ int g_outer_step;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define OT_SET(slot) do { if (threadIdx.x == 0) g_outer_trace[g_outer_step * 40 + (slot)] = gtime(); } while (0)
+#define OT_MAX(slot) do { if ((threadIdx.x & 127) == 0) atomicMax(&g_outer_trace[g_outer_step * 40 + (slot)], gtime()); } while (0)
+#define OT_MIN(slot) do { if ((threadIdx.x & 127) == 0) atomicMin(&g_outer_trace[g_outer_step * 40 + (slot)], gtime()); } while (0)
+#define OT_TILE(slot) do { if (P.trace_kb >= 0) OT_SET(16 + 5 * P.trace_kb + (slot)); } while (0)
+__global__ void outer_trace_begin_kernel(int step) {
+    g_outer_step = step;
+    for (int q = 0; q < 40; ++q) g_outer_trace[step * 40 + q] = (q == 0 || q == 9 || q == 12) ? ~0ull : 0ull;
+}
+#else
+#define OT_SET(slot) do { } while (0)
+#define OT_MAX(slot) do { } while (0)
+#define OT_MIN(slot) do { } while (0)
+#define OT_TILE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj, double* psm, SweepSync& sy) {
     using S = DmmaSmem;
@@ -169,7 +200,9 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
         }
     }
     __syncthreads();
+    OT_TILE(0);
     dmma_sweep(a, ps, psm, kn, sy);
+    OT_TILE(1);
     if (bi == 0 && bj == 0 && tid < 4 * ((kn + 3) >> 2)) P.pivots[k0 + tid] = psm[S::pinfo + tid];
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
@@ -201,6 +234,7 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
         for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
     product(Cs, Qs);
     __syncthreads();                 // every warp is done reading Cpub and Q
+    OT_TILE(2);
     {
         double w[16];
 #pragma unroll
@@ -225,6 +259,7 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
             acc[ti][tj][1] = (r < n && c + 1 < n) ? ldcg(&P.Ain[(size_t)r * n + c + 1]) : 0.0;
         }
     __syncthreads();
+    OT_TILE(3);
     // ---- tile_out = tile_in + CS R
     product(Cs, Qs);
 #pragma unroll
@@ -235,6 +270,7 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
             if (r < n && c < n) P.Aout[(size_t)r * n + c] = acc[ti][tj][0];
             if (r < n && c + 1 < n) P.Aout[(size_t)r * n + c + 1] = acc[ti][tj][1];
         }
+    OT_TILE(4);
 }
 
 
@@ -284,12 +320,17 @@ __device__ __forceinline__ void server_role(const ServerArgs& P, int rank, unsig
     if (tid == 0) mbar_init(sy.bar, DM_NT / 32);
 
     server_barrier(P.counter, nctas, P.err);
+    if (rank == 0) OT_SET(2);
 
     // ---- the block steps
     double *in = P.buf0, *out = P.buf1;
     for (int kb = 0; kb < P.nblk; ++kb) {
         TileStepArgs T{in, out, n, kb, P.pivots};
+#ifdef DAGMA_OUTER_TRACE
+        T.trace_kb = (rank == 0) ? kb : -1;
+#endif
         tile_step(T, bi, bj, psm, sy);
+        if (rank == 0) OT_SET(3 + kb);
         if (kb + 1 < P.nblk) server_barrier(P.counter, nctas * (unsigned)(kb + 2), P.err);
         double* t = in;
         in = out;
@@ -315,16 +356,22 @@ struct OuterArgs {
     double* CSn; double* Rn;                // next:    d x kn1 (ld = kn1), kn1 x d (ld = d)
     int k1, kn1;                            // first column and width of the next block (kn1 = 0: last step)
     const double* Qn;                       // where the server leaves Q' (kn1 x kn1, ld = kn1)
-    unsigned* sync;                         // [0] server barrier [1] queue [2] err [3] col strip [4] row strip [5] server done
-    int* sm_busy;                           // [SM id] 1 while a server CTA runs there
+    unsigned* sync;                         // [0] server barrier [1] queue [2] err [3] col strip [4] row strip [5] server done [6] CS' queue
+    int* sm_busy;                           // [SM id] 1 while a server CTA runs there; [SM_SLOTS + SM id] CS' role claimed
     int nserver;
     ServerArgs srv;
 };
 constexpr int SM_SLOTS = 256;
-constexpr int OU_LDA = 36, OU_LDB = 68, OU_KC = 32;
-constexpr int OU_STAGE = NB * OU_LDA + OU_KC * OU_LDB;                  // doubles per pipeline stage
-static_assert(2 * OU_STAGE <= DmmaSmem::total, "the worker pipeline reuses the server's shared memory");
-constexpr size_t OUTER_SMEM_BYTES = DmmaSmem::bytes;
+// Worker side: a 256-thread CTA is TWO independent 128-thread tile engines (half = tid / 128), each the
+// main loop of gemm_f64_kernel<64, 64, 2, 2> (64 x 64 x 16 slabs, warp tile 32 x 32, 3-stage cp.async
+// pipeline, one barrier per k-slab -- a named barrier of the half).  Four engines per SM cover each
+// other's barrier / copy waits exactly as four CTAs of the stand-alone GEMM do.
+using EngT = GemmTile<64, 64, 2, 2>;
+constexpr int EN_NT = 128;
+constexpr int EN_STG = EngT::A_STAGE + EngT::B_STAGE;                   // doubles per pipeline stage
+constexpr int EN_SMEM = GSTAGES * EN_STG;                               // doubles per engine
+constexpr size_t OUTER_SMEM_BYTES = (2 * (size_t)EN_SMEM > (size_t)DmmaSmem::total ? 2 * (size_t)EN_SMEM : (size_t)DmmaSmem::total) * sizeof(double);
+static_assert(NB * NB <= EN_SMEM, "the split-K partial of a server tile is parked in the engine's stages");
 
 __device__ __forceinline__ unsigned smid() {
     unsigned r;
@@ -340,80 +387,94 @@ __device__ __forceinline__ bool wait_count(volatile unsigned* c, unsigned target
     __threadfence();
     return true;
 }
+__device__ __forceinline__ void half_sync(int half) {            // barrier of one 128-thread engine
+    asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(EN_NT) : "memory");
+}
 
-// acc += Am[r0.., 0..kdim) * Bm[0..kdim, c0..)  for one 64 x 64 tile (warp tile 16 x 32); operands come
-// through L2 (cp.async.cg) 32 k at a time, double buffered.  rmax / cmax: valid rows of Am / columns of Bm.
-__device__ __forceinline__ void tile_gemm(double (&acc)[2][4][2], const double* Am, int lda, const double* Bm, int ldb,
-                                          int r0, int c0, int rmax, int cmax, int kdim, double* psm, uint32_t sbase,
-                                          const DmmaPos& ps, int tid) {
-    const int nchunk = (kdim + OU_KC - 1) / OU_KC;
-    auto issue = [&](int ch) {
-        const int kc = ch * OU_KC;
-        const uint32_t sa = sbase + (uint32_t)((ch & 1) * OU_STAGE) * 8, sb = sa + (uint32_t)(NB * OU_LDA) * 8;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {          // A chunk: 64 rows x 32 k = 1024 16-byte copies
-            const int e = tid + q * DM_NT, r = e >> 4, c = (e & 15) * 2;
-            const bool ok = (r0 + r < rmax) && (kc + c < kdim);
-            cp_async16(sa + (r * OU_LDA + c) * 8, ok ? Am + (size_t)(r0 + r) * lda + kc + c : Am, ok);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {          // B chunk: 32 k x 64 cols
-            const int e = tid + q * DM_NT, r = e >> 5, c = (e & 31) * 2;
-            const bool ok = (kc + r < kdim) && (c0 + c < cmax);
-            cp_async16(sb + (r * OU_LDB + c) * 8, ok ? Bm + (size_t)(kc + r) * ldb + c0 + c : Bm, ok);
+struct EnginePos {          // thread of an engine: warp (wm, wn) of a 2 x 2 grid owns a 32 x 32 tile
+    int htid, lane, wm, wn, qr, qc;
+    __device__ __forceinline__ explicit EnginePos(int tid) {
+        htid = tid & (EN_NT - 1);
+        lane = htid & 31;
+        const int w = htid >> 5;
+        wm = w >> 1; wn = w & 1; qr = lane >> 2; qc = lane & 3;
+    }
+    __device__ __forceinline__ int row(int i) const { return 32 * wm + 8 * i + qr; }
+    __device__ __forceinline__ int col(int j) const { return 32 * wn + 8 * j + 2 * qc; }   // + e
+};
+
+// acc += Am[r0.., kbeg..kend) * Bm[kbeg..kend, c0..)  for one 64 x 64 tile; operands come through L2
+// (cp.async.cg).  rmax / cmax: valid rows of Am / columns of Bm.  lda, ldb even, bases 16-byte aligned.
+__device__ __forceinline__ void engine_gemm(double (&acc)[4][4][2], const double* Am, int lda, const double* Bm, int ldb,
+                                            int r0, int c0, int rmax, int cmax, int kbeg, int kend, double* esm,
+                                            const EnginePos& ep, int half) {
+    const uint32_t ebase = smem_u32(esm);
+    const int nk = (kend - kbeg + GBK - 1) / GBK;
+    auto issue = [&](int kt) {
+        if (kt < nk) {
+            const int st = kt % GSTAGES;
+            const uint32_t sa = ebase + (uint32_t)(st * EN_STG) * 8, sb = sa + (uint32_t)EngT::A_STAGE * 8;
+            const int k0 = kbeg + kt * GBK;
+            load_slab<NB, GBK, EN_NT>(sa, EngT::LDA_N, Am, lda, r0, k0, rmax, kend, true, ep.htid);
+            load_slab<GBK, NB, EN_NT>(sb, EngT::LDB_S, Bm, ldb, k0, c0, kend, cmax, true, ep.htid);
         }
         cp_async_commit();
     };
-    __syncthreads();                           // the stage buffers may still be read by the previous item
-    issue(0);
-    for (int ch = 0; ch < nchunk; ++ch) {
-        if (ch + 1 < nchunk) {
-            issue(ch + 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+    half_sync(half);                           // the stages may still be read by the previous item
+#pragma unroll
+    for (int st = 0; st < GSTAGES - 1; ++st) issue(st);
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<GSTAGES - 2>();
+        half_sync(half);                       // slab kt landed; slab kt-1 is free for reuse
+        issue(kt + GSTAGES - 1);
+        const double* As = esm + (kt % GSTAGES) * EN_STG;
+        const double* Bs = As + EngT::A_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < GBK; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[ep.row(i) * EngT::LDA_N + kk + ep.qc];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[(kk + ep.qc) * EngT::LDB_S + 32 * ep.wn + 8 * j + ep.qr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
-        __syncthreads();
-        const double* As = psm + (ch & 1) * OU_STAGE;
-        const double* Bs = As + NB * OU_LDA;
-#pragma unroll
-        for (int kk = 0; kk < OU_KC; kk += 4) {
-            double an[2], bw[4];
-#pragma unroll
-            for (int ti = 0; ti < 2; ++ti) an[ti] = As[ps.row(ti) * OU_LDA + kk + ps.qc];
-#pragma unroll
-            for (int tj = 0; tj < 4; ++tj) bw[tj] = Bs[(kk + ps.qc) * OU_LDB + 32 * ps.wc + 8 * tj + ps.qr];
-#pragma unroll
-            for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-                for (int tj = 0; tj < 4; ++tj) dmma(acc[ti][tj][0], acc[ti][tj][1], an[ti], bw[tj]);
-        }
-        __syncthreads();
     }
+    cp_async_wait<0>();
 }
 
 __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P) {
     extern __shared__ __align__(16) double psm[];
-    __shared__ unsigned s_tile;
+    __shared__ unsigned s_tile[2];
     const int tid = threadIdx.x;
-    const DmmaPos ps(tid);
-    const uint32_t sbase = smem_u32(psm);
+    const int half = tid >> 7;
+    const EnginePos ep(tid);
+    double* esm = psm + half * EN_SMEM;
     const int d = P.d, kn = P.kn, k1 = P.k1, kn1 = P.kn1;
     int* err = reinterpret_cast<int*>(P.sync + 2);
     volatile int* busy = P.sm_busy + (smid() % SM_SLOTS);
-    double acc[2][4][2];
+    double acc[4][4][2];
+    OT_MIN(0);
 
     auto load_acc = [&](const double* M, int ld, int r0, int c0, int rmax, int cmax) {
 #pragma unroll
-        for (int ti = 0; ti < 2; ++ti)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int tj = 0; tj < 4; ++tj) {
-                const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + ep.row(i), c = c0 + ep.col(j);
                 double2 v = make_double2(0.0, 0.0);
                 if (r < rmax && c < cmax) v = __ldcg(reinterpret_cast<const double2*>(M + (size_t)r * ld + c));
-                acc[ti][tj][0] = v.x;
-                acc[ti][tj][1] = v.y;
+                acc[i][j][0] = v.x;
+                acc[i][j][1] = v.y;
             }
+    };
+    auto zero_acc = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     };
 
     // ================= look-ahead: the CTAs of the next pivot block =================
@@ -421,35 +482,54 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P)
         if (tid == 0) *busy = 1;
         const int nb1 = P.srv.nblk, bi = blockIdx.x / nb1, bj = blockIdx.x % nb1;
         const int r0 = k1 + bi * NB, c0 = k1 + bj * NB;
-        // the pivot-block tile of the update itself; its result is both the new A tile and the server's input
-        load_acc(P.A, d, r0, c0, d, d);
-        tile_gemm(acc, P.CS, kn, P.R, d, r0, c0, d, d, kn, psm, sbase, ps, tid);
+        // the pivot-block tile of the update itself (its result is both the new A tile and the server's input),
+        // split over k between the two engines of the CTA: this product sits on the serial chain
+        const int kmid = ((kn / 2 + GBK - 1) / GBK) * GBK;
+        if (half == 0) load_acc(P.A, d, r0, c0, d, d);
+        else zero_acc();
+        engine_gemm(acc, P.CS, kn, P.R, d, r0, c0, d, d, half ? kmid : 0, half ? kn : kmid, esm, ep, half);
+        half_sync(half);
+        if (half == 1) {
 #pragma unroll
-        for (int ti = 0; ti < 2; ++ti)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int tj = 0; tj < 4; ++tj) {
-                const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
-                if (r < d && c < d) {
-                    const double2 v = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
-                    *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = v;
-                    *reinterpret_cast<double2*>(P.srv.buf0 + (size_t)(r - k1) * kn1 + (c - k1)) = v;
-                }
-            }
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<double2*>(esm + ep.row(i) * NB + ep.col(j)) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
         __syncthreads();
+        if (half == 0) {
+            const double* part = psm + EN_SMEM;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                    if (r < d && c < d) {
+                        const double2 q = *reinterpret_cast<const double2*>(part + ep.row(i) * NB + ep.col(j));
+                        const double2 v = make_double2(acc[i][j][0] + q.x, acc[i][j][1] + q.y);
+                        *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = v;
+                        *reinterpret_cast<double2*>(P.srv.buf0 + (size_t)(r - k1) * kn1 + (c - k1)) = v;
+                    }
+                }
+        }
+        __syncthreads();
+        if (blockIdx.x == 0) OT_SET(1);
         if (tid == 0) {                           // this tile belongs to the column strip and to the row strip
             __threadfence();
             atomicAdd(P.sync + 3, 1u);
             atomicAdd(P.sync + 4, 1u);
         }
         server_role(P.srv, blockIdx.x, (unsigned)P.nserver, psm);
+        OT_MAX(7);
         if (tid == 0) {
             __threadfence();
             atomicAdd(P.sync + 5, 1u);
             *busy = 0;
         }
+        __syncthreads();
     }
 
-    // ================= the queue =================
+    // ================= the queue (each engine pulls its own items) =================
     const int tn = (d + NB - 1) / NB;
     const int cb1 = k1 / NB, nk1 = (kn1 + NB - 1) / NB;          // block-column range of K'
     const int n_cs = tn * nk1 - nk1 * nk1;                       // column strip without the pivot block
@@ -457,18 +537,19 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P)
     const int n_rest = (tn - nk1) * (tn - nk1);
     const int n_upd = n_cs + n_rs + n_rest;
     const int n_csn = tn * nk1, n_rn = nk1 * tn;
-    const int n_items = n_upd + n_csn + n_rn;
+    const int n_items = n_upd + n_rn;
     auto outside = [&](int u) { return u < cb1 ? u : u + nk1; };  // u-th block index not in K'
     for (;;) {
-        __syncthreads();
-        if (tid == 0) {
+        half_sync(half);
+        if (ep.htid == 0) {
             while (*busy) __nanosleep(2000);
-            s_tile = atomicAdd(P.sync + 1, 1u);
+            s_tile[half] = atomicAdd(P.sync + 1, 1u);
         }
-        __syncthreads();
-        int t = (int)s_tile;
+        half_sync(half);
+        int t = (int)s_tile[half];
         if (t >= n_items) break;
         if (t < n_upd) {
+            OT_MIN(12);
             // ---- update tile
             int bi, bj, strip = 0;
             if (t < n_cs) { bi = outside(t / nk1); bj = cb1 + t % nk1; strip = 1; }
@@ -476,59 +557,33 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P)
             else { const int u = t - n_cs - n_rs; bi = outside(u / (tn - nk1)); bj = outside(u % (tn - nk1)); }
             const int r0 = bi * NB, c0 = bj * NB;
             load_acc(P.A, d, r0, c0, d, d);
-            tile_gemm(acc, P.CS, kn, P.R, d, r0, c0, d, d, kn, psm, sbase, ps, tid);
+            engine_gemm(acc, P.CS, kn, P.R, d, r0, c0, d, d, 0, kn, esm, ep, half);
 #pragma unroll
-            for (int ti = 0; ti < 2; ++ti)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int tj = 0; tj < 4; ++tj) {
-                    const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
-                    if (r < d && c < d) *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                    if (r < d && c < d) *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = make_double2(acc[i][j][0], acc[i][j][1]);
                 }
             if (strip) {
-                __syncthreads();
-                if (tid == 0) {
+                half_sync(half);
+                if (ep.htid == 0) {
                     __threadfence();
                     atomicAdd(P.sync + 2 + strip, 1u);
                 }
             }
-        } else if (t < n_upd + n_csn) {
-            // ---- CS' tile: rows of block bi, columns 64 jb.. of the next strip
-            const int u = t - n_upd, bi = u / nk1, jb = u % nk1;
-            if (tid == 0) (void)(wait_count(P.sync + 3, (unsigned)(tn * nk1), err) && wait_count(P.sync + 5, (unsigned)P.nserver, err));
-            __syncthreads();
-            const int r0 = bi * NB, c0 = jb * NB;
-#pragma unroll
-            for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-                for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
-            tile_gemm(acc, P.A + k1, d, P.Qn, kn1, r0, c0, d, kn1, kn1, psm, sbase, ps, tid);
-            const bool inK = (bi >= cb1) && (bi < cb1 + nk1);
-#pragma unroll
-            for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-                for (int tj = 0; tj < 4; ++tj) {
-                    const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
-                    if (r < d && c < kn1) {
-                        double2 v = make_double2(-acc[ti][tj][0], -acc[ti][tj][1]);
-                        if (inK) {
-                            const double2 q = __ldcg(reinterpret_cast<const double2*>(P.Qn + (size_t)(r - k1) * kn1 + c));
-                            v.x += q.x;
-                            v.y += q.y;
-                        }
-                        *reinterpret_cast<double2*>(P.CSn + (size_t)r * kn1 + c) = v;
-                    }
-                }
+            OT_MAX(8);
         } else {
             // ---- R' tile: rows 64 ib.. of the next row strip, columns of block bj
-            const int u = t - n_upd - n_csn, ib = u / tn, bj = u % tn;
-            if (tid == 0) (void)wait_count(P.sync + 4, (unsigned)(tn * nk1), err);
-            __syncthreads();
+            const int u = t - n_upd, ib = u / tn, bj = u % tn;
+            if (ep.htid == 0) (void)wait_count(P.sync + 4, (unsigned)(tn * nk1), err);
+            half_sync(half);
             const int c0 = bj * NB;
 #pragma unroll
-            for (int ti = 0; ti < 2; ++ti)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int tj = 0; tj < 4; ++tj) {
-                    const int rr = ib * NB + ps.row(ti), c = c0 + ps.col(tj);     // rr: row inside the strip
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = ib * NB + ep.row(i), c = c0 + ep.col(j);     // rr: row inside the strip
                     if (rr < kn1 && c < d) {
                         double2 v = __ldcg(reinterpret_cast<const double2*>(P.A + (size_t)(k1 + rr) * d + c));
                         if (c == k1 + rr) v.x += 1.0;
@@ -536,9 +591,78 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P)
                         *reinterpret_cast<double2*>(P.Rn + (size_t)rr * d + c) = v;
                     }
                 }
+            OT_MAX(13);
         }
     }
+
+    // ================= CS' = -(A[:,K'] - E) Q' : the tail of the step, on the serial chain =================
+    // These tiles can only start when the look-ahead is done, i.e. when most engines have run out of work:
+    // ONE CTA per SM (the first to get here) takes them from a second queue and computes each with both of
+    // its engines (split over k), so the 64 nk1-by-tn tiles spread over all SMs instead of piling up on the
+    // SMs whose engines happened to finish first.
+    __syncthreads();
+    if (kn1 > 0) {
+        if (tid == 0) s_tile[0] = (atomicExch(reinterpret_cast<int*>(P.sm_busy) + SM_SLOTS + (smid() % SM_SLOTS), 1) == 0) ? 1u : 0u;
+        __syncthreads();
+        const bool claimed = s_tile[0] != 0u;
+        __syncthreads();
+        const int kmid = ((kn1 / 2 + GBK - 1) / GBK) * GBK;
+        while (claimed) {
+            if (tid == 0) s_tile[0] = atomicAdd(P.sync + 6, 1u);
+            __syncthreads();
+            const int u = (int)s_tile[0];
+            __syncthreads();
+            if (u >= n_csn) break;
+            const int bi = u / nk1, jb = u % nk1;
+            if (tid == 0) (void)(wait_count(P.sync + 3, (unsigned)(tn * nk1), err) && wait_count(P.sync + 5, (unsigned)P.nserver, err));
+            __syncthreads();
+            OT_MIN(9);
+            const int r0 = bi * NB, c0 = jb * NB;
+            zero_acc();
+            engine_gemm(acc, P.A + k1, d, P.Qn, kn1, r0, c0, d, kn1, half ? kmid : 0, half ? kn1 : kmid, esm, ep, half);
+            half_sync(half);
+            if (half == 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<double2*>(esm + ep.row(i) * NB + ep.col(j)) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+            __syncthreads();
+            if (half == 0) {
+                const double* part = psm + EN_SMEM;
+                const bool inK = (bi >= cb1) && (bi < cb1 + nk1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                        if (r < d && c < kn1) {
+                            const double2 q2 = *reinterpret_cast<const double2*>(part + ep.row(i) * NB + ep.col(j));
+                            double2 v = make_double2(-(acc[i][j][0] + q2.x), -(acc[i][j][1] + q2.y));
+                            if (inK) {
+                                const double2 q = __ldcg(reinterpret_cast<const double2*>(P.Qn + (size_t)(r - k1) * kn1 + c));
+                                v.x += q.x;
+                                v.y += q.y;
+                            }
+                            *reinterpret_cast<double2*>(P.CSn + (size_t)r * kn1 + c) = v;
+                        }
+                    }
+            }
+            __syncthreads();
+            OT_MAX(10);
+        }
+    }
+    OT_MAX(11);
 }
+
+#ifdef DAGMA_OUTER_TRACE
+}  // namespace dagma
+extern "C" int dagma_debug_outer_trace(unsigned long long* out_host) {
+    return (int)cudaMemcpyFromSymbol(out_host, dagma::g_outer_trace, sizeof(unsigned long long) * 16 * 40);
+}
+namespace dagma {
+#endif
 
 // per-block partial minima of the inverse (grid-stride; finished by inv_finish_kernel)
 __global__ void __launch_bounds__(256) min_partial_kernel(const double* __restrict__ Minv, size_t total,
@@ -632,7 +756,7 @@ struct LargeWs {                   // offsets in doubles into the caller's works
         Pbuf2 = Pbuf + (size_t)OB * OB;
         pmin = Pbuf2 + (size_t)OB * OB;
         sync = pmin + MIN_PARTIALS + 8;          // barrier counter, tile queue, error flag, per-SM busy flags
-        total = sync + 64 + SM_SLOTS / 2;
+        total = sync + 64 + SM_SLOTS;
     }
 };
 static size_t large_ws_bytes(int d) { return LargeWs(d).total * sizeof(double); }
@@ -774,7 +898,10 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
             const int k1 = k0 + OB, kn1 = more ? ((d - k1) < OB ? (d - k1) : OB) : 0;
             const int nblk1 = (kn1 + NB - 1) / NB;
             double* Qn = (nblk1 & 1) ? Pbuf2 : Pbuf;
-            DAGMA_CUDA_OK(cudaMemsetAsync(sync_words, 0, 32 + SM_SLOTS * sizeof(int), stream));
+            DAGMA_CUDA_OK(cudaMemsetAsync(sync_words, 0, 32 + 2 * SM_SLOTS * sizeof(int), stream));
+#ifdef DAGMA_OUTER_TRACE
+            outer_trace_begin_kernel<<<1, 1, 0, stream>>>(ob);
+#endif
             OuterArgs OA{Mw, d, CSa, Ra, kn, CSb, Rb, k1, kn1, Qn, sync_words, reinterpret_cast<int*>(sync_words + 8),
                          nblk1 * nblk1,
                          ServerArgs{Pbuf, Pbuf2, kn1, nblk1, piv + k1, sync_words, reinterpret_cast<int*>(sync_words + 2)}};
