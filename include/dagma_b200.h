@@ -122,6 +122,16 @@ int dagma_logdet_inv_ws_f64(dagma_stream_t stream, int d, double s, const double
                             double* grad_dev, int ldo, double* min_entry_dev, int* info_dev,
                             double* ws_dev, size_t ws_bytes);
 
+/* the same inverse with a "rider": gc = ga @ gb (all d x d, row-major, ld = d), an independent GEMM of the same
+ * iteration (cov @ W of the l2 score, src/dagma/linear.py:86, 244).  For d > 256 both are ONE dependency-driven
+ * persistent kernel: the rider's 64 x 64 x 256 tiles fill the time the engines would otherwise spend waiting for
+ * the serial pivot chain of the blocked inverse.  Smaller d: the two run back to back.                       */
+int dagma_logdet_inv_gemm_ws_f64(dagma_stream_t stream, int d, double s, const double* a_dev, int lda,
+                                 int square_input, double* logabsdet_dev, double* h_dev, double* minv_dev,
+                                 double* grad_dev, int ldo, double* min_entry_dev, int* info_dev,
+                                 double* ws_dev, size_t ws_bytes, const double* ga_dev, const double* gb_dev,
+                                 double* gc_dev);
+
 /* device-resident iteration state (19 doubles): mu, s, lr, lambda1, beta1, beta2,
  * beta1^it (hi, lo), beta2^it (hi, lo), logabsdet, h, min_entry, score_acc, l1_acc,
  * loss_acc, gscale, then int32 it, halted, info, pad.                                   */
@@ -207,6 +217,9 @@ int dagma_bench_fp64_dmma_tiles(dagma_stream_t stream, int ctas, int threads, in
 /* dependent-issue latencies (cycles / op, one warp): out_dev[0..8] = DFMA, DMMA via C, DMMA via A,
  * 64-bit SHFL, MUFU.RCP64H + DFMA, LDS chase, STS/sync/LDS round trip, DADD, DMUL (16 doubles) */
 int dagma_bench_latency(dagma_stream_t stream, double* out_dev);
+/* serial chain of the on-chip sweep in isolation: out[0] clk per 8 x 8 pivot-block inversion, out[1] with the
+   diagonal warp's DMMAs interleaved, out[2] max |P - inv(inv(P))| */
+int dagma_bench_stage(dagma_stream_t stream, double* out_dev);
 
 #ifdef __cplusplus
 }

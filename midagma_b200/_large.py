@@ -122,9 +122,21 @@ class LargeLinearEngine:
             self.T.data_ptr(), self.cov.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), ptr(self.mask_exc),
             ptr(self.mask_inc)), "dagma_linear_update_f64")
 
+    def _inverse_and_score(self, s: float):
+        """l2: the inverse of sI - W o W and T = cov @ W as one call (one persistent kernel for d > 256: the GEMM
+        tiles fill the time the engines would spend waiting for the pivot chain of the inverse)."""
+        _lib.check(self.lib.dagma_logdet_inv_gemm_ws_f64(
+            _lib.stream_ptr(), self.d, float(s), self.W.data_ptr(), self.d, 1, self._sptr(F_LAD), self._sptr(F_H),
+            self.Minv.data_ptr(), None, self.d, self._sptr(F_MIN), self._iptr(I_INFO), self.ws.data_ptr(),
+            self.ws.numel() * 8, self.cov.data_ptr(), self.W.data_ptr(), self.T.data_ptr()),
+            "dagma_logdet_inv_gemm_ws_f64")
+
     def _iteration(self, s: float):
-        self._inverse(s)
-        self._score_T()
+        if self.loss_type == "l2":
+            self._inverse_and_score(s)
+        else:
+            self._inverse(s)
+            self._score_T()
         self._update()
 
     def _replay(self, s: float, n: int):

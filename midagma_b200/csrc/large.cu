@@ -152,6 +152,12 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define OT_MAX(slot) do { if ((threadIdx.x & 127) == 0) atomicMax(&g_outer_trace[g_outer_step * 40 + (slot)], gtime()); } while (0)
 #define OT_MIN(slot) do { if ((threadIdx.x & 127) == 0) atomicMin(&g_outer_trace[g_outer_step * 40 + (slot)], gtime()); } while (0)
 #define OT_TILE(slot) do { if (P.trace_kb >= 0) OT_SET(16 + 5 * P.trace_kb + (slot)); } while (0)
+#define FT_SET(k, slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_outer_trace[(k) * 40 + (slot)] = gtime(); } while (0)
+#define FT_MAX(k, slot) do { if ((threadIdx.x & 127) == 0) atomicMax(&g_outer_trace[(k) * 40 + (slot)], gtime()); } while (0)
+#define FT_MIN(k, slot) do { if ((threadIdx.x & 127) == 0) atomicMin(&g_outer_trace[(k) * 40 + (slot)], gtime()); } while (0)
+__global__ void flow_trace_begin_kernel() {
+    for (int q = 0; q < 16 * 40; ++q) g_outer_trace[q] = (q % 40 == 12) ? ~0ull : 0ull;
+}
 __global__ void outer_trace_begin_kernel(int step) {
     g_outer_step = step;
     for (int q = 0; q < 40; ++q) g_outer_trace[step * 40 + q] = (q == 0 || q == 9 || q == 12) ? ~0ull : 0ull;
@@ -161,6 +167,9 @@ __global__ void outer_trace_begin_kernel(int step) {
 #define OT_MAX(slot) do { } while (0)
 #define OT_MIN(slot) do { } while (0)
 #define OT_TILE(slot) do { } while (0)
+#define FT_SET(k, slot) do { } while (0)
+#define FT_MAX(k, slot) do { } while (0)
+#define FT_MIN(k, slot) do { } while (0)
 #endif
 
 __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj, double* psm, SweepSync& sy) {
@@ -302,7 +311,8 @@ __device__ __forceinline__ void server_barrier(unsigned* counter, unsigned targe
         atomicAdd(counter, 1u);
         unsigned spins = 0;
         while (*((volatile unsigned*)counter) < target) {
-            if (++spins > (1u << 28)) { *err = 1; break; }
+            if (*(volatile int*)err) break;
+            if (++spins > (1u << 26)) { *err = 1; break; }
         }
         __threadfence();
     }
@@ -656,6 +666,412 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P)
     OT_MAX(11);
 }
 
+// =====================================================================================================
+// Two-level inverse as ONE dependency-driven persistent kernel ("flow" kernel).
+//
+// The multi-kernel version above ends every outer step with a tail that nothing overlaps (CS' of the next
+// step can only start when the look-ahead inversion is done; then kernel exit, launch gap, first slabs of
+// the next kernel).  Here the whole inversion is one launch:
+//   * the chain team (the 16 lowest CTAs, an SM each) runs the serial chain for ALL pivot blocks:
+//       CS_k rows of K_{k+1}  ->  pivot block P_{k+1} = A[K',K'] + CS_k[K',:] A[K_k,K']  ->  4 tile steps -> Q_{k+1}
+//     waiting only for the three groups of tiles it reads;
+//   * every other engine (two per CTA, four per SM) pulls items from one queue that lists, step by step,
+//       R_k tiles (row copies + E^T), the remaining CS_k tiles, the update tiles A[I,J] += CS_k[I,:] R_k[:,J]
+//     (column strip and row strip of K_{k+1} first), and waits for exactly what the item reads:
+//     Q_k, per-tile version counters, per-block-row / per-block-column "CS / R ready" counters.
+// Dependencies always point to earlier queue items or to the chain, and the chain's own dependencies are earlier
+// queue items, so an item that is being waited for is always held by a running engine: progress does not need
+// all CTAs to be co-resident (the chain team is: lowest block indices).  Every wait is bounded.
+constexpr int FL_MAX_OB = 32, FL_MAX_TN = 64, FL_NSRV = (256 / NB) * (256 / NB);
+struct FlowCtr {            // word offsets into the counter block (unsigned)
+    static constexpr int queue = 0, err = 1, bar = 2;
+    static constexpr int q_done = 8;                                   // [k]  servers that left block k's inversion
+    static constexpr int upd_done = q_done + FL_MAX_OB;                // [k]
+    static constexpr int cs_done = upd_done + FL_MAX_OB;               // [k]
+    static constexpr int cs_rows = 128;                                // [k][bi]  CS_k tiles ready in block row bi
+    static constexpr int r_cols = cs_rows + FL_MAX_OB * FL_MAX_TN;     // [k][bj]  R_k tiles ready in block column bj
+    static constexpr int tile_ver = r_cols + FL_MAX_OB * FL_MAX_TN;    // [bi][bj] outer steps applied to the tile
+    static constexpr int fill_ver = tile_ver + FL_MAX_TN * FL_MAX_TN;  // [bi][bj] k-chunks of the rider GEMM applied to the tile
+    static constexpr int busy = fill_ver + FL_MAX_TN * FL_MAX_TN;      // [SM id]
+    static constexpr int total = busy + SM_SLOTS;
+};
+struct FlowArgs {
+    double* A; int d, nob, tn;
+    double* CS[2]; double* R[2];            // per step parity: d x kn (ld = kn), kn x d (ld = d)
+    double* X[2]; double* Y[2];             // per block parity: pivot block ping-pong (ld = kn)
+    double* pivots;
+    unsigned* ctr;
+    // optional rider: gC = gA gB (all d x d, ld = d), an independent GEMM cut into the same 64 x 64 x 256 items
+    // and queued ahead of each outer step's own items, so that it fills the time the engines would otherwise
+    // spend waiting for the serial chain (the score GEMM cov @ W of the same iteration)
+    const double* gA; const double* gB; double* gC;
+    int sleep_coresident;                   // 1: the CTA that shares an SM with a chain-team CTA sleeps while the chain runs
+    int item_base[FL_MAX_OB + 1];           // first queue index of step k
+};
+
+__device__ __forceinline__ bool flow_wait_ge(volatile unsigned* c, unsigned target, unsigned* err, unsigned code) {
+    unsigned spins = 0;
+    while (*c < target) {
+        __nanosleep(200);
+        if (*(volatile unsigned*)err) return false;              // somebody gave up: drain without waiting
+        if (++spins > (1u << 23)) { *err = code; return false; }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(DM_NT, 2) flow_inverse_kernel(const FlowArgs P) {
+    extern __shared__ __align__(16) double psm[];
+    __shared__ unsigned s_tile[2];
+    const int tid = threadIdx.x;
+    const int half = tid >> 7;
+    const EnginePos ep(tid);
+    double* esm = psm + half * EN_SMEM;
+    const int d = P.d, tn = P.tn, nob = P.nob;
+    constexpr int OB = 256, NKB = OB / NB;
+    unsigned* ctr = P.ctr;
+    unsigned* err = ctr + FlowCtr::err;
+    volatile unsigned* vctr = ctr;
+    volatile unsigned* busy = ctr + FlowCtr::busy + (smid() % SM_SLOTS);
+    double acc[4][4][2];
+    auto kn_of = [&](int k) { return min(OB, d - k * OB); };
+    auto nk_of = [&](int k) { return (kn_of(k) + NB - 1) / NB; };
+    auto n_upd_of = [&](int k) { const int n1 = (k + 1 < nob) ? nk_of(k + 1) : 0; return (unsigned)(tn * tn - n1 * n1); };
+    auto zero_acc = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    };
+    auto load_acc = [&](const double* M, int ld, int r0, int c0, int rmax, int cmax) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                double2 v = make_double2(0.0, 0.0);
+                if (r < rmax && c < cmax) v = __ldcg(reinterpret_cast<const double2*>(M + (size_t)r * ld + c));
+                acc[i][j][0] = v.x;
+                acc[i][j][1] = v.y;
+            }
+    };
+    // both engines of the CTA: acc(half 0) += partial(half 1) through the shared memory of engine 1
+    auto combine_halves = [&]() {
+        half_sync(half);
+        if (half == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<double2*>(esm + ep.row(i) * NB + ep.col(j)) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+        __syncthreads();
+        if (half == 0) {
+            const double* part = psm + EN_SMEM;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 q = *reinterpret_cast<const double2*>(part + ep.row(i) * NB + ep.col(j));
+                    acc[i][j][0] += q.x;
+                    acc[i][j][1] += q.y;
+                }
+        }
+    };
+
+    // ================= the chain team =================
+    if ((int)blockIdx.x < FL_NSRV) {
+        const int rank = blockIdx.x;
+        if (tid == 0 && P.sleep_coresident) *busy = 1;
+        unsigned bar_target = 0;
+        auto team_barrier = [&]() {
+            bar_target += FL_NSRV;
+            server_barrier(ctr + FlowCtr::bar, bar_target, reinterpret_cast<int*>(err));
+        };
+        SweepSync sy{smem_u32(psm + DmmaSmem::mbar), 0u};
+        for (int kk = 0; kk < nob; ++kk) {                 // block kk is inverted here
+            const int knk = kn_of(kk), nkk = nk_of(kk), cbk = kk * NKB, k1 = kk * OB;
+            double* X = P.X[kk & 1];
+            double* Y = P.Y[kk & 1];
+            if (kk == 0) {
+                // P_0: plain copy of the leading tiles
+                for (int u = rank; u < nkk * nkk; u += FL_NSRV) {
+                    const int bi = u / nkk, bj = u % nkk;
+                    if (half == 0) {
+                        load_acc(P.A, d, bi * NB, bj * NB, d, d);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int r = bi * NB + ep.row(i), c = bj * NB + ep.col(j);
+                                if (r < knk && c < knk) *reinterpret_cast<double2*>(X + (size_t)r * knk + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+                            }
+                    }
+                }
+            } else {
+                const int k = kk - 1, kn = kn_of(k), nk = nk_of(k), cb = k * NKB, k0 = k * OB;
+                double* CSk = P.CS[k & 1];
+                // ---- wait for what the chain reads: Q_k, tiles (K', K_k), (K_k, K'), (K', K') at version k,
+                //      and the previous users of the buffers
+                {   // one wait per thread: the counters are almost always there already, and a poll is an L2 round trip
+                    const int n1 = nkk * nk, n2 = n1 + nkk, n3 = n2 + nkk * nkk;
+                    if (tid == 0) flow_wait_ge(vctr + FlowCtr::q_done + k, FL_NSRV, err, 10);
+                    else if (tid == 1 && k >= 2) flow_wait_ge(vctr + FlowCtr::upd_done + (k - 2), n_upd_of(k - 2), err, 11);
+                    else if (tid == 2 && k >= 1) flow_wait_ge(vctr + FlowCtr::cs_done + (k - 1), (unsigned)(tn * nk_of(k - 1)), err, 12);
+                    else if (tid >= 32 && tid < 32 + n3) {
+                        const int q = tid - 32;
+                        if (q < n1) flow_wait_ge(vctr + FlowCtr::tile_ver + (cbk + q / nk) * FL_MAX_TN + cb + q % nk, (unsigned)k, err, 13);
+                        else if (q < n2) flow_wait_ge(vctr + FlowCtr::r_cols + k * FL_MAX_TN + cbk + (q - n1), (unsigned)nk, err, 14);
+                        else flow_wait_ge(vctr + FlowCtr::tile_ver + (cbk + (q - n2) / nkk) * FL_MAX_TN + cbk + (q - n2) % nkk, (unsigned)k, err, 15);
+                    }
+                    __threadfence();
+                }
+                __syncthreads();
+                FT_SET(kk, 0);
+                const double* Qk = (nk & 1) ? P.Y[k & 1] : P.X[k & 1];
+                const int kmid = ((kn / 2 + GBK - 1) / GBK) * GBK;
+                // ---- CS_k rows of K': tile (bi, jb) = -A[K'_bi, K_k] Q_k[:, jb]
+                for (int u = rank; u < nkk * nk; u += FL_NSRV) {
+                    const int bi = u / nk, jb = u % nk;
+                    const int r0 = k1 + bi * NB, c0 = jb * NB;
+                    zero_acc();
+                    engine_gemm(acc, P.A + k0, d, Qk, kn, r0, c0, d, kn, half ? kmid : 0, half ? kn : kmid, esm, ep, half);
+                    combine_halves();
+                    if (half == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                                if (r < d && c < kn) *reinterpret_cast<double2*>(CSk + (size_t)r * kn + c) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+                            }
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        __threadfence();
+                        atomicAdd(ctr + FlowCtr::cs_rows + k * FL_MAX_TN + cbk + bi, 1u);
+                        atomicAdd(ctr + FlowCtr::cs_done + k, 1u);
+                    }
+                }
+                team_barrier();
+                FT_SET(kk, 1);
+                // ---- P_{kk} tile (bi, bj) = A[K'_bi, K'_bj] + CS_k[K'_bi, :] R_k[:, K'_bj]   (R_k: A[K_k, K'] is overwritten by step k)
+                for (int u = rank; u < nkk * nkk; u += FL_NSRV) {
+                    const int bi = u / nkk, bj = u % nkk;
+                    const int r0 = k1 + bi * NB, c0 = k1 + bj * NB;
+                    if (half == 0) load_acc(P.A, d, r0, c0, d, d);
+                    else zero_acc();
+                    engine_gemm(acc, CSk, kn, P.R[k & 1], d, r0, c0, d, d, half ? kmid : 0, half ? kn : kmid, esm, ep, half);
+                    combine_halves();
+                    if (half == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                                if (r < d && c < d) {
+                                    const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+                                    *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = v;
+                                    *reinterpret_cast<double2*>(X + (size_t)(r - k1) * knk + (c - k1)) = v;
+                                }
+                            }
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        __threadfence();
+                        atomicAdd(ctr + FlowCtr::tile_ver + (cbk + bi) * FL_MAX_TN + cbk + bj, 1u);
+                    }
+                }
+            }
+            team_barrier();
+            // ---- the inversion of block kk: nkk tile steps, ping-pong X -> Y -> X ...
+            if (tid == 0) mbar_init(sy.bar, DM_NT / 32);      // the engines' slabs overwrite it between blocks
+            sy.phase = 0u;
+            __syncthreads();
+            FT_SET(kk, 2);
+            double *in = X, *out = Y;
+            for (int kb = 0; kb < nkk; ++kb) {
+                if (rank < nkk * nkk) {
+                    TileStepArgs T{in, out, knk, kb, P.pivots + k1};
+                    tile_step(T, rank / nkk, rank % nkk, psm, sy);
+                }
+                if (kb + 1 < nkk) team_barrier();
+                double* t = in;
+                in = out;
+                out = t;
+            }
+            __syncthreads();
+            FT_SET(kk, 3);
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(ctr + FlowCtr::q_done + kk, 1u);
+            }
+            if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sy.bar) : "memory");
+            __syncthreads();
+        }
+        if (tid == 0) {
+            __threadfence();
+            *busy = 0;
+        }
+        __syncthreads();
+    }
+
+    // ================= the queue (each engine pulls its own items) =================
+    const int n_total = P.item_base[nob];
+    int kstep = 0;
+    for (;;) {
+        half_sync(half);
+        if (ep.htid == 0) {
+            unsigned spins = 0;
+            while (P.sleep_coresident && *busy) {
+                __nanosleep(2000);
+                if (++spins > (1u << 22)) { *err = 20; break; }
+            }
+            s_tile[half] = atomicAdd(ctr + FlowCtr::queue, 1u);
+        }
+        half_sync(half);
+        const int t = (int)s_tile[half];
+        if (t >= n_total) break;
+        while (t >= P.item_base[kstep + 1]) ++kstep;
+        const int k = kstep;
+        int u0 = t - P.item_base[k];
+        const int kn = kn_of(k), nk = nk_of(k), cb = k * NKB, k0 = k * OB;
+        const bool more = k + 1 < nob;
+        const int nk1 = more ? nk_of(k + 1) : 0, cb1 = (k + 1) * NKB;
+        double* CSk = P.CS[k & 1];
+        double* Rk = P.R[k & 1];
+        const int n_fill = (P.gC != nullptr) ? tn * tn : 0;
+        const int n_r = nk * tn, n_cs = (tn - nk1) * nk;
+        auto outside = [&](int v) { return v < cb1 ? v : v + nk1; };   // v-th block index not in K'
+        if (u0 < n_fill) {
+            // ---- rider tile: gC[I,J] (+)= gA[I, Kc] gB[Kc, J], k-chunk c = k
+            const int bi = u0 / tn, bj = u0 % tn;
+            if (ep.htid == 0 && k > 0) {
+                flow_wait_ge(vctr + FlowCtr::fill_ver + bi * FL_MAX_TN + bj, (unsigned)k, err, 29);
+                __threadfence();
+            }
+            half_sync(half);
+            const int r0 = bi * NB, c0 = bj * NB;
+            if (k > 0) load_acc(P.gC, d, r0, c0, d, d);
+            else zero_acc();
+            engine_gemm(acc, P.gA, d, P.gB, d, r0, c0, d, d, k0, k0 + kn, esm, ep, half);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                    if (r < d && c < d) *reinterpret_cast<double2*>(P.gC + (size_t)r * d + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+            half_sync(half);
+            if (ep.htid == 0) {
+                __threadfence();
+                atomicAdd(ctr + FlowCtr::fill_ver + bi * FL_MAX_TN + bj, 1u);
+            }
+            continue;
+        }
+        u0 -= n_fill;
+        if (u0 < n_r) {
+            // ---- R_k tile: rows 64 ib.. of the row strip K_k, columns of block bj (+ E^T)
+            const int ib = u0 / tn, bj = u0 % tn;
+            if (ep.htid < 2) {
+                if (ep.htid == 0) flow_wait_ge(vctr + FlowCtr::tile_ver + (cb + ib) * FL_MAX_TN + bj, (unsigned)k, err, 21);
+                else if (k >= 2) flow_wait_ge(vctr + FlowCtr::upd_done + (k - 2), n_upd_of(k - 2), err, 22);
+                __threadfence();
+            }
+            half_sync(half);
+            const int c0 = bj * NB;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = ib * NB + ep.row(i), c = c0 + ep.col(j);     // rr: row inside the strip
+                    if (rr < kn && c < d) {
+                        double2 v = __ldcg(reinterpret_cast<const double2*>(P.A + (size_t)(k0 + rr) * d + c));
+                        if (c == k0 + rr) v.x += 1.0;
+                        if (c + 1 == k0 + rr) v.y += 1.0;
+                        *reinterpret_cast<double2*>(Rk + (size_t)rr * d + c) = v;
+                    }
+                }
+            half_sync(half);
+            if (ep.htid == 0) {
+                __threadfence();
+                atomicAdd(ctr + FlowCtr::r_cols + k * FL_MAX_TN + bj, 1u);
+            }
+        } else if (u0 < n_r + n_cs) {
+            // ---- CS_k tile outside the rows of K': -(A[I, K_k] - [I in K_k] I) Q_k
+            const int u = u0 - n_r, bi = more ? outside(u / nk) : u / nk, jb = u % nk;
+            if (ep.htid < 8) {
+                if (ep.htid == 0) flow_wait_ge(vctr + FlowCtr::q_done + k, FL_NSRV, err, 23);
+                else if (ep.htid == 1) { if (k >= 2) flow_wait_ge(vctr + FlowCtr::upd_done + (k - 2), n_upd_of(k - 2), err, 24); }
+                else if (ep.htid - 2 < nk) flow_wait_ge(vctr + FlowCtr::tile_ver + bi * FL_MAX_TN + cb + (ep.htid - 2), (unsigned)k, err, 25);
+                __threadfence();
+            }
+            half_sync(half);
+            const double* Qk = (nk & 1) ? P.Y[k & 1] : P.X[k & 1];
+            const int r0 = bi * NB, c0 = jb * NB;
+            zero_acc();
+            engine_gemm(acc, P.A + k0, d, Qk, kn, r0, c0, d, kn, 0, kn, esm, ep, half);
+            const bool inK = (bi >= cb) && (bi < cb + nk);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                    if (r < d && c < kn) {
+                        double2 v = make_double2(-acc[i][j][0], -acc[i][j][1]);
+                        if (inK) {
+                            const double2 q = __ldcg(reinterpret_cast<const double2*>(Qk + (size_t)(r - k0) * kn + c));
+                            v.x += q.x;
+                            v.y += q.y;
+                        }
+                        *reinterpret_cast<double2*>(CSk + (size_t)r * kn + c) = v;
+                    }
+                }
+            half_sync(half);
+            if (ep.htid == 0) {
+                __threadfence();
+                atomicAdd(ctr + FlowCtr::cs_rows + k * FL_MAX_TN + bi, 1u);
+                atomicAdd(ctr + FlowCtr::cs_done + k, 1u);
+            }
+        } else {
+            // ---- update tile A[I,J] += CS_k[I,:] R_k[:,J]; column strip of K' first, then its row strip, then the rest
+            const int u = u0 - n_r - n_cs;
+            int bi, bj;
+            if (!more) { bi = u / tn; bj = u % tn; }
+            else {
+                const int n_c = (tn - nk1) * nk1, n_rw = nk1 * (tn - nk1);
+                if (u < n_c) { bi = outside(u / nk1); bj = cb1 + u % nk1; }
+                else if (u < n_c + n_rw) { const int v = u - n_c; bi = cb1 + v / (tn - nk1); bj = outside(v % (tn - nk1)); }
+                else { const int v = u - n_c - n_rw; bi = outside(v / (tn - nk1)); bj = outside(v % (tn - nk1)); }
+            }
+            if (ep.htid < 3) {
+                if (ep.htid == 0) flow_wait_ge(vctr + FlowCtr::cs_rows + k * FL_MAX_TN + bi, (unsigned)nk, err, 26);
+                else if (ep.htid == 1) flow_wait_ge(vctr + FlowCtr::r_cols + k * FL_MAX_TN + bj, (unsigned)nk, err, 27);
+                else flow_wait_ge(vctr + FlowCtr::tile_ver + bi * FL_MAX_TN + bj, (unsigned)k, err, 28);
+                __threadfence();
+            }
+            half_sync(half);
+            FT_MIN(k, 12);
+            const int r0 = bi * NB, c0 = bj * NB;
+            load_acc(P.A, d, r0, c0, d, d);
+            engine_gemm(acc, CSk, kn, Rk, d, r0, c0, d, d, 0, kn, esm, ep, half);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                    if (r < d && c < d) *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+            half_sync(half);
+            if (ep.htid == 0) {
+                __threadfence();
+                atomicAdd(ctr + FlowCtr::tile_ver + bi * FL_MAX_TN + bj, 1u);
+                atomicAdd(ctr + FlowCtr::upd_done + k, 1u);
+            }
+            FT_MAX(k, 8);
+        }
+    }
+}
+
 #ifdef DAGMA_OUTER_TRACE
 }  // namespace dagma
 extern "C" int dagma_debug_outer_trace(unsigned long long* out_host) {
@@ -741,7 +1157,7 @@ static int outer_block() {
 }
 
 struct LargeWs {                   // offsets in doubles into the caller's workspace
-    size_t M, CS, Rbuf, CS2, Rbuf2, piv, Pbuf, Pbuf2, pmin, sync, total;
+    size_t M, CS, Rbuf, CS2, Rbuf2, piv, Pbuf, Pbuf2, Pbuf3, Pbuf4, pmin, sync, flow, total;
     explicit LargeWs(int d) {
         const int OB = outer_block();
         const size_t dd = ((size_t)d * d + 1) & ~(size_t)1;        // keep every buffer 16-byte aligned
@@ -754,9 +1170,12 @@ struct LargeWs {                   // offsets in doubles into the caller's works
         piv = Rbuf2 + strip;
         Pbuf = piv + (((size_t)d + 64 + 1) & ~(size_t)1);
         Pbuf2 = Pbuf + (size_t)OB * OB;
-        pmin = Pbuf2 + (size_t)OB * OB;
+        Pbuf3 = Pbuf2 + (size_t)OB * OB;
+        Pbuf4 = Pbuf3 + (size_t)OB * OB;
+        pmin = Pbuf4 + (size_t)OB * OB;
         sync = pmin + MIN_PARTIALS + 8;          // barrier counter, tile queue, error flag, per-SM busy flags
-        total = sync + 64 + SM_SLOTS;
+        flow = sync + 64 + SM_SLOTS;
+        total = flow + (FlowCtr::total + 1) / 2;
     }
 };
 static size_t large_ws_bytes(int d) { return LargeWs(d).total * sizeof(double); }
@@ -840,7 +1259,7 @@ static int lookahead_mode() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("DAGMA_LOOKAHEAD");
-        v = e ? atoi(e) : 1;
+        v = e ? atoi(e) : 2;
     }
     return v;
 }
@@ -853,7 +1272,27 @@ static int lookahead_mode() {
 // Look-ahead: the next pivot block P' = A[K',K'] + CS[K',:] R[:,K'] is formed first (a 256^3 GEMM) and
 // inverted on a side stream while the main stream runs the d x d update, so the serial panel chain
 // (4 sweeps + 4 small GEMMs) is off the critical path.
-static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* ws) {
+struct RiderGemm {        // C = A B (all d x d, ld = d) carried out by the flow kernel beside the inversion; C == nullptr: none
+    const double* A = nullptr;
+    const double* B = nullptr;
+    double* C = nullptr;
+};
+// can the rider of this size be carried by the flow kernel?  (otherwise the caller runs a plain GEMM)
+static bool flow_supported(int d) {
+    const int OB = outer_block();
+    return lookahead_mode() == 2 && (d % 2 == 0) && OB == 256 && d > OB && (d + OB - 1) / OB <= FL_MAX_OB &&
+           (d + NB - 1) / NB <= FL_MAX_TN;
+}
+static int flow_sleep_mode(bool rider) {     // DAGMA_FLOW_SLEEP (A-B timing): default 1 without a rider, 0 with one
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("DAGMA_FLOW_SLEEP");
+        v = e ? atoi(e) : -1;
+    }
+    return v >= 0 ? v : (rider ? 0 : 1);
+}
+
+static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* ws, const RiderGemm& rider) {
     const int OB = outer_block();
     const LargeWs L(d);
     double *CS = ws + L.CS, *Rbuf = ws + L.Rbuf, *piv = ws + L.piv, *Pbuf = ws + L.Pbuf, *Pbuf2 = ws + L.Pbuf2;
@@ -862,6 +1301,43 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
     int rc = lookahead_get(&la);
     if (rc) return rc;
     const int nob = (d + OB - 1) / OB;
+    if (flow_supported(d)) {
+        // the whole inversion as one dependency-driven kernel
+        static bool attr = false;
+        if (!attr) {
+            DAGMA_CUDA_OK(cudaFuncSetAttribute(flow_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)OUTER_SMEM_BYTES));
+            DAGMA_CUDA_OK(cudaFuncSetAttribute(flow_inverse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               cudaSharedmemCarveoutMaxShared));
+            attr = true;
+        }
+        int sms = 0, dev = 0;
+        DAGMA_CUDA_OK(cudaGetDevice(&dev));
+        DAGMA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        unsigned* ctr = reinterpret_cast<unsigned*>(ws + L.flow);
+        DAGMA_CUDA_OK(cudaMemsetAsync(ctr, 0, FlowCtr::total * sizeof(unsigned), stream));
+        FlowArgs FA{};
+        FA.A = Mw; FA.d = d; FA.nob = nob; FA.tn = (d + NB - 1) / NB;
+        FA.CS[0] = CS; FA.CS[1] = ws + L.CS2; FA.R[0] = Rbuf; FA.R[1] = ws + L.Rbuf2;
+        FA.X[0] = Pbuf; FA.Y[0] = Pbuf2; FA.X[1] = ws + L.Pbuf3; FA.Y[1] = ws + L.Pbuf4;
+        FA.pivots = piv; FA.ctr = ctr;
+        FA.gA = rider.A; FA.gB = rider.B; FA.gC = rider.C;
+        FA.sleep_coresident = flow_sleep_mode(rider.C != nullptr);
+        const int n_fill = rider.C ? FA.tn * FA.tn : 0;
+        FA.item_base[0] = 0;
+        for (int k = 0; k < nob; ++k) {
+            const int kn = (d - k * OB) < OB ? (d - k * OB) : OB, nk = (kn + NB - 1) / NB;
+            const int kn1 = (k + 1 < nob) ? ((d - (k + 1) * OB) < OB ? (d - (k + 1) * OB) : OB) : 0, nk1 = (kn1 + NB - 1) / NB;
+            FA.item_base[k + 1] = FA.item_base[k] + n_fill + nk * FA.tn + (FA.tn - nk1) * nk + (FA.tn * FA.tn - nk1 * nk1);
+        }
+#ifdef DAGMA_OUTER_TRACE
+        flow_trace_begin_kernel<<<1, 1, 0, stream>>>();
+#endif
+        const int grid = 2 * sms > FL_NSRV ? 2 * sms : FL_NSRV;
+        flow_inverse_kernel<<<grid, DM_NT, OUTER_SMEM_BYTES, stream>>>(FA);
+        DAGMA_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     {   // first pivot block
         const int kn = d < OB ? d : OB;
         copy_block_kernel<<<64, 256, 0, stream>>>(Mw, d, Pbuf, kn, kn, kn, 0, 0.0);
@@ -869,7 +1345,7 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         rc = gj_nb64(stream, Pbuf, Pbuf2, kn, piv, &Q);
         if (rc) return rc;
     }
-    const bool fused = (lookahead_mode() == 1) && (d % 2 == 0);
+    const bool fused = (lookahead_mode() >= 1) && (d % 2 == 0);
     unsigned* sync_words = reinterpret_cast<unsigned*>(ws + L.sync);
     if (fused) {
         static bool attr = false;
@@ -944,7 +1420,7 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
 // one problem; ws layout: see large_ws_bytes
 static int logdet_inv_blocked(cudaStream_t stream, int d, double s, const double* a_dev, int lda, int square,
                               double* logabsdet, double* h, double* minv, double* grad, int ldo,
-                              double* min_entry, int* info, double* ws) {
+                              double* min_entry, int* info, double* ws, const RiderGemm& rider = RiderGemm()) {
     double scale = 1.0;
     if (s > 0.0 && isfinite(s)) {
         int e = 0;
@@ -961,7 +1437,7 @@ static int logdet_inv_blocked(cudaStream_t stream, int d, double s, const double
     DAGMA_CUDA_OK(cudaGetLastError());
     int rc = 0;
     if (d > outer_block()) {
-        rc = gj_inplace_two_level(stream, Mw, d, ws);
+        rc = gj_inplace_two_level(stream, Mw, d, ws, rider);
     } else {                                   // ping-pong between Mw and the CS strip (d * OB >= d * d here)
         double* res = nullptr;
         rc = gj_nb64(stream, Mw, ws + L.CS, d, piv, &res);
@@ -1182,6 +1658,25 @@ extern "C" int dagma_logdet_inv_ws_f64(dagma_stream_t stream, int d, double s, c
     DAGMA_REQUIRE(ws_dev && ws_bytes >= large_ws_bytes(d), "workspace too small (dagma_large_workspace_bytes)");
     return logdet_inv_blocked((cudaStream_t)stream, d, s, a_dev, lda, square_input, logabsdet_dev, h_dev, minv_dev,
                               grad_dev, ldo, min_entry_dev, info_dev, ws_dev);
+}
+
+extern "C" int dagma_logdet_inv_gemm_ws_f64(dagma_stream_t stream, int d, double s, const double* a_dev, int lda,
+                                            int square_input, double* logabsdet_dev, double* h_dev, double* minv_dev,
+                                            double* grad_dev, int ldo, double* min_entry_dev, int* info_dev,
+                                            double* ws_dev, size_t ws_bytes, const double* ga_dev,
+                                            const double* gb_dev, double* gc_dev) {
+    DAGMA_REQUIRE(d >= 1 && a_dev && ga_dev && gb_dev && gc_dev, "bad arguments");
+    if (d > DAGMA_ONCHIP_INV_MAX_D && flow_supported(d)) {
+        DAGMA_REQUIRE(ws_dev && ws_bytes >= large_ws_bytes(d), "workspace too small (dagma_large_workspace_bytes)");
+        RiderGemm rider;
+        rider.A = ga_dev; rider.B = gb_dev; rider.C = gc_dev;
+        return logdet_inv_blocked((cudaStream_t)stream, d, s, a_dev, lda, square_input, logabsdet_dev, h_dev, minv_dev,
+                                  grad_dev, ldo, min_entry_dev, info_dev, ws_dev, rider);
+    }
+    int rc = dagma_logdet_inv_ws_f64(stream, d, s, a_dev, lda, square_input, logabsdet_dev, h_dev, minv_dev, grad_dev, ldo,
+                                     min_entry_dev, info_dev, ws_dev, ws_bytes);
+    if (rc) return rc;
+    return gemm_launch((cudaStream_t)stream, 0, d, d, d, 1.0, ga_dev, d, gb_dev, d, 0.0, gc_dev, d, EPI_NONE, nullptr, 0);
 }
 
 extern "C" int dagma_linear_update_f64(dagma_stream_t stream, int d, void* state_dev, double* w_dev,

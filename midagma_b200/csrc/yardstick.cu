@@ -1,6 +1,7 @@
 // FP64 pipe yardsticks: dependent-chain-free DFMA and DMMA.8x8x4 loops whose only
 // purpose is to measure the machine's FP64 issue rate for the roofline denominator.
 #include "common.cuh"
+#include "small_dmma.cuh"
 #include "../../include/dagma_b200.h"
 
 namespace dagma {
@@ -212,6 +213,63 @@ __global__ void latency_probe(double* out, double seed) {
 
 extern "C" int dagma_bench_latency(dagma_stream_t stream, double* out_dev) {
     dagma::latency_probe<<<1, 32, 0, (cudaStream_t)stream>>>(out_dev, 1.5);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- serial chain of the sweep in isolation: one warp inverts an 8 x 8 pivot block over and over
+// (P -> P^{-1} -> P ...), through the same shared-memory hand-over the block step uses.
+// out[0]: clk per stage_pivot_block + read-back; out[1]: the same with 10 independent DMMAs issued inside
+// (the diagonal warp's publish-critical tiles); out[2]: max |P - inv(inv(P))| as a sanity check
+namespace dagma {
+__global__ void stage_probe_kernel(double* out) {
+    extern __shared__ __align__(16) double sm[];
+    const DmmaPos ps(threadIdx.x);
+    double a[2][4][2];
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) a[ti][tj][0] = a[ti][tj][1] = 0.0;
+    const int i = ps.qr;
+    auto p_of = [&](int r, int c) { return (r == c) ? 1.0 : -0.01 * (1 + ((r * 8 + c) % 5)); };
+    a[0][0][0] = p_of(i, 2 * ps.qc);
+    a[0][0][1] = p_of(i, 2 * ps.qc + 1);
+    const int n0 = 2 * ps.qc, n1 = 2 * ps.qc + 1;
+    const double* qd = sm + DmmaSmem::qbuf + 32 * (i >> 2) + (i & 3);
+    constexpr int N = 512;
+    double g[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    for (int variant = 0; variant < 2; ++variant) {
+        __syncwarp();
+        const long long t0 = clock64();
+        for (int it = 0; it < N; ++it) {
+            if (variant == 0)
+                stage_pivot_block<0, 0>(a, ps, sm, 0, 0, [](int) {});
+            else
+                stage_pivot_block<0, 0>(a, ps, sm, 0, 0, [&](int k) {
+                    if (k < 5) {
+                        dmma(g[k & 3][0], g[k & 3][1], a[0][0][0], a[0][0][1]);
+                        dmma(g[(k + 1) & 3][0], g[(k + 1) & 3][1], a[0][0][1], a[0][0][0]);
+                    }
+                });
+            __syncwarp();
+            a[0][0][0] = -qd[4 * (2 * (n0 & 3) + (n0 >> 2))];
+            a[0][0][1] = -qd[4 * (2 * (n1 & 3) + (n1 >> 2))];
+            __syncwarp();
+        }
+        const long long t1 = clock64();
+        if (ps.lane == 0) out[variant] = double(t1 - t0) / N;
+    }
+    double e = fmax(fabs(a[0][0][0] - p_of(i, n0)), fabs(a[0][0][1] - p_of(i, n1)));
+    for (int off = 16; off > 0; off >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, off));
+    if (ps.lane == 0) out[2] = e;
+    if (g[0][0] + g[1][1] + g[2][0] + g[3][1] == 123.456) out[3] = g[0][0];
+}
+}  // namespace dagma
+
+extern "C" int dagma_bench_stage(dagma_stream_t stream, double* out_dev) {
+    DAGMA_CUDA_OK(cudaFuncSetAttribute(dagma::stage_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)dagma::DmmaSmem::bytes));
+    dagma::stage_probe_kernel<<<1, 32, dagma::DmmaSmem::bytes, (cudaStream_t)stream>>>(out_dev);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -11,3 +11,6 @@ names = ["DFMA", "DMMA (acc chain)", "DMMA (A-operand chain)", "SHFL.64", "MUFU.
          "STS+syncwarp+LDS+syncwarp", "DADD", "DMUL"]
 for n, v in zip(names, out.tolist()): print(f"{n:28s} {v:7.1f} clk")
 print(f"rcp.approx.ftz.f64 max rel err {out[9].item():.3e}   rsqrt.approx.ftz.f64 max rel err {out[10].item():.3e}")
+_lib.check(lib.dagma_bench_stage(_lib.stream_ptr(), out.data_ptr())); torch.cuda.synchronize()
+print(f"8x8 pivot-block inversion (stage_pivot_block + hand-over): {out[0].item():.0f} clk; with 10 DMMAs interleaved: "
+      f"{out[1].item():.0f} clk; |P - inv(inv(P))| = {out[2].item():.2e}")

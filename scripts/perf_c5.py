@@ -37,5 +37,7 @@ t_it = timed(eng._graph)
 t_inv = timed(graph_of(lambda: eng._inverse(1.0)))
 t_gemm = timed(graph_of(lambda: eng._score_T()))
 t_upd = timed(graph_of(lambda: eng._update()))
+t_fused = timed(graph_of(lambda: eng._inverse_and_score(1.0)))
 print(f"d={d}: iteration {t_it*1e3:.3f} ms = {4*d**3/t_it/1e12:.2f} TF/s (4d^3) | inverse {t_inv*1e3:.3f} ms = "
-      f"{2*d**3/t_inv/1e12:.2f} TF/s | cov@W {t_gemm*1e3:.3f} ms = {2*d**3/t_gemm/1e12:.2f} TF/s | update {t_upd*1e3:.3f} ms")
+      f"{2*d**3/t_inv/1e12:.2f} TF/s | cov@W {t_gemm*1e3:.3f} ms = {2*d**3/t_gemm/1e12:.2f} TF/s | update {t_upd*1e3:.3f} ms | "
+      f"inverse+cov@W fused {t_fused*1e3:.3f} ms = {4*d**3/t_fused/1e12:.2f} TF/s")

@@ -63,6 +63,40 @@ def test_blocked_logdet_inv_vs_numpy(d, square):
     assert int(out["info"][0].item()) != 0
 
 
+@pytest.mark.parametrize("d", [130, 258, 300, 520, 1000, 1234])
+def test_inverse_with_rider_gemm(d):
+    """dagma_logdet_inv_gemm_ws_f64: the inverse and an independent d x d GEMM in one call (for even d > 256 one
+    dependency-driven kernel); both results against numpy."""
+    from midagma_b200 import _lib
+    lib = _lib.load()
+    _lib.require_device()
+    rng = np.random.default_rng(d)
+    W = rng.normal(size=(d, d)) * (rng.random((d, d)) < 0.05)
+    rho = max(np.abs(np.linalg.eigvals(W * W)).max(), 1e-12)
+    W *= np.sqrt(0.6 / rho)
+    cov = rng.normal(size=(d, d))
+    s = 0.8
+    f64 = dict(dtype=torch.float64, device="cuda")
+    Wd, covd = torch.from_numpy(W).cuda(), torch.from_numpy(cov).cuda()
+    minv, T = torch.empty(d, d, **f64), torch.full((d, d), float("nan"), **f64)
+    sc = torch.zeros(4, **f64)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.dagma_large_workspace_bytes(d) // 8 + 8, **f64)
+    for _ in range(2):      # twice: the counters of the workspace are re-armed by every call
+        _lib.check(lib.dagma_logdet_inv_gemm_ws_f64(
+            _lib.stream_ptr(), d, s, Wd.data_ptr(), d, 1, sc.data_ptr(), sc.data_ptr() + 8, minv.data_ptr(), None, d,
+            sc.data_ptr() + 16, info.data_ptr(), ws.data_ptr(), ws.numel() * 8, covd.data_ptr(), Wd.data_ptr(),
+            T.data_ptr()), "dagma_logdet_inv_gemm_ws_f64")
+    torch.cuda.synchronize()
+    M = s * np.eye(d) - W * W
+    assert int(info.item()) == 0
+    assert _relmax(minv.cpu().numpy(), np.linalg.inv(M)) <= 1e-10
+    lad = np.linalg.slogdet(M)[1]
+    assert abs(sc[0].item() - lad) <= 1e-10 * max(1.0, abs(lad))
+    assert abs(sc[1].item() - (-lad + d * np.log(s))) <= 1e-9 * max(1.0, abs(lad))
+    assert _relmax(T.cpu().numpy(), cov @ W) <= 1e-13
+
+
 def _edges(g, key):
     return tuple(tuple(int(x) for x in e) for e in g[key]) if key in g.files else None
 
