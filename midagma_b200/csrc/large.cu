@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P)
         const int r0 = k1 + bi * NB, c0 = k1 + bj * NB;
         // the pivot-block tile of the update itself (its result is both the new A tile and the server's input),
         // split over k between the two engines of the CTA: this product sits on the serial chain
-        const int kmid = ((kn / 2 + GBK - 1) / GBK) * GBK;
+        const int kmid = min(kn, ((kn / 2 + GBK - 1) / GBK) * GBK);
         if (half == 0) load_acc(P.A, d, r0, c0, d, d);
         else zero_acc();
         engine_gemm(acc, P.CS, kn, P.R, d, r0, c0, d, d, half ? kmid : 0, half ? kn : kmid, esm, ep, half);
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P)
         __syncthreads();
         const bool claimed = s_tile[0] != 0u;
         __syncthreads();
-        const int kmid = ((kn1 / 2 + GBK - 1) / GBK) * GBK;
+        const int kmid = min(kn1, ((kn1 / 2 + GBK - 1) / GBK) * GBK);
         while (claimed) {
             if (tid == 0) s_tile[0] = atomicAdd(P.sync + 6, 1u);
             __syncthreads();
@@ -706,6 +706,7 @@ struct FlowArgs {
     // spend waiting for the serial chain (the score GEMM cov @ W of the same iteration)
     const double* gA; const double* gB; double* gC;
     int sleep_coresident;                   // 1: the CTA that shares an SM with a chain-team CTA sleeps while the chain runs
+    int rider_only;                         // debug / timing: skip the inversion, run only the rider's items
     int item_base[FL_MAX_OB + 1];           // first queue index of step k
 };
 
@@ -721,7 +722,6 @@ __device__ __forceinline__ bool flow_wait_ge(volatile unsigned* c, unsigned targ
 
 __global__ void __launch_bounds__(DM_NT, 2) flow_inverse_kernel(const FlowArgs P) {
     extern __shared__ __align__(16) double psm[];
-    __shared__ unsigned s_tile[2];
     const int tid = threadIdx.x;
     const int half = tid >> 7;
     const EnginePos ep(tid);
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(DM_NT, 2) flow_inverse_kernel(const FlowArgs P
     };
 
     // ================= the chain team =================
-    if ((int)blockIdx.x < FL_NSRV) {
+    if ((int)blockIdx.x < FL_NSRV && !P.rider_only) {
         const int rank = blockIdx.x;
         if (tid == 0 && P.sleep_coresident) *busy = 1;
         unsigned bar_target = 0;
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(DM_NT, 2) flow_inverse_kernel(const FlowArgs P
                 __syncthreads();
                 FT_SET(kk, 0);
                 const double* Qk = (nk & 1) ? P.Y[k & 1] : P.X[k & 1];
-                const int kmid = ((kn / 2 + GBK - 1) / GBK) * GBK;
+                const int kmid = min(kn, ((kn / 2 + GBK - 1) / GBK) * GBK);
                 // ---- CS_k rows of K': tile (bi, jb) = -A[K'_bi, K_k] Q_k[:, jb]
                 for (int u = rank; u < nkk * nk; u += FL_NSRV) {
                     const int bi = u / nk, jb = u % nk;
@@ -916,160 +916,297 @@ __global__ void __launch_bounds__(DM_NT, 2) flow_inverse_kernel(const FlowArgs P
     }
 
     // ================= the queue (each engine pulls its own items) =================
+    // Every engine runs ONE continuous stream of 64 x 16 / 16 x 64 operand slabs through its 3-stage cp.async
+    // pipeline: while the last slabs of an item are multiplied, the next item has already been pulled from the
+    // queue, its dependencies polled and its first two slabs requested, so that an item boundary costs the
+    // epilogue only (accumulators start at zero and are added to the tile by red.global.add.f64: no load).
     const int n_total = P.item_base[nob];
+    enum { IT_NONE = 0, IT_FILL = 1, IT_R = 2, IT_CS = 3, IT_UPD = 4 };
+    struct Item {
+        int type, k, bi, bj;               // CS: bj = column tile jb of the strip; R: bi = row tile ib of the strip
+        const double* Am; const double* Bm;
+        int lda, ldb, r0, c0, rmax, cmax, kbeg, kend;
+    };
     int kstep = 0;
-    for (;;) {
-        half_sync(half);
-        if (ep.htid == 0) {
-            unsigned spins = 0;
-            while (P.sleep_coresident && *busy) {
-                __nanosleep(2000);
-                if (++spins > (1u << 22)) { *err = 20; break; }
-            }
-            s_tile[half] = atomicAdd(ctr + FlowCtr::queue, 1u);
-        }
-        half_sync(half);
-        const int t = (int)s_tile[half];
-        if (t >= n_total) break;
+    auto decode = [&](int t) {
+        Item it{};
+        if (t >= n_total) return it;
         while (t >= P.item_base[kstep + 1]) ++kstep;
         const int k = kstep;
         int u0 = t - P.item_base[k];
-        const int kn = kn_of(k), nk = nk_of(k), cb = k * NKB, k0 = k * OB;
+        const int kn = kn_of(k), nk = nk_of(k), k0 = k * OB;
         const bool more = k + 1 < nob;
         const int nk1 = more ? nk_of(k + 1) : 0, cb1 = (k + 1) * NKB;
-        double* CSk = P.CS[k & 1];
-        double* Rk = P.R[k & 1];
         const int n_fill = (P.gC != nullptr) ? tn * tn : 0;
-        const int n_r = nk * tn, n_cs = (tn - nk1) * nk;
+        const int n_r = P.rider_only ? 0 : nk * tn, n_cs = P.rider_only ? 0 : (tn - nk1) * nk;
         auto outside = [&](int v) { return v < cb1 ? v : v + nk1; };   // v-th block index not in K'
-        if (u0 < n_fill) {
-            // ---- rider tile: gC[I,J] (+)= gA[I, Kc] gB[Kc, J], k-chunk c = k
-            const int bi = u0 / tn, bj = u0 % tn;
-            if (ep.htid == 0 && k > 0) {
-                flow_wait_ge(vctr + FlowCtr::fill_ver + bi * FL_MAX_TN + bj, (unsigned)k, err, 29);
-                __threadfence();
-            }
-            half_sync(half);
-            const int r0 = bi * NB, c0 = bj * NB;
-            if (k > 0) load_acc(P.gC, d, r0, c0, d, d);
-            else zero_acc();
-            engine_gemm(acc, P.gA, d, P.gB, d, r0, c0, d, d, k0, k0 + kn, esm, ep, half);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = r0 + ep.row(i), c = c0 + ep.col(j);
-                    if (r < d && c < d) *reinterpret_cast<double2*>(P.gC + (size_t)r * d + c) = make_double2(acc[i][j][0], acc[i][j][1]);
-                }
-            half_sync(half);
-            if (ep.htid == 0) {
-                __threadfence();
-                atomicAdd(ctr + FlowCtr::fill_ver + bi * FL_MAX_TN + bj, 1u);
-            }
-            continue;
+        it.k = k;
+        if (u0 < n_r) {                 // R_k tile: rows 64 ib.. of the row strip K_k, columns of block bj (+ E^T)
+            it.type = IT_R; it.bi = u0 / tn; it.bj = u0 % tn;
+            return it;
+        }
+        u0 -= n_r;
+        if (u0 < n_fill) {              // rider tile: gC[I,J] (+)= gA[I, Kc] gB[Kc, J], k-chunk c = k
+            it.type = IT_FILL; it.bi = u0 / tn; it.bj = u0 % tn;
+            it.Am = P.gA; it.lda = d; it.Bm = P.gB; it.ldb = d;
+            it.r0 = it.bi * NB; it.c0 = it.bj * NB; it.rmax = d; it.cmax = d; it.kbeg = k0; it.kend = k0 + kn;
+            return it;
         }
         u0 -= n_fill;
-        if (u0 < n_r) {
-            // ---- R_k tile: rows 64 ib.. of the row strip K_k, columns of block bj (+ E^T)
-            const int ib = u0 / tn, bj = u0 % tn;
-            if (ep.htid < 2) {
-                if (ep.htid == 0) flow_wait_ge(vctr + FlowCtr::tile_ver + (cb + ib) * FL_MAX_TN + bj, (unsigned)k, err, 21);
-                else if (k >= 2) flow_wait_ge(vctr + FlowCtr::upd_done + (k - 2), n_upd_of(k - 2), err, 22);
-                __threadfence();
+        if (u0 < n_cs) {                // CS_k tile outside the rows of K': -(A[I, K_k] - [I in K_k] I) Q_k
+            it.type = IT_CS; it.bi = more ? outside(u0 / nk) : u0 / nk; it.bj = u0 % nk;
+            it.Am = P.A + k0; it.lda = d; it.Bm = (nk & 1) ? P.Y[k & 1] : P.X[k & 1]; it.ldb = kn;
+            it.r0 = it.bi * NB; it.c0 = it.bj * NB; it.rmax = d; it.cmax = kn; it.kbeg = 0; it.kend = kn;
+            return it;
+        }
+        u0 -= n_cs;                     // update tile: column strip of K' first, then its row strip, then the rest
+        it.type = IT_UPD;
+        if (!more) { it.bi = u0 / tn; it.bj = u0 % tn; }
+        else {
+            const int n_c = (tn - nk1) * nk1, n_rw = nk1 * (tn - nk1);
+            if (u0 < n_c) { it.bi = outside(u0 / nk1); it.bj = cb1 + u0 % nk1; }
+            else if (u0 < n_c + n_rw) { const int v = u0 - n_c; it.bi = cb1 + v / (tn - nk1); it.bj = outside(v % (tn - nk1)); }
+            else { const int v = u0 - n_c - n_rw; it.bi = outside(v / (tn - nk1)); it.bj = outside(v % (tn - nk1)); }
+        }
+        it.Am = P.CS[k & 1]; it.lda = kn; it.Bm = P.R[k & 1]; it.ldb = d;
+        it.r0 = it.bi * NB; it.c0 = it.bj * NB; it.rmax = d; it.cmax = d; it.kbeg = 0; it.kend = kn;
+        return it;
+    };
+    // dependency q (q < 8) of an item: counter and the value it must have reached; false: no such dependency
+    auto dep_of = [&](const Item& it, int q, volatile unsigned*& c, unsigned& target) {
+        const int k = it.k;
+        switch (it.type) {
+        case IT_FILL:
+            if (q == 0 && k > 0) { c = vctr + FlowCtr::fill_ver + it.bi * FL_MAX_TN + it.bj; target = (unsigned)k; return true; }
+            return false;
+        case IT_R:
+            if (q == 0) { c = vctr + FlowCtr::tile_ver + (k * NKB + it.bi) * FL_MAX_TN + it.bj; target = (unsigned)k; return true; }
+            if (q == 1 && k >= 2) { c = vctr + FlowCtr::upd_done + (k - 2); target = n_upd_of(k - 2); return true; }
+            return false;
+        case IT_CS:
+            if (q == 0) { c = vctr + FlowCtr::q_done + k; target = FL_NSRV; return true; }
+            if (q == 1 && k >= 2) { c = vctr + FlowCtr::upd_done + (k - 2); target = n_upd_of(k - 2); return true; }
+            if (q >= 2 && q - 2 < nk_of(k)) { c = vctr + FlowCtr::tile_ver + it.bi * FL_MAX_TN + k * NKB + (q - 2); target = (unsigned)k; return true; }
+            return false;
+        case IT_UPD:
+            if (q == 0) { c = vctr + FlowCtr::cs_rows + k * FL_MAX_TN + it.bi; target = (unsigned)nk_of(k); return true; }
+            if (q == 1) { c = vctr + FlowCtr::r_cols + k * FL_MAX_TN + it.bj; target = (unsigned)nk_of(k); return true; }
+            if (q == 2) { c = vctr + FlowCtr::tile_ver + it.bi * FL_MAX_TN + it.bj; target = (unsigned)k; return true; }
+            return false;
+        }
+        return false;
+    };
+    auto wait_deps = [&](const Item& it) {                 // blocking; lanes 0..7 of the engine's first warp
+        if (ep.htid < 8) {
+            volatile unsigned* c; unsigned target;
+            if (dep_of(it, ep.htid, c, target)) flow_wait_ge(c, target, err, 30 + it.type);
+            __threadfence();
+        }
+        half_sync(half);
+    };
+    auto deps_ready = [&](const Item& it) -> bool {        // non-blocking; called by the engine's first warp
+        volatile unsigned* c; unsigned target;
+        bool ok = true;
+        if (ep.lane < 8 && dep_of(it, ep.lane, c, target)) ok = (*c >= target);
+        ok = __all_sync(0xffffffffu, ok);
+        if (ok) __threadfence();
+        return ok;
+    };
+    auto pull = [&]() -> unsigned {                        // engine leader only
+        unsigned spins = 0;
+        while (P.sleep_coresident && *busy) {
+            __nanosleep(2000);
+            if (++spins > (1u << 22)) { *err = 20; break; }
+        }
+        return atomicAdd(ctr + FlowCtr::queue, 1u);
+    };
+    auto signal_done = [&](const Item& it) {               // all threads of the engine; their stores are issued
+        half_sync(half);
+        if (ep.htid == 0) {
+            __threadfence();
+            const int k = it.k;
+            if (it.type == IT_FILL) atomicAdd(ctr + FlowCtr::fill_ver + it.bi * FL_MAX_TN + it.bj, 1u);
+            else if (it.type == IT_R) atomicAdd(ctr + FlowCtr::r_cols + k * FL_MAX_TN + it.bj, 1u);
+            else if (it.type == IT_CS) {
+                atomicAdd(ctr + FlowCtr::cs_rows + k * FL_MAX_TN + it.bi, 1u);
+                atomicAdd(ctr + FlowCtr::cs_done + k, 1u);
+            } else {
+                atomicAdd(ctr + FlowCtr::tile_ver + it.bi * FL_MAX_TN + it.bj, 1u);
+                atomicAdd(ctr + FlowCtr::upd_done + k, 1u);
             }
-            half_sync(half);
-            const int c0 = bj * NB;
+        }
+    };
+#ifndef DAGMA_FLOW_RED
+#define DAGMA_FLOW_RED 1      // 1: add the accumulators to the tile with red.global.add.f64 (measured faster), 0: load / add / store
+#endif
+    auto add2 = [](double* p, double v0, double v1) {      // the tile has one writer at a time (version counters)
+#if DAGMA_FLOW_RED
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v0) : "memory");
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p + 1)), "d"(v1) : "memory");
+#else
+        double2 o = __ldcg(reinterpret_cast<const double2*>(p));
+        o.x += v0;
+        o.y += v1;
+        *reinterpret_cast<double2*>(p) = o;
+#endif
+    };
+    auto epilogue = [&](const Item& it) {
+        const int k = it.k;
+        if (it.type == IT_FILL) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int rr = ib * NB + ep.row(i), c = c0 + ep.col(j);     // rr: row inside the strip
-                    if (rr < kn && c < d) {
-                        double2 v = __ldcg(reinterpret_cast<const double2*>(P.A + (size_t)(k0 + rr) * d + c));
-                        if (c == k0 + rr) v.x += 1.0;
-                        if (c + 1 == k0 + rr) v.y += 1.0;
-                        *reinterpret_cast<double2*>(Rk + (size_t)rr * d + c) = v;
+                    const int r = it.r0 + ep.row(i), c = it.c0 + ep.col(j);
+                    if (r < d && c < d) {
+                        double* p = P.gC + (size_t)r * d + c;
+                        if (k == 0) *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+                        else add2(p, acc[i][j][0], acc[i][j][1]);
                     }
                 }
-            half_sync(half);
-            if (ep.htid == 0) {
-                __threadfence();
-                atomicAdd(ctr + FlowCtr::r_cols + k * FL_MAX_TN + bj, 1u);
-            }
-        } else if (u0 < n_r + n_cs) {
-            // ---- CS_k tile outside the rows of K': -(A[I, K_k] - [I in K_k] I) Q_k
-            const int u = u0 - n_r, bi = more ? outside(u / nk) : u / nk, jb = u % nk;
-            if (ep.htid < 8) {
-                if (ep.htid == 0) flow_wait_ge(vctr + FlowCtr::q_done + k, FL_NSRV, err, 23);
-                else if (ep.htid == 1) { if (k >= 2) flow_wait_ge(vctr + FlowCtr::upd_done + (k - 2), n_upd_of(k - 2), err, 24); }
-                else if (ep.htid - 2 < nk) flow_wait_ge(vctr + FlowCtr::tile_ver + bi * FL_MAX_TN + cb + (ep.htid - 2), (unsigned)k, err, 25);
-                __threadfence();
-            }
-            half_sync(half);
-            const double* Qk = (nk & 1) ? P.Y[k & 1] : P.X[k & 1];
-            const int r0 = bi * NB, c0 = jb * NB;
-            zero_acc();
-            engine_gemm(acc, P.A + k0, d, Qk, kn, r0, c0, d, kn, 0, kn, esm, ep, half);
-            const bool inK = (bi >= cb) && (bi < cb + nk);
+        } else if (it.type == IT_UPD) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                    const int r = it.r0 + ep.row(i), c = it.c0 + ep.col(j);
+                    if (r < d && c < d) {
+                        double* p = P.A + (size_t)r * d + c;
+                        add2(p, acc[i][j][0], acc[i][j][1]);
+                    }
+                }
+            FT_MAX(k, 8);
+        } else if (it.type == IT_CS) {
+            const int kn = kn_of(k), k0 = k * OB, cb = k * NKB;
+            const bool inK = (it.bi >= cb) && (it.bi < cb + nk_of(k));
+            double* CSk = P.CS[k & 1];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = it.r0 + ep.row(i), c = it.c0 + ep.col(j);
                     if (r < d && c < kn) {
                         double2 v = make_double2(-acc[i][j][0], -acc[i][j][1]);
                         if (inK) {
-                            const double2 q = __ldcg(reinterpret_cast<const double2*>(Qk + (size_t)(r - k0) * kn + c));
+                            const double2 q = __ldcg(reinterpret_cast<const double2*>(it.Bm + (size_t)(r - k0) * kn + c));
                             v.x += q.x;
                             v.y += q.y;
                         }
                         *reinterpret_cast<double2*>(CSk + (size_t)r * kn + c) = v;
                     }
                 }
-            half_sync(half);
-            if (ep.htid == 0) {
-                __threadfence();
-                atomicAdd(ctr + FlowCtr::cs_rows + k * FL_MAX_TN + bi, 1u);
-                atomicAdd(ctr + FlowCtr::cs_done + k, 1u);
-            }
-        } else {
-            // ---- update tile A[I,J] += CS_k[I,:] R_k[:,J]; column strip of K' first, then its row strip, then the rest
-            const int u = u0 - n_r - n_cs;
-            int bi, bj;
-            if (!more) { bi = u / tn; bj = u % tn; }
-            else {
-                const int n_c = (tn - nk1) * nk1, n_rw = nk1 * (tn - nk1);
-                if (u < n_c) { bi = outside(u / nk1); bj = cb1 + u % nk1; }
-                else if (u < n_c + n_rw) { const int v = u - n_c; bi = cb1 + v / (tn - nk1); bj = outside(v % (tn - nk1)); }
-                else { const int v = u - n_c - n_rw; bi = outside(v / (tn - nk1)); bj = outside(v % (tn - nk1)); }
-            }
-            if (ep.htid < 3) {
-                if (ep.htid == 0) flow_wait_ge(vctr + FlowCtr::cs_rows + k * FL_MAX_TN + bi, (unsigned)nk, err, 26);
-                else if (ep.htid == 1) flow_wait_ge(vctr + FlowCtr::r_cols + k * FL_MAX_TN + bj, (unsigned)nk, err, 27);
-                else flow_wait_ge(vctr + FlowCtr::tile_ver + bi * FL_MAX_TN + bj, (unsigned)k, err, 28);
-                __threadfence();
-            }
-            half_sync(half);
-            FT_MIN(k, 12);
-            const int r0 = bi * NB, c0 = bj * NB;
-            load_acc(P.A, d, r0, c0, d, d);
-            engine_gemm(acc, CSk, kn, Rk, d, r0, c0, d, d, 0, kn, esm, ep, half);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = r0 + ep.row(i), c = c0 + ep.col(j);
-                    if (r < d && c < d) *reinterpret_cast<double2*>(P.A + (size_t)r * d + c) = make_double2(acc[i][j][0], acc[i][j][1]);
-                }
-            half_sync(half);
-            if (ep.htid == 0) {
-                __threadfence();
-                atomicAdd(ctr + FlowCtr::tile_ver + bi * FL_MAX_TN + bj, 1u);
-                atomicAdd(ctr + FlowCtr::upd_done + k, 1u);
-            }
-            FT_MAX(k, 8);
         }
+    };
+    auto copy_r = [&](const Item& it) {
+        const int k = it.k, kn = kn_of(k), k0 = k * OB, c0 = it.bj * NB;
+        double* Rk = P.R[k & 1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int rr = it.bi * NB + ep.row(i), c = c0 + ep.col(j);     // rr: row inside the strip
+                if (rr < kn && c < d) {
+                    double2 v = __ldcg(reinterpret_cast<const double2*>(P.A + (size_t)(k0 + rr) * d + c));
+                    if (c == k0 + rr) v.x += 1.0;
+                    if (c + 1 == k0 + rr) v.y += 1.0;
+                    *reinterpret_cast<double2*>(Rk + (size_t)rr * d + c) = v;
+                }
+            }
+    };
+    const uint32_t ebase = smem_u32(esm);
+    unsigned gslab = 0;                                    // running slab count: stage = gslab % 3
+    auto issue_slab = [&](const Item& it, int kt, unsigned g) {
+        const int st = (int)(g % GSTAGES);
+        const uint32_t sa = ebase + (uint32_t)(st * EN_STG) * 8, sb = sa + (uint32_t)EngT::A_STAGE * 8;
+        const int k0 = it.kbeg + kt * GBK;
+        load_slab<NB, GBK, EN_NT>(sa, EngT::LDA_N, it.Am, it.lda, it.r0, k0, it.rmax, it.kend, true, ep.htid);
+        load_slab<GBK, NB, EN_NT>(sb, EngT::LDB_S, it.Bm, it.ldb, k0, it.c0, it.kend, it.cmax, true, ep.htid);
+    };
+
+    __shared__ unsigned s_next[2], s_ready[2];
+    half_sync(half);
+    if (ep.htid == 0) s_next[half] = pull();
+    half_sync(half);
+    Item cur = decode((int)s_next[half]);
+    int prefetched = 0;                                    // slabs of `cur` already requested
+    bool cur_ready = false;
+    while (cur.type != IT_NONE) {
+        if (!cur_ready) wait_deps(cur);
+        if (cur.type == IT_R) {
+            copy_r(cur);
+            signal_done(cur);
+            half_sync(half);
+            if (ep.htid == 0) s_next[half] = pull();
+            half_sync(half);
+            cur = decode((int)s_next[half]);
+            cur_ready = false;
+            prefetched = 0;
+            continue;
+        }
+        if (cur.type == IT_UPD) FT_MIN(cur.k, 12);
+        // ---- a GEMM item: pull the next one right away (the atomic's latency hides behind the first slabs)
+        unsigned nxt_raw = 0;
+        if (ep.htid == 0) nxt_raw = pull();
+        const int nk = (cur.kend - cur.kbeg + GBK - 1) / GBK;
+        half_sync(half);                                   // the stages may still be read (first item / after a copy)
+        for (int st = prefetched; st < GSTAGES - 1; ++st) {
+            if (st < nk) issue_slab(cur, st, gslab + st);
+            cp_async_commit();
+        }
+        zero_acc();
+        Item nxt{};
+        bool nxt_ready = false;
+        const int kt_publish = (nk > 4) ? 1 : -1, kt_poll = nk - 4;     // short items (tail block): no look-ahead
+        for (int kt = 0; kt < nk; ++kt) {
+            cp_async_wait<GSTAGES - 2>();
+            half_sync(half);                               // slab kt landed; slab kt-1 is free for reuse
+            if (kt == kt_publish + 1 && kt_publish >= 0) nxt = decode((int)s_next[half]);
+            if (kt == kt_poll + 1 && kt_publish >= 0) nxt_ready = (s_ready[half] != 0u);
+            {   // request slab kt+2: of this item, or of the next one when it is known to be ready
+                const int s2 = kt + GSTAGES - 1;
+                if (s2 < nk) issue_slab(cur, s2, gslab + s2);
+                else if (nxt_ready && s2 - nk < GSTAGES - 1) {
+                    const int nkn = (nxt.kend - nxt.kbeg + GBK - 1) / GBK;
+                    if (s2 - nk < nkn) issue_slab(nxt, s2 - nk, gslab + s2);
+                }
+                cp_async_commit();
+            }
+            const double* As = esm + ((gslab + kt) % GSTAGES) * EN_STG;
+            const double* Bs = As + EngT::A_STAGE;
+#pragma unroll
+            for (int kk = 0; kk < GBK; kk += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = As[ep.row(i) * EngT::LDA_N + kk + ep.qc];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = Bs[(kk + ep.qc) * EngT::LDB_S + 32 * ep.wn + 8 * j + ep.qr];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+            if (kt == kt_publish && ep.htid == 0) s_next[half] = nxt_raw;
+            if (kt == kt_poll && kt_publish >= 0 && ep.htid < 32) {
+                // only GEMM items are looked ahead; a copy item or the end of the queue is handled at the boundary
+                bool ok = (nxt.type == IT_FILL || nxt.type == IT_CS || nxt.type == IT_UPD) && deps_ready(nxt);
+                if (ep.htid == 0) s_ready[half] = ok ? 1u : 0u;
+            }
+        }
+        epilogue(cur);
+        signal_done(cur);
+        if (kt_publish < 0) {                              // short item: the next index was not handed over inside the loop
+            if (ep.htid == 0) s_next[half] = nxt_raw;
+            half_sync(half);
+            nxt = decode((int)s_next[half]);
+            nxt_ready = false;
+        }
+        gslab += (unsigned)(nk > GSTAGES - 1 ? nk : GSTAGES - 1);
+        // slabs nk, nk+1 of the stream (the first two of the next item) were requested iff nxt_ready
+        prefetched = nxt_ready ? GSTAGES - 1 : 0;
+        cur_ready = nxt_ready;
+        cur = nxt;
     }
+    cp_async_wait<0>();
 }
 
 #ifdef DAGMA_OUTER_TRACE
@@ -1253,13 +1390,16 @@ static int lookahead_get(LookAhead** out) {
     return 0;
 }
 
-// DAGMA_LOOKAHEAD (A-B timing): 1 = persistent update kernel with the look-ahead inside (default, even d),
+// DAGMA_LOOKAHEAD (A-B timing): 1 = one persistent kernel per outer step with the look-ahead inside (default, even d),
+// 2 = the whole inversion as ONE dependency-driven kernel (flow_inverse_kernel; can carry a rider GEMM) -- measured
+//     on par for the inverse alone (1.01 vs 0.97 ms at d = 2000) and for inverse + cov@W (1.58 vs 1.52 ms): its
+//     engines reach the same ~65 % of the DMMA pipe as the per-step kernels, so it stays opt-in,
 // 0 = plain GEMM update + chain of small kernels on a high-priority side stream
 static int lookahead_mode() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("DAGMA_LOOKAHEAD");
-        v = e ? atoi(e) : 2;
+        v = e ? atoi(e) : 1;
     }
     return v;
 }
@@ -1323,12 +1463,13 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         FA.pivots = piv; FA.ctr = ctr;
         FA.gA = rider.A; FA.gB = rider.B; FA.gC = rider.C;
         FA.sleep_coresident = flow_sleep_mode(rider.C != nullptr);
+        FA.rider_only = (rider.C != nullptr && getenv("DAGMA_FLOW_RIDER_ONLY") != nullptr) ? 1 : 0;
         const int n_fill = rider.C ? FA.tn * FA.tn : 0;
         FA.item_base[0] = 0;
         for (int k = 0; k < nob; ++k) {
             const int kn = (d - k * OB) < OB ? (d - k * OB) : OB, nk = (kn + NB - 1) / NB;
             const int kn1 = (k + 1 < nob) ? ((d - (k + 1) * OB) < OB ? (d - (k + 1) * OB) : OB) : 0, nk1 = (kn1 + NB - 1) / NB;
-            FA.item_base[k + 1] = FA.item_base[k] + n_fill + nk * FA.tn + (FA.tn - nk1) * nk + (FA.tn * FA.tn - nk1 * nk1);
+            FA.item_base[k + 1] = FA.item_base[k] + n_fill + (FA.rider_only ? 0 : nk * FA.tn + (FA.tn - nk1) * nk + (FA.tn * FA.tn - nk1 * nk1));
         }
 #ifdef DAGMA_OUTER_TRACE
         flow_trace_begin_kernel<<<1, 1, 0, stream>>>();
@@ -1346,7 +1487,8 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         if (rc) return rc;
     }
     const bool fused = (lookahead_mode() >= 1) && (d % 2 == 0);
-    unsigned* sync_words = reinterpret_cast<unsigned*>(ws + L.sync);
+    unsigned* sync_base = reinterpret_cast<unsigned*>(ws + L.sync);
+    unsigned* flow_words = reinterpret_cast<unsigned*>(ws + L.flow);
     if (fused) {
         static bool attr = false;
         if (!attr) {
@@ -1374,7 +1516,19 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
             const int k1 = k0 + OB, kn1 = more ? ((d - k1) < OB ? (d - k1) : OB) : 0;
             const int nblk1 = (kn1 + NB - 1) / NB;
             double* Qn = (nblk1 & 1) ? Pbuf2 : Pbuf;
-            DAGMA_CUDA_OK(cudaMemsetAsync(sync_words, 0, 32 + 2 * SM_SLOTS * sizeof(int), stream));
+            // every outer step has its own zeroed sync block (one memset for all of them: no memset node
+            // between two step kernels); beyond the space of the flow counters: one memset per step
+            constexpr int SYNC_STRIDE = 8 + 2 * SM_SLOTS;
+            unsigned* sync_words = sync_base;
+            if ((ob + 1) * SYNC_STRIDE <= FlowCtr::total) {
+                if (ob == 0) {
+                    const int nfit = FlowCtr::total / SYNC_STRIDE < nob ? FlowCtr::total / SYNC_STRIDE : nob;
+                    DAGMA_CUDA_OK(cudaMemsetAsync(flow_words, 0, (size_t)nfit * SYNC_STRIDE * sizeof(unsigned), stream));
+                }
+                sync_words = flow_words + ob * SYNC_STRIDE;
+            } else {
+                DAGMA_CUDA_OK(cudaMemsetAsync(sync_words, 0, SYNC_STRIDE * sizeof(unsigned), stream));
+            }
 #ifdef DAGMA_OUTER_TRACE
             outer_trace_begin_kernel<<<1, 1, 0, stream>>>(ob);
 #endif

@@ -97,6 +97,18 @@ def test_inverse_with_rider_gemm(d):
     assert _relmax(T.cpu().numpy(), cov @ W) <= 1e-13
 
 
+def test_flow_kernel_mode():
+    """The opt-in single-kernel ("flow") variant of the large-d inverse, with and without the rider GEMM
+    (DAGMA_LOOKAHEAD=2 is read once per process, hence the subprocess)."""
+    import os, subprocess, sys
+    env = dict(os.environ, DAGMA_LOOKAHEAD="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_large_gpu.py"),
+                        "-k", "rider_gemm or (blocked_logdet and (500 or 1000))"], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def _edges(g, key):
     return tuple(tuple(int(x) for x in e) for e in g[key]) if key in g.files else None
 
