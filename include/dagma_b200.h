@@ -142,6 +142,13 @@ int dagma_linear_update_f64(dagma_stream_t stream, int d, void* state_dev, doubl
                             const double* minv_dev, const double* t_dev, const double* cov_dev,
                             double* m_dev, double* v_dev, const uint8_t* mask_exc_dev,
                             const uint8_t* mask_inc_dev);
+/* the same update with one more gradient term  extra_scale * 2 W o extra_t^T  (extra_t_dev row-major d x d or NULL):
+ * the trek regulariser in mode "opt", weight * d pst / d W  (src/dagma/linear.py:251-258, src/notreks/notreks.py:
+ * 454-619; for PST seq="inv" extra_t = X M_s H with X = (I - W o W)^{-1}, H = X^T X, M_s the symmetrised pair mask) */
+int dagma_linear_update_ex_f64(dagma_stream_t stream, int d, void* state_dev, double* w_dev,
+                               const double* minv_dev, const double* t_dev, const double* cov_dev,
+                               double* m_dev, double* v_dev, const uint8_t* mask_exc_dev,
+                               const uint8_t* mask_inc_dev, const double* extra_t_dev, double extra_scale);
 /* W += sign * lr * (previous Adam direction)     src/dagma/linear.py:235, 239           */
 int dagma_linear_apply_dir_f64(dagma_stream_t stream, int d, const void* state_dev, double* w_dev,
                                const double* m_dev, const double* v_dev, double sign);

@@ -69,6 +69,54 @@ class LargeLinearEngine:
         self._graph = None
         self._model_cov_ptr = model._cov_dev.data_ptr()
         self.launches_per_iter = None
+        self._trek_setup(getattr(model, "_trek_plan", None))
+
+    # ------------------------------------------------------------------ trek regulariser
+    def _trek_setup(self, plan):
+        """PST ``seq="inv"`` (src/notreks/notreks.py:500-507, 558-619): pst = agg_{(i,j) in I} H[i,j] with
+        X = ((1 + eps) I - W o W)^{-1}, H = X^T X.  Closed-form adjoint instead of autograd:
+        d pst / d W = 2 W o (X^T X M_s X^T) = 2 W o (X M_s H)^T with M_s = (M + M^T) * agg-scale, M the pair mask --
+        one more fused inverse and three DMMA GEMMs per iteration."""
+        self.trek = plan
+        if plan is None:
+            return
+        d = self.d
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        Mk = torch.zeros(d, d, **f64)
+        idx = torch.as_tensor(np.asarray(plan["I"], dtype=np.int64), device=self.dev)
+        Mk[idx[:, 0], idx[:, 1]] = 1.0                    # H[rows, cols]: duplicates in I count once per listing below
+        cnt = torch.zeros(d, d, **f64)
+        cnt.index_put_((idx[:, 0], idx[:, 1]), torch.ones(idx.shape[0], **f64), accumulate=True)
+        scale = 1.0 / idx.shape[0] if plan["agg"] == "mean" else 1.0
+        self.trek_mask = cnt * scale                      # value = sum(trek_mask o H)
+        self.trek_Ms = (self.trek_mask + self.trek_mask.T).contiguous()
+        self.trek_X = torch.empty(d, d, **f64)
+        self.trek_H = torch.empty(d, d, **f64)
+        self.trek_B = torch.empty(d, d, **f64)
+        self.trek_GT = torch.zeros(d, d, **f64)
+        self.trek_sc = torch.zeros(4, **f64)
+        self.trek_info = torch.zeros(1, dtype=torch.int32, device=self.dev)
+
+    def _trek_forward(self):
+        """X and H at the current W."""
+        p = self.trek
+        _lib.check(self.lib.dagma_logdet_inv_ws_f64(
+            _lib.stream_ptr(), self.d, 1.0 + p["eps_inv"], self.W.data_ptr(), self.d, 1, self.trek_sc.data_ptr(),
+            self.trek_sc.data_ptr() + 8, self.trek_X.data_ptr(), None, self.d, self.trek_sc.data_ptr() + 16,
+            self.trek_info.data_ptr(), self.ws.data_ptr(), self.ws.numel() * 8), "dagma_logdet_inv_ws_f64")
+        gemm(self.trek_X, self.trek_X, self.trek_H, trans_a=True)
+
+    def _trek_grad(self):
+        """trek_GT = X M_s H, so that d pst / d W = 2 W o trek_GT^T (consumed by the update kernel)."""
+        self._trek_forward()
+        gemm(self.trek_Ms, self.trek_H, self.trek_B)
+        gemm(self.trek_X, self.trek_B, self.trek_GT)
+
+    def _trek_value(self) -> float:
+        if self.trek is None:
+            return 0.0
+        self._trek_forward()
+        return float((self.trek_mask * self.trek_H).sum().item())
 
     def stale(self, model) -> bool:
         return model._cov_dev.data_ptr() != self._model_cov_ptr or model.d != self.d
@@ -115,12 +163,17 @@ class LargeLinearEngine:
                 if self.group is not None:
                     torch.distributed.all_reduce(self.T, group=self.group)
 
+    def _trek_opt(self) -> bool:
+        return self.trek is not None and self.trek["mode"] == "opt"
+
     def _update(self):
         ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
-        _lib.check(self.lib.dagma_linear_update_f64(
+        opt = self._trek_opt()
+        _lib.check(self.lib.dagma_linear_update_ex_f64(
             _lib.stream_ptr(), self.d, self.state.data_ptr(), self.W.data_ptr(), self.Minv.data_ptr(),
             self.T.data_ptr(), self.cov.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), ptr(self.mask_exc),
-            ptr(self.mask_inc)), "dagma_linear_update_f64")
+            ptr(self.mask_inc), self.trek_GT.data_ptr() if opt else None, self.trek["weight"] if opt else 0.0),
+            "dagma_linear_update_ex_f64")
 
     def _inverse_and_score(self, s: float):
         """l2: the inverse of sI - W o W and T = cov @ W as one call (one persistent kernel for d > 256: the GEMM
@@ -131,12 +184,17 @@ class LargeLinearEngine:
             self.ws.numel() * 8, self.cov.data_ptr(), self.W.data_ptr(), self.T.data_ptr()),
             "dagma_logdet_inv_gemm_ws_f64")
 
-    def _iteration(self, s: float):
+    def _gradient_pieces(self, s: float):
         if self.loss_type == "l2":
             self._inverse_and_score(s)
         else:
             self._inverse(s)
             self._score_T()
+        if self._trek_opt():
+            self._trek_grad()
+
+    def _iteration(self, s: float):
+        self._gradient_pieces(s)
         self._update()
 
     def _replay(self, s: float, n: int):
@@ -188,6 +246,9 @@ class LargeLinearEngine:
             st, *_ = self._pull()
         h, l1 = float(st[F_H]), float(st[F_L1])
         obj = mu * (score + lambda1 * l1) + h
+        self.last_trek_val = self._trek_value()                  # linear.py:122-133
+        if self._trek_opt():
+            obj = obj + self.trek["weight"] * self.last_trek_val
         return obj, score, h
 
     def _logistic_loss(self, W) -> float:
@@ -223,8 +284,49 @@ class LargeLinearEngine:
             G = self.T / self.n_total - self.cov
         return loss, G
 
-    def minimize(self, W_np: np.ndarray, mu, max_iter, s, lr, tol, beta_1, beta_2, lambda1, checkpoint, log=None):
-        """linear.py:165-333 on device; returns (status, iterations done).  ``W_np`` is updated in place."""
+    def _verbose_iteration(self, s, mu, lambda1):
+        """The checkpoint iteration with the reference's gradient diagnostics (linear.py:262-273): the same launch
+        sequence as every other iteration, plus device-side norms of the pieces it already computed."""
+        self._gradient_pieces(s)
+        _, _, halted, info = self._pull()
+        if halted or info:
+            self._update()                       # latches `halted`; the caller's back-tracking path takes over
+            return None
+        W = self.W
+        sgn = torch.sign(W)
+        gscale = 1.0 if self.loss_type == "l2" else 1.0 / self.n_total
+        G_score = mu * (gscale * self.T - self.cov)
+        G_h = 2.0 * W * (self.Minv.T + 1e-16)
+        G_l1 = (mu * lambda1) * sgn
+        G_inc = (-2.0 * mu * lambda1) * sgn * self.mask_inc.to(torch.float64) if self.mask_inc is not None else None
+        Gobj = G_score + G_l1 + G_h
+        if G_inc is not None:
+            Gobj = Gobj + G_inc
+        G_trek = None
+        if self._trek_opt():
+            G_trek = self.trek["weight"] * 2.0 * W * self.trek_GT.T
+            Gobj = Gobj + G_trek
+        zero = torch.zeros((), dtype=torch.float64, device=self.dev)
+        norms = torch.stack([torch.linalg.norm(Gobj), torch.linalg.norm(G_score), torch.linalg.norm(G_h),
+                             torch.linalg.norm(G_l1), torch.linalg.norm(G_inc) if G_inc is not None else zero,
+                             torch.linalg.norm(G_trek) if G_trek is not None else zero])
+        self._update()
+        st, it, _, _ = self._pull()
+        c1 = 1.0 / ((1.0 - float(st[F_P1H])) - float(st[F_P1L]))
+        c2 = 1.0 / ((1.0 - float(st[F_P2H])) - float(st[F_P2L]))
+        step = torch.linalg.norm((self.m * c1) / (torch.sqrt(self.v * c2) + 1e-8))
+        Wa = self.W.abs()
+        nz = Wa[Wa > 0]
+        wst = torch.stack([torch.linalg.norm(self.W), Wa.sum(), Wa.max(), nz.min() if nz.numel() else zero, step])
+        vals = torch.cat([norms, wst]).cpu().tolist()
+        keys = ("grad_raw_norm", "grad_score_norm", "grad_dag_norm", "grad_l1_norm", "grad_inc_norm", "grad_trek_norm",
+                "w_norm", "w_abs_sum", "max_abs_w", "min_abs_w_nonzero", "grad_step_norm")
+        return dict(zip(keys, vals))
+
+    def minimize(self, W_np: np.ndarray, mu, max_iter, s, lr, tol, beta_1, beta_2, lambda1, checkpoint, log=None,
+                 telemetry=None):
+        """linear.py:165-333 on device; returns (status, iterations done).  ``W_np`` is updated in place.
+        ``telemetry(diag, it, obj, score, h, trek_val, lr)`` is called at every checkpoint when given."""
         self.W.copy_(torch.from_numpy(np.ascontiguousarray(W_np)))
         self.m.zero_()
         self.v.zero_()
@@ -240,7 +342,15 @@ class LargeLinearEngine:
         max_iter = int(max_iter)
         while it_done < max_iter:
             chunk_end = min((it_done // checkpoint + 1) * checkpoint, max_iter)
-            self._replay(s, chunk_end - it_done)
+            diag = None
+            if telemetry is None:
+                self._replay(s, chunk_end - it_done)
+            else:                                # the last iteration of the chunk also reports its gradient norms
+                if chunk_end - it_done > 1:
+                    self._replay(s, chunk_end - it_done - 1)
+                _, _, halted0, _ = self._pull()
+                if not halted0:
+                    diag = self._verbose_iteration(s, mu, lambda1)
             st, it_dev, halted, info = self._pull()
             if halted:
                 it_done = it_dev
@@ -269,6 +379,8 @@ class LargeLinearEngine:
             obj, score, h = self._objective(mu, s, lambda1)      # linear.py:279-280
             if log is not None:
                 log.append((0, it_done, obj, score, h, lr))
+            if telemetry is not None and diag is not None:
+                telemetry(diag, it_done, obj, score, h, self.last_trek_val, lr)
             if np.abs((obj_prev - obj) / obj_prev) <= tol:       # linear.py:328
                 break
             obj_prev = obj

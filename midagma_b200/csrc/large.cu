@@ -1654,8 +1654,10 @@ __global__ void __launch_bounds__(256) linear_update_kernel(LinState* st, int d,
                                                              const double* __restrict__ T,
                                                              const double* __restrict__ cov, double* __restrict__ m,
                                                              double* __restrict__ v, const uint8_t* mask_exc,
-                                                             const uint8_t* mask_inc) {
+                                                             const uint8_t* mask_inc, const double* __restrict__ extraT,
+                                                             double extra_scale) {
     __shared__ double tile[32][33];
+    __shared__ double tile2[32][33];
     const bool stop = (st->halted != 0) || (st->info != 0);
     if (stop) return;                        // latching is done by linear_advance_kernel
     const double mu = st->mu, lr = st->lr, lambda1 = st->lambda1, b1 = st->beta1, b2 = st->beta2;
@@ -1670,6 +1672,7 @@ __global__ void __launch_bounds__(256) linear_update_kernel(LinState* st, int d,
     for (int y = y0; y < 32; y += 8) {
         const int r = bx + y, c = by + x;
         tile[y][x] = (r < d && c < d) ? Minv[(size_t)r * d + c] : 0.0;
+        if (extraT) tile2[y][x] = (r < d && c < d) ? extraT[(size_t)r * d + c] : 0.0;
     }
     __syncthreads();
     for (int y = y0; y < 32; y += 8) {
@@ -1683,6 +1686,7 @@ __global__ void __launch_bounds__(256) linear_update_kernel(LinState* st, int d,
         double go = fma(mu, gsc, mu * lambda1 * sg);
         go = fma(2.0 * w, minvT + 1e-16, go);
         if (mask_inc && mask_inc[e]) go = fma(-2.0 * mu * lambda1, sg, go);
+        if (extraT) go = fma(extra_scale * (2.0 * w), tile2[x][y], go);      // + weight * 2 W o G^T (trek regulariser)
         const double mn = fma(m[e], b1, (1.0 - b1) * go);
         const double vn = fma(v[e], b2, (1.0 - b2) * (go * go));
         m[e] = mn;
@@ -1833,18 +1837,27 @@ extern "C" int dagma_logdet_inv_gemm_ws_f64(dagma_stream_t stream, int d, double
     return gemm_launch((cudaStream_t)stream, 0, d, d, d, 1.0, ga_dev, d, gb_dev, d, 0.0, gc_dev, d, EPI_NONE, nullptr, 0);
 }
 
-extern "C" int dagma_linear_update_f64(dagma_stream_t stream, int d, void* state_dev, double* w_dev,
-                                       const double* minv_dev, const double* t_dev, const double* cov_dev,
-                                       double* m_dev, double* v_dev, const uint8_t* mask_exc_dev,
-                                       const uint8_t* mask_inc_dev) {
+extern "C" int dagma_linear_update_ex_f64(dagma_stream_t stream, int d, void* state_dev, double* w_dev,
+                                          const double* minv_dev, const double* t_dev, const double* cov_dev,
+                                          double* m_dev, double* v_dev, const uint8_t* mask_exc_dev,
+                                          const uint8_t* mask_inc_dev, const double* extra_t_dev, double extra_scale) {
     DAGMA_REQUIRE(state_dev && w_dev && minv_dev && t_dev && cov_dev && m_dev && v_dev, "null pointer");
     dim3 grid((d + 31) / 32, (d + 31) / 32);
     linear_update_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((LinState*)state_dev, d, w_dev, minv_dev, t_dev,
-                                                                        cov_dev, m_dev, v_dev, mask_exc_dev, mask_inc_dev);
+                                                                        cov_dev, m_dev, v_dev, mask_exc_dev, mask_inc_dev,
+                                                                        extra_t_dev, extra_scale);
     DAGMA_CUDA_OK(cudaGetLastError());
     linear_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((LinState*)state_dev);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int dagma_linear_update_f64(dagma_stream_t stream, int d, void* state_dev, double* w_dev,
+                                       const double* minv_dev, const double* t_dev, const double* cov_dev,
+                                       double* m_dev, double* v_dev, const uint8_t* mask_exc_dev,
+                                       const uint8_t* mask_inc_dev) {
+    return dagma_linear_update_ex_f64(stream, d, state_dev, w_dev, minv_dev, t_dev, cov_dev, m_dev, v_dev, mask_exc_dev,
+                                      mask_inc_dev, nullptr, 0.0);
 }
 
 extern "C" int dagma_linear_apply_dir_f64(dagma_stream_t stream, int d, const void* state_dev, double* w_dev,

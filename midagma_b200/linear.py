@@ -222,6 +222,34 @@ def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1
 
 # =============================================================================
 # the drop-in class
+def _trek_plan(tr) -> typing.Optional[dict]:
+    """Which trek regulariser the accelerated path carries: PST with ``seq="inv"`` and
+    ``agg`` in {"mean", "sum"} (src/notreks/notreks.py:500-507, 558-619), in mode "opt" or "log".  A disabled
+    regulariser or an empty pair list is the reference's no-op branch (notreks.py:684-689)."""
+    if tr is None or not tr.enabled():
+        return None
+    I = tr.cfg.get("I") if tr.cfg is not None else None
+    if I is None or len(I) == 0:
+        return None
+    name = tr.name.lower().strip()
+    kwargs = dict(tr.cfg.get("kwargs", {}) or {})
+    seq = str(tr.cfg.get("seq", "exp")).lower().strip()
+    agg = str(kwargs.pop("agg", "mean")).lower().strip()
+    eps_inv = float(kwargs.pop("eps_inv", 1e-8))
+    kwargs.pop("s", None)                       # never reaches the "inv" series (notreks.py:500-507)
+    kwargs.pop("K_log", None)
+    if name != "pst" or seq != "inv" or agg not in ("mean", "sum") or kwargs:
+        raise NotImplementedError(
+            f"trek regulariser {tr.name!r} (seq={seq!r}, agg={agg!r}) is outside the B200 hot path (SURVEY.md 8f3): "
+            "only PST with seq='inv' and agg in {'mean', 'sum'} is accelerated")
+    if eps_inv < 0:
+        raise ValueError("eps_inv must be >= 0")
+    I_np = np.asarray(I, dtype=np.int64)
+    if I_np.ndim != 2 or I_np.shape[1] != 2:
+        raise ValueError("I must be array-like of shape (m,2)")
+    return {"I": I_np, "agg": agg, "eps_inv": eps_inv, "weight": float(tr.weight), "mode": tr.mode}
+
+
 # =============================================================================
 class DagmaLinear:
     """DAGMA for linear SEMs on B200 (same surface as the reference class, linear.py:20)."""
@@ -233,15 +261,16 @@ class DagmaLinear:
         self.loss_type = loss_type
         self.dtype = dtype
         self.vprint = print if verbose else lambda *a, **k: None
-        if trek_reg is not None and getattr(trek_reg, "enabled", lambda: False)() \
-                and getattr(trek_reg, "mode", "off") == "opt":
-            raise NotImplementedError(
-                "trek regularisers in mode='opt' are outside the B200 hot path (SURVEY.md 8f3); "
-                "only the no-regulariser path of DagmaLinear is accelerated")
         self.trek_reg = trek_reg
+        self._trek_plan = _trek_plan(trek_reg)          # None, or the PST seq="inv" plan (else NotImplementedError)
         self._torch_dtype = torch.double
         self._device = torch.device("cuda")
-        self._logger, self._log_cfg = logger, log_cfg
+        # telemetry: same defaults as the reference (linear.py:65-67) -- a logger that is silent unless verbose
+        import logging
+        from .logger import LogConfig, StructuredLogger, build_default_logger
+        self._logger = logger or build_default_logger(level=logging.INFO if verbose else logging.WARNING)
+        self._log_cfg = log_cfg or LogConfig(enabled=verbose)
+        self._slog = StructuredLogger(self._logger, self._log_cfg)
         self._large = None
         self._group = None                  # torch.distributed group when the rows of X are sharded
         self.checkpoint_log = []            # rows (stage, iter, obj, score, h, lr) of the last calls
@@ -259,7 +288,10 @@ class DagmaLinear:
         return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(self._device)
 
     def _small_ok(self) -> bool:
-        return self.loss_type == 'l2' and self.d <= _lib.SMALL_MAX_D and self._group is None
+        # the one-launch on-chip path keeps nothing in HBM between checkpoints: runs with telemetry or with a trek
+        # regulariser go through the multi-CTA engine, whose whole state is device-resident and host-visible
+        return (self.loss_type == 'l2' and self.d <= _lib.SMALL_MAX_D and self._group is None
+                and not self._log_cfg.enabled and self._trek_plan is None)
 
     def _large_engine(self):
         from ._large import LargeLinearEngine
@@ -282,7 +314,14 @@ class DagmaLinear:
         score, _ = self._score(W)
         h, _ = self._h(W, s)
         obj = mu * (score + self.lambda1 * np.abs(W).sum()) + h
-        return obj, score, h, 0.0
+        trek_val = 0.0
+        if self._trek_plan is not None:
+            eng = self._large_engine()
+            eng.W.copy_(self._dev(W))
+            trek_val = eng._trek_value()
+            if self._trek_plan["mode"] == "opt":
+                obj = obj + self._trek_plan["weight"] * trek_val
+        return obj, score, h, trek_val
 
     # ------------------------------------------------------------------ _adam_update (linear.py:138-163)
     def _adam_update(self, grad: np.ndarray, iter: int, beta_1: float, beta_2: float) -> np.ndarray:
@@ -312,8 +351,9 @@ class DagmaLinear:
             self._record_log(res)
         else:
             log = []
-            status, iters_done = self._large_engine().minimize(W, mu, int(max_iter), s, lr, tol, beta_1, beta_2,
-                                                               self.lambda1, int(self.checkpoint), log)
+            status, iters_done = self._large_engine().minimize(
+                W, mu, int(max_iter), s, lr, tol, beta_1, beta_2, self.lambda1, int(self.checkpoint), log,
+                telemetry=self._checkpoint_emitter(mu, s) if self._log_cfg.enabled else None)
             self.checkpoint_log.extend(log)
         self.last_iters = iters_done
         success = (status & _lib.ST_OUT_OF_DOMAIN) == 0
@@ -322,6 +362,31 @@ class DagmaLinear:
         if pbar is not None:
             pbar.update(int(max_iter))
         return W, success
+
+    def _checkpoint_emitter(self, mu: float, s: float):
+        """The 25-key ``minimize.checkpoint`` row of the reference (linear.py:279-326)."""
+        t0 = time.time()
+        stage = getattr(self, "_stage", 0)
+        tr = self.trek_reg
+        trek_cfg = {k: v for k, v in tr.cfg.items() if k != "I"} if tr is not None else {}
+
+        def emit(diag, it, obj, score, h, trek_val, lr):
+            self._slog.emit("minimize.checkpoint", {
+                "iter": int(it), "stage": int(stage), "elapsed_sec": float(time.time() - t0),
+                "obj_total": float(obj), "score_datafit": float(score),
+                "reg_dag_name": "dagma_logdet", "reg_dag_value": float(h), "reg_dag_cfg": {"s": float(s)},
+                "reg_trek_name": tr.name if tr is not None else "none", "reg_trek_value": float(trek_val),
+                "reg_trek_cfg": trek_cfg, "trek_mode": tr.mode if tr is not None else "off",
+                "trek_weight": float(tr.weight) if tr is not None else 0.0,
+                "mu": float(mu), "lr": float(lr),
+                "w_norm": diag["w_norm"], "w_abs_sum": diag["w_abs_sum"], "max_abs_w": diag["max_abs_w"],
+                "min_abs_w_nonzero": diag["min_abs_w_nonzero"],
+                "grad_raw_norm": diag["grad_raw_norm"], "grad_step_norm": diag["grad_step_norm"],
+                "step_norm": float(lr * diag["grad_step_norm"]), "grad_score_norm": diag["grad_score_norm"],
+                "grad_dag_norm": diag["grad_dag_norm"], "grad_l1_norm": diag["grad_l1_norm"],
+                "grad_inc_norm": diag["grad_inc_norm"], "grad_trek_norm": diag["grad_trek_norm"],
+            })
+        return emit
 
     def _record_log(self, res: SmallFitResult) -> None:
         if res.ckpt_log is None:
@@ -442,5 +507,6 @@ class DagmaLinear:
             del eng
         self.W_raw = self.W_est.copy()
         self.W_est[np.abs(self.W_est) < w_threshold] = 0
+        self._slog.close()                                  # linear.py:460
         self.fit_seconds = time.time() - t0
         return self.W_est

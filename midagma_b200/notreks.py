@@ -7,7 +7,9 @@ In scope:
 * ``trek_value_grad`` no-op path (no / disabled regulariser)    notreks.py:684-689
 * the regulariser dataclasses, so objects built for the reference can be passed around.
 
-The PST family and the spectral TCC penalty are outside the accelerated path
+* PST with ``seq="inv"`` (value and closed-form gradient on the inverse + GEMM kernels)   notreks.py:500-507, 558-619
+
+The other PST series and the spectral TCC penalty are outside the accelerated path
  and raise ``NotImplementedError``.
 """
 from __future__ import annotations
@@ -123,13 +125,48 @@ def trek_cycle_coupling_value_gradW(W: torch.Tensor, I, *, w: float = 1.0, cycle
     return penalty.to(W.device, W.dtype), grad.to(W.device, W.dtype)
 
 
+def pst_inv_value_grad(W, I, *, agg: str = "mean", eps_inv: float = 1e-8, want_grad: bool = True):
+    """PST penalty with ``seq="inv"`` (notreks.py:500-507, 558-619) and its gradient w.r.t. W, on device:
+    X = ((1 + eps) I - W o W)^{-1} (fused inverse kernel), H = X^T X, pst = agg_{(i,j) in I} H[i,j],
+    d pst / d W = 2 W o (X M_s H)^T with M_s the symmetrised, agg-scaled pair mask (closed form of the
+    reference's autograd).  Returns (float, ndarray or None)."""
+    from ._large import gemm
+    _lib.require_device()
+    Wd = torch.as_tensor(np.ascontiguousarray(W, dtype=np.float64)).cuda()
+    d = Wd.shape[0]
+    I_np = np.asarray(I, dtype=np.int64)
+    idx = torch.as_tensor(I_np, device="cuda")
+    mask = torch.zeros(d, d, dtype=torch.float64, device="cuda")
+    mask.index_put_((idx[:, 0], idx[:, 1]), torch.ones(idx.shape[0], dtype=torch.float64, device="cuda"), accumulate=True)
+    if agg == "mean":
+        mask /= idx.shape[0]
+    elif agg != "sum":
+        raise NotImplementedError("only agg in {'mean', 'sum'} is accelerated (SURVEY.md 8f3)")
+    out = logdet_inv(Wd[None].contiguous(), s=1.0 + float(eps_inv), square_input=True, want_inv=True, want_grad=False)
+    if int(out["info"][0].item()) != 0:
+        raise _lib.DagmaB200Error("(1 + eps) I - W o W is not an M-matrix: outside the domain of the fused inverse")
+    X = out["minv"][0].contiguous()
+    H = torch.empty_like(X)
+    gemm(X, X, H, trans_a=True)
+    val = float((mask * H).sum().item())
+    if not want_grad:
+        return val, None
+    B, GT = torch.empty_like(X), torch.empty_like(X)
+    gemm((mask + mask.T).contiguous(), H, B)
+    gemm(X, B, GT)
+    return val, (2.0 * Wd * GT.T).cpu().numpy()
+
+
 def trek_value_grad(W: np.ndarray, tr: Optional[TrekRegularizer], *, torch_dtype: torch.dtype = torch.double,
                     device: Optional[torch.device] = None) -> Tuple[float, np.ndarray]:
-    """(value, grad) of a trek regulariser; the hot path only ever takes the no-op branch."""
+    """(value, grad) of a trek regulariser (notreks.py:667-736): the no-op branch, and PST ``seq="inv"``."""
+    from .linear import _trek_plan
     W_np = np.asarray(W)
-    if tr is None or not tr.enabled():
+    plan = _trek_plan(tr)               # None: disabled / empty I; NotImplementedError outside the accelerated set
+    if plan is None:
         return 0.0, np.zeros_like(W_np)
-    if tr.cfg["I"] is None or len(tr.cfg["I"]) == 0:
-        return 0.0, np.zeros_like(W_np)
-    raise NotImplementedError(
-        f"trek regulariser {tr.name!r} in mode {tr.mode!r} is outside the B200 hot path (SURVEY.md 8f3)")
+    val, grad = pst_inv_value_grad(W_np, plan["I"], agg=plan["agg"], eps_inv=plan["eps_inv"],
+                                   want_grad=(tr.mode == "opt"))
+    if tr.mode != "opt":
+        return val, np.zeros_like(W_np)
+    return val, grad.astype(W_np.dtype, copy=False)

@@ -62,3 +62,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_structured_logger_sinks(tmp_path):
+    """midagma_b200.logger mirrors the fork's src/logger.py interface: rows in memory, jsonl / csv files, callback."""
+    import json
+    from midagma_b200.logger import LogConfig, StructuredLogger, build_default_logger
+    seen = []
+    cfg = LogConfig(enabled=True, store_jsonl=True, store_csv=True, run_dir=str(tmp_path / "run"), run_name="t",
+                    meta={"k": 1}, callback=seen.append)
+    lg = StructuredLogger(build_default_logger(name="t_logger", stream=False), cfg)
+    lg.emit("minimize.checkpoint", {"iter": 100, "obj_total": 1.5, "reg_dag_cfg": {"s": 1.0}})
+    lg.emit("other", {"iter": 200, "obj_total": 2.5, "reg_dag_cfg": {"s": 0.9}})
+    cols = lg.load(event="minimize.checkpoint")
+    assert list(cols["iter"]) == [100] and seen[1]["event"] == "other"
+    lg.close()
+    lines = [json.loads(x) for x in open(tmp_path / "run" / "metrics.jsonl")]
+    assert [r["iter"] for r in lines] == [100, 200]
+    assert json.load(open(tmp_path / "run" / "meta.json"))["k"] == 1
+    assert open(tmp_path / "run" / "metrics.csv").read().splitlines()[0].startswith("event,iter,obj_total")
+    off = StructuredLogger(build_default_logger(name="t_logger", stream=False), LogConfig(enabled=False))
+    off.emit("x", {"a": 1})
+    assert off._rows == [] and off.run_dir is None

@@ -1,0 +1,88 @@
+"""SURVEY.md 8f2 / 8f3 on the GPU: the 25-key ``minimize.checkpoint`` telemetry rows and the PST ``seq="inv"`` trek
+regulariser (modes "opt" and "log"), against rows / trajectories recorded from the unmodified reference
+(oracle/make_golden_trek.py -> tests/golden/linear_trek_events.npz)."""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _reg(name, pairs):
+    from midagma_b200.notreks import PSTRegularizer
+    return {
+        "plain": None,
+        "pst_opt": PSTRegularizer(I=pairs, seq="inv", weight=0.7, mode="opt"),
+        "pst_log": PSTRegularizer(I=pairs, seq="inv", weight=0.7, mode="log"),
+        "pst_opt_sum": PSTRegularizer(I=pairs, seq="inv", weight=0.05, mode="opt", kwargs={"agg": "sum"}),
+    }[name]
+
+
+@pytest.mark.parametrize("agg", ["mean", "sum"])
+def test_pst_inv_value_grad(golden, agg):
+    from midagma_b200.notreks import PSTRegularizer, trek_value_grad
+    g = golden("linear_trek_events")
+    reg = PSTRegularizer(I=g["pairs"], seq="inv", weight=1.0, mode="opt", kwargs={"agg": agg})
+    val, grad = trek_value_grad(g["pst_W"], reg)
+    ref_v, ref_g = float(g[f"pst_val_{agg}"]), g[f"pst_grad_{agg}"]
+    assert abs(val - ref_v) <= 1e-11 * max(1.0, abs(ref_v))
+    assert np.abs(grad - ref_g).max() <= 1e-10 * max(1.0, np.abs(ref_g).max())
+    # mode "log": value only
+    v2, g2 = trek_value_grad(g["pst_W"], PSTRegularizer(I=g["pairs"], seq="inv", weight=1.0, mode="log", kwargs={"agg": agg}))
+    assert abs(v2 - ref_v) <= 1e-11 * max(1.0, abs(ref_v)) and not g2.any()
+    # disabled / empty pair list: the reference's no-op branch
+    v3, g3 = trek_value_grad(g["pst_W"], PSTRegularizer(I=np.zeros((0, 2), dtype=np.int64), seq="inv", weight=1.0))
+    assert v3 == 0.0 and not g3.any()
+    with pytest.raises(NotImplementedError):
+        trek_value_grad(g["pst_W"], PSTRegularizer(I=g["pairs"], seq="exp", weight=1.0))
+
+
+@pytest.mark.parametrize("case", ["plain", "pst_opt", "pst_log", "pst_opt_sum"])
+def test_checkpoint_events_and_trajectory(golden, case):
+    from midagma_b200 import DagmaLinear
+    from midagma_b200.logger import LogConfig
+    g = golden("linear_trek_events")
+    meta = json.loads(str(g["meta_json"]))[case]
+    keys = [str(k) for k in g["numeric_keys"]]
+    rows = []
+    cfg = LogConfig(enabled=True, store_jsonl=False, store_csv=False, keep_in_memory=True, callback=rows.append)
+    m = DagmaLinear("l2", trek_reg=_reg(case, g["pairs"]), log_cfg=cfg)
+    X = g[f"{case}_X"].copy()
+    d = X.shape[1]
+    m.fit(X, lambda1=0.02, T=1, warm_iter=0, max_iter=0, checkpoint=100,
+          include_edges=((0, 3), (2, 5)) if case == "plain" else None)
+    W = np.zeros((d, d))
+    for si, (mu, iters, s, lr) in enumerate(g["stages"]):
+        W, ok = m.minimize(W, float(mu), int(iters), float(s), float(lr))
+        assert ok == bool(g[f"{case}_ok"][si])
+        assert np.abs(W - g[f"{case}_W"][si]).max() <= 1e-9
+    ref = g[f"{case}_events"]
+    assert len(rows) == meta["n_events"] == ref.shape[0]
+    assert sorted(rows[0].keys()) == meta["keys"]                     # the same 25 (+ "event") columns
+    assert rows[0]["event"] == meta["event"] and rows[0]["reg_dag_name"] == meta["reg_dag_name"]
+    assert rows[0]["reg_trek_name"] == meta["reg_trek_name"] and rows[0]["trek_mode"] == meta["trek_mode"]
+    assert rows[0]["reg_dag_cfg"] == meta["reg_dag_cfg"]
+    assert sorted(rows[0]["reg_trek_cfg"].keys()) == meta["reg_trek_cfg_keys"]
+    got = np.array([[float(r[k]) for k in keys] for r in rows])
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
+    worst = {k: float(err[:, i].max()) for i, k in enumerate(keys)}
+    assert err.max() <= 1e-7, worst
+    # the same rows through the logger's own loader
+    cols = m._slog.load(event="minimize.checkpoint")
+    assert list(cols["iter"]) == [int(x) for x in ref[:, 0]]
+
+
+def test_telemetry_small_d_fit_routes_through_engine():
+    """With telemetry on, a d <= 64 fit runs on the multi-CTA engine (state visible at checkpoints) and recovers
+    the same graph as the one-launch on-chip path."""
+    from midagma_b200 import DagmaLinear
+    from midagma_b200.logger import LogConfig
+    from oracle import simulate
+    X, _ = simulate.config_c1(3)
+    a = DagmaLinear("l2").fit(X.copy(), lambda1=0.02, T=2, warm_iter=2000, max_iter=3000, s=[1.0, 0.9])
+    rows = []
+    cfg = LogConfig(enabled=True, store_jsonl=False, callback=rows.append)
+    b = DagmaLinear("l2", log_cfg=cfg).fit(X.copy(), lambda1=0.02, T=2, warm_iter=2000, max_iter=3000, s=[1.0, 0.9])
+    assert rows and rows[0]["iter"] == 1000
+    assert simulate.edge_set_distance(a, b) == 0
