@@ -331,8 +331,8 @@ def run_b200(args):
         extra["roofline"] = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this configuration (4096 problems x 1000
-            # iterations), ncu --set full capture of round 1: profiles/small_fit_dmma_d64_r1_bench.txt
-            "traffic": 375.9e6 if (nprob == 4096 and ITERS_PER_STEP == 1000) else None,
+            # iterations), ncu --set full capture of round 1: profiles/small_fit_dmma_d64_r1_final.txt
+            "traffic": 375.0e6 if (nprob == 4096 and ITERS_PER_STEP == 1000) else None,
             "traffic_unit": "bytes per launch (algorithmic I/O: cov + W in, W out = 402.7e6)",
             "kernel": "fit_small_dmma_kernel (one launch per step)",
             "peak_source": "measured live: FP64 pipe yardsticks " + json.dumps({k: round(v, 2) for k, v in peaks.items()})

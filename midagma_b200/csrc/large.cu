@@ -707,6 +707,7 @@ struct FlowArgs {
     const double* gA; const double* gB; double* gC;
     int sleep_coresident;                   // 1: the CTA that shares an SM with a chain-team CTA sleeps while the chain runs
     int rider_only;                         // debug / timing: skip the inversion, run only the rider's items
+    int fill_k;                             // k extent of a rider item (256 = the outer block; rider_only timing: any multiple of 16)
     int item_base[FL_MAX_OB + 1];           // first queue index of step k
 };
 
@@ -949,7 +950,8 @@ __global__ void __launch_bounds__(DM_NT, 2) flow_inverse_kernel(const FlowArgs P
         if (u0 < n_fill) {              // rider tile: gC[I,J] (+)= gA[I, Kc] gB[Kc, J], k-chunk c = k
             it.type = IT_FILL; it.bi = u0 / tn; it.bj = u0 % tn;
             it.Am = P.gA; it.lda = d; it.Bm = P.gB; it.ldb = d;
-            it.r0 = it.bi * NB; it.c0 = it.bj * NB; it.rmax = d; it.cmax = d; it.kbeg = k0; it.kend = k0 + kn;
+            it.r0 = it.bi * NB; it.c0 = it.bj * NB; it.rmax = d; it.cmax = d;
+            it.kbeg = k * P.fill_k; it.kend = min(d, (k + 1) * P.fill_k);
             return it;
         }
         u0 -= n_fill;
@@ -1464,9 +1466,14 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         FA.gA = rider.A; FA.gB = rider.B; FA.gC = rider.C;
         FA.sleep_coresident = flow_sleep_mode(rider.C != nullptr);
         FA.rider_only = (rider.C != nullptr && getenv("DAGMA_FLOW_RIDER_ONLY") != nullptr) ? 1 : 0;
+        FA.fill_k = OB;
+        if (FA.rider_only && getenv("DAGMA_FLOW_FILL_K")) {          // timing experiment: longer rider items
+            FA.fill_k = atoi(getenv("DAGMA_FLOW_FILL_K"));
+            FA.nob = (d + FA.fill_k - 1) / FA.fill_k;
+        }
         const int n_fill = rider.C ? FA.tn * FA.tn : 0;
         FA.item_base[0] = 0;
-        for (int k = 0; k < nob; ++k) {
+        for (int k = 0; k < FA.nob; ++k) {
             const int kn = (d - k * OB) < OB ? (d - k * OB) : OB, nk = (kn + NB - 1) / NB;
             const int kn1 = (k + 1 < nob) ? ((d - (k + 1) * OB) < OB ? (d - (k + 1) * OB) : OB) : 0, nk1 = (kn1 + NB - 1) / NB;
             FA.item_base[k + 1] = FA.item_base[k] + n_fill + (FA.rider_only ? 0 : nk * FA.tn + (FA.tn - nk1) * nk + (FA.tn * FA.tn - nk1 * nk1));
