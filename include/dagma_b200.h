@@ -227,6 +227,10 @@ int dagma_bench_latency(dagma_stream_t stream, double* out_dev);
 /* serial chain of the on-chip sweep in isolation: out[0] clk per 8 x 8 pivot-block inversion, out[1] with the
    diagonal warp's DMMAs interleaved, out[2] max |P - inv(inv(P))| */
 int dagma_bench_stage(dagma_stream_t stream, double* out_dev);
+/* timing experiment: c = a @ b (d x d, d even) by the engine pairs of the persistent inverse kernels, one 64 x 64 tile
+   per engine (persistent = 0) or from an atomic queue (persistent = 1; queue_dev: one unsigned) */
+int dagma_bench_engine_gemm(dagma_stream_t stream, int d, const double* a_dev, const double* b_dev, double* c_dev,
+                            int persistent, unsigned* queue_dev);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,7 @@ EXPORTS = {
     "dagma_bench_fp64_dmma": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dagma_bench_latency": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dagma_bench_stage": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dagma_bench_engine_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dagma_bench_fp64_dmma_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 

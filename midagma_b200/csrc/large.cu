@@ -397,8 +397,16 @@ __device__ __forceinline__ bool wait_count(volatile unsigned* c, unsigned target
     __threadfence();
     return true;
 }
+#ifndef DAGMA_HALF_SYNC_IMM
+#define DAGMA_HALF_SYNC_IMM 1
+#endif
 __device__ __forceinline__ void half_sync(int half) {            // barrier of one 128-thread engine
+#if DAGMA_HALF_SYNC_IMM
+    if (half) asm volatile("bar.sync 2, %0;" ::"n"(EN_NT) : "memory");
+    else asm volatile("bar.sync 1, %0;" ::"n"(EN_NT) : "memory");
+#else
     asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(EN_NT) : "memory");
+#endif
 }
 
 struct EnginePos {          // thread of an engine: warp (wm, wn) of a 2 x 2 grid owns a 32 x 32 tile
@@ -415,28 +423,39 @@ struct EnginePos {          // thread of an engine: warp (wm, wn) of a 2 x 2 gri
 
 // acc += Am[r0.., kbeg..kend) * Bm[kbeg..kend, c0..)  for one 64 x 64 tile; operands come through L2
 // (cp.async.cg).  rmax / cmax: valid rows of Am / columns of Bm.  lda, ldb even, bases 16-byte aligned.
+// engine_prefetch requests the first two slabs (two commit groups, stages 0 and 1); engine_gemm with
+// prefetched = true continues from there, so the requests can be made before the previous tile's epilogue.
+__device__ __forceinline__ void engine_issue(const double* Am, int lda, const double* Bm, int ldb, int r0, int c0,
+                                             int rmax, int cmax, int kbeg, int kend, int kt, uint32_t ebase, int htid) {
+    const int nk = (kend - kbeg + GBK - 1) / GBK;
+    if (kt < nk) {
+        const int st = kt % GSTAGES;
+        const uint32_t sa = ebase + (uint32_t)(st * EN_STG) * 8, sb = sa + (uint32_t)EngT::A_STAGE * 8;
+        const int k0 = kbeg + kt * GBK;
+        load_slab<NB, GBK, EN_NT>(sa, EngT::LDA_N, Am, lda, r0, k0, rmax, kend, true, htid);
+        load_slab<GBK, NB, EN_NT>(sb, EngT::LDB_S, Bm, ldb, k0, c0, kend, cmax, true, htid);
+    }
+    cp_async_commit();
+}
+__device__ __forceinline__ void engine_prefetch(const double* Am, int lda, const double* Bm, int ldb, int r0, int c0,
+                                                int rmax, int cmax, int kbeg, int kend, double* esm, int htid) {
+    const uint32_t ebase = smem_u32(esm);
+#pragma unroll
+    for (int st = 0; st < GSTAGES - 1; ++st) engine_issue(Am, lda, Bm, ldb, r0, c0, rmax, cmax, kbeg, kend, st, ebase, htid);
+}
 __device__ __forceinline__ void engine_gemm(double (&acc)[4][4][2], const double* Am, int lda, const double* Bm, int ldb,
                                             int r0, int c0, int rmax, int cmax, int kbeg, int kend, double* esm,
-                                            const EnginePos& ep, int half) {
+                                            const EnginePos& ep, int half, bool prefetched = false) {
     const uint32_t ebase = smem_u32(esm);
     const int nk = (kend - kbeg + GBK - 1) / GBK;
-    auto issue = [&](int kt) {
-        if (kt < nk) {
-            const int st = kt % GSTAGES;
-            const uint32_t sa = ebase + (uint32_t)(st * EN_STG) * 8, sb = sa + (uint32_t)EngT::A_STAGE * 8;
-            const int k0 = kbeg + kt * GBK;
-            load_slab<NB, GBK, EN_NT>(sa, EngT::LDA_N, Am, lda, r0, k0, rmax, kend, true, ep.htid);
-            load_slab<GBK, NB, EN_NT>(sb, EngT::LDB_S, Bm, ldb, k0, c0, kend, cmax, true, ep.htid);
-        }
-        cp_async_commit();
-    };
-    half_sync(half);                           // the stages may still be read by the previous item
-#pragma unroll
-    for (int st = 0; st < GSTAGES - 1; ++st) issue(st);
+    if (!prefetched) {
+        half_sync(half);                       // the stages may still be read by the previous item
+        engine_prefetch(Am, lda, Bm, ldb, r0, c0, rmax, cmax, kbeg, kend, esm, ep.htid);
+    }
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<GSTAGES - 2>();
         half_sync(half);                       // slab kt landed; slab kt-1 is free for reuse
-        issue(kt + GSTAGES - 1);
+        engine_issue(Am, lda, Bm, ldb, r0, c0, rmax, cmax, kbeg, kend, kt + GSTAGES - 1, ebase, ep.htid);
         const double* As = esm + (kt % GSTAGES) * EN_STG;
         const double* Bs = As + EngT::A_STAGE;
 #pragma unroll
@@ -664,6 +683,43 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P)
         }
     }
     OT_MAX(11);
+}
+
+// ---- timing experiment: the stand-alone GEMM's tiles computed by engine pairs (256-thread CTAs, two per SM,
+// named barriers) -- isolates the engine structure from the queue / dependency logic of the persistent kernels
+__global__ void __launch_bounds__(DM_NT, 2) engine_pair_gemm_kernel(const double* A, const double* B, double* C, int d,
+                                                                    int persistent, unsigned* queue) {
+    extern __shared__ __align__(16) double psm[];
+    __shared__ unsigned s_t[2];
+    const int tid = threadIdx.x, half = tid >> 7;
+    const EnginePos ep(tid);
+    double* esm = psm + half * EN_SMEM;
+    const int tn = (d + NB - 1) / NB, ntiles = tn * tn;
+    double acc[4][4][2];
+    int t = 2 * blockIdx.x + half;
+    for (;;) {
+        if (persistent) {
+            half_sync(half);
+            if (ep.htid == 0) s_t[half] = atomicAdd(queue, 1u);
+            half_sync(half);
+            t = (int)s_t[half];
+        }
+        if (t >= ntiles) break;
+        const int r0 = (t / tn) * NB, c0 = (t % tn) * NB;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        engine_gemm(acc, A, d, B, d, r0, c0, d, d, 0, d, esm, ep, half);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                if (r < d && c < d) *reinterpret_cast<double2*>(C + (size_t)r * d + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+        if (!persistent) break;
+    }
 }
 
 // =====================================================================================================
@@ -1115,23 +1171,13 @@ __global__ void __launch_bounds__(DM_NT, 2) flow_inverse_kernel(const FlowArgs P
                 }
             }
     };
-    const uint32_t ebase = smem_u32(esm);
-    unsigned gslab = 0;                                    // running slab count: stage = gslab % 3
-    auto issue_slab = [&](const Item& it, int kt, unsigned g) {
-        const int st = (int)(g % GSTAGES);
-        const uint32_t sa = ebase + (uint32_t)(st * EN_STG) * 8, sb = sa + (uint32_t)EngT::A_STAGE * 8;
-        const int k0 = it.kbeg + kt * GBK;
-        load_slab<NB, GBK, EN_NT>(sa, EngT::LDA_N, it.Am, it.lda, it.r0, k0, it.rmax, it.kend, true, ep.htid);
-        load_slab<GBK, NB, EN_NT>(sb, EngT::LDB_S, it.Bm, it.ldb, k0, it.c0, it.kend, it.cmax, true, ep.htid);
-    };
-
     __shared__ unsigned s_next[2], s_ready[2];
     half_sync(half);
     if (ep.htid == 0) s_next[half] = pull();
     half_sync(half);
-    Item cur = decode((int)s_next[half]);
-    int prefetched = 0;                                    // slabs of `cur` already requested
-    bool cur_ready = false;
+    int t_cur = (int)s_next[half];
+    Item cur = decode(t_cur);
+    bool cur_ready = false, prefetched = false;
     while (cur.type != IT_NONE) {
         if (!cur_ready) wait_deps(cur);
         if (cur.type == IT_R) {
@@ -1141,72 +1187,35 @@ __global__ void __launch_bounds__(DM_NT, 2) flow_inverse_kernel(const FlowArgs P
             if (ep.htid == 0) s_next[half] = pull();
             half_sync(half);
             cur = decode((int)s_next[half]);
-            cur_ready = false;
-            prefetched = 0;
+            cur_ready = prefetched = false;
             continue;
         }
         if (cur.type == IT_UPD) FT_MIN(cur.k, 12);
-        // ---- a GEMM item: pull the next one right away (the atomic's latency hides behind the first slabs)
-        unsigned nxt_raw = 0;
-        if (ep.htid == 0) nxt_raw = pull();
-        const int nk = (cur.kend - cur.kbeg + GBK - 1) / GBK;
-        half_sync(half);                                   // the stages may still be read (first item / after a copy)
-        for (int st = prefetched; st < GSTAGES - 1; ++st) {
-            if (st < nk) issue_slab(cur, st, gslab + st);
-            cp_async_commit();
+        // ---- a GEMM item.  Request its first slabs (unless the previous item already did), then look ahead while
+        //      they are in flight: pull the next item, poll its dependencies once, remember only the index.
+        half_sync(half);
+        if (!prefetched)
+            engine_prefetch(cur.Am, cur.lda, cur.Bm, cur.ldb, cur.r0, cur.c0, cur.rmax, cur.cmax, cur.kbeg, cur.kend, esm, ep.htid);
+        if (ep.htid == 0) s_next[half] = pull();
+        half_sync(half);
+        const int t_nxt = (int)s_next[half];
+        if (ep.htid < 32) {
+            const Item peek = decode(t_nxt);
+            const bool ok = (peek.type == IT_FILL || peek.type == IT_CS || peek.type == IT_UPD) && deps_ready(peek);
+            if (ep.htid == 0) s_ready[half] = ok ? 1u : 0u;
         }
         zero_acc();
-        Item nxt{};
-        bool nxt_ready = false;
-        const int kt_publish = (nk > 4) ? 1 : -1, kt_poll = nk - 4;     // short items (tail block): no look-ahead
-        for (int kt = 0; kt < nk; ++kt) {
-            cp_async_wait<GSTAGES - 2>();
-            half_sync(half);                               // slab kt landed; slab kt-1 is free for reuse
-            if (kt == kt_publish + 1 && kt_publish >= 0) nxt = decode((int)s_next[half]);
-            if (kt == kt_poll + 1 && kt_publish >= 0) nxt_ready = (s_ready[half] != 0u);
-            {   // request slab kt+2: of this item, or of the next one when it is known to be ready
-                const int s2 = kt + GSTAGES - 1;
-                if (s2 < nk) issue_slab(cur, s2, gslab + s2);
-                else if (nxt_ready && s2 - nk < GSTAGES - 1) {
-                    const int nkn = (nxt.kend - nxt.kbeg + GBK - 1) / GBK;
-                    if (s2 - nk < nkn) issue_slab(nxt, s2 - nk, gslab + s2);
-                }
-                cp_async_commit();
-            }
-            const double* As = esm + ((gslab + kt) % GSTAGES) * EN_STG;
-            const double* Bs = As + EngT::A_STAGE;
-#pragma unroll
-            for (int kk = 0; kk < GBK; kk += 4) {
-                double a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = As[ep.row(i) * EngT::LDA_N + kk + ep.qc];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Bs[(kk + ep.qc) * EngT::LDB_S + 32 * ep.wn + 8 * j + ep.qr];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-            if (kt == kt_publish && ep.htid == 0) s_next[half] = nxt_raw;
-            if (kt == kt_poll && kt_publish >= 0 && ep.htid < 32) {
-                // only GEMM items are looked ahead; a copy item or the end of the queue is handled at the boundary
-                bool ok = (nxt.type == IT_FILL || nxt.type == IT_CS || nxt.type == IT_UPD) && deps_ready(nxt);
-                if (ep.htid == 0) s_ready[half] = ok ? 1u : 0u;
-            }
-        }
+        engine_gemm(acc, cur.Am, cur.lda, cur.Bm, cur.ldb, cur.r0, cur.c0, cur.rmax, cur.cmax, cur.kbeg, cur.kend, esm, ep,
+                    half, true);
+        half_sync(half);                                   // every warp is done with the stages (and s_ready is visible)
+        const Item nxt = decode(t_nxt);
+        const bool nxt_ready = (s_ready[half] != 0u);
+        if (nxt_ready)                                     // its first slabs fly during this item's epilogue
+            engine_prefetch(nxt.Am, nxt.lda, nxt.Bm, nxt.ldb, nxt.r0, nxt.c0, nxt.rmax, nxt.cmax, nxt.kbeg, nxt.kend, esm, ep.htid);
         epilogue(cur);
         signal_done(cur);
-        if (kt_publish < 0) {                              // short item: the next index was not handed over inside the loop
-            if (ep.htid == 0) s_next[half] = nxt_raw;
-            half_sync(half);
-            nxt = decode((int)s_next[half]);
-            nxt_ready = false;
-        }
-        gslab += (unsigned)(nk > GSTAGES - 1 ? nk : GSTAGES - 1);
-        // slabs nk, nk+1 of the stream (the first two of the next item) were requested iff nxt_ready
-        prefetched = nxt_ready ? GSTAGES - 1 : 0;
-        cur_ready = nxt_ready;
         cur = nxt;
+        cur_ready = prefetched = nxt_ready;
     }
     cp_async_wait<0>();
 }
@@ -1842,6 +1851,19 @@ extern "C" int dagma_logdet_inv_gemm_ws_f64(dagma_stream_t stream, int d, double
                                      min_entry_dev, info_dev, ws_dev, ws_bytes);
     if (rc) return rc;
     return gemm_launch((cudaStream_t)stream, 0, d, d, d, 1.0, ga_dev, d, gb_dev, d, 0.0, gc_dev, d, EPI_NONE, nullptr, 0);
+}
+
+extern "C" int dagma_bench_engine_gemm(dagma_stream_t stream, int d, const double* a_dev, const double* b_dev,
+                                       double* c_dev, int persistent, unsigned* queue_dev) {
+    DAGMA_REQUIRE(d % 2 == 0 && a_dev && b_dev && c_dev, "bad arguments");
+    DAGMA_CUDA_OK(cudaFuncSetAttribute(engine_pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)OUTER_SMEM_BYTES));
+    const int tn = (d + NB - 1) / NB, ntiles = tn * tn;
+    if (persistent) DAGMA_CUDA_OK(cudaMemsetAsync(queue_dev, 0, sizeof(unsigned), (cudaStream_t)stream));
+    engine_pair_gemm_kernel<<<persistent ? 296 : (ntiles + 1) / 2, DM_NT, OUTER_SMEM_BYTES, (cudaStream_t)stream>>>(
+        a_dev, b_dev, c_dev, d, persistent, queue_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int dagma_linear_update_ex_f64(dagma_stream_t stream, int d, void* state_dev, double* w_dev,
