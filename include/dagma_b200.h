@@ -231,6 +231,12 @@ int dagma_bench_stage(dagma_stream_t stream, double* out_dev);
    per engine (persistent = 0) or from an atomic queue (persistent = 1; queue_dev: one unsigned) */
 int dagma_bench_engine_gemm(dagma_stream_t stream, int d, const double* a_dev, const double* b_dev, double* c_dev,
                             int persistent, unsigned* queue_dev);
+/* timing experiment: c = alpha a @ b + beta c by the TMA-fed GEMM (cp.async.bulk.tensor slabs + mbarrier pipeline;
+   a: M x K, b: K x N, row-major, even leading dimensions, 16-byte aligned); mode 0 = static tile striding,
+   1 = tiles from an atomic queue (queue_dev: one unsigned) */
+int dagma_bench_tma_gemm(dagma_stream_t stream, int M, int N, int K, const double* a_dev, int lda,
+                         const double* b_dev, int ldb, double* c_dev, int ldc, double alpha, double beta, int mode,
+                         unsigned* queue_dev);
 
 #ifdef __cplusplus
 }

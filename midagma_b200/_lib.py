@@ -87,6 +87,8 @@ EXPORTS = {
     "dagma_bench_latency": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dagma_bench_stage": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dagma_bench_engine_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "dagma_bench_tma_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p]),
     "dagma_bench_fp64_dmma_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 

@@ -16,6 +16,7 @@
 // rank-256 GEMMs.  log|det| comes from the pivots of all 4 x 4 pivot blocks.
 #include "common.cuh"
 #include "gemm_f64.cuh"
+#include "gemm_tma.cuh"
 #include "small_gj.cuh"
 #include "small_dmma.cuh"
 #include <cstdlib>
@@ -88,10 +89,19 @@ static int gemm_tile_variant() {
     return v;
 }
 
+static unsigned* tma_queue(cudaStream_t stream);
+static int tma_mode();
+static bool gemm_use_tma(int M, int N, int K);
+static bool gemm_tma_ok(int transA, int M, int N, int K, const double* A, int lda, const double* B, int ldb);
+static int gemm_tma_launch(cudaStream_t stream, int M, int N, int K, double alpha, const double* A, int lda,
+                           const double* B, int ldb, double beta, double* C, int ldc, int epi, unsigned* queue);
+
 static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, double alpha, const double* A, int lda,
                        const double* B, int ldb, double beta, double* C, int ldc, int epi, double* ws,
                        size_t ws_bytes) {
     if (M <= 0 || N <= 0) return 0;
+    if (gemm_use_tma(M, N, K) && gemm_tma_ok(transA, M, N, K, A, lda, B, ldb))
+        return gemm_tma_launch(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, tma_queue(stream));
     if (gemm_tile_variant() == 1)
         return gemm_launch_tile<128, 128, 4, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
     if (gemm_tile_variant() == 2)
@@ -101,6 +111,9 @@ static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, dou
 
 // ------------------------------------------------------------------ blocked inverse
 constexpr int NB = 64;
+#ifndef DAGMA_TMA_DEFAULT
+#define DAGMA_TMA_DEFAULT 5      // outer-step update tiles + long stand-alone GEMMs (see tma_mode)
+#endif
 
 // build M = s I - (square ? A o A : A), scaled by inv_scale, into out (d x d, ld = d)
 __global__ void build_m_kernel(const double* __restrict__ A, int lda, double* __restrict__ out, int d, double s,
@@ -370,6 +383,7 @@ struct OuterArgs {
     int* sm_busy;                           // [SM id] 1 while a server CTA runs there; [SM_SLOTS + SM id] CS' role claimed
     int nserver;
     ServerArgs srv;
+    int use_tma;                            // update tiles fed by TMA (gemm_tma.cuh) instead of cp.async
 };
 constexpr int SM_SLOTS = 256;
 // Worker side: a 256-thread CTA is TWO independent 128-thread tile engines (half = tid / 128), each the
@@ -474,13 +488,23 @@ __device__ __forceinline__ void engine_gemm(double (&acc)[4][4][2], const double
     cp_async_wait<0>();
 }
 
-__global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P) {
+__global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
+                                                              const __grid_constant__ CUtensorMap mapCS,
+                                                              const __grid_constant__ CUtensorMap mapR) {
     extern __shared__ __align__(16) double psm[];
     __shared__ unsigned s_tile[2];
+    __shared__ __align__(8) unsigned long long s_tbars[2][2 * TM_STAGES];
     const int tid = threadIdx.x;
     const int half = tid >> 7;
     const EnginePos ep(tid);
     double* esm = psm + half * EN_SMEM;
+    TmaPipe pipe;
+    tm_pipe_init(pipe, smem_u32(esm), smem_u32(s_tbars[half]), P.use_tma && ep.htid == 0);
+    if (P.use_tma && ep.htid == 0) {
+        tm_prefetch_map(&mapCS);
+        tm_prefetch_map(&mapR);
+    }
+    __syncthreads();
     const int d = P.d, kn = P.kn, k1 = P.k1, kn1 = P.kn1;
     int* err = reinterpret_cast<int*>(P.sync + 2);
     volatile int* busy = P.sm_busy + (smid() % SM_SLOTS);
@@ -568,6 +592,98 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P)
     const int n_csn = tn * nk1, n_rn = nk1 * tn;
     const int n_items = n_upd + n_rn;
     auto outside = [&](int u) { return u < cb1 ? u : u + nk1; };  // u-th block index not in K'
+    auto upd_tile = [&](int t, int& bi, int& bj, int& strip) {
+        strip = 0;
+        if (t < n_cs) { bi = outside(t / nk1); bj = cb1 + t % nk1; strip = 1; }
+        else if (t < n_cs + n_rs) { const int u = t - n_cs; bi = cb1 + u / (tn - nk1); bj = outside(u % (tn - nk1)); strip = 2; }
+        else { const int u = t - n_cs - n_rs; bi = outside(u / (tn - nk1)); bj = outside(u % (tn - nk1)); }
+    };
+    if (P.use_tma) {
+        // ---- TMA-fed engines: one continuous slab stream per engine.  The index of the NEXT item is pulled when
+        // an update tile starts (the atomic's latency hides behind the tile) and its first slabs are requested
+        // during the tile's last slabs; accumulators start at zero and are added to A by red.global.add.f64.
+        const TmaFrag fr(ep.wm, ep.wn, ep.qr, ep.qc);
+        const bool elected = (ep.htid == 0);
+        const int nkt = (kn + TM_BK - 1) / TM_BK;
+        constexpr unsigned T_NONE = 0xffffffffu;
+        tm_fence_proxy();                        // the stages may have been written through the generic proxy
+        half_sync(half);
+        if (elected) {
+            while (*busy) __nanosleep(2000);
+            s_tile[half] = atomicAdd(P.sync + 1, 1u);
+        }
+        half_sync(half);
+        int t = (int)s_tile[half];
+        int primed = 0;
+        while (t < n_items) {
+            unsigned tnx = T_NONE;
+            if (t < n_upd) {
+                OT_MIN(12);
+                int bi, bj, strip;
+                upd_tile(t, bi, bj, strip);
+                const TmaTile cur{bi * NB, bj * NB, 0, nkt};
+                TmaTile nxt{0, 0, 0, 0};
+                if (elected && !*busy) {
+                    tnx = atomicAdd(P.sync + 1, 1u);
+                    if ((int)tnx < n_upd) {
+                        int bi2, bj2, st2;
+                        upd_tile((int)tnx, bi2, bj2, st2);
+                        nxt = TmaTile{bi2 * NB, bj2 * NB, 0, nkt};
+                    }
+                }
+                zero_acc();
+                primed = tm_tile_gemm(pipe, fr, acc, &mapCS, &mapR, cur, primed, nxt, elected, ep.lane);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = cur.r0 + ep.row(i), c = cur.c0 + ep.col(j);
+                        if (r < d && c < d) {
+                            double* q = P.A + (size_t)r * d + c;
+                            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(q)), "d"(acc[i][j][0]) : "memory");
+                            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(q + 1)), "d"(acc[i][j][1]) : "memory");
+                        }
+                    }
+                if (strip) {
+                    half_sync(half);
+                    if (elected) {
+                        __threadfence();
+                        atomicAdd(P.sync + 2 + strip, 1u);
+                    }
+                }
+                OT_MAX(8);
+            } else {
+                // ---- R' tile: rows 64 ib.. of the next row strip, columns of block bj
+                const int u = t - n_upd, ib = u / tn, bj = u % tn;
+                if (elected) (void)wait_count(P.sync + 4, (unsigned)(tn * nk1), err);
+                half_sync(half);
+                const int c0 = bj * NB;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int rr = ib * NB + ep.row(i), c = c0 + ep.col(j);     // rr: row inside the strip
+                        if (rr < kn1 && c < d) {
+                            double2 v = __ldcg(reinterpret_cast<const double2*>(P.A + (size_t)(k1 + rr) * d + c));
+                            if (c == k1 + rr) v.x += 1.0;
+                            if (c + 1 == k1 + rr) v.y += 1.0;
+                            *reinterpret_cast<double2*>(P.Rn + (size_t)rr * d + c) = v;
+                        }
+                    }
+                OT_MAX(13);
+            }
+            if (elected) {
+                if (tnx == T_NONE) {
+                    while (*busy) __nanosleep(2000);
+                    tnx = atomicAdd(P.sync + 1, 1u);
+                }
+                s_tile[half] = tnx;
+            }
+            half_sync(half);
+            t = (int)s_tile[half];
+        }
+        half_sync(half);
+    } else
     for (;;) {
         half_sync(half);
         if (ep.htid == 0) {
@@ -720,6 +836,137 @@ __global__ void __launch_bounds__(DM_NT, 2) engine_pair_gemm_kernel(const double
             }
         if (!persistent) break;
     }
+}
+
+// ---- TMA-fed GEMM (gemm_tma.cuh): C = alpha A B + beta C, A row-major M x K, B row-major K x N, 64 x 64 tiles
+// pulled from an atomic queue by persistent 128-thread CTAs (four per SM); the first slabs of the next tile are
+// requested during the last slabs of the current one, so the slab stream never drains between tiles.
+struct TmaGemmArgs {
+    int M, N, K;
+    double* C; int ldc;
+    double alpha, beta;
+    int epi;
+    unsigned* queue;            // zeroed before the launch
+};
+constexpr size_t TMA_GEMM_SMEM_BYTES = TM_PIPE_BYTES + 1024;
+__global__ void __launch_bounds__(128, 4) gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                          const __grid_constant__ CUtensorMap mapB,
+                                                          const TmaGemmArgs P) {
+    extern __shared__ __align__(1024) unsigned char tsm[];
+    __shared__ __align__(8) unsigned long long bars[2 * TM_STAGES];
+    __shared__ unsigned s_next;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1, qr = lane >> 2, qc = lane & 3;
+    const bool elected = (tid == 0);
+    TmaPipe pipe;
+    tm_pipe_init(pipe, smem_u32(tsm), smem_u32(bars), elected);
+    if (elected) {
+        tm_prefetch_map(&mapA);
+        tm_prefetch_map(&mapB);
+    }
+    __syncthreads();
+    const TmaFrag fr(wm, wn, qr, qc);
+    const int tn = (P.N + 63) / 64, tmr = (P.M + 63) / 64, ntiles = tn * tmr;
+    const int nk = (P.K + TM_BK - 1) / TM_BK;
+    const bool vecC = ((P.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    int t = blockIdx.x, primed = 0;
+    while (t < ntiles) {
+        unsigned t_next = (unsigned)t + gridDim.x;           // static striding unless a queue is given
+        if (P.queue && elected) t_next = atomicAdd(P.queue, 1u) + gridDim.x;
+        const TmaTile cur{(t / tn) * 64, (t % tn) * 64, 0, nk};
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        TmaTile nxt{0, 0, 0, 0};
+        if (elected) {
+            if (P.queue) s_next = t_next;
+            if ((int)t_next < ntiles) nxt = TmaTile{((int)t_next / tn) * 64, ((int)t_next % tn) * 64, 0, nk};
+        }
+        primed = tm_tile_gemm(pipe, fr, acc, &mapA, &mapB, cur, primed, nxt, elected, lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = cur.r0 + 32 * wm + 8 * i + qr;
+            if (r >= P.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = cur.c0 + 32 * wn + 8 * j + 2 * qc;
+                if (c >= P.N) continue;
+                double* p = P.C + (size_t)r * P.ldc + c;
+                const bool two = (c + 1 < P.N);
+                double v0 = P.alpha * acc[i][j][0], v1 = P.alpha * acc[i][j][1];
+                if (P.beta != 0.0) {
+                    v0 = fma(P.beta, p[0], v0);
+                    if (two) v1 = fma(P.beta, p[1], v1);
+                }
+                if (P.epi == EPI_SIGMOID) {
+                    v0 = 1.0 / (1.0 + exp(-v0));
+                    v1 = 1.0 / (1.0 + exp(-v1));
+                }
+                if (two && vecC) *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+                else {
+                    p[0] = v0;
+                    if (two) p[1] = v1;
+                }
+            }
+        }
+        if (P.queue) {
+            __syncthreads();
+            t_next = s_next;
+            __syncthreads();
+        }
+        t = (int)t_next;
+    }
+}
+
+static int gemm_tma_launch(cudaStream_t stream, int M, int N, int K, double alpha, const double* A, int lda,
+                           const double* B, int ldb, double beta, double* C, int ldc, int epi, unsigned* queue) {
+    static bool attr = false;
+    if (!attr) {
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_GEMM_SMEM_BYTES));
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr = true;
+    }
+    CUtensorMap mapA, mapB;
+    int rc = tm_make_a_map(&mapA, A, M, K, lda);
+    if (rc) return rc;
+    rc = tm_make_b_map(&mapB, B, K, N, ldb);
+    if (rc) return rc;
+    int sms = 0, dev = 0;
+    DAGMA_CUDA_OK(cudaGetDevice(&dev));
+    DAGMA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ntiles = ((M + 63) / 64) * ((N + 63) / 64);
+    const int grid = ntiles < 4 * sms ? ntiles : 4 * sms;
+    if (queue) DAGMA_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(unsigned), stream));
+    TmaGemmArgs P{M, N, K, C, ldc, alpha, beta, epi, queue};
+    gemm_tma_kernel<<<grid, 128, TMA_GEMM_SMEM_BYTES, stream>>>(mapA, mapB, P);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+// tile-queue words of the stand-alone TMA GEMM: a small ring in device memory, allocated once per process
+// (outside stream capture: the first GEMM of a process is never captured -- engines warm up before they record
+// a graph); nullptr (static tile striding) if that first call happens during a capture
+static unsigned* tma_queue(cudaStream_t stream) {
+    static unsigned* ring = nullptr;
+    static unsigned next = 0;
+    if (!ring) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+        if (cudaMalloc((void**)&ring, 64 * sizeof(unsigned)) != cudaSuccess) {
+            ring = nullptr;
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+    }
+    return ring + (next++ % 64);
+}
+// can the TMA GEMM take this problem?  (16-byte aligned operands, even leading dimensions, enough tiles to
+// fill the machine without split-K)
+static bool gemm_tma_ok(int transA, int M, int N, int K, const double* A, int lda, const double* B, int ldb) {
+    return !transA && M > 0 && N > 0 && K > 0 && (lda % 2 == 0) && (ldb % 2 == 0) &&
+           (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0) &&
+           ((M + 63) / 64) * ((N + 63) / 64) >= 296;
 }
 
 // =====================================================================================================
@@ -1415,6 +1662,28 @@ static int lookahead_mode() {
     return v;
 }
 
+// DAGMA_TMA: which slab pipelines are fed by TMA (cp.async.bulk.tensor + mbarrier pipeline, gemm_tma.cuh) instead
+// of per-thread cp.async.  Bit 0: the update tiles of the outer step of the two-level inverse; bit 1: the
+// stand-alone GEMM whenever its operands qualify.  Unset: bit 0, and the stand-alone GEMM only when it is long
+// enough for the persistent kernel to pay (measured on B200, scripts/perf_tma.py: 34.1 vs 32.1 TFLOP/s at 4096^3,
+// but 27.0 vs 28.9 at 2000^3 and 24.0 vs 25.9 on the 2000 x 2000 x 256 update, where the per-tile hand-over costs
+// more than the barrier-free slab loop gains).  0 = cp.async everywhere.
+static int tma_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_TMA");
+        v = e ? atoi(e) : DAGMA_TMA_DEFAULT;
+        if (v && !tm_encode_fn()) v = 0;
+    }
+    return v;
+}
+static bool gemm_use_tma(int M, int N, int K) {
+    const int m = tma_mode();
+    if (m & 2) return true;
+    if (m & 4) return (long long)((M + 63) / 64) * ((N + 63) / 64) >= 4 * 592 && K >= 1024;
+    return false;
+}
+
 // two-level block Gauss-Jordan, outer block OB = 256: per outer block K
 //   Q  = P^{-1}, P = A[K,K]          (single-level sweep on a copy of the 256 x 256 block)
 //   CS = -A[:,K] Q, CS[K,:] += Q      (= -(A[:,K] - E_K) Q : the "- I" of the publish identity)
@@ -1550,8 +1819,18 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
 #endif
             OuterArgs OA{Mw, d, CSa, Ra, kn, CSb, Rb, k1, kn1, Qn, sync_words, reinterpret_cast<int*>(sync_words + 8),
                          nblk1 * nblk1,
-                         ServerArgs{Pbuf, Pbuf2, kn1, nblk1, piv + k1, sync_words, reinterpret_cast<int*>(sync_words + 2)}};
-            outer_step_kernel<<<2 * sms, DM_NT, OUTER_SMEM_BYTES, stream>>>(OA);
+                         ServerArgs{Pbuf, Pbuf2, kn1, nblk1, piv + k1, sync_words, reinterpret_cast<int*>(sync_words + 2)},
+                         tma_mode() & 1};
+            CUtensorMap mapCS, mapR;
+            memset(&mapCS, 0, sizeof(mapCS));
+            memset(&mapR, 0, sizeof(mapR));
+            if (OA.use_tma) {
+                rc = tm_make_a_map(&mapCS, CSa, d, kn, kn);
+                if (rc) return rc;
+                rc = tm_make_b_map(&mapR, Ra, kn, d, d);
+                if (rc) return rc;
+            }
+            outer_step_kernel<<<2 * sms, DM_NT, OUTER_SMEM_BYTES, stream>>>(OA, mapCS, mapR);
             DAGMA_CUDA_OK(cudaGetLastError());
             double* t = CSa; CSa = CSb; CSb = t;
             t = Ra; Ra = Rb; Rb = t;
@@ -1864,6 +2143,15 @@ extern "C" int dagma_bench_engine_gemm(dagma_stream_t stream, int d, const doubl
         a_dev, b_dev, c_dev, d, persistent, queue_dev);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// timing experiment: C = A B by the TMA-fed GEMM; mode 0 = static tile striding, 1 = atomic tile queue
+extern "C" int dagma_bench_tma_gemm(dagma_stream_t stream, int M, int N, int K, const double* a_dev, int lda,
+                                    const double* b_dev, int ldb, double* c_dev, int ldc, double alpha, double beta,
+                                    int mode, unsigned* queue_dev) {
+    DAGMA_REQUIRE(a_dev && b_dev && c_dev, "bad arguments");
+    return gemm_tma_launch((cudaStream_t)stream, M, N, K, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc, EPI_NONE,
+                           mode ? queue_dev : nullptr);
 }
 
 extern "C" int dagma_linear_update_ex_f64(dagma_stream_t stream, int d, void* state_dev, double* w_dev,

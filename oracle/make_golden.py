@@ -126,10 +126,12 @@ def linear_full_fit(name, d, n, k, seed, lambda1, graph="ER", **fit_kw):
 
 
 def mlp_case(name, d, m1, n, seed, steps, lambda1=0.02, lambda2=0.005, mu=0.1, s=1.0, lr=2e-4,
-             init_scale=0.1):
+             init_scale=0.1, dims=None):
     Xn, B = simulate.config_c3(seed=seed, n=n, d=d)
     torch.manual_seed(seed)
-    model = DagmaMLP(dims=[d, m1, 1], bias=True, dtype=torch.double)
+    dims = list(dims) if dims is not None else [d, m1, 1]
+    m1 = dims[1]
+    model = DagmaMLP(dims=dims, bias=True, dtype=torch.double)
     # fc1 is zero-initialised in the reference (nonlinear.py:37-38): perturb it so the
     # gradient KAT is non-trivial, then also record a run from the true zero init.
     g = torch.Generator().manual_seed(seed + 1)
@@ -137,7 +139,7 @@ def mlp_case(name, d, m1, n, seed, steps, lambda1=0.02, lambda2=0.005, mu=0.1, s
         model.fc1.weight.copy_(init_scale * torch.randn(d * m1, d, generator=g, dtype=torch.double))
         model.fc1.bias.copy_(init_scale * torch.randn(d * m1, generator=g, dtype=torch.double))
     X = torch.from_numpy(Xn)
-    out = {"X": Xn, "B": B, "dims": np.array([d, m1, 1]), "hyper": np.array([lambda1, lambda2, mu, s, lr])}
+    out = {"X": Xn, "B": B, "dims": np.array(dims), "hyper": np.array([lambda1, lambda2, mu, s, lr])}
     for k_, v in model.state_dict().items():
         out["init." + k_] = v.detach().numpy().copy()
     # one autograd evaluation (nonlinear.py:213-222)
@@ -164,6 +166,13 @@ def mlp_case(name, d, m1, n, seed, steps, lambda1=0.02, lambda2=0.005, mu=0.1, s
     out["steps"] = steps
     np.savez_compressed(os.path.join(GOLD, name), **out)
     print(name, "obj", out["obj"], "ok", ok)
+
+
+def mlp_deep_cases():
+    """Deeper LocallyConnected stacks and the degenerate dims = [d, 1] (nonlinear.py:39-43)."""
+    mlp_case("mlp_deep_d6", 6, 5, 60, 3, steps=20, dims=[6, 5, 3, 1])
+    mlp_case("mlp_deep4_d5", 5, 4, 40, 4, steps=15, dims=[5, 4, 3, 2, 1])
+    mlp_case("mlp_lin_d6", 6, 1, 60, 5, steps=20, dims=[6, 1])
 
 
 def mlp_fit_case(name, d, m1, n, seed, **kw):
@@ -214,6 +223,10 @@ def notreks_case(name, d, seed):
     print(name, out["h_s1.0"], out["tcc_pen_DAG_learning"])
 
 
+if __name__ == "__main__" and "--deep-only" in sys.argv:
+    mlp_deep_cases()
+    sys.exit(0)
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     # chained short stages (step-level / short-horizon parity)
@@ -237,3 +250,4 @@ if __name__ == "__main__":
     mlp_fit_case("mlp_fit_d5", 5, 4, 200, 2, T=2, warm_iter=300, max_iter=400, checkpoint=100,
                  lambda1=0.02, lambda2=0.005)
     notreks_case("notreks_logdet", 6, 0)
+    mlp_deep_cases()

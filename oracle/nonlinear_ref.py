@@ -15,8 +15,8 @@ bit-exact, because the summation order of the reductions differs.
 
 Parameter naming follows the reference ``state_dict``: ``fc1.weight [d*m1, d]``,
 ``fc1.bias [d*m1]``, ``fc2.0.weight [d, m1, 1]``, ``fc2.0.bias [d, 1]``
-(nonlinear.py:36-43).  Only the two-layer form ``dims = [d, m1, 1]`` is restated
-for gradients (the BASELINE config); ``forward`` handles deeper stacks.
+(nonlinear.py:36-43); deeper stacks ``dims = [d, m1, m2, ..., 1]`` add ``fc2.l.weight
+[d, m_l, m_{l+1}]`` / ``fc2.l.bias [d, m_{l+1}]``; ``dims = [d, 1]`` has no ``fc2`` at all.
 """
 from __future__ import annotations
 
@@ -63,38 +63,43 @@ class OracleMLP:
     def fc1_to_adj(self):                                     # nonlinear.py:110-115
         return np.sqrt(self.adj_sq())
 
-    # value and gradient of  mu*(score + lambda1*|fc1|_1) + h   (nonlinear.py:214-222)
+    # value and gradient of  mu*(score + lambda1*|fc1|_1) + h   (nonlinear.py:214-222), any stack
+    # dims = [d, m1, ..., 1] of LocallyConnected layers (nonlinear.py:39-43, 60-65)
     def obj_and_grads(self, X, lambda1, mu, s):
         d, m1 = self.d, self.dims[1]
         n = X.shape[0]
+        L = len(self.dims) - 2
         w1, b1 = self.p["fc1.weight"], self.p["fc1.bias"]
-        W2, b2 = self.p["fc2.0.weight"], self.p["fc2.0.bias"]
         A = self.adj_sq()
         Mm = s * np.eye(d) - A
         h = -np.linalg.slogdet(Mm)[1] + d * np.log(s)
         Minv = np.linalg.inv(Mm)
-        Z = X @ w1.T + b1
-        H = _sigmoid(Z).reshape(n, d, m1)
-        out = np.einsum("njk,jk->nj", H, W2[:, :, 0]) + b2[:, 0]
+        x = (X @ w1.T + b1).reshape(n, d, m1)
+        acts = []
+        for l in range(L):
+            H = _sigmoid(x)
+            acts.append(H)
+            x = np.einsum("njk,jkm->njm", H, self.p[f"fc2.{l}.weight"]) + self.p[f"fc2.{l}.bias"]
+        out = x[:, :, 0]
         res = out - X
         S = (res ** 2).sum()
         score = 0.5 * d * np.log(S / n)                        # nonlinear.py:158
-        dout = (d / S) * res
-        gW2 = np.einsum("nj,njk->jk", dout, H)[:, :, None]
-        gb2 = dout.sum(axis=0)[:, None]
-        dZ = (dout[:, :, None] * W2[None, :, :, 0] * H * (1 - H)).reshape(n, d * m1)
+        dx = ((d / S) * res)[:, :, None]
+        grads = {}
+        for l in reversed(range(L)):
+            H, Wl = acts[l], self.p[f"fc2.{l}.weight"]
+            grads[f"fc2.{l}.weight"] = mu * np.einsum("njk,njm->jkm", H, dx)
+            grads[f"fc2.{l}.bias"] = mu * dx.sum(axis=0)
+            dx = np.einsum("njm,jkm->njk", dx, Wl) * H * (1 - H)
+        dZ = dx.reshape(n, d * m1)
         gw1_score = dZ.T @ X
         gb1 = dZ.sum(axis=0)
         # dh/dw[j,k,i] = 2 w[j,k,i] * Minv[j,i]
         w3 = w1.reshape(d, m1, d)
         gh = (2.0 * w3 * Minv[:, None, :]).reshape(d * m1, d)
         obj = mu * (score + lambda1 * np.abs(w1).sum()) + h
-        grads = {
-            "fc1.weight": mu * (gw1_score + lambda1 * np.sign(w1)) + gh,
-            "fc1.bias": mu * gb1,
-            "fc2.0.weight": mu * gW2,
-            "fc2.0.bias": mu * gb2,
-        }
+        grads["fc1.weight"] = mu * (gw1_score + lambda1 * np.sign(w1)) + gh
+        grads["fc1.bias"] = mu * gb1
         return obj, score, h, grads
 
 
