@@ -193,6 +193,25 @@ int dagma_mlp_backward_f64(dagma_stream_t stream, int n, int d, int m1, double* 
 /* torch.optim.Adam(betas, weight_decay = mu lambda2) over theta + ExponentialLR   nonlinear.py:208-225 */
 int dagma_mlp_adam_f64(dagma_stream_t stream, int d, int m1, void* state_dev, double* theta_dev,
                        const double* grads_dev, double* m_dev, double* v_dev, const double* minv_dev);
+/* same step over a flat theta of `total` doubles whose first d*m1*d entries are fc1.weight (any stack) */
+int dagma_mlp_adam_ex_f64(dagma_stream_t stream, int d, int m1, size_t total, void* state_dev, double* theta_dev,
+                          const double* grads_dev, double* m_dev, double* v_dev, const double* minv_dev);
+/* General LocallyConnected stacks dims = [d, m_1, ..., 1] (nonlinear.py:39-43, 60-65), transposed activations
+ * [d * width][n], one call per layer.
+ *   lc_forward : in ([d*mi][n]; + bias_in for the first layer) is replaced by H = sigmoid(in);
+ *                out[(j*mo+o)][s] = b[j][o] + sum_k H[j*mi+k][s] w[j][k][o]          locally_connected.py:70-74
+ *   residual   : res = out (+ bias) - xt, S = sum res^2 and l1 -> state (the tail of nonlinear.py:60-66, 158)
+ *   lc_backward: H is replaced by dZ = (sum_o w[j][k][o] dzn[j*mo+o]) H (1 - H); grads = [gW (d*mi*mo) | gb (d*mo)]
+ *                un-scaled sums over the samples (part_dev: ceil(n/256) rows of that width)
+ *   row_sums   : out[r] = sum_s a[r][s]  (fc1.bias gradient)                                              */
+int dagma_lc_forward_f64(dagma_stream_t stream, int n, int d, int mi, int mo, double* in_dev,
+                         const double* bias_in_dev, const double* w_dev, const double* b_dev, double* out_dev);
+int dagma_mlp_residual_f64(dagma_stream_t stream, int n, int d, const double* out_dev, const double* bias_dev,
+                           const double* xt_dev, double* res_dev, double* out_opt_dev, double* s_partial_dev,
+                           const double* l1_partial_dev, void* state_dev);
+int dagma_lc_backward_f64(dagma_stream_t stream, int n, int d, int mi, int mo, double* h_dev, const double* dzn_dev,
+                          const double* w_dev, double* part_dev, double* grads_dev);
+int dagma_row_sums_f64(dagma_stream_t stream, int rows, int n, const double* a_dev, double* out_dev);
 /* LocallyConnected.forward                                       locally_connected.py:55-75     */
 int dagma_locally_connected_f64(dagma_stream_t stream, int n, int d, int m1, int m2, const double* in_dev,
                                 const double* w_dev, const double* b_dev, double* out_dev);

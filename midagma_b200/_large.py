@@ -73,50 +73,24 @@ class LargeLinearEngine:
 
     # ------------------------------------------------------------------ trek regulariser
     def _trek_setup(self, plan):
-        """PST ``seq="inv"`` (src/notreks/notreks.py:500-507, 558-619): pst = agg_{(i,j) in I} H[i,j] with
-        X = ((1 + eps) I - W o W)^{-1}, H = X^T X.  Closed-form adjoint instead of autograd:
-        d pst / d W = 2 W o (X^T X M_s X^T) = 2 W o (X M_s H)^T with M_s = (M + M^T) * agg-scale, M the pair mask --
-        one more fused inverse and three DMMA GEMMs per iteration."""
+        """PST penalty of any series / aggregation (src/notreks/notreks.py:454-619) through ``_pst.PstEngine``:
+        closed-form adjoints instead of autograd, d pst / d W = 2 W o trek_GT^T -- for ``seq="inv"`` one more fused
+        inverse and four DMMA GEMMs per iteration, GEMM chains for the other series."""
         self.trek = plan
         if plan is None:
             return
-        d = self.d
-        f64 = dict(dtype=torch.float64, device=self.dev)
-        Mk = torch.zeros(d, d, **f64)
-        idx = torch.as_tensor(np.asarray(plan["I"], dtype=np.int64), device=self.dev)
-        Mk[idx[:, 0], idx[:, 1]] = 1.0                    # H[rows, cols]: duplicates in I count once per listing below
-        cnt = torch.zeros(d, d, **f64)
-        cnt.index_put_((idx[:, 0], idx[:, 1]), torch.ones(idx.shape[0], **f64), accumulate=True)
-        scale = 1.0 / idx.shape[0] if plan["agg"] == "mean" else 1.0
-        self.trek_mask = cnt * scale                      # value = sum(trek_mask o H)
-        self.trek_Ms = (self.trek_mask + self.trek_mask.T).contiguous()
-        self.trek_X = torch.empty(d, d, **f64)
-        self.trek_H = torch.empty(d, d, **f64)
-        self.trek_B = torch.empty(d, d, **f64)
-        self.trek_GT = torch.zeros(d, d, **f64)
-        self.trek_sc = torch.zeros(4, **f64)
-        self.trek_info = torch.zeros(1, dtype=torch.int32, device=self.dev)
-
-    def _trek_forward(self):
-        """X and H at the current W."""
-        p = self.trek
-        _lib.check(self.lib.dagma_logdet_inv_ws_f64(
-            _lib.stream_ptr(), self.d, 1.0 + p["eps_inv"], self.W.data_ptr(), self.d, 1, self.trek_sc.data_ptr(),
-            self.trek_sc.data_ptr() + 8, self.trek_X.data_ptr(), None, self.d, self.trek_sc.data_ptr() + 16,
-            self.trek_info.data_ptr(), self.ws.data_ptr(), self.ws.numel() * 8), "dagma_logdet_inv_ws_f64")
-        gemm(self.trek_X, self.trek_X, self.trek_H, trans_a=True)
+        from ._pst import PstEngine
+        self.pst = PstEngine(self.d, plan["I"], plan["seq"], plan["agg"], eps_inv=plan["eps_inv"], K_log=plan["K_log"])
+        self.trek_GT = self.pst.GT
 
     def _trek_grad(self):
-        """trek_GT = X M_s H, so that d pst / d W = 2 W o trek_GT^T (consumed by the update kernel)."""
-        self._trek_forward()
-        gemm(self.trek_Ms, self.trek_H, self.trek_B)
-        gemm(self.trek_X, self.trek_B, self.trek_GT)
+        """trek_GT (consumed by the update kernel) at the current W; no host synchronisation (graph-captured)."""
+        self.pst.grad(self.W)
 
     def _trek_value(self) -> float:
         if self.trek is None:
             return 0.0
-        self._trek_forward()
-        return float((self.trek_mask * self.trek_H).sum().item())
+        return float(self.pst.value(self.W).item())
 
     def stale(self, model) -> bool:
         return model._cov_dev.data_ptr() != self._model_cov_ptr or model.d != self.d

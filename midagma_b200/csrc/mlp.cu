@@ -235,6 +235,159 @@ extern "C" int dagma_mlp_adam_f64(dagma_stream_t stream, int d, int m1, void* st
     return 0;
 }
 
+// ---- general LocallyConnected stacks  dims = [d, m_1, ..., m_L, 1]  (nonlinear.py:39-43, 60-65) ----------
+// Same transposed activations ([d * width][n]) and un-scaled sums as the fused [d, m1, 1] kernels above; one
+// forward and one backward launch per layer.  theta = [W1 | b1 | W_0 | b_0 | ... | W_{L-1} | b_{L-1}] with
+// W_l = fc2.l.weight [d][mi][mo] and b_l = fc2.l.bias [d][mo].
+namespace dagma {
+// in: pre-activations of the layer's input ([d*mi][n]; + bias_in[d*mi] for the first layer), replaced by
+// H = sigmoid(.) for the backward pass; out[(j*mo+o)][s] = b[j][o] + sum_k H[j*mi+k][s] W[j][k][o]
+__global__ void __launch_bounds__(256) lc_forward_kernel(double* __restrict__ in, const double* __restrict__ bias_in,
+                                                         const double* __restrict__ W, const double* __restrict__ b,
+                                                         double* __restrict__ out, int n, int d, int mi, int mo) {
+    const int j = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    for (int k = 0; k < mi; ++k) {
+        const int p = j * mi + k;
+        const double zz = in[(size_t)p * n + s] + (bias_in ? bias_in[p] : 0.0);
+        in[(size_t)p * n + s] = 1.0 / (1.0 + exp(-zz));
+    }
+    for (int o = 0; o < mo; ++o) {
+        double acc = b ? b[j * mo + o] : 0.0;
+        for (int k = 0; k < mi; ++k)
+            acc = fma(in[(size_t)(j * mi + k) * n + s], W[((size_t)j * mi + k) * mo + o], acc);
+        out[(size_t)(j * mo + o) * n + s] = acc;
+    }
+}
+// res = out (+ bias) - Xt, partial sums of res^2 (one per block); optional row-major copy of the prediction
+__global__ void __launch_bounds__(256) mlp_residual_kernel(const double* __restrict__ out, const double* __restrict__ bias,
+                                                           const double* __restrict__ Xt, int n, int d,
+                                                           double* __restrict__ res, double* __restrict__ out_opt,
+                                                           double* __restrict__ S_partial) {
+    __shared__ double red[96];
+    const int j = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    double sq = 0.0, z1 = 0.0, z2 = 0.0;
+    if (s < n) {
+        const double o = out[(size_t)j * n + s] + (bias ? bias[j] : 0.0);
+        const double r = o - Xt[(size_t)j * n + s];
+        res[(size_t)j * n + s] = r;
+        if (out_opt) out_opt[(size_t)s * d + j] = o;
+        sq = r * r;
+    }
+    block_sum3<256>(sq, z1, z2, red, threadIdx.x);
+    if (threadIdx.x == 0) S_partial[blockIdx.y * gridDim.x + blockIdx.x] = sq;
+}
+// H ([d*mi][n], from lc_forward_kernel) is replaced by dZ = (sum_o W[j][k][o] dZn[j*mo+o]) H (1 - H);
+// part row of this sample chunk: [gW (d*mi*mo) | gb (d*mo)] = sums over the chunk of H dZn and dZn
+__global__ void __launch_bounds__(256) lc_backward_kernel(double* __restrict__ H, const double* __restrict__ dZn,
+                                                          const double* __restrict__ W, int n, int d, int mi, int mo,
+                                                          double* __restrict__ part) {
+    __shared__ double red[96];
+    const int j = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = s < n;
+    double* row = part + (size_t)blockIdx.x * ((size_t)d * mi * mo + (size_t)d * mo);
+    for (int k = 0; k < mi; ++k) {
+        const int p = j * mi + k;
+        const double hh = ok ? H[(size_t)p * n + s] : 0.0;
+        double dh = 0.0;
+        for (int o = 0; o < mo; o += 3) {
+            double g[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (o + q < mo && ok) {
+                    const double dz = dZn[(size_t)(j * mo + o + q) * n + s];
+                    g[q] = hh * dz;
+                    dh = fma(W[((size_t)j * mi + k) * mo + o + q], dz, dh);
+                }
+            block_sum3<256>(g[0], g[1], g[2], red, threadIdx.x);
+            if (threadIdx.x == 0)
+                for (int q = 0; q < 3 && o + q < mo; ++q) row[((size_t)j * mi + k) * mo + o + q] = g[q];
+        }
+        if (ok) H[(size_t)p * n + s] = dh * hh * (1.0 - hh);
+    }
+    for (int o = 0; o < mo; o += 3) {
+        double g[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (o + q < mo && ok) g[q] = dZn[(size_t)(j * mo + o + q) * n + s];
+        block_sum3<256>(g[0], g[1], g[2], red, threadIdx.x);
+        if (threadIdx.x == 0)
+            for (int q = 0; q < 3 && o + q < mo; ++q) row[(size_t)d * mi * mo + (size_t)j * mo + o + q] = g[q];
+    }
+}
+// out[r] = sum_s a[r][s]   (one block per row, fixed order)
+__global__ void __launch_bounds__(256) row_sums_kernel(const double* __restrict__ a, int n, double* __restrict__ out) {
+    __shared__ double red[96];
+    double acc = 0.0, z1 = 0.0, z2 = 0.0;
+    const double* row = a + (size_t)blockIdx.x * n;
+    for (int s = threadIdx.x; s < n; s += 256) acc += row[s];
+    block_sum3<256>(acc, z1, z2, red, threadIdx.x);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+}  // namespace dagma
+
+extern "C" int dagma_lc_forward_f64(dagma_stream_t stream, int n, int d, int mi, int mo, double* in_dev,
+                                    const double* bias_in_dev, const double* w_dev, const double* b_dev,
+                                    double* out_dev) {
+    DAGMA_REQUIRE(in_dev && w_dev && out_dev && n >= 1 && d >= 1 && mi >= 1 && mo >= 1, "bad arguments");
+    dim3 grid((n + 255) / 256, d);
+    dagma::lc_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in_dev, bias_in_dev, w_dev, b_dev, out_dev, n, d, mi, mo);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dagma_mlp_residual_f64(dagma_stream_t stream, int n, int d, const double* out_dev,
+                                      const double* bias_dev, const double* xt_dev, double* res_dev,
+                                      double* out_opt_dev, double* s_partial_dev, const double* l1_partial_dev,
+                                      void* state_dev) {
+    DAGMA_REQUIRE(out_dev && xt_dev && res_dev && s_partial_dev && state_dev, "null pointer");
+    dim3 grid((n + 255) / 256, d);
+    dagma::mlp_residual_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_dev, bias_dev, xt_dev, n, d, res_dev, out_opt_dev,
+                                                                      s_partial_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    mlp_finish_forward_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((MlpState*)state_dev, s_partial_dev, grid.x * grid.y,
+                                                                 l1_partial_dev, l1_partial_dev ? (d * d + 255) / 256 : 0, 0, d);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dagma_lc_backward_f64(dagma_stream_t stream, int n, int d, int mi, int mo, double* h_dev,
+                                     const double* dzn_dev, const double* w_dev, double* part_dev,
+                                     double* grads_dev) {
+    DAGMA_REQUIRE(h_dev && dzn_dev && w_dev && part_dev && grads_dev, "null pointer");
+    const int chunks = (n + 255) / 256, width = d * mi * mo + d * mo;
+    dim3 grid(chunks, d);
+    dagma::lc_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h_dev, dzn_dev, w_dev, n, d, mi, mo, part_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    mlp_reduce_parts_kernel<<<(width + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part_dev, chunks, width, grads_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dagma_row_sums_f64(dagma_stream_t stream, int rows, int n, const double* a_dev, double* out_dev) {
+    DAGMA_REQUIRE(a_dev && out_dev && rows >= 1 && n >= 1, "bad arguments");
+    dagma::row_sums_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(a_dev, n, out_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dagma_mlp_adam_ex_f64(dagma_stream_t stream, int d, int m1, size_t total, void* state_dev,
+                                     double* theta_dev, const double* grads_dev, double* m_dev, double* v_dev,
+                                     const double* minv_dev) {
+    DAGMA_REQUIRE(state_dev && theta_dev && grads_dev && m_dev && v_dev && minv_dev, "null pointer");
+    DAGMA_REQUIRE(total >= (size_t)d * m1 * d, "total is smaller than fc1.weight");
+    const int blocks = (int)((total + 255) / 256);
+    mlp_adam_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, (cudaStream_t)stream>>>((const MlpState*)state_dev, theta_dev,
+                                                                                     grads_dev, m_dev, v_dev, minv_dev, d, m1, total);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    mlp_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((MlpState*)state_dev);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ---- stand-alone helpers of the public surface -------------------------------------------
 namespace dagma {
 // LocallyConnected.forward (locally_connected.py:70-74): out[n,j,:] = in[n,j,:] @ W[j] + b[j]

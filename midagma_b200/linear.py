@@ -223,31 +223,42 @@ def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1
 # =============================================================================
 # the drop-in class
 def _trek_plan(tr) -> typing.Optional[dict]:
-    """Which trek regulariser the accelerated path carries: PST with ``seq="inv"`` and
-    ``agg`` in {"mean", "sum"} (src/notreks/notreks.py:500-507, 558-619), in mode "opt" or "log".  A disabled
-    regulariser or an empty pair list is the reference's no-op branch (notreks.py:684-689)."""
+    """Which trek regulariser the accelerated path carries: PST with any series (``inv``, ``log``,
+    ``exp``, ``binom``) and any scalar aggregation (``mean``, ``sum``, ``max``, ``lse``)
+    (src/notreks/notreks.py:454-619), in mode "opt" or "log".  A disabled regulariser or an empty pair list is the
+    reference's no-op branch (notreks.py:684-689).  TCC goes through ``trek_value_grad`` with the reference's
+    default ``cycle_penalty="spectral"`` (a dense non-symmetric eigendecomposition), which stays out of scope."""
     if tr is None or not tr.enabled():
         return None
     I = tr.cfg.get("I") if tr.cfg is not None else None
     if I is None or len(I) == 0:
         return None
     name = tr.name.lower().strip()
+    if name != "pst":
+        raise NotImplementedError(
+            f"trek regulariser {tr.name!r} is outside the B200 hot path (SURVEY.md 8f3): the reference dispatches TCC "
+            "to the spectral penalty (LAPACK geev); only PST is accelerated")
     kwargs = dict(tr.cfg.get("kwargs", {}) or {})
     seq = str(tr.cfg.get("seq", "exp")).lower().strip()
     agg = str(kwargs.pop("agg", "mean")).lower().strip()
     eps_inv = float(kwargs.pop("eps_inv", 1e-8))
-    kwargs.pop("s", None)                       # never reaches the "inv" series (notreks.py:500-507)
-    kwargs.pop("K_log", None)
-    if name != "pst" or seq != "inv" or agg not in ("mean", "sum") or kwargs:
-        raise NotImplementedError(
-            f"trek regulariser {tr.name!r} (seq={seq!r}, agg={agg!r}) is outside the B200 hot path (SURVEY.md 8f3): "
-            "only PST with seq='inv' and agg in {'mean', 'sum'} is accelerated")
+    K_log = kwargs.pop("K_log", None)
+    kwargs.pop("s", None)                       # never reaches any series (notreks.py:509-513 vs 521-525, Q14)
+    if kwargs:
+        raise TypeError(f"pst() got unexpected keyword arguments {sorted(kwargs)}")
+    if seq not in ("exp", "log", "inv", "binom"):
+        raise ValueError("seq must be one of {'exp','log','inv','binom'}")
+    if agg == "none":
+        raise RuntimeError("agg='none' is not a scalar penalty (the reference fails in .item())")
+    if agg not in ("mean", "sum", "max", "lse"):
+        raise ValueError("agg must be one of {'mean','sum','max','lse','none'}")
     if eps_inv < 0:
         raise ValueError("eps_inv must be >= 0")
     I_np = np.asarray(I, dtype=np.int64)
     if I_np.ndim != 2 or I_np.shape[1] != 2:
         raise ValueError("I must be array-like of shape (m,2)")
-    return {"I": I_np, "agg": agg, "eps_inv": eps_inv, "weight": float(tr.weight), "mode": tr.mode}
+    return {"I": I_np, "seq": seq, "agg": agg, "eps_inv": eps_inv, "K_log": K_log, "weight": float(tr.weight),
+            "mode": tr.mode}
 
 
 # =============================================================================
@@ -262,7 +273,7 @@ class DagmaLinear:
         self.dtype = dtype
         self.vprint = print if verbose else lambda *a, **k: None
         self.trek_reg = trek_reg
-        self._trek_plan = _trek_plan(trek_reg)          # None, or the PST seq="inv" plan (else NotImplementedError)
+        self._trek_plan = _trek_plan(trek_reg)          # None, or the PST plan (TCC: NotImplementedError)
         self._torch_dtype = torch.double
         self._device = torch.device("cuda")
         # telemetry: same defaults as the reference (linear.py:65-67) -- a logger that is silent unless verbose

@@ -9,7 +9,9 @@ the exponential decay and retries with ``s = 1``).  The reference differentiates
 autograd on the CPU; here one inner iteration is a fixed sequence of hand-written kernels
 (closed-form backward, see csrc/mlp.cu) replayed as a CUDA graph, and the host only
 synchronises at the convergence checkpoints.  ``dims = [d, m1, 1]`` (the reference's and
-BASELINE.json's configuration) is the supported architecture.
+BASELINE.json's configuration) runs on fused forward / backward kernels; any other stack
+``[d, m1, ..., 1]`` (and the degenerate ``[d, 1]``) runs layer by layer on the generic
+LocallyConnected kernels.
 """
 from __future__ import annotations
 
@@ -92,20 +94,22 @@ class DagmaMLP(nn.Module):
             layers.append(LocallyConnected(self.d, dims[l + 1], dims[l + 2], bias=bias))
         self.fc2 = nn.ModuleList(layers)
 
-    # ---- flat parameter vector  theta = [W1 | b1 | W2 | b2]
-    def _check_arch(self):
-        if len(self.dims) != 3:
-            raise NotImplementedError("the B200 path implements dims = [d, m1, 1] (SURVEY.md 8a row a8)")
+    # ---- flat parameter vector  theta = [W1 | b1 | fc2.0.weight | fc2.0.bias | fc2.1.weight | ...]
+    def _params(self):
+        if self.fc1.bias is None or any(fc.bias is None for fc in self.fc2):
+            raise NotImplementedError("the B200 path implements bias=True (the reference's default)")
+        out = [self.fc1.weight, self.fc1.bias]
+        for fc in self.fc2:
+            out += [fc.weight, fc.bias]
+        return out
 
     def pack(self) -> torch.Tensor:
-        self._check_arch()
-        parts = [self.fc1.weight, self.fc1.bias, self.fc2[0].weight, self.fc2[0].bias]
-        return torch.cat([_cuda64(p).reshape(-1) for p in parts])
+        return torch.cat([_cuda64(p).reshape(-1) for p in self._params()])
 
     @torch.no_grad()
     def unpack(self, theta: torch.Tensor) -> None:
         off = 0
-        for p in (self.fc1.weight, self.fc1.bias, self.fc2[0].weight, self.fc2[0].bias):
+        for p in self._params():
             k = p.numel()
             p.copy_(theta[off:off + k].reshape(p.shape).to(p.device, p.dtype))
             off += k
@@ -139,15 +143,23 @@ class _MlpEngine:
 
     def __init__(self, model: DagmaMLP, X: typing.Optional[torch.Tensor], group=None, n_total=None):
         _lib.require_device()
-        model._check_arch()
         self.lib = _lib.load()
         self.model = model
         self.d, self.m1 = model.d, model.dims[1]
         d, P = self.d, self.d * self.m1
         self.P = P
+        self.widths = [int(w) for w in model.dims[1:]]         # LC layer l maps widths[l] -> widths[l + 1]
+        self.L = len(self.widths) - 1
+        self.fused = (self.L == 1)                             # [d, m1, 1]: fused forward / backward kernels
+        self.lc_off, off = [], P * d + P                       # (offset of fc2.l.weight, of fc2.l.bias) in theta
+        for l in range(self.L):
+            mi, mo = self.widths[l], self.widths[l + 1]
+            self.lc_off.append((off, off + d * mi * mo))
+            off += d * mi * mo + d * mo
         f64 = dict(dtype=torch.float64, device="cuda")
         self.theta = model.pack()
         self.total = self.theta.numel()
+        assert self.total == off, (self.total, off)
         self.m = torch.zeros_like(self.theta)
         self.v = torch.zeros_like(self.theta)
         self.grads = torch.zeros_like(self.theta)
@@ -167,7 +179,12 @@ class _MlpEngine:
             self.res = torch.empty(d, self.n, **f64)
             chunks = (self.n + 255) // 256
             self.S_partial = torch.empty(chunks * d, **f64)
-            self.part = torch.empty(chunks * (2 * P + d), **f64)
+            width = 2 * P + d
+            if not self.fused:                                 # activations of every layer, [d * width][n]
+                self.acts = [self.Zt] + [torch.empty(d * w, self.n, **f64) for w in self.widths[1:]]
+                width = max([d * self.widths[l] * self.widths[l + 1] + d * self.widths[l + 1]
+                             for l in range(self.L)] + [1])
+            self.part = torch.empty(chunks * width, **f64)
             self.kws = torch.empty(148 * P * d + 8, **f64)
 
     def _sptr(self, f):
@@ -197,9 +214,47 @@ class _MlpEngine:
             self.Minv.data_ptr(), None, self.d, self._sptr(F_MIN), self._iptr(I_INFO), self.ws.data_ptr(),
             self.ws.numel() * 8), "dagma_logdet_inv_ws_f64")
 
+    def _tptr(self, off):
+        return self.theta.data_ptr() + 8 * off
+
+    def _forward_stack(self, out=None):
+        """Layer-by-layer forward of a general LocallyConnected stack (nonlinear.py:60-65)."""
+        d, n, P, S = self.d, self.n, self.P, _lib.stream_ptr()
+        optr = out.data_ptr() if out is not None else None
+        if self.L == 0:                                        # dims = [d, 1]: x_hat = fc1(x)
+            _lib.check(self.lib.dagma_mlp_residual_f64(
+                S, n, d, self.Zt.data_ptr(), self._tptr(P * d), self.Xt.data_ptr(), self.res.data_ptr(), optr,
+                self.S_partial.data_ptr(), self.l1_partial.data_ptr(), self.state.data_ptr()), "dagma_mlp_residual_f64")
+            return
+        for l in range(self.L):
+            ow, ob = self.lc_off[l]
+            _lib.check(self.lib.dagma_lc_forward_f64(
+                S, n, d, self.widths[l], self.widths[l + 1], self.acts[l].data_ptr(),
+                self._tptr(P * d) if l == 0 else None, self._tptr(ow), self._tptr(ob), self.acts[l + 1].data_ptr()),
+                "dagma_lc_forward_f64")
+        _lib.check(self.lib.dagma_mlp_residual_f64(
+            S, n, d, self.acts[self.L].data_ptr(), None, self.Xt.data_ptr(), self.res.data_ptr(), optr,
+            self.S_partial.data_ptr(), self.l1_partial.data_ptr(), self.state.data_ptr()), "dagma_mlp_residual_f64")
+
+    def _backward_stack(self):
+        """Closed-form backward of the stack: un-scaled sums into self.grads (all but fc1.weight)."""
+        d, n, P, S = self.d, self.n, self.P, _lib.stream_ptr()
+        dzn = self.res
+        for l in reversed(range(self.L)):
+            ow, _ = self.lc_off[l]
+            _lib.check(self.lib.dagma_lc_backward_f64(
+                S, n, d, self.widths[l], self.widths[l + 1], self.acts[l].data_ptr(), dzn.data_ptr(), self._tptr(ow),
+                self.part.data_ptr(), self.grads.data_ptr() + 8 * ow), "dagma_lc_backward_f64")
+            dzn = self.acts[l]
+        _lib.check(self.lib.dagma_row_sums_f64(S, P, n, dzn.data_ptr(), self.grads.data_ptr() + 8 * P * d),
+                   "dagma_row_sums_f64")
+        return dzn
+
     def _forward(self, out=None):
         W1 = self.theta[:self.P * self.d].view(self.P, self.d)
         gemm(W1, self.Xt, self.Zt)
+        if not self.fused:
+            return self._forward_stack(out)
         _lib.check(self.lib.dagma_mlp_forward_f64(
             _lib.stream_ptr(), self.n, self.d, self.m1, self.Zt.data_ptr(), self.theta.data_ptr(), self.Xt.data_ptr(),
             self.res.data_ptr(), out.data_ptr() if out is not None else None, self.S_partial.data_ptr(),
@@ -213,9 +268,9 @@ class _MlpEngine:
 
     def iteration(self, s: float):
         self.evaluate(s)
-        _lib.check(self.lib.dagma_mlp_adam_f64(
-            _lib.stream_ptr(), self.d, self.m1, self.state.data_ptr(), self.theta.data_ptr(), self.grads.data_ptr(),
-            self.m.data_ptr(), self.v.data_ptr(), self.Minv.data_ptr()), "dagma_mlp_adam_f64")
+        _lib.check(self.lib.dagma_mlp_adam_ex_f64(
+            _lib.stream_ptr(), self.d, self.m1, self.total, self.state.data_ptr(), self.theta.data_ptr(),
+            self.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.Minv.data_ptr()), "dagma_mlp_adam_ex_f64")
 
     def evaluate(self, s: float):
         """h, forward, objective and the (un-scaled) gradient sums at the current parameters."""
@@ -225,11 +280,15 @@ class _MlpEngine:
             torch.distributed.all_reduce(self.state[F_SS:F_SS + 1], group=self.group)
         _lib.check(self.lib.dagma_mlp_objective_f64(_lib.stream_ptr(), self.state.data_ptr(), self.n_total, self.d),
                    "dagma_mlp_objective_f64")
-        _lib.check(self.lib.dagma_mlp_backward_f64(
-            _lib.stream_ptr(), self.n, self.d, self.m1, self.Zt.data_ptr(), self.theta.data_ptr(), self.res.data_ptr(),
-            self.part.data_ptr(), self.grads.data_ptr() + 8 * self.P * self.d), "dagma_mlp_backward_f64")
+        dZt = self.Zt
+        if self.fused:
+            _lib.check(self.lib.dagma_mlp_backward_f64(
+                _lib.stream_ptr(), self.n, self.d, self.m1, self.Zt.data_ptr(), self.theta.data_ptr(), self.res.data_ptr(),
+                self.part.data_ptr(), self.grads.data_ptr() + 8 * self.P * self.d), "dagma_mlp_backward_f64")
+        else:
+            dZt = self._backward_stack()
         gW1 = self.grads[:self.P * self.d].view(self.P, self.d)
-        gemm(self.Zt, self.X, gW1, ws=self.kws)
+        gemm(dZt, self.X, gW1, ws=self.kws)
         if self.group is not None:
             torch.distributed.all_reduce(self.grads, group=self.group)
 
@@ -260,11 +319,13 @@ class _MlpEngine:
         P, d, m1 = self.P, self.d, self.m1
         w1 = self.theta[:P * d].view(d, m1, d)
         g[:P * d] += (mu * lam1 * torch.sign(w1) + 2.0 * w1 * self.Minv[:, None, :]).reshape(-1)
-        names = ("fc1.weight", "fc1.bias", "fc2.0.weight", "fc2.0.bias")
-        sizes = (P * d, P, P, d)
+        names = ["fc1.weight", "fc1.bias"]
+        for l in range(self.L):
+            names += [f"fc2.{l}.weight", f"fc2.{l}.bias"]
         out, off = {}, 0
-        for nme, k in zip(names, sizes):
-            out[nme] = g[off:off + k].cpu().numpy()
+        for nme, prm in zip(names, self.model._params()):
+            k = prm.numel()
+            out[nme] = g[off:off + k].cpu().numpy().reshape(tuple(prm.shape))
             off += k
         return out
 

@@ -7,10 +7,11 @@ In scope:
 * ``trek_value_grad`` no-op path (no / disabled regulariser)    notreks.py:684-689
 * the regulariser dataclasses, so objects built for the reference can be passed around.
 
-* PST with ``seq="inv"`` (value and closed-form gradient on the inverse + GEMM kernels)   notreks.py:500-507, 558-619
+* PST penalties, every series (``inv``, ``log``, ``exp``, ``binom``) and aggregation (``mean``, ``sum``, ``max``,
+  ``lse``): value and closed-form gradient on the inverse + GEMM kernels (``_pst.PstEngine``)   notreks.py:454-619
 
-The other PST series and the spectral TCC penalty are outside the accelerated path
- and raise ``NotImplementedError``.
+The spectral TCC penalty (dense non-symmetric eigendecomposition, LAPACK geev in the reference) is outside the
+accelerated path and raises ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -125,48 +126,80 @@ def trek_cycle_coupling_value_gradW(W: torch.Tensor, I, *, w: float = 1.0, cycle
     return penalty.to(W.device, W.dtype), grad.to(W.device, W.dtype)
 
 
-def pst_inv_value_grad(W, I, *, agg: str = "mean", eps_inv: float = 1e-8, want_grad: bool = True):
-    """PST penalty with ``seq="inv"`` (notreks.py:500-507, 558-619) and its gradient w.r.t. W, on device:
-    X = ((1 + eps) I - W o W)^{-1} (fused inverse kernel), H = X^T X, pst = agg_{(i,j) in I} H[i,j],
-    d pst / d W = 2 W o (X M_s H)^T with M_s the symmetrised, agg-scaled pair mask (closed form of the
-    reference's autograd).  Returns (float, ndarray or None)."""
-    from ._large import gemm
-    _lib.require_device()
-    Wd = torch.as_tensor(np.ascontiguousarray(W, dtype=np.float64)).cuda()
-    d = Wd.shape[0]
+def _pst_engine(d: int, I, seq, agg, eps_inv, K_log):
+    from ._pst import PstEngine
+    return PstEngine(d, I, seq, agg, eps_inv=eps_inv, K_log=K_log)
+
+
+def pst_mat(W, seq="exp", *, K_log: Optional[int] = None, eps_inv: float = 1e-8, s: float = 1.0) -> torch.Tensor:
+    """H = F(W o W)^T F(W o W) for the series ``seq`` (notreks.py:454-527); ``s`` is accepted and ignored as in the
+    reference (dead duplicate branch).  No autograd: gradients come from ``pst_value_grad``."""
+    seq = str(seq).lower().strip()
+    if seq not in {"exp", "log", "inv", "binom"}:
+        raise ValueError("seq must be one of {'exp','log','inv','binom'}")
+    if not isinstance(W, torch.Tensor):
+        W = torch.as_tensor(W, dtype=torch.double, device=torch.device("cpu"))
+    if W.ndim != 2 or W.shape[0] != W.shape[1]:
+        raise ValueError("W must be a square matrix tensor")
+    if eps_inv < 0:
+        raise ValueError("eps_inv must be >= 0")
+    eng = _pst_engine(W.shape[0], np.zeros((1, 2), dtype=np.int64), seq, "sum", eps_inv, K_log)
+    Wd = _dev64(W)
+    eng.forward(Wd)
+    eng.check_domain(Wd)
+    return eng.H.to(W.device, W.dtype)
+
+
+def get_no_trek_pairs(W, seq="exp", *, K_log: Optional[int] = None, eps_inv: float = 1e-8) -> np.ndarray:
+    """Pairs (i, j), i < j, with H[i, j] == 0 (notreks.py:529-554)."""
+    H = pst_mat(W, seq, K_log=K_log, eps_inv=eps_inv)
+    upper = torch.triu(torch.ones_like(H, dtype=torch.bool), diagonal=1)
+    rows, cols = torch.nonzero((H == 0) & upper, as_tuple=True)
+    return torch.stack([rows, cols], dim=1).cpu().numpy().astype(np.int64, copy=False)
+
+
+def pst(W: torch.Tensor, I, seq="exp", *, K_log: Optional[int] = None, eps_inv: float = 1e-8, s: float = 1.,
+        agg: str = "mean") -> torch.Tensor:
+    """PST penalty value (notreks.py:557-619); ``agg="none"`` returns the vector of pair values."""
+    agg = str(agg).lower().strip()
     I_np = np.asarray(I, dtype=np.int64)
-    idx = torch.as_tensor(I_np, device="cuda")
-    mask = torch.zeros(d, d, dtype=torch.float64, device="cuda")
-    mask.index_put_((idx[:, 0], idx[:, 1]), torch.ones(idx.shape[0], dtype=torch.float64, device="cuda"), accumulate=True)
-    if agg == "mean":
-        mask /= idx.shape[0]
-    elif agg != "sum":
-        raise NotImplementedError("only agg in {'mean', 'sum'} is accelerated (SURVEY.md 8f3)")
-    out = logdet_inv(Wd[None].contiguous(), s=1.0 + float(eps_inv), square_input=True, want_inv=True, want_grad=False)
-    if int(out["info"][0].item()) != 0:
-        raise _lib.DagmaB200Error("(1 + eps) I - W o W is not an M-matrix: outside the domain of the fused inverse")
-    X = out["minv"][0].contiguous()
-    H = torch.empty_like(X)
-    gemm(X, X, H, trans_a=True)
-    val = float((mask * H).sum().item())
-    if not want_grad:
-        return val, None
-    B, GT = torch.empty_like(X), torch.empty_like(X)
-    gemm((mask + mask.T).contiguous(), H, B)
-    gemm(X, B, GT)
-    return val, (2.0 * Wd * GT.T).cpu().numpy()
+    if I_np.size == 0:
+        return W.sum() * 0.0
+    if agg not in {"mean", "sum", "max", "lse", "none"}:
+        raise ValueError("agg must be one of {'mean','sum','max','lse','none'}")
+    eng = _pst_engine(W.shape[0], I_np, seq, "sum" if agg == "none" else agg, eps_inv, K_log)
+    Wd = _dev64(W)
+    val = eng.value(Wd)
+    eng.check_domain(Wd)
+    if agg == "none":
+        return eng.pair_values().to(W.device, W.dtype)
+    return val.clone().to(W.device, W.dtype)
+
+
+def pst_value_grad(W, I, *, seq: str = "exp", agg: str = "mean", eps_inv: float = 1e-8, K_log: Optional[int] = None,
+                   want_grad: bool = True):
+    """(value, d value / d W) of the PST penalty on device -- closed-form adjoints of every series (see ``_pst``)
+    in place of the reference's autograd (notreks.py:717-736).  Returns (float, ndarray or None)."""
+    W_np = np.asarray(W, dtype=np.float64)
+    eng = _pst_engine(W_np.shape[0], I, seq, agg, eps_inv, K_log)
+    return eng.value_grad_host(W_np, want_grad)
+
+
+def pst_inv_value_grad(W, I, *, agg: str = "mean", eps_inv: float = 1e-8, want_grad: bool = True):
+    """PST with ``seq="inv"`` (notreks.py:500-507): X = ((1 + eps) I - W o W)^{-1}, H = X^T X."""
+    return pst_value_grad(W, I, seq="inv", agg=agg, eps_inv=eps_inv, want_grad=want_grad)
 
 
 def trek_value_grad(W: np.ndarray, tr: Optional[TrekRegularizer], *, torch_dtype: torch.dtype = torch.double,
                     device: Optional[torch.device] = None) -> Tuple[float, np.ndarray]:
-    """(value, grad) of a trek regulariser (notreks.py:667-736): the no-op branch, and PST ``seq="inv"``."""
+    """(value, grad) of a trek regulariser (notreks.py:667-736): the no-op branch and every PST penalty."""
     from .linear import _trek_plan
     W_np = np.asarray(W)
-    plan = _trek_plan(tr)               # None: disabled / empty I; NotImplementedError outside the accelerated set
+    plan = _trek_plan(tr)               # None: disabled / empty I; NotImplementedError for TCC (spectral default)
     if plan is None:
         return 0.0, np.zeros_like(W_np)
-    val, grad = pst_inv_value_grad(W_np, plan["I"], agg=plan["agg"], eps_inv=plan["eps_inv"],
-                                   want_grad=(tr.mode == "opt"))
+    val, grad = pst_value_grad(W_np, plan["I"], seq=plan["seq"], agg=plan["agg"], eps_inv=plan["eps_inv"],
+                               K_log=plan["K_log"], want_grad=(tr.mode == "opt"))
     if tr.mode != "opt":
         return val, np.zeros_like(W_np)
     return val, grad.astype(W_np.dtype, copy=False)

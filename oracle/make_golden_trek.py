@@ -92,5 +92,51 @@ def main():
     print("wrote linear_trek_events.npz")
 
 
+def pst_series():
+    """tests/golden/pst_series.npz: value and autograd gradient of the PST penalty for every series x aggregation
+    of the reference at two fixed matrices (notreks.py:454-619, 717-736), the matrix H of ``pst_mat``, the pair
+    values of ``agg="none"``, and short ``minimize`` trajectories with the exp / log / binom series in mode "opt"."""
+    d, n = 12, 300
+    rng = np.random.default_rng(7)
+    pairs = np.array([(i, j) for i in range(d) for j in range(i + 1, d) if rng.random() < 0.25], dtype=np.int64)
+    out = {"pairs": pairs}
+    Ws = {"a": np.random.default_rng(3).uniform(-0.4, 0.4, size=(d, d)) * (np.random.default_rng(4).random((d, d)) < 0.3),
+          "b": np.random.default_rng(5).uniform(-1.2, 1.2, size=(d, d)) * (np.random.default_rng(6).random((d, d)) < 0.2)}
+    np.fill_diagonal(Ws["b"], 0.0)
+    Ws["b"] = np.triu(Ws["b"], 1) + 0.05 * np.tril(Ws["b"], -1)      # near-DAG with larger weights
+    import torch
+    for wn, Wp in Ws.items():
+        out[f"W_{wn}"] = Wp
+        for seq in ("inv", "log", "exp", "binom"):
+            H = ref_nt.pst_mat(torch.from_numpy(Wp), seq)
+            out[f"H_{wn}_{seq}"] = H.numpy()
+            out[f"none_{wn}_{seq}"] = ref_nt.pst(torch.from_numpy(Wp), pairs, seq, agg="none").numpy()
+            for agg in ("mean", "sum", "max", "lse"):
+                reg = ref_nt.PSTRegularizer(I=pairs, seq=seq, weight=1.0, mode="opt", kwargs={"agg": agg})
+                v, g = ref_nt.trek_value_grad(Wp, reg)
+                out[f"val_{wn}_{seq}_{agg}"] = np.array(v)
+                out[f"grad_{wn}_{seq}_{agg}"] = g
+    reg = ref_nt.PSTRegularizer(I=pairs, seq="log", weight=1.0, mode="opt", kwargs={"agg": "mean", "K_log": 5})
+    v, g = ref_nt.trek_value_grad(Ws["a"], reg)
+    out["val_a_log_K5"], out["grad_a_log_K5"] = np.array(v), g
+    stages = [(1.0, 200, 1.0, 3e-4), (0.1, 200, 0.9, 3e-4)]
+    for name, reg in {
+        "exp_mean": ref_nt.PSTRegularizer(I=pairs, seq="exp", weight=0.7, mode="opt"),
+        "log_lse": ref_nt.PSTRegularizer(I=pairs, seq="log", weight=0.3, mode="opt", kwargs={"agg": "lse"}),
+        "binom_max": ref_nt.PSTRegularizer(I=pairs, seq="binom", weight=0.5, mode="opt", kwargs={"agg": "max"}),
+    }.items():
+        X, Wt, oks, rows = run(d, n, 11, reg, stages)
+        out[f"{name}_X"], out[f"{name}_W"], out[f"{name}_ok"] = X, Wt, np.array(oks)
+        out[f"{name}_trek_vals"] = np.array([float(r["reg_trek_value"]) for r in rows])
+        print(name, "ok", oks, "max|W|", float(np.abs(Wt[-1]).max()), "trek", out[f"{name}_trek_vals"][-1])
+    out["stages"] = np.array(stages)
+    np.savez_compressed(os.path.join(GOLD, "pst_series.npz"), **out)
+    print("wrote pst_series.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if "--pst-series" in sys.argv:
+        pst_series()
+    else:
+        main()
+        pst_series()

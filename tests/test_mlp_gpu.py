@@ -22,7 +22,7 @@ def _model_from(g, prefix="init."):
     return model
 
 
-@pytest.mark.parametrize("name", ["mlp_d7", "mlp_d40"])
+@pytest.mark.parametrize("name", ["mlp_d7", "mlp_d40", "mlp_deep_d6", "mlp_deep4_d5", "mlp_lin_d6"])
 def test_mlp_value_grad_steps_vs_reference(golden, name):
     from midagma_b200.nonlinear import DagmaNonlinear, _MlpEngine, F_MU, F_S, F_LAM1, F_LAM2, F_OBJ, F_SCORE, F_H
     g = golden(name)
@@ -51,7 +51,7 @@ def test_mlp_value_grad_steps_vs_reference(golden, name):
         assert abs(float(st[f]) - float(g[key])) <= 1e-9 * max(abs(float(g[key])), 1e-3), key
     grads = eng.grads_scaled()
     for k, gk in grads.items():
-        ref = g["grad." + k].reshape(-1)
+        ref = g["grad." + k].reshape(gk.shape)
         assert _relmax(gk, ref) <= 1e-9, k
     # `steps` iterations of minimize: parameters match torch.optim.Adam
     steps = int(g["steps"])

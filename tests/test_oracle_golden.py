@@ -59,7 +59,7 @@ def test_linear_short_fit_c4(golden):
     assert np.array_equal(W, g["W_est"])
 
 
-@pytest.mark.parametrize("name", ["mlp_d7", "mlp_d40"])
+@pytest.mark.parametrize("name", ["mlp_d7", "mlp_d40", "mlp_deep_d6", "mlp_deep4_d5", "mlp_lin_d6"])
 def test_mlp_value_grad_and_steps(golden, name):
     g = golden(name)
     dims = [int(x) for x in g["dims"]]
