@@ -27,10 +27,22 @@
 
 namespace dagma {
 
-constexpr int TM_BK = 16, TM_STAGES = 3;
-constexpr int TM_A_BYTES = 64 * TM_BK * 8, TM_B_BYTES = TM_BK * 64 * 8;
-constexpr int TM_STAGE_BYTES = TM_A_BYTES + TM_B_BYTES;                       // 16384
-constexpr int TM_PIPE_BYTES = TM_STAGES * TM_STAGE_BYTES;                     // 49152 (+ up to 1023 alignment slack)
+constexpr int TM_BK = 16;
+// CTA (or engine) tile BM x BN, warps in a (BM / 32) x (BN / 32) grid, STAGES slabs of BM x 16 + 16 x BN doubles
+template <int BM_, int BN_, int STAGES_>
+struct TmaCfg {
+    static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_;
+    static constexpr int WM = BM / 32, WN = BN / 32, WARPS = WM * WN, THREADS = 32 * WARPS;
+    static constexpr int A_BYTES = BM * TM_BK * 8, B_BYTES = TM_BK * BN * 8;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;                   // (+ up to 1023 bytes of alignment slack)
+    static_assert(BM % 32 == 0 && BN % 32 == 0 && BM <= 256 && BN <= 256, "whole 32 x 32 warp tiles, box <= 256");
+    static_assert(A_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "swizzled boxes start on 1024-byte boundaries");
+};
+using Tm64 = TmaCfg<64, 64, 3>;       // the 128-thread engine of the persistent inverse kernels (16 KB stages)
+using Tm128 = TmaCfg<128, 128, 6>;    // one 512-thread CTA per SM (32 KB stages, 192 KB pipeline)
+constexpr int TM_STAGES = Tm64::STAGES;
+constexpr int TM_PIPE_BYTES = Tm64::PIPE_BYTES;
 
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*TmEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -69,11 +81,11 @@ inline int tm_make_map(CUtensorMap* map, const double* base, int rows, int cols,
     }
     return 0;
 }
-inline int tm_make_a_map(CUtensorMap* map, const double* A, int M, int K, int lda) {      // A: M x K, box 64 x 16, swizzled
-    return tm_make_map(map, A, M, K, lda, 64, TM_BK, true);
+inline int tm_make_a_map(CUtensorMap* map, const double* A, int M, int K, int lda, int bm = 64) {   // A: M x K, box bm x 16, swizzled
+    return tm_make_map(map, A, M, K, lda, bm, TM_BK, true);
 }
-inline int tm_make_b_map(CUtensorMap* map, const double* B, int K, int N, int ldb) {      // B: K x N, box 16 x 64, dense
-    return tm_make_map(map, B, K, N, ldb, TM_BK, 64, false);
+inline int tm_make_b_map(CUtensorMap* map, const double* B, int K, int N, int ldb, int bn = 64) {   // B: K x N, box 16 x bn, dense
+    return tm_make_map(map, B, K, N, ldb, TM_BK, bn, false);
 }
 
 // ------------------------------------------------------------------ device: mbarrier / TMA primitives
@@ -114,7 +126,8 @@ __device__ __forceinline__ double tm_lds(uint32_t a) {
     return v;
 }
 
-// ------------------------------------------------------------------ the pipeline of one 128-thread engine
+// ------------------------------------------------------------------ the pipeline of one engine (Cfg::THREADS threads)
+template <class Cfg>
 struct TmaPipe {
     uint32_t stage0;        // shared address of stage 0 (1024-byte aligned)
     uint32_t bars;          // shared address of full[0..S), then empty[0..S)
@@ -122,39 +135,42 @@ struct TmaPipe {
     uint32_t wrapped;       // issue side: every stage has been filled at least once
     uint32_t cs, cph;       // consume side (every thread): next stage, parity of full[cs]
     __device__ __forceinline__ uint32_t full(uint32_t s) const { return bars + 8u * s; }
-    __device__ __forceinline__ uint32_t empty(uint32_t s) const { return bars + 8u * (TM_STAGES + s); }
+    __device__ __forceinline__ uint32_t empty(uint32_t s) const { return bars + 8u * (Cfg::STAGES + s); }
 };
-// `region`: >= TM_PIPE_BYTES + 1023 bytes of shared memory owned by the engine; `bars`: 2 * TM_STAGES mbarriers.
+// `region`: >= Cfg::PIPE_BYTES + 1023 bytes of shared memory owned by the engine; `bars`: 2 * STAGES mbarriers.
 // Called by all threads of the engine; the caller synchronises the engine afterwards.
-__device__ __forceinline__ void tm_pipe_init(TmaPipe& p, uint32_t region, uint32_t bars, bool elected) {
+template <class Cfg>
+__device__ __forceinline__ void tm_pipe_init(TmaPipe<Cfg>& p, uint32_t region, uint32_t bars, bool elected) {
     p.stage0 = (region + 1023u) & ~1023u;
     p.bars = bars;
     p.is = p.iph = p.wrapped = p.cs = p.cph = 0u;
     if (elected) {
 #pragma unroll
-        for (int s = 0; s < TM_STAGES; ++s) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
             tm_mbar_init(p.full(s), 1);
-            tm_mbar_init(p.empty(s), 4);
+            tm_mbar_init(p.empty(s), Cfg::WARPS);
         }
         tm_fence_init();
     }
 }
-// elected thread: request the slab A[r0.., k0..k0+16) / B[k0.., c0..c0+64) into the next stage
-__device__ __forceinline__ void tm_issue(TmaPipe& p, const CUtensorMap* mapA, const CUtensorMap* mapB, int r0, int c0,
-                                         int ka, int kb) {
+// elected thread: request the slab A[r0.., k..k+16) / B[k.., c0..) into the next stage
+template <class Cfg>
+__device__ __forceinline__ void tm_issue(TmaPipe<Cfg>& p, const CUtensorMap* mapA, const CUtensorMap* mapB, int r0, int c0,
+                                         int k) {
     const uint32_t s = p.is;
     if (p.wrapped) tm_mbar_wait(p.empty(s), p.iph);
-    const uint32_t dst = p.stage0 + s * TM_STAGE_BYTES, bar = p.full(s);
-    tm_mbar_expect_tx(bar, TM_STAGE_BYTES);
-    tm_load_2d(dst, mapA, ka, r0, bar);
-    tm_load_2d(dst + TM_A_BYTES, mapB, c0, kb, bar);
-    if (++p.is == TM_STAGES) {
+    const uint32_t dst = p.stage0 + s * Cfg::STAGE_BYTES, bar = p.full(s);
+    tm_mbar_expect_tx(bar, Cfg::STAGE_BYTES);
+    tm_load_2d(dst, mapA, k, r0, bar);
+    tm_load_2d(dst + Cfg::A_BYTES, mapB, c0, k, bar);
+    if (++p.is == Cfg::STAGES) {
         p.is = 0;
         if (p.wrapped) p.iph ^= 1u;
         p.wrapped = 1u;
     }
 }
 
+template <class Cfg>
 struct TmaFrag {            // per-thread constants of the fragment addressing
     uint32_t a_row[4];      // byte offset of row 32 wm + 8 i + qr in the A box, + (qc & 1) * 8
     uint32_t a_x;           // (qc >> 1) ^ qr : chunk index of k = kk + qc is (kk >> 1) ^ a_x
@@ -163,14 +179,15 @@ struct TmaFrag {            // per-thread constants of the fragment addressing
 #pragma unroll
         for (int i = 0; i < 4; ++i) a_row[i] = (uint32_t)((32 * wm + 8 * i + qr) * 128 + (qc & 1) * 8);
         a_x = (uint32_t)((qc >> 1) ^ qr);
-        b_off = (uint32_t)((qc * 64 + 32 * wn + qr) * 8);
+        b_off = (uint32_t)((qc * Cfg::BN + 32 * wn + qr) * 8);
     }
 };
 // every thread of the engine: wait for the next slab, multiply it into acc, release the stage
-__device__ __forceinline__ void tm_consume(TmaPipe& p, const TmaFrag& f, double (&acc)[4][4][2], int lane) {
+template <class Cfg>
+__device__ __forceinline__ void tm_consume(TmaPipe<Cfg>& p, const TmaFrag<Cfg>& f, double (&acc)[4][4][2], int lane) {
     const uint32_t s = p.cs;
     tm_mbar_wait(p.full(s), p.cph);
-    const uint32_t sa = p.stage0 + s * TM_STAGE_BYTES, sb = sa + TM_A_BYTES;
+    const uint32_t sa = p.stage0 + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
 #pragma unroll
     for (int kk = 0; kk < TM_BK; kk += 4) {
         double a[4], b[4];
@@ -178,7 +195,7 @@ __device__ __forceinline__ void tm_consume(TmaPipe& p, const TmaFrag& f, double 
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = tm_lds(sa + f.a_row[i] + ch);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = tm_lds(sb + f.b_off + (uint32_t)(kk * 64 + 8 * j) * 8);
+        for (int j = 0; j < 4; ++j) b[j] = tm_lds(sb + f.b_off + (uint32_t)(kk * Cfg::BN + 8 * j) * 8);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -188,13 +205,13 @@ __device__ __forceinline__ void tm_consume(TmaPipe& p, const TmaFrag& f, double 
     }
     __syncwarp();
     if (lane == 0) tm_mbar_arrive(p.empty(s));
-    if (++p.cs == TM_STAGES) {
+    if (++p.cs == Cfg::STAGES) {
         p.cs = 0;
         p.cph ^= 1u;
     }
 }
 
-// acc += A[r0..r0+64, kbeg..kbeg+16 nk) B[.., c0..c0+64) for one tile.  `primed` slabs of this tile have already
+// acc += A[r0..r0+BM, kbeg..kbeg+16 nk) B[.., c0..c0+BN) for one tile.  `primed` slabs of this tile have already
 // been requested (by the previous tile's tail; only the elected thread's value matters).  After it has
 // multiplied a slab the elected thread requests ONE more slab -- of this tile while it has any, then the
 // first S - 1 of the next tile -- which goes into the stage the warps released one slab ago.  Returns the
@@ -202,25 +219,26 @@ __device__ __forceinline__ void tm_consume(TmaPipe& p, const TmaFrag& f, double 
 struct TmaTile {
     int r0, c0, kbeg, nk;       // nk = 0: no tile
 };
-__device__ __forceinline__ int tm_tile_gemm(TmaPipe& p, const TmaFrag& f, double (&acc)[4][4][2],
+template <class Cfg>
+__device__ __forceinline__ int tm_tile_gemm(TmaPipe<Cfg>& p, const TmaFrag<Cfg>& f, double (&acc)[4][4][2],
                                             const CUtensorMap* mapA, const CUtensorMap* mapB, const TmaTile& t,
                                             int primed, const TmaTile& nxt, bool elected, int lane) {
-    constexpr int D = TM_STAGES - 1;
+    constexpr int D = Cfg::STAGES - 1;
     int issued = primed, nissued = 0;
     const int nlim = nxt.nk < D ? nxt.nk : D;
     if (elected)
         while (issued < D && issued < t.nk) {
-            tm_issue(p, mapA, mapB, t.r0, t.c0, t.kbeg + issued * TM_BK, t.kbeg + issued * TM_BK);
+            tm_issue(p, mapA, mapB, t.r0, t.c0, t.kbeg + issued * TM_BK);
             ++issued;
         }
     for (int kt = 0; kt < t.nk; ++kt) {
         tm_consume(p, f, acc, lane);
         if (elected) {
             if (issued < t.nk) {
-                tm_issue(p, mapA, mapB, t.r0, t.c0, t.kbeg + issued * TM_BK, t.kbeg + issued * TM_BK);
+                tm_issue(p, mapA, mapB, t.r0, t.c0, t.kbeg + issued * TM_BK);
                 ++issued;
             } else if (nissued < nlim) {
-                tm_issue(p, mapA, mapB, nxt.r0, nxt.c0, nxt.kbeg + nissued * TM_BK, nxt.kbeg + nissued * TM_BK);
+                tm_issue(p, mapA, mapB, nxt.r0, nxt.c0, nxt.kbeg + nissued * TM_BK);
                 ++nissued;
             }
         }

@@ -94,14 +94,17 @@ static int tma_mode();
 static bool gemm_use_tma(int M, int N, int K);
 static bool gemm_tma_ok(int transA, int M, int N, int K, const double* A, int lda, const double* B, int ldb);
 static int gemm_tma_launch(cudaStream_t stream, int M, int N, int K, double alpha, const double* A, int lda,
-                           const double* B, int ldb, double beta, double* C, int ldc, int epi, unsigned* queue);
+                           const double* B, int ldb, double beta, double* C, int ldc, int epi, unsigned* queue,
+                           int mode);
+static int gemm_tma_sched(int M, int N, int K, double beta, int epi);
 
 static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, double alpha, const double* A, int lda,
                        const double* B, int ldb, double beta, double* C, int ldc, int epi, double* ws,
                        size_t ws_bytes) {
     if (M <= 0 || N <= 0) return 0;
     if (gemm_use_tma(M, N, K) && gemm_tma_ok(transA, M, N, K, A, lda, B, ldb))
-        return gemm_tma_launch(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, tma_queue(stream));
+        return gemm_tma_launch(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, tma_queue(stream),
+                               gemm_tma_sched(M, N, K, beta, epi));
     if (gemm_tile_variant() == 1)
         return gemm_launch_tile<128, 128, 4, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
     if (gemm_tile_variant() == 2)
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
     const int half = tid >> 7;
     const EnginePos ep(tid);
     double* esm = psm + half * EN_SMEM;
-    TmaPipe pipe;
+    TmaPipe<Tm64> pipe;
     tm_pipe_init(pipe, smem_u32(esm), smem_u32(s_tbars[half]), P.use_tma && ep.htid == 0);
     if (P.use_tma && ep.htid == 0) {
         tm_prefetch_map(&mapCS);
@@ -602,7 +605,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
         // ---- TMA-fed engines: one continuous slab stream per engine.  The index of the NEXT item is pulled when
         // an update tile starts (the atomic's latency hides behind the tile) and its first slabs are requested
         // during the tile's last slabs; accumulators start at zero and are added to A by red.global.add.f64.
-        const TmaFrag fr(ep.wm, ep.wn, ep.qr, ep.qc);
+        const TmaFrag<Tm64> fr(ep.wm, ep.wn, ep.qr, ep.qc);
         const bool elected = (ep.htid == 0);
         const int nkt = (kn + TM_BK - 1) / TM_BK;
         constexpr unsigned T_NONE = 0xffffffffu;
@@ -838,42 +841,69 @@ __global__ void __launch_bounds__(DM_NT, 2) engine_pair_gemm_kernel(const double
     }
 }
 
-// ---- TMA-fed GEMM (gemm_tma.cuh): C = alpha A B + beta C, A row-major M x K, B row-major K x N, 64 x 64 tiles
-// pulled from an atomic queue by persistent 128-thread CTAs (four per SM); the first slabs of the next tile are
-// requested during the last slabs of the current one, so the slab stream never drains between tiles.
+// ---- TMA-fed GEMM (gemm_tma.cuh): C = alpha A B + beta C, A row-major M x K, B row-major K x N, persistent CTAs.
+// Two tile configurations: 64 x 64 (128 threads, four CTAs per SM, 3 stages) and 128 x 128 (512 threads, ONE CTA
+// per SM, 6 stages of 32 KB: half the L2 -> SM operand traffic per flop -- at 64 x 64 the slab stream is 8 flop per
+// byte, about 4 TB/s at the FP64 peak).  Three schedules:
+//   static   tile t, t + grid, ...                                   (queue == nullptr, balanced == 0)
+//   queue    tiles pulled from an atomic counter
+//   balanced every CTA gets the same number of 16-wide k-slabs: the (tile, slab) sequence is cut into grid equal
+//            ranges ("stream-K").  A tile that straddles a cut is shared by exactly two CTAs (a range is at least one
+//            tile long); both add their partial product to the zero-initialised tile with red.global.add.f64, and
+//            0 + a + b = 0 + b + a exactly, so the result does not depend on the order.  Needs beta = 0, no epilogue.
+// The first slabs of the next tile are requested during the last slabs of the current one, so the slab stream never
+// drains between tiles.
 struct TmaGemmArgs {
     int M, N, K;
     double* C; int ldc;
     double alpha, beta;
     int epi;
-    unsigned* queue;            // zeroed before the launch
+    unsigned* queue;            // zeroed before the launch (queue schedule)
+    int balanced;
 };
-constexpr size_t TMA_GEMM_SMEM_BYTES = TM_PIPE_BYTES + 1024;
-__global__ void __launch_bounds__(128, 4) gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                          const __grid_constant__ CUtensorMap mapB,
-                                                          const TmaGemmArgs P) {
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 512 / Cfg::THREADS) gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                                   const __grid_constant__ CUtensorMap mapB,
+                                                                                   const TmaGemmArgs P) {
     extern __shared__ __align__(1024) unsigned char tsm[];
-    __shared__ __align__(8) unsigned long long bars[2 * TM_STAGES];
+    __shared__ __align__(8) unsigned long long bars[2 * Cfg::STAGES];
     __shared__ unsigned s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1, qr = lane >> 2, qc = lane & 3;
+    const int wm = warp / Cfg::WN, wn = warp % Cfg::WN, qr = lane >> 2, qc = lane & 3;
     const bool elected = (tid == 0);
-    TmaPipe pipe;
+    TmaPipe<Cfg> pipe;
     tm_pipe_init(pipe, smem_u32(tsm), smem_u32(bars), elected);
     if (elected) {
         tm_prefetch_map(&mapA);
         tm_prefetch_map(&mapB);
     }
     __syncthreads();
-    const TmaFrag fr(wm, wn, qr, qc);
-    const int tn = (P.N + 63) / 64, tmr = (P.M + 63) / 64, ntiles = tn * tmr;
+    const TmaFrag<Cfg> fr(wm, wn, qr, qc);
+    const int tn = (P.N + Cfg::BN - 1) / Cfg::BN, tmr = (P.M + Cfg::BM - 1) / Cfg::BM, ntiles = tn * tmr;
     const int nk = (P.K + TM_BK - 1) / TM_BK;
     const bool vecC = ((P.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    // the work of this CTA as a range [u, hi) of (tile, slab) units; tile schedules: whole tiles only
+    long long u = 0, hi = 0;
+    if (P.balanced) {
+        const long long U = (long long)ntiles * nk;
+        u = U * blockIdx.x / gridDim.x;
+        hi = U * (blockIdx.x + 1) / gridDim.x;
+    }
+    auto segment = [&](long long v, long long lim, int t) {      // balanced: the piece of a tile that starts at unit v
+        if (P.balanced) {
+            if (v >= lim) return TmaTile{0, 0, 0, 0};
+            const int tile = (int)(v / nk), kb = (int)(v - (long long)tile * nk);
+            const int len = (int)((lim - v) < (long long)(nk - kb) ? (lim - v) : (long long)(nk - kb));
+            return TmaTile{(tile / tn) * Cfg::BM, (tile % tn) * Cfg::BN, kb * TM_BK, len};
+        }
+        if (t >= ntiles) return TmaTile{0, 0, 0, 0};
+        return TmaTile{(t / tn) * Cfg::BM, (t % tn) * Cfg::BN, 0, nk};
+    };
     int t = blockIdx.x, primed = 0;
-    while (t < ntiles) {
+    TmaTile cur = segment(u, hi, t);
+    while (cur.nk > 0) {
         unsigned t_next = (unsigned)t + gridDim.x;           // static striding unless a queue is given
         if (P.queue && elected) t_next = atomicAdd(P.queue, 1u) + gridDim.x;
-        const TmaTile cur{(t / tn) * 64, (t % tn) * 64, 0, nk};
         double acc[4][4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -882,9 +912,10 @@ __global__ void __launch_bounds__(128, 4) gemm_tma_kernel(const __grid_constant_
         TmaTile nxt{0, 0, 0, 0};
         if (elected) {
             if (P.queue) s_next = t_next;
-            if ((int)t_next < ntiles) nxt = TmaTile{((int)t_next / tn) * 64, ((int)t_next % tn) * 64, 0, nk};
+            nxt = segment(u + cur.nk, hi, (int)t_next);
         }
         primed = tm_tile_gemm(pipe, fr, acc, &mapA, &mapB, cur, primed, nxt, elected, lane);
+        const bool partial = P.balanced && cur.nk < nk;       // a piece of a shared tile: add to the zeroed tile
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = cur.r0 + 32 * wm + 8 * i + qr;
@@ -896,6 +927,11 @@ __global__ void __launch_bounds__(128, 4) gemm_tma_kernel(const __grid_constant_
                 double* p = P.C + (size_t)r * P.ldc + c;
                 const bool two = (c + 1 < P.N);
                 double v0 = P.alpha * acc[i][j][0], v1 = P.alpha * acc[i][j][1];
+                if (partial) {
+                    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v0) : "memory");
+                    if (two) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p + 1)), "d"(v1) : "memory");
+                    continue;
+                }
                 if (P.beta != 0.0) {
                     v0 = fma(P.beta, p[0], v0);
                     if (two) v1 = fma(P.beta, p[1], v1);
@@ -917,32 +953,69 @@ __global__ void __launch_bounds__(128, 4) gemm_tma_kernel(const __grid_constant_
             __syncthreads();
         }
         t = (int)t_next;
+        u += cur.nk;
+        cur = segment(u, hi, t);
+    }
+}
+// balanced schedule: zero the tiles that straddle a cut (CTA b looks at the start of its own range)
+template <class Cfg>
+__global__ void __launch_bounds__(256) gemm_tma_zero_shared_kernel(double* C, int ldc, int M, int N, int K, int grid_main) {
+    const int tn = (N + Cfg::BN - 1) / Cfg::BN, tmr = (M + Cfg::BM - 1) / Cfg::BM;
+    const int nk = (K + TM_BK - 1) / TM_BK;
+    const long long U = (long long)tn * tmr * nk;
+    const long long lo = U * blockIdx.x / grid_main;
+    if (lo % nk == 0) return;
+    const int tile = (int)(lo / nk), r0 = (tile / tn) * Cfg::BM, c0 = (tile % tn) * Cfg::BN;
+    for (int e = threadIdx.x; e < Cfg::BM * Cfg::BN; e += 256) {
+        const int r = r0 + e / Cfg::BN, c = c0 + e % Cfg::BN;
+        if (r < M && c < N) C[(size_t)r * ldc + c] = 0.0;
     }
 }
 
-static int gemm_tma_launch(cudaStream_t stream, int M, int N, int K, double alpha, const double* A, int lda,
-                           const double* B, int ldb, double beta, double* C, int ldc, int epi, unsigned* queue) {
+template <class Cfg>
+static int gemm_tma_launch_cfg(cudaStream_t stream, int M, int N, int K, double alpha, const double* A, int lda,
+                               const double* B, int ldb, double beta, double* C, int ldc, int epi, unsigned* queue,
+                               int balanced) {
+    constexpr size_t SMEM = Cfg::PIPE_BYTES + 1024;
     static bool attr = false;
     if (!attr) {
-        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_GEMM_SMEM_BYTES));
-        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tma_kernel<Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
     CUtensorMap mapA, mapB;
-    int rc = tm_make_a_map(&mapA, A, M, K, lda);
+    int rc = tm_make_a_map(&mapA, A, M, K, lda, Cfg::BM);
     if (rc) return rc;
-    rc = tm_make_b_map(&mapB, B, K, N, ldb);
+    rc = tm_make_b_map(&mapB, B, K, N, ldb, Cfg::BN);
     if (rc) return rc;
     int sms = 0, dev = 0;
     DAGMA_CUDA_OK(cudaGetDevice(&dev));
     DAGMA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int ntiles = ((M + 63) / 64) * ((N + 63) / 64);
-    const int grid = ntiles < 4 * sms ? ntiles : 4 * sms;
+    const int ntiles = ((M + Cfg::BM - 1) / Cfg::BM) * ((N + Cfg::BN - 1) / Cfg::BN);
+    const int nk = (K + TM_BK - 1) / TM_BK;
+    const int slots = (512 / Cfg::THREADS) * sms;
+    const int grid = ntiles < slots ? ntiles : slots;
+    // balanced needs: no epilogue on shared tiles, every range at least one tile long
+    if (balanced && !(beta == 0.0 && epi == EPI_NONE && (long long)ntiles * nk / grid >= nk)) balanced = 0;
+    if (balanced) {
+        queue = nullptr;
+        gemm_tma_zero_shared_kernel<Cfg><<<grid, 256, 0, stream>>>(C, ldc, M, N, K, grid);
+        DAGMA_CUDA_OK(cudaGetLastError());
+    }
     if (queue) DAGMA_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(unsigned), stream));
-    TmaGemmArgs P{M, N, K, C, ldc, alpha, beta, epi, queue};
-    gemm_tma_kernel<<<grid, 128, TMA_GEMM_SMEM_BYTES, stream>>>(mapA, mapB, P);
+    TmaGemmArgs P{M, N, K, C, ldc, alpha, beta, epi, queue, balanced};
+    gemm_tma_kernel<Cfg><<<grid, Cfg::THREADS, SMEM, stream>>>(mapA, mapB, P);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
+}
+// mode: bit 0 = atomic tile queue, bit 1 = balanced k-slab ranges, bit 2 = 128 x 128 tiles (else 64 x 64)
+static int gemm_tma_launch(cudaStream_t stream, int M, int N, int K, double alpha, const double* A, int lda,
+                           const double* B, int ldb, double beta, double* C, int ldc, int epi, unsigned* queue,
+                           int mode) {
+    if (!(mode & 1)) queue = nullptr;
+    if (mode & 4)
+        return gemm_tma_launch_cfg<Tm128>(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, queue, (mode >> 1) & 1);
+    return gemm_tma_launch_cfg<Tm64>(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, queue, (mode >> 1) & 1);
 }
 // tile-queue words of the stand-alone TMA GEMM: a small ring in device memory, allocated once per process
 // (outside stream capture: the first GEMM of a process is never captured -- engines warm up before they record
@@ -967,6 +1040,18 @@ static bool gemm_tma_ok(int transA, int M, int N, int K, const double* A, int ld
     return !transA && M > 0 && N > 0 && K > 0 && (lda % 2 == 0) && (ldb % 2 == 0) &&
            (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0) &&
            ((M + 63) / 64) * ((N + 63) / 64) >= 296;
+}
+// schedule / tile of the stand-alone TMA GEMM (DAGMA_TMA_GEMM_MODE overrides; bits as in gemm_tma_launch):
+// 128 x 128 tiles; balanced k-slab ranges when the epilogue allows it, else the tile queue
+static int gemm_tma_sched(int M, int N, int K, double beta, int epi) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("DAGMA_TMA_GEMM_MODE");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 0) return forced;
+    (void)M; (void)N; (void)K;
+    return (beta == 0.0 && epi == EPI_NONE) ? (4 | 2) : (4 | 1);
 }
 
 // =====================================================================================================
@@ -2151,7 +2236,7 @@ extern "C" int dagma_bench_tma_gemm(dagma_stream_t stream, int M, int N, int K, 
                                     int mode, unsigned* queue_dev) {
     DAGMA_REQUIRE(a_dev && b_dev && c_dev, "bad arguments");
     return gemm_tma_launch((cudaStream_t)stream, M, N, K, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc, EPI_NONE,
-                           mode ? queue_dev : nullptr);
+                           queue_dev, mode);
 }
 
 extern "C" int dagma_linear_update_ex_f64(dagma_stream_t stream, int d, void* state_dev, double* w_dev,

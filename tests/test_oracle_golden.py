@@ -137,3 +137,22 @@ def test_generators():
     X, W = simulate.config_c2(0, n=200, d=10)
     assert set(np.unique(X)) <= {0.0, 1.0}
     assert not simulate.is_dag(np.array([[0, 1.0], [1.0, 0]]))
+
+
+@pytest.mark.parametrize("seq", ["inv", "log", "exp", "binom"])
+@pytest.mark.parametrize("wn", ["a", "b"])
+def test_pst_series_value_grad(golden, seq, wn):
+    """Closed-form adjoints of every PST series / aggregation against the reference's autograd."""
+    from oracle.notreks_ref import pst_value_grad
+    g = golden("pst_series")
+    W = g[f"W_{wn}"]
+    for agg in ("mean", "sum", "max", "lse"):
+        val, grad, H = pst_value_grad(W, g["pairs"], seq=seq, agg=agg)
+        ref_v, ref_g = float(g[f"val_{wn}_{seq}_{agg}"]), g[f"grad_{wn}_{seq}_{agg}"]
+        assert abs(val - ref_v) <= 1e-11 * max(abs(ref_v), 1e-3), (seq, agg)
+        assert np.abs(grad - ref_g).max() <= 1e-10 * max(np.abs(ref_g).max(), 1e-6), (seq, agg)
+    assert np.abs(H - g[f"H_{wn}_{seq}"]).max() <= 1e-11 * np.abs(g[f"H_{wn}_{seq}"]).max()
+    if seq == "log" and wn == "a":
+        val, grad, _ = pst_value_grad(W, g["pairs"], seq="log", agg="mean", K_log=5)
+        assert abs(val - float(g["val_a_log_K5"])) <= 1e-12
+        assert np.abs(grad - g["grad_a_log_K5"]).max() <= 1e-12

@@ -34,8 +34,9 @@ def test_pst_inv_value_grad(golden, agg):
     # disabled / empty pair list: the reference's no-op branch
     v3, g3 = trek_value_grad(g["pst_W"], PSTRegularizer(I=np.zeros((0, 2), dtype=np.int64), seq="inv", weight=1.0))
     assert v3 == 0.0 and not g3.any()
-    with pytest.raises(NotImplementedError):
-        trek_value_grad(g["pst_W"], PSTRegularizer(I=g["pairs"], seq="exp", weight=1.0))
+    from midagma_b200.notreks import TCCRegularizer
+    with pytest.raises(NotImplementedError):                          # TCC dispatches to the spectral penalty (geev)
+        trek_value_grad(g["pst_W"], TCCRegularizer(I=g["pairs"], weight=1.0))
 
 
 @pytest.mark.parametrize("case", ["plain", "pst_opt", "pst_log", "pst_opt_sum"])
@@ -86,3 +87,63 @@ def test_telemetry_small_d_fit_routes_through_engine():
     b = DagmaLinear("l2", log_cfg=cfg).fit(X.copy(), lambda1=0.02, T=2, warm_iter=2000, max_iter=3000, s=[1.0, 0.9])
     assert rows and rows[0]["iter"] == 1000
     assert simulate.edge_set_distance(a, b) == 0
+
+
+@pytest.mark.parametrize("seq", ["inv", "log", "exp", "binom"])
+@pytest.mark.parametrize("wn", ["a", "b"])
+def test_pst_series_value_grad(golden, seq, wn):
+    """Every PST series x aggregation on the GEMM kernels against the reference's autograd
+    (oracle/make_golden_trek.py --pst-series -> tests/golden/pst_series.npz)."""
+    import torch
+    from midagma_b200.notreks import PSTRegularizer, trek_value_grad, pst_mat, pst, get_no_trek_pairs
+    g = golden("pst_series")
+    W, pairs = g[f"W_{wn}"], g["pairs"]
+    for agg in ("mean", "sum", "max", "lse"):
+        reg = PSTRegularizer(I=pairs, seq=seq, weight=1.0, mode="opt", kwargs={"agg": agg})
+        val, grad = trek_value_grad(W, reg)
+        ref_v, ref_g = float(g[f"val_{wn}_{seq}_{agg}"]), g[f"grad_{wn}_{seq}_{agg}"]
+        assert abs(val - ref_v) <= 1e-9 * max(abs(ref_v), 1e-3), (seq, agg, val, ref_v)
+        assert np.abs(grad - ref_g).max() <= 1e-9 * max(np.abs(ref_g).max(), 1e-6), (seq, agg)
+        v2, g2 = trek_value_grad(W, PSTRegularizer(I=pairs, seq=seq, weight=1.0, mode="log", kwargs={"agg": agg}))
+        assert abs(v2 - ref_v) <= 1e-9 * max(abs(ref_v), 1e-3) and not g2.any()
+    H_ref = g[f"H_{wn}_{seq}"]
+    H = pst_mat(torch.from_numpy(W), seq).numpy()
+    assert np.abs(H - H_ref).max() <= 1e-10 * np.abs(H_ref).max()
+    vec = pst(torch.from_numpy(W), pairs, seq, agg="none").numpy()
+    assert np.abs(vec - g[f"none_{wn}_{seq}"]).max() <= 1e-10 * max(np.abs(H_ref).max(), 1e-6)
+    if seq == "log" and wn == "a":
+        reg = PSTRegularizer(I=pairs, seq="log", weight=1.0, mode="opt", kwargs={"agg": "mean", "K_log": 5})
+        val, grad = trek_value_grad(W, reg)
+        assert abs(val - float(g["val_a_log_K5"])) <= 1e-11 and np.abs(grad - g["grad_a_log_K5"]).max() <= 1e-11
+    if seq == "exp":                                                   # pairs with no trek: H == 0 exactly
+        Wd = np.triu(W, 1) * (np.abs(np.triu(W, 1)) > 0.25)
+        ref_pairs = {(i, j) for i in range(W.shape[0]) for j in range(i + 1, W.shape[0])}
+        got = {tuple(p) for p in get_no_trek_pairs(torch.from_numpy(Wd), "exp")}
+        assert got <= ref_pairs
+
+
+@pytest.mark.parametrize("case", ["exp_mean", "log_lse", "binom_max"])
+def test_pst_series_trajectory(golden, case):
+    """``minimize`` in mode "opt" with the exp / log / binom series: W after each stage and the logged trek value."""
+    from midagma_b200 import DagmaLinear
+    from midagma_b200.logger import LogConfig
+    from midagma_b200.notreks import PSTRegularizer
+    g = golden("pst_series")
+    pairs = g["pairs"]
+    reg = {"exp_mean": PSTRegularizer(I=pairs, seq="exp", weight=0.7, mode="opt"),
+           "log_lse": PSTRegularizer(I=pairs, seq="log", weight=0.3, mode="opt", kwargs={"agg": "lse"}),
+           "binom_max": PSTRegularizer(I=pairs, seq="binom", weight=0.5, mode="opt", kwargs={"agg": "max"})}[case]
+    rows = []
+    cfg = LogConfig(enabled=True, store_jsonl=False, store_csv=False, keep_in_memory=True, callback=rows.append)
+    m = DagmaLinear("l2", trek_reg=reg, log_cfg=cfg)
+    X = g[f"{case}_X"].copy()
+    d = X.shape[1]
+    m.fit(X, lambda1=0.02, T=1, warm_iter=0, max_iter=0, checkpoint=100)
+    W = np.zeros((d, d))
+    for si, (mu, iters, s, lr) in enumerate(g["stages"]):
+        W, ok = m.minimize(W, float(mu), int(iters), float(s), float(lr))
+        assert ok == bool(g[f"{case}_ok"][si])
+        assert np.abs(W - g[f"{case}_W"][si]).max() <= 1e-9, case
+    ref = g[f"{case}_trek_vals"]
+    got = np.array([float(r["reg_trek_value"]) for r in rows])
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-8 * max(np.abs(ref).max(), 1e-3)
