@@ -28,10 +28,14 @@
 namespace dagma {
 
 constexpr int TM_BK = 16;
+#ifndef DAGMA_TM_FIX
+#define DAGMA_TM_FIX 0          // debug: bit 0 proxy fence after the full wait, bit 1 warp sync there, bit 2 proxy fence before the release
+#endif
 // CTA (or engine) tile BM x BN, warps in a (BM / 32) x (BN / 32) grid, STAGES slabs of BM x 16 + 16 x BN doubles
-template <int BM_, int BN_, int STAGES_>
+template <int BM_, int BN_, int STAGES_, int DIST_ = STAGES_ - 1>
 struct TmaCfg {
     static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_;
+    static constexpr int DIST = DIST_;      // slabs requested ahead of the one being multiplied (<= STAGES - 1)
     static constexpr int WM = BM / 32, WN = BN / 32, WARPS = WM * WN, THREADS = 32 * WARPS;
     static constexpr int A_BYTES = BM * TM_BK * 8, B_BYTES = TM_BK * BN * 8;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -39,7 +43,11 @@ struct TmaCfg {
     static_assert(BM % 32 == 0 && BN % 32 == 0 && BM <= 256 && BN <= 256, "whole 32 x 32 warp tiles, box <= 256");
     static_assert(A_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "swizzled boxes start on 1024-byte boundaries");
 };
+#if DAGMA_TM_FIX & 8
+using Tm64 = TmaCfg<64, 64, 4, 2>;    // debug: one spare stage between release and refill
+#else
 using Tm64 = TmaCfg<64, 64, 3>;       // the 128-thread engine of the persistent inverse kernels (16 KB stages)
+#endif
 using Tm128 = TmaCfg<128, 128, 6>;    // one 512-thread CTA per SM (32 KB stages, 192 KB pipeline)
 constexpr int TM_STAGES = Tm64::STAGES;
 constexpr int TM_PIPE_BYTES = Tm64::PIPE_BYTES;
@@ -187,6 +195,12 @@ template <class Cfg>
 __device__ __forceinline__ void tm_consume(TmaPipe<Cfg>& p, const TmaFrag<Cfg>& f, double (&acc)[4][4][2], int lane) {
     const uint32_t s = p.cs;
     tm_mbar_wait(p.full(s), p.cph);
+#if DAGMA_TM_FIX & 1
+    tm_fence_proxy();
+#endif
+#if DAGMA_TM_FIX & 2
+    __syncwarp();
+#endif
     const uint32_t sa = p.stage0 + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
 #pragma unroll
     for (int kk = 0; kk < TM_BK; kk += 4) {
@@ -203,6 +217,9 @@ __device__ __forceinline__ void tm_consume(TmaPipe<Cfg>& p, const TmaFrag<Cfg>& 
                 asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                     : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
     }
+#if DAGMA_TM_FIX & 4
+    tm_fence_proxy();
+#endif
     __syncwarp();
     if (lane == 0) tm_mbar_arrive(p.empty(s));
     if (++p.cs == Cfg::STAGES) {
@@ -223,7 +240,7 @@ template <class Cfg>
 __device__ __forceinline__ int tm_tile_gemm(TmaPipe<Cfg>& p, const TmaFrag<Cfg>& f, double (&acc)[4][4][2],
                                             const CUtensorMap* mapA, const CUtensorMap* mapB, const TmaTile& t,
                                             int primed, const TmaTile& nxt, bool elected, int lane) {
-    constexpr int D = Cfg::STAGES - 1;
+    constexpr int D = Cfg::DIST;
     int issued = primed, nissued = 0;
     const int nlim = nxt.nk < D ? nxt.nk : D;
     if (elected)
