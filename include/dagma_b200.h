@@ -234,6 +234,22 @@ int dagma_tcc_fold_f64(dagma_stream_t stream, int d, const double* w_dev, const 
 int dagma_center_cov_f64(dagma_stream_t stream, int batch, int n, int d, double* x_dev,
                          int center, double* cov_dev);
 
+/* ---- pairwise independence tests in front of the path ----------------
+ * Replaces: hsic_stat / dcor_stat / permutation_pvalue      src/notreks/mi_tests.py:19-135
+ * Every variable's double-centred Gram matrix (RBF kernel: kind 0, sigma2_dev[v]; absolute distance: kind 1)
+ * is built once, g_dev [nvars][n][n]; a permuted statistic is the gathered dot product
+ * out[q * nperm + p] = scale * sum_ab G[vi[q]][a][b] * G[vj[q]][pi(a)][pi(b)], pi = perms_dev[q][p][0..n).
+ * dagma_mi_upper_d2_f64 writes the n (n - 1) / 2 squared distances of one column (input of the median
+ * heuristic, mi_tests.py:41-46).                                                                        */
+int dagma_mi_upper_d2_f64(dagma_stream_t stream, int n, int d, int col, const double* x_dev, double* out_dev);
+int dagma_mi_centered_gram_f64(dagma_stream_t stream, int n, int d, int nvars, const int* cols_dev,
+                               const double* x_dev, const double* sigma2_dev, int kind, double* g_dev,
+                               double* rowmean_dev, double* allmean_dev);
+size_t dagma_mi_perm_workspace_bytes(int n, int npairs, int nperm);
+int dagma_mi_perm_dots_f64(dagma_stream_t stream, int n, const double* g_dev, int npairs, const int* vi_dev,
+                           const int* vj_dev, const int* perms_dev, int nperm, double scale, double* ws_dev,
+                           size_t ws_bytes, double* out_dev);
+
 /* ---- FP64 pipe yardsticks used by bench.py for the roofline denominator ---------- */
 int dagma_bench_fp64_fma(dagma_stream_t stream, int ctas, int threads, int iters, double* sink_dev);
 int dagma_bench_fp64_dmma(dagma_stream_t stream, int ctas, int threads, int iters, double* sink_dev);

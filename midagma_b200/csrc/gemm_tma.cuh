@@ -6,9 +6,10 @@
 // warp that is late on its sub-partition's FP64 pipe stalls the other three.  Here a slab is TWO bulk
 // tensor copies (cp.async.bulk.tensor.2d, SASS UTMALDG) issued by one elected thread and tracked by
 // mbarriers: full[s] (count 1 + transaction bytes) is what a warp waits for before it reads stage s,
-// empty[s] (count 4, one arrive per warp) is what the elected thread waits for before it refills the
-// stage -- one slab LATER than the warps released it, so that no warp waits for another warp unless it
-// is a whole slab ahead.  The pipeline state (stage, phase bits) runs on across tiles.
+// empty[s] (one arrive per warp, after a fence.proxy.async of every thread: generic-proxy reads before the
+// async-proxy refill) is what the elected thread waits for before it refills the stage -- one slab LATER
+// than the warps released it, so that no warp waits for another warp unless it is a whole slab ahead.
+// The pipeline state (stage, phase bits) runs on across tiles.
 //
 // Shared layout of a stage (16 KB, 1024-byte aligned):
 //   A box  [64 rows m][16 k]  = 64 x 128 B, CU_TENSOR_MAP_SWIZZLE_128B: the 16-byte chunk c of row r
@@ -28,8 +29,13 @@
 namespace dagma {
 
 constexpr int TM_BK = 16;
+// DAGMA_TM_FIX (A-B experiments, scripts/check_tma_repeat2.py): bit 2 = every thread executes fence.proxy.async
+// before its warp releases a stage -- REQUIRED: the stage is read through the generic proxy (ld.shared) and
+// refilled through the async proxy (TMA), and without the cross-proxy fence the refill can overtake the last
+// reads (measured on B200: 7 % of 2000^3 products wrong in the balanced schedule without it, 0 of 300 with it).
+// bit 0 / bit 1 = proxy fence / warp sync after the full wait (no effect), bit 3 = a spare stage (also hides it).
 #ifndef DAGMA_TM_FIX
-#define DAGMA_TM_FIX 0          // debug: bit 0 proxy fence after the full wait, bit 1 warp sync there, bit 2 proxy fence before the release
+#define DAGMA_TM_FIX 4
 #endif
 // CTA (or engine) tile BM x BN, warps in a (BM / 32) x (BN / 32) grid, STAGES slabs of BM x 16 + 16 x BN doubles
 template <int BM_, int BN_, int STAGES_, int DIST_ = STAGES_ - 1>

@@ -91,7 +91,6 @@ static int gemm_tile_variant() {
 
 static unsigned* tma_queue(cudaStream_t stream);
 static int tma_mode();
-static bool gemm_use_tma(int M, int N, int K);
 static bool gemm_tma_ok(int transA, int M, int N, int K, const double* A, int lda, const double* B, int ldb);
 static int gemm_tma_launch(cudaStream_t stream, int M, int N, int K, double alpha, const double* A, int lda,
                            const double* B, int ldb, double beta, double* C, int ldc, int epi, unsigned* queue,
@@ -102,9 +101,12 @@ static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, dou
                        const double* B, int ldb, double beta, double* C, int ldc, int epi, double* ws,
                        size_t ws_bytes) {
     if (M <= 0 || N <= 0) return 0;
-    if (gemm_use_tma(M, N, K) && gemm_tma_ok(transA, M, N, K, A, lda, B, ldb))
-        return gemm_tma_launch(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, tma_queue(stream),
-                               gemm_tma_sched(M, N, K, beta, epi));
+    if (gemm_tma_ok(transA, M, N, K, A, lda, B, ldb)) {
+        const int sched = gemm_tma_sched(M, N, K, beta, epi);
+        if (sched >= 0)
+            return gemm_tma_launch(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi,
+                                   (sched & 1) ? tma_queue(stream) : nullptr, sched);
+    }
     if (gemm_tile_variant() == 1)
         return gemm_launch_tile<128, 128, 4, 2>(stream, transA, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epi, ws, ws_bytes);
     if (gemm_tile_variant() == 2)
@@ -1041,19 +1043,6 @@ static bool gemm_tma_ok(int transA, int M, int N, int K, const double* A, int ld
            (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0) &&
            ((M + 63) / 64) * ((N + 63) / 64) >= 296;
 }
-// schedule / tile of the stand-alone TMA GEMM (DAGMA_TMA_GEMM_MODE overrides; bits as in gemm_tma_launch):
-// 128 x 128 tiles; balanced k-slab ranges when the epilogue allows it, else the tile queue
-static int gemm_tma_sched(int M, int N, int K, double beta, int epi) {
-    static int forced = -2;
-    if (forced == -2) {
-        const char* e = getenv("DAGMA_TMA_GEMM_MODE");
-        forced = e ? atoi(e) : -1;
-    }
-    if (forced >= 0) return forced;
-    (void)M; (void)N; (void)K;
-    return (beta == 0.0 && epi == EPI_NONE) ? (4 | 2) : (4 | 1);
-}
-
 // =====================================================================================================
 // Two-level inverse as ONE dependency-driven persistent kernel ("flow" kernel).
 //
@@ -1749,10 +1738,13 @@ static int lookahead_mode() {
 
 // DAGMA_TMA: which slab pipelines are fed by TMA (cp.async.bulk.tensor + mbarrier pipeline, gemm_tma.cuh) instead
 // of per-thread cp.async.  Bit 0: the update tiles of the outer step of the two-level inverse; bit 1: the
-// stand-alone GEMM whenever its operands qualify.  Unset: bit 0, and the stand-alone GEMM only when it is long
-// enough for the persistent kernel to pay (measured on B200, scripts/perf_tma.py: 34.1 vs 32.1 TFLOP/s at 4096^3,
-// but 27.0 vs 28.9 at 2000^3 and 24.0 vs 25.9 on the 2000 x 2000 x 256 update, where the per-tile hand-over costs
-// more than the barrier-free slab loop gains).  0 = cp.async everywhere.
+// stand-alone GEMM whenever its operands qualify; bit 2: the stand-alone GEMM where it was measured to win
+// (scripts/perf_tma.py on B200, TFLOP/s):            2000^3    4096^3    2000 x 2000 x 256 (+= C)
+//     cp.async 64 x 64, four CTAs per SM               28.9      32.2        25.9
+//     TMA 128 x 128, balanced k-slab ranges            32.4      35.5         --      (cuBLAS: 32.7 / 35.4)
+//     TMA 128 x 128, tile queue                        28.8      35.2        22.4
+// i.e. the balanced schedule once the output has a 128 x 128 tile per SM and K is long, the queue only for
+// large outputs; short-K updates stay on cp.async.  Unset = bits 0 and 2.  0 = cp.async everywhere.
 static int tma_mode() {
     static int v = -1;
     if (v < 0) {
@@ -1762,11 +1754,23 @@ static int tma_mode() {
     }
     return v;
 }
-static bool gemm_use_tma(int M, int N, int K) {
+// schedule / tile of the stand-alone TMA GEMM (bits as in gemm_tma_launch: 1 queue, 2 balanced, 4 = 128 x 128
+// tiles), or -1: stay on the cp.async kernel.  DAGMA_TMA_GEMM_MODE forces a mode.
+static int gemm_tma_sched(int M, int N, int K, double beta, int epi) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("DAGMA_TMA_GEMM_MODE");
+        forced = e ? atoi(e) : -1;
+    }
     const int m = tma_mode();
-    if (m & 2) return true;
-    if (m & 4) return (long long)((M + 63) / 64) * ((N + 63) / 64) >= 4 * 592 && K >= 1024;
-    return false;
+    if (!(m & 6)) return -1;
+    if (forced >= 0) return forced;
+    const long long t128 = (long long)((M + 127) / 128) * ((N + 127) / 128);
+    const bool plain = (beta == 0.0 && epi == EPI_NONE);
+    if (m & 2) return plain ? (4 | 2) : (4 | 1);
+    if (plain && t128 >= 148 && K >= 512) return 4 | 2;
+    if (t128 >= 4 * 148 && K >= 1024) return 4 | 1;
+    return -1;
 }
 
 // two-level block Gauss-Jordan, outer block OB = 256: per outer block K

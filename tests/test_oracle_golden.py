@@ -156,3 +156,17 @@ def test_pst_series_value_grad(golden, seq, wn):
         val, grad, _ = pst_value_grad(W, g["pairs"], seq="log", agg="mean", K_log=5)
         assert abs(val - float(g["val_a_log_K5"])) <= 1e-12
         assert np.abs(grad - g["grad_a_log_K5"]).max() <= 1e-12
+
+
+def test_mi_tests_oracle(golden):
+    """HSIC / dCor permutation tests restated in numpy against the unmodified reference."""
+    from oracle import mi_ref
+    g = golden("mi_tests")
+    X = g["X"]
+    pairs = [tuple(int(v) for v in p) for p in g["pairs"]]
+    for test in ("hsic", "dcor"):
+        res = mi_ref.pairwise(X, pairs, test=test, num_perm=40, seed=3)
+        np.testing.assert_allclose([r[2] for r in res], g[f"{test}_stat"], rtol=1e-12, atol=1e-15)
+        assert np.array_equal(np.array([r[3] for r in res]), g[f"{test}_p"])
+    assert abs(mi_ref.hsic_stat(X[:, 0], X[:, 1], 0.8, 1.3) - float(g["hsic_01_sig"])) <= 1e-15
+    assert abs(mi_ref.dcor_stat(X[:, 0], X[:, 3]) - float(g["dcor_03"])) <= 1e-15
