@@ -36,5 +36,11 @@ def test_trek_value_grad_noop():
     off = notreks.TCCRegularizer(I=[(0, 1)], mode="off")
     v, gr = notreks.trek_value_grad(W, off)
     assert v == 0.0 and not gr.any()
-    with pytest.raises(NotImplementedError):
-        notreks.trek_value_grad(W, notreks.PSTRegularizer(I=[(0, 1)], weight=0.1))
+    # an enabled PST regulariser (default series "exp") is computed on the GPU: check it against the numpy oracle
+    from oracle.notreks_ref import pst_value_grad
+    Ws = 0.1 * W
+    v, gr = notreks.trek_value_grad(Ws, notreks.PSTRegularizer(I=[(0, 1)], weight=0.1))
+    rv, rg, _ = pst_value_grad(Ws, [(0, 1)], seq="exp", agg="mean")
+    assert abs(v - rv) <= 1e-12 * abs(rv) and np.abs(gr - rg).max() <= 1e-12 * np.abs(rg).max()
+    with pytest.raises(NotImplementedError):                      # TCC: the reference dispatches to the spectral penalty
+        notreks.trek_value_grad(W, notreks.TCCRegularizer(I=[(0, 1)], weight=0.1))
