@@ -231,6 +231,74 @@ def bench_c5(torch, _lib, peak_tflops, with_cpu):
     return out
 
 
+def bench_c2_c3(torch, with_cpu):
+    """BASELINE.json configs[1] and [2]: logistic DagmaLinear (ER2 d=100 n=10000) and DagmaMLP (d=40 m1=10 n=2000):
+    wall clock per graph-replayed inner iteration (the host synchronises only at the checkpoints), the numpy
+    restatement of the reference beside it on a few iterations."""
+    import numpy as np
+    from oracle import simulate
+    from midagma_b200 import DagmaLinear
+    from midagma_b200.nonlinear import DagmaMLP, DagmaNonlinear
+    out = {}
+    # ---- C2
+    X, _ = simulate.config_c2(0)
+    d, n = X.shape[1], X.shape[0]
+    m = DagmaLinear("logistic")
+    m.fit(X.copy(), lambda1=0.02, T=1, warm_iter=0, max_iter=0)
+    W = np.zeros((d, d))
+    m.minimize(W, 1.0, 200, 1.0, lr=3e-4)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m.minimize(W, 1.0, 4000, 1.0, lr=3e-4, tol=0.0)
+    torch.cuda.synchronize()
+    t = (time.perf_counter() - t0) / 4000
+    flop = 4.0 * n * d * d + 2.0 * d ** 3
+    c2 = {"workload": "C2: DagmaLinear logistic, ER2 d=100 n=10000, mu=1 s=1 lr=3e-4 (4000 graph-replayed inner iterations, wall clock)",
+          "us_per_iter": t * 1e6, "iters_per_s": 1.0 / t, "flop_per_iter": flop, "tflops": flop / t / 1e12}
+    if with_cpu:
+        from oracle.linear_ref import OracleLinear
+        o = OracleLinear("logistic").prepare(X.copy(), 0.02, checkpoint=1000)
+        Wc = np.zeros((d, d))
+        o.minimize(Wc, 1.0, 1, 1.0, 3e-4, tol=0.0)
+        t0 = time.perf_counter()
+        o.minimize(Wc, 1.0, 10, 1.0, 3e-4, tol=0.0)
+        cpu = (time.perf_counter() - t0) / 10
+        c2.update({"cpu_ms_per_iter": cpu * 1e3, "speedup_vs_cpu": cpu / t,
+                   "cpu_sample": f"10 iterations of oracle/linear_ref.py with all host BLAS threads ({len(os.sched_getaffinity(0))} cores)"})
+    out["c2"] = c2
+    # ---- C3
+    X, _ = simulate.config_c3(0)
+    d, m1, n = X.shape[1], 10, X.shape[0]
+    torch.manual_seed(0)
+    model = DagmaMLP(dims=[d, m1, 1], bias=True)
+    init = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    nl = DagmaNonlinear(model)
+    nl.X = torch.from_numpy(X).cuda()
+    nl.checkpoint = 1000
+    nl.minimize(1000, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nl.minimize(4000, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0)
+    torch.cuda.synchronize()
+    t = (time.perf_counter() - t0) / 4000
+    flop = 2.0 * (2.0 * n * d * d * m1) + 6.0 * n * d * m1 + 2.0 * d ** 3
+    c3 = {"workload": "C3: DagmaMLP [40, 10, 1] n=2000, mu=0.1 s=1 lr=2e-4 (4000 graph-replayed inner iterations incl. engine set-up, wall clock)",
+          "us_per_iter": t * 1e6, "iters_per_s": 1.0 / t, "flop_per_iter": flop}
+    if with_cpu:
+        from oracle.nonlinear_ref import OracleMLP, OracleNonlinear
+        om = OracleMLP([d, m1, 1], {k: v.numpy() for k, v in init.items()})
+        on = OracleNonlinear(om)
+        on.minimize(X, 2, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0, checkpoint=10 ** 9)
+        t0 = time.perf_counter()
+        on.minimize(X, 20, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0, checkpoint=10 ** 9)
+        cpu = (time.perf_counter() - t0) / 20
+        c3.update({"cpu_ms_per_iter": cpu * 1e3, "speedup_vs_cpu": cpu / t,
+                   "cpu_sample": "20 iterations of oracle/nonlinear_ref.py (closed-form numpy backward; the reference's torch-autograd "
+                                 "iteration is 14.8 ms, SURVEY.md 6.2)"})
+    out["c3"] = c3
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -359,6 +427,7 @@ def run_b200(args):
         if args.c5 and world == 1:
             del W_host, cov_host
             extra["c5"] = bench_c5(torch, _lib, peak, args.cpu_baseline)
+            extra.update(bench_c2_c3(torch, args.cpu_baseline))
 
     if rank == 0:
         line = {

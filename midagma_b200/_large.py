@@ -67,6 +67,7 @@ class LargeLinearEngine:
             self.R = torch.empty(self.n, d, **f64)
             self.partial = torch.empty(1024, **f64)
         self._graph = None
+        self._side = None
         self._model_cov_ptr = model._cov_dev.data_ptr()
         self.launches_per_iter = None
         self._trek_setup(getattr(model, "_trek_plan", None))
@@ -159,11 +160,20 @@ class LargeLinearEngine:
             "dagma_logdet_inv_gemm_ws_f64")
 
     def _gradient_pieces(self, s: float):
-        if self.loss_type == "l2":
-            self._inverse_and_score(s)
+        if self.loss_type == "l2" and self.d > 256:
+            self._inverse_and_score(s)           # both saturate the GPU: back to back
         else:
+            # the inverse of sI - W o W (a few CTAs at these sizes, a serial pivot chain) and the score products are
+            # independent: fork the score onto a side stream, join before the update (captured as parallel graph
+            # branches; the multi-GPU all-reduce of the partial gradient rides on the side stream as well)
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._score_T()
             self._inverse(s)
-            self._score_T()
+            cur.wait_stream(self._side)
         if self._trek_opt():
             self._trek_grad()
 

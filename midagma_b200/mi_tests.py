@@ -6,9 +6,9 @@ Same names and signatures: ``hsic_stat``, ``dcor_stat``, ``permutation_pvalue``,
 correlation run on the GPU: each variable's centred Gram matrix is built once and every permuted statistic is a
 gathered dot product (csrc/mi.cu), instead of the reference's full rebuild per permutation.  The permutations
 themselves come from the same ``numpy.random.Generator`` stream as the reference (``rng.permutation(n)`` per
-permutation, pairs in order), so p-values are comparable one to one.  ``pearson`` / ``spearman`` have analytic
-scipy p-values in the reference (no permutation loop, O(n) per pair): they are not part of the accelerated path
-and raise ``NotImplementedError``.
+permutation, pairs in order), so p-values are comparable one to one.  ``pearson`` / ``spearman``: all correlations
+from one fused centring + covariance launch (on the data or on its tie-averaged ranks), the analytic p-values are
+scipy's closed forms evaluated on the host (d^2 scalars).
 """
 from __future__ import annotations
 
@@ -20,8 +20,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["IndepTestResult", "hsic_stat", "dcor_stat", "permutation_pvalue", "test_pairwise_independence",
-           "get_I_from_full_pairwise_tests"]
+__all__ = ["IndepTestResult", "hsic_stat", "dcor_stat", "permutation_pvalue", "pearson_stat_pvalue",
+           "spearman_stat_pvalue", "test_pairwise_independence", "get_I_from_full_pairwise_tests"]
 
 
 @dataclass(frozen=True)
@@ -161,14 +161,91 @@ def permutation_pvalue(stat_fn, x: np.ndarray, y: np.ndarray, *, num_perm: int =
     return float(stats[0]), float((ge + 1) / (num_perm + 1))
 
 
+def _corr_matrix(Xd: "torch.Tensor") -> np.ndarray:
+    """Pearson correlation matrix of the columns of a device matrix via the fused centring + covariance kernel
+    (``dagma_center_cov_f64``: X <- X - mean, cov = X^T X / n)."""
+    lib = _lib.load()
+    n, d = Xd.shape
+    Xc = Xd.clone().contiguous()
+    cov = torch.empty(d, d, dtype=torch.float64, device="cuda")
+    _lib.check(lib.dagma_center_cov_f64(_lib.stream_ptr(), 1, n, d, Xc.data_ptr(), 1, cov.data_ptr()), "dagma_center_cov_f64")
+    c = cov.cpu().numpy()
+    sd = np.sqrt(np.diag(c))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return c / np.outer(sd, sd)
+
+
+def _average_ranks(Xd: "torch.Tensor") -> "torch.Tensor":
+    """Column-wise ranks 1..n with ties averaged (scipy.stats.rankdata, the ranking behind spearmanr)."""
+    n, d = Xd.shape
+    srt, order = torch.sort(Xd, dim=0, stable=True)
+    first = torch.ones(n, d, dtype=torch.bool, device=Xd.device)
+    first[1:] = srt[1:] != srt[:-1]
+    pos = torch.arange(1, n + 1, dtype=torch.float64, device=Xd.device)[:, None].expand(n, d)
+    start = torch.cummax(torch.where(first, pos, torch.zeros_like(pos)), dim=0).values       # first position of the tie group
+    last = torch.ones(n, d, dtype=torch.bool, device=Xd.device)
+    last[:-1] = srt[1:] != srt[:-1]
+    big = torch.full_like(pos, float(n + 1))
+    end = torch.flip(torch.cummin(torch.flip(torch.where(last, pos, big), [0]), dim=0).values, [0])
+    avg = 0.5 * (start + end)
+    ranks = torch.empty_like(avg)
+    ranks.scatter_(0, order, avg)
+    return ranks
+
+
+def _analytic_tests(X: np.ndarray, pairs, test: str) -> List[IndepTestResult]:
+    """``pearson`` / ``spearman`` (mi_tests.py:137-162): the correlations come from one covariance launch over all
+    columns (of the data or of its ranks); the analytic two-sided p-values are scipy's formulas (the reference calls
+    ``scipy.stats.pearsonr`` / ``spearmanr``): pearson  p = 2 * Beta(n/2 - 1, n/2 - 1).sf on [-1, 1],
+    spearman  t = r sqrt((n - 2) / ((1 + r)(1 - r))),  p = 2 * t_{n-2}.sf(|t|)."""
+    from scipy import special, stats
+    _lib.require_device()
+    Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).cuda()
+    n = Xd.shape[0]
+    R = _corr_matrix(_average_ranks(Xd) if test == "spearman" else Xd)
+    out = []
+    for i, j in pairs:
+        r = float(R[i, j])
+        if not np.isfinite(r):
+            if test == "pearson":                                              # constant input: scipy returns (nan, nan)
+                out.append(IndepTestResult(i=i, j=j, stat=float("nan"), pvalue=float("nan")))
+            else:
+                out.append(IndepTestResult(i=i, j=j, stat=0.0, pvalue=1.0))    # mi_tests.py:158-160
+            continue
+        r = max(-1.0, min(1.0, r))
+        if test == "pearson":
+            ab = n / 2.0 - 1.0
+            p = 2.0 * float(special.betainc(ab, ab, 0.5 * (1.0 - abs(r))))
+        else:
+            dof = n - 2
+            with np.errstate(divide="ignore"):
+                t = r * np.sqrt(dof / ((r + 1.0) * (1.0 - r)))
+            p = 2.0 * float(stats.t.sf(abs(t), dof))
+        out.append(IndepTestResult(i=i, j=j, stat=abs(r), pvalue=min(p, 1.0)))
+    return out
+
+
+def pearson_stat_pvalue(x: np.ndarray, y: np.ndarray) -> Tuple[float, float]:
+    """(|r|, p) of the Pearson correlation test (mi_tests.py:137-145)."""
+    X, _ = _two_col(x, y)
+    r = _analytic_tests(X, [(0, 1)], "pearson")[0]
+    return r.stat, r.pvalue
+
+
+def spearman_stat_pvalue(x: np.ndarray, y: np.ndarray) -> Tuple[float, float]:
+    """(|rho|, p) of the Spearman rank correlation test (mi_tests.py:148-162)."""
+    X, _ = _two_col(x, y)
+    r = _analytic_tests(X, [(0, 1)], "spearman")[0]
+    return r.stat, r.pvalue
+
+
 def test_pairwise_independence(X: np.ndarray, pairs: Iterable[Tuple[int, int]], *, test: str = "hsic",
                                num_perm: int = 200, seed: int = 0) -> List[IndepTestResult]:
     """(stat, p-value) per pair (mi_tests.py:165-203): one RNG stream over the pairs in order, as the reference."""
     X = np.asarray(X)
     pairs = [(int(i), int(j)) for i, j in pairs]
     if test in ("pearson", "spearman"):
-        raise NotImplementedError(f"test={test!r} has an analytic scipy p-value in the reference; only the "
-                                  "permutation tests 'hsic' and 'dcor' are accelerated (SURVEY.md 8f4)")
+        return _analytic_tests(X, pairs, test)
     if test not in ("hsic", "dcor"):
         raise ValueError("test must be one of 'hsic', 'dcor', 'pearson', 'spearman'")
     if not pairs:

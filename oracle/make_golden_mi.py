@@ -44,6 +44,18 @@ def main():
         out[f"{test}_I"] = ref.get_I_from_full_pairwise_tests(X, alpha=0.05, test=test, num_perm=25, seed=1)
         out[f"{test}_I_dir"] = ref.get_I_from_full_pairwise_tests(X, alpha=0.2, test=test, num_perm=10, seed=2,
                                                                    bonferroni=False, undirected=False)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                            # ConstantInputWarning for the constant column
+        for test in ("pearson", "spearman"):
+            res = ref.test_pairwise_independence(X, pairs, test=test)
+            out[f"{test}_stat"] = np.array([r.stat for r in res])
+            out[f"{test}_p"] = np.array([r.pvalue for r in res])
+        Xt = np.round(X[:, :5] * 2.0) / 2.0                        # ties in every column
+        res = ref.test_pairwise_independence(Xt, [q for q in pairs if q[1] < 5], test="spearman")
+        out["X_ties"] = Xt
+        out["spearman_ties_stat"] = np.array([r.stat for r in res])
+        out["spearman_ties_p"] = np.array([r.pvalue for r in res])
     out["hsic_01"] = np.array(ref.hsic_stat(X[:, 0], X[:, 1]))
     out["hsic_01_sig"] = np.array(ref.hsic_stat(X[:, 0], X[:, 1], sigma_x=0.8, sigma_y=1.3))
     out["dcor_03"] = np.array(ref.dcor_stat(X[:, 0], X[:, 3]))

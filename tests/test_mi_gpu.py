@@ -37,8 +37,6 @@ def test_stat_functions_and_permutation_pvalue(golden):
     assert abs(s - g["perm_hsic_02"][0]) <= 1e-13 and p == g["perm_hsic_02"][1]
     s, p = mi.permutation_pvalue(mi.dcor_stat, X[:, 1], X[:, 3], num_perm=50)
     assert abs(s - g["perm_dcor_13"][0]) <= 1e-12 and p == g["perm_dcor_13"][1]
-    with pytest.raises(NotImplementedError):
-        mi.test_pairwise_independence(X, [(0, 1)], test="pearson")
     with pytest.raises(ValueError):
         mi.test_pairwise_independence(X, [(0, 1)], test="nope")
     assert mi.test_pairwise_independence(X, [], test="hsic") == []
@@ -58,3 +56,27 @@ def test_larger_n_against_oracle():
         ref = mi_ref.pairwise(X, pairs, test=test, num_perm=12, seed=7)
         for r, q in zip(got, ref):
             assert abs(r.stat - q[2]) <= 1e-11 * max(abs(q[2]), 1e-6) and r.pvalue == q[3], (test, r, q)
+
+
+@pytest.mark.parametrize("test", ["pearson", "spearman"])
+def test_analytic_tests_vs_reference(golden, test):
+    """Pearson / Spearman: correlations from the fused covariance kernel, scipy's closed-form p-values."""
+    from midagma_b200 import mi_tests as mi
+    g = golden("mi_tests")
+    X = g["X"]
+    pairs = [tuple(int(v) for v in p) for p in g["pairs"]]
+    res = mi.test_pairwise_independence(X, pairs, test=test)
+    stat, p = np.array([r.stat for r in res]), np.array([r.pvalue for r in res])
+    np.testing.assert_allclose(stat, g[f"{test}_stat"], rtol=1e-11, atol=1e-14, equal_nan=True)
+    np.testing.assert_allclose(p, g[f"{test}_p"], rtol=1e-9, atol=1e-300, equal_nan=True)
+    if test == "spearman":
+        res = mi.test_pairwise_independence(g["X_ties"], [q for q in pairs if q[1] < 5], test="spearman")
+        np.testing.assert_allclose([r.stat for r in res], g["spearman_ties_stat"], rtol=1e-11, atol=1e-14)
+        np.testing.assert_allclose([r.pvalue for r in res], g["spearman_ties_p"], rtol=1e-9)
+        s, pv = mi.spearman_stat_pvalue(X[:, 0], X[:, 3])
+        k = pairs.index((0, 3))
+        assert abs(s - g["spearman_stat"][k]) <= 1e-12 and abs(pv - g["spearman_p"][k]) <= 1e-9 * g["spearman_p"][k]
+    else:
+        s, pv = mi.pearson_stat_pvalue(X[:, 0], X[:, 3])
+        k = pairs.index((0, 3))
+        assert abs(s - g["pearson_stat"][k]) <= 1e-12 and abs(pv - g["pearson_p"][k]) <= 1e-9 * g["pearson_p"][k]
