@@ -203,6 +203,9 @@ def _analytic_tests(X: np.ndarray, pairs, test: str) -> List[IndepTestResult]:
     Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).cuda()
     n = Xd.shape[0]
     R = _corr_matrix(_average_ranks(Xd) if test == "spearman" else Xd)
+    const = (Xd == Xd[0:1]).all(dim=0).cpu().numpy()           # scipy: a constant input has no correlation (nan)
+    R[const, :] = np.nan
+    R[:, const] = np.nan
     out = []
     for i, j in pairs:
         r = float(R[i, j])

@@ -170,6 +170,7 @@ class _MlpEngine:
         self.state_host = torch.zeros(ST_DOUBLES, dtype=torch.float64).pin_memory()
         self.ws = torch.empty(self.lib.dagma_large_workspace_bytes(d) // 8 + 8, **f64)
         self.group, self.graph = group, None
+        self._side = None
         if X is not None:
             self.X = X
             self.n = X.shape[0]
@@ -209,6 +210,9 @@ class _MlpEngine:
 
     def h(self, s: float):
         self.adj()
+        self._h_inverse(s)
+
+    def _h_inverse(self, s: float):
         _lib.check(self.lib.dagma_logdet_inv_ws_f64(
             _lib.stream_ptr(), self.d, float(s), self.A.data_ptr(), self.d, 0, self._sptr(F_LAD), self._sptr(F_H),
             self.Minv.data_ptr(), None, self.d, self._sptr(F_MIN), self._iptr(I_INFO), self.ws.data_ptr(),
@@ -274,8 +278,17 @@ class _MlpEngine:
 
     def evaluate(self, s: float):
         """h, forward, objective and the (un-scaled) gradient sums at the current parameters."""
-        self.h(s)
+        # the on-chip inverse of sI - A (one CTA, a serial pivot chain) runs on a side stream beside the forward pass;
+        # they meet again at the objective (captured as parallel graph branches)
+        self.adj()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self._h_inverse(s)
         self._forward()
+        cur.wait_stream(self._side)
         if self.group is not None:
             torch.distributed.all_reduce(self.state[F_SS:F_SS + 1], group=self.group)
         _lib.check(self.lib.dagma_mlp_objective_f64(_lib.stream_ptr(), self.state.data_ptr(), self.n_total, self.d),
