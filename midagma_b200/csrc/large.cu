@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
     const int n_cs = tn * nk1 - nk1 * nk1;                       // column strip without the pivot block
     const int n_rs = nk1 * (tn - nk1);                           // row strip without the pivot block
     const int n_rest = (tn - nk1) * (tn - nk1);
-    const int n_upd = n_cs + n_rs + n_rest;
+    const int n_upd = (kn > 0) ? n_cs + n_rs + n_rest : 0;       // kn = 0: the step in front of the first block (nothing to apply)
     const int n_csn = tn * nk1, n_rn = nk1 * tn;
     const int n_items = n_upd + n_rn;
     auto outside = [&](int u) { return u < cb1 ? u : u + nk1; };  // u-th block index not in K'
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
             } else {
                 // ---- R' tile: rows 64 ib.. of the next row strip, columns of block bj
                 const int u = t - n_upd, ib = u / tn, bj = u % tn;
-                if (elected) (void)wait_count(P.sync + 4, (unsigned)(tn * nk1), err);
+                if (elected && kn > 0) (void)wait_count(P.sync + 4, (unsigned)(tn * nk1), err);
                 half_sync(half);
                 const int c0 = bj * NB;
 #pragma unroll
@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
         } else {
             // ---- R' tile: rows 64 ib.. of the next row strip, columns of block bj
             const int u = t - n_upd, ib = u / tn, bj = u % tn;
-            if (ep.htid == 0) (void)wait_count(P.sync + 4, (unsigned)(tn * nk1), err);
+            if (ep.htid == 0 && kn > 0) (void)wait_count(P.sync + 4, (unsigned)(tn * nk1), err);
             half_sync(half);
             const int c0 = bj * NB;
 #pragma unroll
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
             __syncthreads();
             if (u >= n_csn) break;
             const int bi = u / nk1, jb = u % nk1;
-            if (tid == 0) (void)(wait_count(P.sync + 3, (unsigned)(tn * nk1), err) && wait_count(P.sync + 5, (unsigned)P.nserver, err));
+            if (tid == 0) (void)((kn == 0 || wait_count(P.sync + 3, (unsigned)(tn * nk1), err)) && wait_count(P.sync + 5, (unsigned)P.nserver, err));
             __syncthreads();
             OT_MIN(9);
             const int r0 = bi * NB, c0 = jb * NB;
@@ -1722,6 +1722,19 @@ static int lookahead_get(LookAhead** out) {
     return 0;
 }
 
+// DAGMA_FIRST_BLOCK (A-B timing): 1 = the first pivot block is inverted and its CS / R strips are formed by a step of
+// outer_step_kernel with nothing to apply (one launch), 0 (default) = by copy + 4 tile-step launches + a GEMM + a prep
+// kernel (seven launches).  Measured equal at d = 2000 (inverse 0.960 vs 0.957 ms): the first block is bound by its
+// own serial pivot chain either way, so the proven sequence stays the default.
+static bool first_block_fused() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_FIRST_BLOCK");
+        v = e ? atoi(e) : 0;
+    }
+    return v != 0;
+}
+
 // DAGMA_LOOKAHEAD (A-B timing): 1 = one persistent kernel per outer step with the look-ahead inside (default, even d),
 // 2 = the whole inversion as ONE dependency-driven kernel (flow_inverse_kernel; can carry a rider GEMM) -- measured
 //     on par for the inverse alone (1.01 vs 0.97 ms at d = 2000) and for inverse + cov@W (1.58 vs 1.52 ms): its
@@ -1853,7 +1866,8 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         DAGMA_CUDA_OK(cudaGetLastError());
         return 0;
     }
-    {   // first pivot block
+    const bool fused_first = (lookahead_mode() >= 1) && (d % 2 == 0) && first_block_fused();
+    if (!fused_first) {   // first pivot block by the plain kernels
         const int kn = d < OB ? d : OB;
         copy_block_kernel<<<64, 256, 0, stream>>>(Mw, d, Pbuf, kn, kn, kn, 0, 0.0);
         DAGMA_CUDA_OK(cudaGetLastError());
@@ -1875,41 +1889,46 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         int sms = 0, dev = 0;
         DAGMA_CUDA_OK(cudaGetDevice(&dev));
         DAGMA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        // CS / R of the first block by the plain kernels; every later pair is produced by the previous fused step
+        // CS / R of the first block: by the plain kernels (default), or by a step "-1" of the same persistent kernel
+        // with nothing to apply (kn = 0) -- its look-ahead CTAs invert A[K0,K0] in place of the 4 tile-step launches,
+        // its CS' / R' items replace the first CS GEMM and the prep kernel; every later pair is produced by the
+        // previous step
         double *CSa = CS, *Ra = Rbuf, *CSb = ws + L.CS2, *Rb = ws + L.Rbuf2;
-        {
+        if (!fused_first) {
             const int kn = d < OB ? d : OB;
             rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw, d, Q, kn, 0.0, CSa, kn, EPI_NONE, nullptr, 0);
             if (rc) return rc;
             outer_prep_kernel<<<296, 256, 0, stream>>>(Q, CSa, kn, Mw, d, 0, Ra);
             DAGMA_CUDA_OK(cudaGetLastError());
         }
-        for (int ob = 0; ob < nob; ++ob) {
-            const int k0 = ob * OB, kn = (d - k0) < OB ? (d - k0) : OB;
+        for (int ob = fused_first ? -1 : 0; ob < nob; ++ob) {
+            const bool pre = ob < 0;                       // the step in front of the first block
+            const int k0 = pre ? 0 : ob * OB, kn = pre ? 0 : ((d - k0) < OB ? (d - k0) : OB);
             const bool more = ob + 1 < nob;
-            const int k1 = k0 + OB, kn1 = more ? ((d - k1) < OB ? (d - k1) : OB) : 0;
+            const int k1 = pre ? 0 : k0 + OB, kn1 = more ? ((d - k1) < OB ? (d - k1) : OB) : 0;
             const int nblk1 = (kn1 + NB - 1) / NB;
             double* Qn = (nblk1 & 1) ? Pbuf2 : Pbuf;
             // every outer step has its own zeroed sync block (one memset for all of them: no memset node
             // between two step kernels); beyond the space of the flow counters: one memset per step
             constexpr int SYNC_STRIDE = 8 + 2 * SM_SLOTS;
             unsigned* sync_words = sync_base;
-            if ((ob + 1) * SYNC_STRIDE <= FlowCtr::total) {
-                if (ob == 0) {
-                    const int nfit = FlowCtr::total / SYNC_STRIDE < nob ? FlowCtr::total / SYNC_STRIDE : nob;
+            const int slot = ob + 1;                       // slot 0: the step in front of the first block
+            if ((slot + 1) * SYNC_STRIDE <= FlowCtr::total) {
+                if (ob == (fused_first ? -1 : 0)) {
+                    const int nfit = FlowCtr::total / SYNC_STRIDE < nob + 1 ? FlowCtr::total / SYNC_STRIDE : nob + 1;
                     DAGMA_CUDA_OK(cudaMemsetAsync(flow_words, 0, (size_t)nfit * SYNC_STRIDE * sizeof(unsigned), stream));
                 }
-                sync_words = flow_words + ob * SYNC_STRIDE;
+                sync_words = flow_words + slot * SYNC_STRIDE;
             } else {
                 DAGMA_CUDA_OK(cudaMemsetAsync(sync_words, 0, SYNC_STRIDE * sizeof(unsigned), stream));
             }
 #ifdef DAGMA_OUTER_TRACE
-            outer_trace_begin_kernel<<<1, 1, 0, stream>>>(ob);
+            outer_trace_begin_kernel<<<1, 1, 0, stream>>>(ob < 0 ? 15 : ob);
 #endif
             OuterArgs OA{Mw, d, CSa, Ra, kn, CSb, Rb, k1, kn1, Qn, sync_words, reinterpret_cast<int*>(sync_words + 8),
                          nblk1 * nblk1,
                          ServerArgs{Pbuf, Pbuf2, kn1, nblk1, piv + k1, sync_words, reinterpret_cast<int*>(sync_words + 2)},
-                         tma_mode() & 1};
+                         pre ? 0 : (tma_mode() & 1)};
             CUtensorMap mapCS, mapR;
             memset(&mapCS, 0, sizeof(mapCS));
             memset(&mapR, 0, sizeof(mapR));

@@ -109,6 +109,20 @@ def test_flow_kernel_mode():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("env", [{"DAGMA_FIRST_BLOCK": "1"}, {"DAGMA_TMA": "0"}, {"DAGMA_TMA": "3"}],
+                         ids=["first-block-step", "cp-async-only", "tma-gemm-everywhere"])
+def test_optional_variants(env):
+    """The A/B switches of the multi-CTA path stay correct: the first pivot block as a step of the persistent kernel,
+    cp.async slabs everywhere, and the TMA GEMM for every product that qualifies (alpha / beta / sigmoid epilogues
+    through the 128 x 128 kernel).  The switches are read once per process, hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_large_gpu.py"),
+                        "-k", "gemm_vs_numpy or rider_gemm or (blocked_logdet and (500 or 513 or 1000))"],
+                       env=dict(os.environ, **env), cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def _edges(g, key):
     return tuple(tuple(int(x) for x in e) for e in g[key]) if key in g.files else None
 
