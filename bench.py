@@ -232,7 +232,7 @@ def bench_c5(torch, _lib, peak_tflops, with_cpu):
 
 
 def bench_c2_c3(torch, with_cpu):
-    """BASELINE.json configs[1] and [2]: logistic DagmaLinear (ER2 d=100 n=10000) and DagmaMLP (d=40 m1=10 n=2000):
+    """BASELINE.json configs[0] (full fit wall clock of the reference's own case), configs[1] and [2]: logistic DagmaLinear (ER2 d=100 n=10000) and DagmaMLP (d=40 m1=10 n=2000):
     wall clock per graph-replayed inner iteration (the host synchronises only at the checkpoints), the numpy
     restatement of the reference beside it on a few iterations."""
     import numpy as np
@@ -240,6 +240,28 @@ def bench_c2_c3(torch, with_cpu):
     from midagma_b200 import DagmaLinear
     from midagma_b200.nonlinear import DagmaMLP, DagmaNonlinear
     out = {}
+    # ---- C1: the reference's own CPU-runnable case, full default fit (one launch of the on-chip kernel)
+    X, W_true = simulate.config_c1(0)
+    model = DagmaLinear("l2")
+    model.fit(X.copy(), lambda1=0.02, s=[1.0, .9, .8, .7, .6])            # warm-up (library load, allocations)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    W_gpu = model.fit(X.copy(), lambda1=0.02, s=[1.0, .9, .8, .7, .6])
+    torch.cuda.synchronize()
+    t_fit = time.perf_counter() - t0
+    iters = int(sum(model.stage_iters))
+    c1 = {"workload": "C1: DagmaLinear l2 full default fit, ER2 d=20 n=500 (host arrays in, thresholded W_est out)",
+          "fit_wall_s": t_fit, "inner_iters": iters, "us_per_iter": t_fit / iters * 1e6,
+          "shd_vs_truth": int(simulate.count_accuracy(W_true != 0, W_gpu != 0)["shd"])}
+    if with_cpu:
+        from oracle.linear_ref import OracleLinear
+        t0 = time.perf_counter()
+        W_cpu = OracleLinear("l2").fit(X.copy(), lambda1=0.02)
+        cpu = time.perf_counter() - t0
+        c1.update({"cpu_fit_wall_s": cpu, "speedup_vs_cpu": cpu / t_fit,
+                   "edge_set_distance_vs_cpu": int(simulate.edge_set_distance(W_gpu, W_cpu)),
+                   "cpu_sample": "the same full default fit by oracle/linear_ref.py (bit-identical port of the reference)"})
+    out["c1"] = c1
     # ---- C2
     X, _ = simulate.config_c2(0)
     d, n = X.shape[1], X.shape[0]
