@@ -5,6 +5,8 @@
 // lies in (0.5, 1] (exact), which keeps the sweep's publish identity in its accurate range.
 #include "common.cuh"
 #include "small_gj.cuh"
+#include "small_dmma.cuh"
+#include <cstdlib>
 #include "../../include/dagma_b200.h"
 
 namespace dagma {
@@ -79,6 +81,87 @@ __global__ void __launch_bounds__(C::NT, 1) logdet_inv_small_kernel(const InvArg
     }
 }
 
+// 32 < d <= 64: the tensor-core sweep of small_dmma.cuh (8 x 8 pivot blocks, rank-8 DMMA updates, one barrier per
+// block step instead of one per pivot) -- the sweep the fit kernel and the tile steps of the blocked inverse use.
+// One 256-thread CTA per problem, two per SM; the matrix lives in the DMMA accumulator layout
+// a[ti][tj][e] = M[16 wr + 8 ti + lane/4][32 wc + 8 tj + 2 (lane%4) + e], identity padded to 64 x 64.
+__global__ void __launch_bounds__(DM_NT, 2) logdet_inv_dmma_kernel(const InvArgs P) {
+    extern __shared__ __align__(16) double psm[];
+    using S = DmmaSmem;
+    const int tid = threadIdx.x, d = P.d;
+    const DmmaPos ps(tid);
+    double* red = psm + S::red;
+    SweepSync sy{smem_u32(psm + S::mbar), 0u};
+    if (tid == 0) mbar_init(sy.bar, DM_NT / 32);
+    __syncthreads();
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+        const double* A = P.a + (size_t)b * d * P.lda;
+        double a[2][4][2];
+#pragma unroll
+        for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < 4; ++tj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = ps.row(ti), c = ps.col(tj) + e;
+                    double v = (r == c) ? 1.0 : 0.0;
+                    if (r < d && c < d) {
+                        double x = A[(size_t)r * P.lda + c];
+                        if (P.square) x *= x;
+                        v = (((r == c) ? P.s : 0.0) - x) * P.inv_scale;
+                    }
+                    a[ti][tj][e] = v;
+                }
+        dmma_sweep(a, ps, psm, d, sy);
+        // log|det| from the fraction-free pivots: sum_k ((k & 3) - 2) log|p_k| over whole groups of four
+        double ld = 0.0, zero1 = 0.0, zero2 = 0.0;
+        bool badpiv = false;
+        if (tid < ((d + 3) & ~3)) {
+            const double p = psm[S::pinfo + tid];
+            ld = (double)((tid & 3) - 2) * log(fabs(p));
+            badpiv = !(p > 0.0);
+        }
+        double mn = INFINITY;
+#pragma unroll
+        for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < 4; ++tj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = ps.row(ti), c = ps.col(tj) + e;
+                    if (r < d && c < d) {
+                        const double mi = a[ti][tj][e] * P.inv_scale;
+                        mn = fmin(mn, mi);
+                        if (P.minv) P.minv[((size_t)b * d + r) * P.ldo + c] = mi;
+                        if (P.grad) {   // grad[c][r] = (square ? 2 A[c][r] : 1) * Minv[r][c]
+                            const double f = P.square ? 2.0 * A[(size_t)c * P.lda + r] : 1.0;
+                            P.grad[((size_t)b * d + c) * P.ldo + r] = f * mi;
+                        }
+                    }
+                }
+        block_sum3<DM_NT>(ld, zero1, zero2, red, tid);
+        mn = block_min<DM_NT>(mn, red, tid);
+        const int anybad = __syncthreads_or(badpiv);
+        if (tid == 0) {
+            const double lad = ld + (double)d * P.log_scale;
+            if (P.logabsdet) P.logabsdet[b] = lad;
+            if (P.h) P.h[b] = -lad + (double)d * log(P.s);
+            if (P.min_entry) P.min_entry[b] = mn;
+            if (P.info) P.info[b] = anybad ? 1 : ((mn + 1e-16 < 0.0) ? 2 : 0);
+        }
+        __syncthreads();
+    }
+}
+// DAGMA_SMALL_INV_DMMA (A-B timing): 1 (default) = tensor-core sweep for 32 < d <= 64, 0 = scalar rank-1 sweep
+static bool small_inv_dmma() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_SMALL_INV_DMMA");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
 template <class C>
 static int launch_inv(cudaStream_t stream, const InvArgs& a, int ctas) {
     logdet_inv_small_kernel<C><<<ctas, C::NT, 0, stream>>>(a);
@@ -101,6 +184,17 @@ int logdet_inv_small(cudaStream_t stream, int batch, int d, double s, const doub
     }
     InvArgs P{batch, d, lda, ldo, square, s, 1.0 / scale, log(scale), a_dev, logabsdet, h, minv, grad,
               min_entry, info};
+    if (d > 32 && d <= 64 && small_inv_dmma()) {
+        static bool attr = false;
+        if (!attr) {
+            DAGMA_CUDA_OK(cudaFuncSetAttribute(logdet_inv_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)DmmaSmem::bytes));
+            attr = true;
+        }
+        logdet_inv_dmma_kernel<<<batch < 2 * sms ? batch : 2 * sms, DM_NT, DmmaSmem::bytes, stream>>>(P);
+        DAGMA_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     const int ctas = batch < 4 * sms ? batch : 4 * sms;
     if (d <= 16) return launch_inv<Cfg<1, 1, 16, 16>>(stream, P, ctas);
     if (d <= 32) return launch_inv<Cfg<2, 2, 16, 16>>(stream, P, ctas);
