@@ -13,7 +13,7 @@ def timed(fn, reps=50):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e-3 / reps
 rng = np.random.default_rng(0)
-for d in (40, 48, 64):
+for d in [int(x) for x in os.environ.get("DS", "40,48,64").split(",")]:
     for batch in (1, 4096):
         W = rng.uniform(-0.1, 0.1, size=(batch, d, d))
         A = torch.from_numpy(W).cuda()
