@@ -389,6 +389,7 @@ struct OuterArgs {
     int nserver;
     ServerArgs srv;
     int use_tma;                            // update tiles fed by TMA (gemm_tma.cuh) instead of cp.async
+    int sleep;                              // 1: a worker CTA that shares its SM with a look-ahead CTA sleeps meanwhile
 };
 constexpr int SM_SLOTS = 256;
 // Worker side: a 256-thread CTA is TWO independent 128-thread tile engines (half = tid / 128), each the
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
         tm_fence_proxy();                        // the stages may have been written through the generic proxy
         half_sync(half);
         if (elected) {
-            while (*busy) __nanosleep(2000);
+            while (P.sleep && *busy) __nanosleep(2000);
             s_tile[half] = atomicAdd(P.sync + 1, 1u);
         }
         half_sync(half);
@@ -628,7 +629,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
                 upd_tile(t, bi, bj, strip);
                 const TmaTile cur{bi * NB, bj * NB, 0, nkt};
                 TmaTile nxt{0, 0, 0, 0};
-                if (elected && !*busy) {
+                if (elected && !(P.sleep && *busy)) {
                     tnx = atomicAdd(P.sync + 1, 1u);
                     if ((int)tnx < n_upd) {
                         int bi2, bj2, st2;
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
             }
             if (elected) {
                 if (tnx == T_NONE) {
-                    while (*busy) __nanosleep(2000);
+                    while (P.sleep && *busy) __nanosleep(2000);
                     tnx = atomicAdd(P.sync + 1, 1u);
                 }
                 s_tile[half] = tnx;
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
     for (;;) {
         half_sync(half);
         if (ep.htid == 0) {
-            while (*busy) __nanosleep(2000);
+            while (P.sleep && *busy) __nanosleep(2000);
             s_tile[half] = atomicAdd(P.sync + 1, 1u);
         }
         half_sync(half);
@@ -1722,6 +1723,17 @@ static int lookahead_get(LookAhead** out) {
     return 0;
 }
 
+// DAGMA_OUTER_SLEEP (A-B timing): 1 (default) = the worker CTA that shares an SM with a CTA of the look-ahead chain
+// sleeps while the chain runs (the chain has its SMs to itself), 0 = it keeps pulling update tiles
+static int outer_sleep() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_OUTER_SLEEP");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 // DAGMA_FIRST_BLOCK (A-B timing): 1 = the first pivot block is inverted and its CS / R strips are formed by a step of
 // outer_step_kernel with nothing to apply (one launch), 0 (default) = by copy + 4 tile-step launches + a GEMM + a prep
 // kernel (seven launches).  Measured equal at d = 2000 (inverse 0.960 vs 0.957 ms): the first block is bound by its
@@ -1928,7 +1940,7 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
             OuterArgs OA{Mw, d, CSa, Ra, kn, CSb, Rb, k1, kn1, Qn, sync_words, reinterpret_cast<int*>(sync_words + 8),
                          nblk1 * nblk1,
                          ServerArgs{Pbuf, Pbuf2, kn1, nblk1, piv + k1, sync_words, reinterpret_cast<int*>(sync_words + 2)},
-                         pre ? 0 : (tma_mode() & 1)};
+                         pre ? 0 : (tma_mode() & 1), outer_sleep()};
             CUtensorMap mapCS, mapR;
             memset(&mapCS, 0, sizeof(mapCS));
             memset(&mapR, 0, sizeof(mapR));
