@@ -2062,6 +2062,29 @@ __device__ __forceinline__ void dd_mul(double& hi, double& lo, double b) {
     hi = s;
 }
 
+// end of an inner iteration: latch `halted` when the inverse was infeasible, else advance beta^it and the counter
+__device__ __forceinline__ void linear_advance(LinState* st) {
+    if (st->halted != 0) return;
+    if (st->info != 0) {
+        st->halted = 1;
+        return;
+    }
+    double p1h = st->p1_hi, p1l = st->p1_lo, p2h = st->p2_hi, p2l = st->p2_lo;
+    dd_mul(p1h, p1l, st->beta1);
+    dd_mul(p2h, p2l, st->beta2);
+    st->p1_hi = p1h; st->p1_lo = p1l; st->p2_hi = p2h; st->p2_lo = p2l;
+    st->it += 1;
+}
+// called by thread 0 of every block when the block is done with the state block: the LAST block to get here has seen
+// every other block finish (so nobody reads the state any more) and advances it -- no separate 1-thread launch
+__device__ __forceinline__ void linear_advance_by_last_block(LinState* st, int blocks) {
+    __threadfence();
+    if (atomicAdd(&st->pad, 1) == blocks - 1) {
+        st->pad = 0;
+        linear_advance(st);
+    }
+}
+
 // Gobj, Adam, step, masks for one inner iteration (linear.py:248, 158-162, 275-276).
 // No-op (and latches `halted`) when the inverse of this iteration was infeasible.
 __global__ void __launch_bounds__(256) linear_update_kernel(LinState* st, int d, double* __restrict__ W,
@@ -2074,7 +2097,12 @@ __global__ void __launch_bounds__(256) linear_update_kernel(LinState* st, int d,
     __shared__ double tile[32][33];
     __shared__ double tile2[32][33];
     const bool stop = (st->halted != 0) || (st->info != 0);
-    if (stop) return;                        // latching is done by linear_advance_kernel
+    const bool leader = (threadIdx.x == 0 && threadIdx.y == 0);
+    const int nblocks = gridDim.x * gridDim.y;
+    if (stop) {                              // uniform over the grid: only the latch / advance remains
+        if (leader) linear_advance_by_last_block(st, nblocks);
+        return;
+    }
     const double mu = st->mu, lr = st->lr, lambda1 = st->lambda1, b1 = st->beta1, b2 = st->beta2;
     double p1h = st->p1_hi, p1l = st->p1_lo, p2h = st->p2_hi, p2l = st->p2_lo;
     dd_mul(p1h, p1l, b1);
@@ -2111,20 +2139,10 @@ __global__ void __launch_bounds__(256) linear_update_kernel(LinState* st, int d,
         if (mask_exc && mask_exc[e]) wn = 0.0;
         W[e] = wn;
     }
+    __syncthreads();                                         // no thread of this block uses the state block any more
+    if (leader) linear_advance_by_last_block(st, nblocks);
 }
 
-__global__ void linear_advance_kernel(LinState* st) {
-    if (st->halted != 0) return;
-    if (st->info != 0) {
-        st->halted = 1;
-        return;
-    }
-    double p1h = st->p1_hi, p1l = st->p1_lo, p2h = st->p2_hi, p2l = st->p2_lo;
-    dd_mul(p1h, p1l, st->beta1);
-    dd_mul(p2h, p2l, st->beta2);
-    st->p1_hi = p1h; st->p1_lo = p1l; st->p2_hi = p2h; st->p2_lo = p2l;
-    st->it += 1;
-}
 
 // W += sign * lr * dir(m, v, it)   (back-tracking, linear.py:235, 239)
 __global__ void linear_apply_dir_kernel(const LinState* st, int d, double* __restrict__ W,
@@ -2283,8 +2301,6 @@ extern "C" int dagma_linear_update_ex_f64(dagma_stream_t stream, int d, void* st
     linear_update_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((LinState*)state_dev, d, w_dev, minv_dev, t_dev,
                                                                         cov_dev, m_dev, v_dev, mask_exc_dev, mask_inc_dev,
                                                                         extra_t_dev, extra_scale);
-    DAGMA_CUDA_OK(cudaGetLastError());
-    linear_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((LinState*)state_dev);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -137,6 +137,20 @@ __global__ void mlp_reduce_parts_kernel(const double* __restrict__ part, int chu
     out[e] = s;
 }
 
+// end of an iteration: step counter and ExponentialLR (nonlinear.py:224-225).  Called by thread 0 of every block of the
+// Adam kernel when the block is done; the LAST block to get here has seen all others finish (nobody reads the state
+// any more) and advances it -- no separate 1-thread launch.
+__device__ __forceinline__ void mlp_advance_by_last_block(MlpState* st, int blocks) {
+    __threadfence();
+    if (atomicAdd(&st->pad, 1) == blocks - 1) {
+        st->pad = 0;
+        if (st->halted == 0) {
+            st->step += 1;
+            if (st->lr_gamma != 1.0 && (st->step % 1000) == 0) st->lr *= st->lr_gamma;
+        }
+    }
+}
+
 // torch.optim.Adam step (single-tensor form, weight decay added to the gradient) over theta.
 // grads hold UN-SCALED score sums; the factor d/S and mu are applied here; fc1.weight also gets
 // mu*lambda1*sign(w) and dh/dw = 2 w Minv[j][i]   (nonlinear.py:208, 220-223).
@@ -144,7 +158,10 @@ __global__ void __launch_bounds__(256) mlp_adam_kernel(const MlpState* st, doubl
                                                        const double* __restrict__ grads, double* __restrict__ m,
                                                        double* __restrict__ v, const double* __restrict__ Minv,
                                                        int d, int m1, size_t total) {
-    if (st->halted != 0) return;
+    if (st->halted != 0) {                    // uniform over the grid
+        if (threadIdx.x == 0) mlp_advance_by_last_block(const_cast<MlpState*>(st), gridDim.x);
+        return;
+    }
     const double mu = st->mu, lr = st->lr, b1 = st->beta1, b2 = st->beta2;
     const double wd = mu * st->lambda2, l1c = mu * st->lambda1;
     const double gs = mu * (double)d / st->S;
@@ -169,11 +186,8 @@ __global__ void __launch_bounds__(256) mlp_adam_kernel(const MlpState* st, doubl
         const double denom = sqrt(vn) / bc2s + 1e-8;
         theta[e] = p - step_size * (mn / denom);
     }
-}
-__global__ void mlp_advance_kernel(MlpState* st) {
-    if (st->halted != 0) return;
-    st->step += 1;
-    if (st->lr_gamma != 1.0 && (st->step % 1000) == 0) st->lr *= st->lr_gamma;   // ExponentialLR, nonlinear.py:224-225
+    __syncthreads();                           // every thread of the block has read the state
+    if (threadIdx.x == 0) mlp_advance_by_last_block(const_cast<MlpState*>(st), gridDim.x);
 }
 
 }  // namespace dagma
@@ -229,8 +243,6 @@ extern "C" int dagma_mlp_adam_f64(dagma_stream_t stream, int d, int m1, void* st
     const int blocks = (int)((total + 255) / 256);
     mlp_adam_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, (cudaStream_t)stream>>>((const MlpState*)state_dev, theta_dev,
                                                                                      grads_dev, m_dev, v_dev, minv_dev, d, m1, total);
-    DAGMA_CUDA_OK(cudaGetLastError());
-    mlp_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((MlpState*)state_dev);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -382,8 +394,6 @@ extern "C" int dagma_mlp_adam_ex_f64(dagma_stream_t stream, int d, int m1, size_
     const int blocks = (int)((total + 255) / 256);
     mlp_adam_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, (cudaStream_t)stream>>>((const MlpState*)state_dev, theta_dev,
                                                                                      grads_dev, m_dev, v_dev, minv_dev, d, m1, total);
-    DAGMA_CUDA_OK(cudaGetLastError());
-    mlp_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((MlpState*)state_dev);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }
