@@ -294,25 +294,29 @@ def bench_c2_c3(torch, with_cpu):
     torch.manual_seed(0)
     model = DagmaMLP(dims=[d, m1, 1], bias=True)
     init = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    nl = DagmaNonlinear(model)
-    nl.X = torch.from_numpy(X).cuda()
-    nl.checkpoint = 1000
-    nl.minimize(1000, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0)
+    # the launch sequence DagmaNonlinear.minimize replays (one CUDA graph per iteration), timed with CUDA events
+    from midagma_b200 import nonlinear as nlmod
+    eng = nlmod._MlpEngine(model, torch.from_numpy(X).cuda())
+    sh = eng.state_host
+    sh.zero_()
+    for f, val in ((nlmod.F_MU, 0.1), (nlmod.F_S, 1.0), (nlmod.F_LR, 2e-4), (nlmod.F_LAM1, 0.02), (nlmod.F_LAM2, 0.005),
+                   (nlmod.F_B1, 0.99), (nlmod.F_B2, 0.999), (nlmod.F_GAMMA, 1.0)):
+        sh[f] = float(val)
+    eng.state.copy_(sh)
+    eng.replay(1.0, 500)                                   # warm-up iteration, graph capture, 500 replays
     torch.cuda.synchronize()
-
-    def run(iters):                # every minimize() re-creates the engine and its graph (the optimizer is re-created, Q13)
-        t0 = time.perf_counter()
-        nl.minimize(iters, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0)
-        torch.cuda.synchronize()
-        return time.perf_counter() - t0
-
-    t_short, t_long = run(2000), run(6000)
-    t = (t_long - t_short) / 4000
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.replay(1.0, 4000)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / 4000
+    _, step, halted = eng.pull()
     flop = 2.0 * (2.0 * n * d * d * m1) + 6.0 * n * d * m1 + 2.0 * d ** 3
-    c3 = {"workload": "C3: DagmaMLP [40, 10, 1] n=2000, mu=0.1 s=1 lr=2e-4 (graph-replayed inner iterations: wall-clock difference "
-                      "of a 6000- and a 2000-iteration minimize, so the per-call engine set-up cancels)",
+    c3 = {"workload": "C3: DagmaMLP [40, 10, 1] n=2000, mu=0.1 s=1 lr=2e-4 (4000 replays of the per-iteration CUDA graph of "
+                      "DagmaNonlinear.minimize, CUDA events)",
           "us_per_iter": t * 1e6, "iters_per_s": 1.0 / t, "flop_per_iter": flop, "tflops": flop / t / 1e12,
-          "setup_ms_per_minimize": (t_short - 2000 * t) * 1e3}
+          "iterations_done": int(step), "halted": int(halted)}
     if with_cpu:
         from oracle.nonlinear_ref import OracleMLP, OracleNonlinear
         om = OracleMLP([d, m1, 1], {k: v.numpy() for k, v in init.items()})

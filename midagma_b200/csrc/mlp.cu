@@ -44,11 +44,33 @@ __global__ void mlp_adj_kernel(const double* __restrict__ W1, int d, int m1, dou
     if (threadIdx.x == 0) l1_partial[blockIdx.x] = l1;
 }
 
+// thread 0 of every block, after the block's partial results are written: true in the LAST block to get here, which has
+// then seen the partial results of all the others (fence / atomic / fence) -- it finishes the reduction in a fixed
+// order, so the result does not depend on which block that is and no separate reduction launch is needed
+__device__ __forceinline__ bool mlp_last_block(MlpState* st, int blocks) {
+    __threadfence();
+    const bool last = (atomicAdd(&st->pad, 1) == blocks - 1);
+    if (last) {
+        st->pad = 0;
+        __threadfence();
+    }
+    return last;
+}
+// S = sum res^2 and l1 = sum |W1| -> state (fixed order)
+__device__ __forceinline__ void mlp_finish_forward(MlpState* st, const double* S_partial, int nS, const double* l1_partial,
+                                                   int nl1) {
+    double S = 0.0, l1 = 0.0;
+    for (int i = 0; i < nS; ++i) S += __ldcg(S_partial + i);
+    for (int i = 0; i < nl1; ++i) l1 += __ldcg(l1_partial + i);
+    st->S = S;
+    st->l1 = l1;
+}
 // forward tail: H = sigmoid(Zt + b1) (in place), out = sum_k H W2 + b2, res = out - Xt, partial S
 __global__ void __launch_bounds__(256) mlp_forward_kernel(double* __restrict__ Zt, const double* __restrict__ theta,
                                                           const double* __restrict__ Xt, int n, int d, int m1,
                                                           double* __restrict__ res, double* __restrict__ out_opt,
-                                                          double* __restrict__ S_partial) {
+                                                          double* __restrict__ S_partial, MlpState* st,
+                                                          const double* l1_partial, int nl1) {
     __shared__ double red[96];
     const int P = d * m1;
     const double* b1 = theta + (size_t)P * d;
@@ -72,20 +94,12 @@ __global__ void __launch_bounds__(256) mlp_forward_kernel(double* __restrict__ Z
         sq = r * r;
     }
     block_sum3<256>(sq, z1, z2, red, threadIdx.x);
-    if (threadIdx.x == 0) S_partial[blockIdx.y * gridDim.x + blockIdx.x] = sq;
+    if (threadIdx.x == 0) {
+        S_partial[blockIdx.y * gridDim.x + blockIdx.x] = sq;
+        if (mlp_last_block(st, gridDim.x * gridDim.y)) mlp_finish_forward(st, S_partial, gridDim.x * gridDim.y, l1_partial, nl1);
+    }
 }
 
-// S, l1 -> state; score, obj; latch `halted` when h < 0 (nonlinear.py:215-221)
-__global__ void mlp_finish_forward_kernel(MlpState* st, const double* S_partial, int nS, const double* l1_partial,
-                                          int nl1, int n_total, int d) {
-    if (threadIdx.x != 0) return;
-    double S = 0.0, l1 = 0.0;
-    for (int i = 0; i < nS; ++i) S += S_partial[i];
-    for (int i = 0; i < nl1; ++i) l1 += l1_partial[i];
-    st->S = S;
-    st->l1 = l1;
-    (void)n_total; (void)d;
-}
 // after the (optional) all-reduce of S
 __global__ void mlp_objective_kernel(MlpState* st, int n_total, int d) {
     if (threadIdx.x != 0) return;
@@ -209,10 +223,8 @@ extern "C" int dagma_mlp_forward_f64(dagma_stream_t stream, int n, int d, int m1
     DAGMA_REQUIRE(zt_dev && theta_dev && xt_dev && res_dev && s_partial_dev && state_dev, "null pointer");
     dim3 grid((n + 255) / 256, d);
     mlp_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(zt_dev, theta_dev, xt_dev, n, d, m1, res_dev, out_opt_dev,
-                                                              s_partial_dev);
-    DAGMA_CUDA_OK(cudaGetLastError());
-    mlp_finish_forward_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((MlpState*)state_dev, s_partial_dev, grid.x * grid.y,
-                                                                 l1_partial_dev, l1_partial_dev ? (d * d + 255) / 256 : 0, 0, d);
+                                                              s_partial_dev, (MlpState*)state_dev, l1_partial_dev,
+                                                              l1_partial_dev ? (d * d + 255) / 256 : 0);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -276,7 +288,8 @@ __global__ void __launch_bounds__(256) lc_forward_kernel(double* __restrict__ in
 __global__ void __launch_bounds__(256) mlp_residual_kernel(const double* __restrict__ out, const double* __restrict__ bias,
                                                            const double* __restrict__ Xt, int n, int d,
                                                            double* __restrict__ res, double* __restrict__ out_opt,
-                                                           double* __restrict__ S_partial) {
+                                                           double* __restrict__ S_partial, MlpState* st,
+                                                          const double* l1_partial, int nl1) {
     __shared__ double red[96];
     const int j = blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,7 +302,10 @@ __global__ void __launch_bounds__(256) mlp_residual_kernel(const double* __restr
         sq = r * r;
     }
     block_sum3<256>(sq, z1, z2, red, threadIdx.x);
-    if (threadIdx.x == 0) S_partial[blockIdx.y * gridDim.x + blockIdx.x] = sq;
+    if (threadIdx.x == 0) {
+        S_partial[blockIdx.y * gridDim.x + blockIdx.x] = sq;
+        if (mlp_last_block(st, gridDim.x * gridDim.y)) mlp_finish_forward(st, S_partial, gridDim.x * gridDim.y, l1_partial, nl1);
+    }
 }
 // H ([d*mi][n], from lc_forward_kernel) is replaced by dZ = (sum_o W[j][k][o] dZn[j*mo+o]) H (1 - H);
 // part row of this sample chunk: [gW (d*mi*mo) | gb (d*mo)] = sums over the chunk of H dZn and dZn
@@ -358,10 +374,8 @@ extern "C" int dagma_mlp_residual_f64(dagma_stream_t stream, int n, int d, const
     DAGMA_REQUIRE(out_dev && xt_dev && res_dev && s_partial_dev && state_dev, "null pointer");
     dim3 grid((n + 255) / 256, d);
     dagma::mlp_residual_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_dev, bias_dev, xt_dev, n, d, res_dev, out_opt_dev,
-                                                                      s_partial_dev);
-    DAGMA_CUDA_OK(cudaGetLastError());
-    mlp_finish_forward_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((MlpState*)state_dev, s_partial_dev, grid.x * grid.y,
-                                                                 l1_partial_dev, l1_partial_dev ? (d * d + 255) / 256 : 0, 0, d);
+                                                                      s_partial_dev, (MlpState*)state_dev, l1_partial_dev,
+                                                                      l1_partial_dev ? (d * d + 255) / 256 : 0);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }
