@@ -70,6 +70,9 @@ extern "C" int dagma_linear_fit_small_host_f64(dagma_stream_t stream_, const dag
     int32_t* cnt_d = (int32_t*)take(B * sizeof(int32_t));
     uint32_t* ctr_d = (uint32_t*)take(64);
     int rc = 0;
+    // outputs of stages / problems the kernel never reaches (out of domain, retry limit, T = 0) must read as zero
+    if (cudaMemsetAsync(status_d, 0, (size_t)((base + off) - (unsigned char*)status_d), stream) != cudaSuccess)
+        rc = set_error(-3, "memset of the output block failed");
 #define H2D(dst, src, n) if (!rc && cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = set_error(-3, "H2D copy failed")
 #define D2H(dst, src, n) if (!rc && (dst) && cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, stream) != cudaSuccess) rc = set_error(-3, "D2H copy failed")
     H2D(cov_d, host->cov_dev, n_mat);

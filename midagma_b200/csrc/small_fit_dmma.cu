@@ -311,7 +311,17 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                 if (bad) {
                     if (it == 0 || s_cur <= 0.9) {            // linear.py:231-233
                         if (P.retry_on_fail) {
-                            if (++retries > 64) { status |= DAGMA_ST_RETRY_LIMIT; write_W(); goto problem_done; }
+                            if (++retries > 64) {
+                                // the reference would keep retrying; give up on the stage's restart point, but
+                                // leave complete outputs: stage stats, status, and the final h / score of that W
+                                status |= DAGMA_ST_RETRY_LIMIT;
+                                --retries;
+                                read_W();
+                                write_stage_stats();
+                                if (!P.final_dev) goto problem_done;
+                                final_phase = true;
+                                continue;
+                            }
                             lr_adam *= 0.5;                    // linear.py:450-451
                             s_cur += 0.1;
                             read_W();

@@ -63,7 +63,10 @@ def _run_small(cov: torch.Tensor, W: torch.Tensor, lambda1: torch.Tensor, mus, s
     lib = _lib.load()
     batch, d, _ = cov.shape
     T = len(mus)
-    assert T <= _lib.MAX_STAGES, f"at most {_lib.MAX_STAGES} stages per launch"
+    if T > _lib.MAX_STAGES:
+        return _run_small_chunked(cov, W, lambda1, mus, ss, iters, lr=lr, tol=tol, beta1=beta1, beta2=beta2,
+                                  checkpoint=checkpoint, retry=retry, mask_exc=mask_exc, mask_inc=mask_inc,
+                                  ckpt_log_cap=ckpt_log_cap, want_final=want_final)
     assert cov.is_cuda and W.is_cuda and cov.dtype == torch.float64 and W.dtype == torch.float64
     assert cov.is_contiguous() and W.is_contiguous() and lambda1.is_contiguous()
     dev = cov.device
@@ -91,6 +94,35 @@ def _run_small(cov: torch.Tensor, W: torch.Tensor, lambda1: torch.Tensor, mus, s
     a.work_counter = counter.data_ptr()
     _lib.check(lib.dagma_linear_fit_small_f64(_lib.stream_ptr(), C.byref(a)), "dagma_linear_fit_small_f64")
     return SmallFitResult(W, status, stats, final, log, cnt)
+
+
+def _run_small_chunked(cov, W, lambda1, mus, ss, iters, *, ckpt_log_cap=0, want_final=True, **kw) -> SmallFitResult:
+    """More stages than one launch carries (DAGMA_MAX_STAGES): the stages of ``fit`` only communicate through W
+    (linear.py:441-453), so the schedule is cut into consecutive launches; the final h / score come from the last."""
+    T, step = len(mus), _lib.MAX_STAGES
+    parts = []
+    for lo in range(0, T, step):
+        hi = min(lo + step, T)
+        parts.append(_run_small(cov, W, lambda1, mus[lo:hi], ss[lo:hi], iters[lo:hi], ckpt_log_cap=ckpt_log_cap,
+                                want_final=want_final and hi == T, **kw))
+    status = parts[0].status.clone()
+    for p in parts[1:]:
+        status |= p.status
+    stats = torch.cat([p.stage_stats for p in parts], dim=1)
+    log = cnt = None
+    if ckpt_log_cap > 0:
+        # rows keep their launch-local stage index; shift it to the global one and pack the launches back to back
+        batch = cov.shape[0]
+        log = torch.zeros(batch, ckpt_log_cap * len(parts), 6, dtype=torch.float64, device=cov.device)
+        cnt = torch.zeros(batch, dtype=torch.int32, device=cov.device)
+        for k, p in enumerate(parts):
+            rows = p.ckpt_log.clone()
+            rows[:, :, 0] += k * step
+            for b in range(batch):
+                n, c = int(p.ckpt_count[b]), int(cnt[b])
+                log[b, c:c + n] = rows[b, :n]
+                cnt[b] = c + n
+    return SmallFitResult(W, status, stats, parts[-1].final, log, cnt)
 
 
 def center_cov(X: torch.Tensor, center: bool) -> torch.Tensor:
@@ -131,6 +163,17 @@ def logdet_inv(A: torch.Tensor, s: float = 1.0, square_input: bool = True, want_
 # =============================================================================
 # batched entry points
 # =============================================================================
+def _warn_retry_limit(status: torch.Tensor) -> None:
+    """The reference keeps retrying a failing stage for ever (linear.py:446-451); the kernels give up after 64
+    retries of one stage and say so."""
+    n = int(((status & _lib.ST_RETRY_LIMIT) != 0).sum().item())
+    if n:
+        import warnings
+        warnings.warn(f"{n} problem(s) hit the stage-retry limit (64 retries with lr/2, s+0.1): their W is the last "
+                      "restart point, not a converged solution", RuntimeWarning, stacklevel=3)
+
+
+
 def _as_dev(x, device, dtype=torch.float64) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=dtype).contiguous()
@@ -147,8 +190,19 @@ def _lam_dev(lambda1, batch: int, device) -> torch.Tensor:
     return _as_dev(np.broadcast_to(np.asarray(lambda1, dtype=np.float64), (batch,)), device)
 
 
+def _batch_masks(exclude_edges, include_edges, d, device):
+    """Edge lists shared by the whole batch -> the [d, d] byte masks of the kernels.  Same acceptance rule as the
+    reference (linear.py:416-426, Q5): anything but a tuple of 2-tuples is silently ignored."""
+    out = []
+    for edges in (exclude_edges, include_edges):
+        ok = (edges is not None and type(edges) is tuple and len(edges) > 0 and type(edges[0]) is tuple
+              and bool(np.all(np.array([len(e) for e in edges]) == 2)))
+        out.append(_edge_mask(edges, d, device) if ok else None)
+    return out
+
+
 def minimize_batch(W, cov, lambda1, mu, max_iter, s, lr, *, tol=1e-6, beta_1=0.99, beta_2=0.999,
-                   checkpoint=1000, device=None):
+                   checkpoint=1000, device=None, exclude_edges=None, include_edges=None):
     """One ``DagmaLinear.minimize`` call (linear.py:165-333, l2 loss) for a batch of
     independent problems.  ``W``/``cov``: [batch, d, d] numpy arrays or torch tensors on
     host (pinned or not) or device.  Like the reference, ``W`` is updated in place and
@@ -161,8 +215,9 @@ def minimize_batch(W, cov, lambda1, mu, max_iter, s, lr, *, tol=1e-6, beta_1=0.9
     batch, d, _ = covd.shape
     assert d <= _lib.SMALL_MAX_D, "minimize_batch uses the on-chip path (d <= 64)"
     lam = _lam_dev(lambda1, batch, device)
+    mask_exc, mask_inc = _batch_masks(exclude_edges, include_edges, d, device)
     res = _run_small(covd, Wd, lam, [mu], [s], [int(max_iter)], lr=lr, tol=tol, beta1=beta_1, beta2=beta_2,
-                     checkpoint=checkpoint, retry=False, want_final=False)
+                     checkpoint=checkpoint, retry=False, want_final=False, mask_exc=mask_exc, mask_inc=mask_inc)
     ok = (res.status & _lib.ST_OUT_OF_DOMAIN) == 0
     if on_device:
         if Wd is not W:
@@ -177,13 +232,15 @@ def minimize_batch(W, cov, lambda1, mu, max_iter, s, lr, *, tol=1e-6, beta_1=0.9
 
 def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1.0, mu_factor=0.1,
               s=(1.0, .9, .8, .7, .6), warm_iter=3e4, max_iter=6e4, lr=0.0003, checkpoint=1000,
-              beta_1=0.99, beta_2=0.999, tol=1e-6, device=None, return_info=False):
+              beta_1=0.99, beta_2=0.999, tol=1e-6, device=None, return_info=False,
+              exclude_edges=None, include_edges=None):
     """``DagmaLinear('l2').fit`` (linear.py:335-462) for a batch of independent problems.
 
     ``X``: [batch, n, d] (centred on device, the caller's array is not modified) or
     ``cov``: [batch, d, d].  ``lambda1``: scalar or [batch].  Each problem follows the
     reference schedule independently (own convergence checks, retries, back-tracking);
     problems are pulled from a device-side work queue by persistent CTAs.
+    ``exclude_edges`` / ``include_edges``: tuples of 2-tuples shared by the batch (linear.py:416-426).
     Returns thresholded ``W_est`` [batch, d, d] as numpy (+ info dict)."""
     _lib.require_device()
     device = torch.device(device or "cuda")
@@ -205,8 +262,10 @@ def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1
     mus = _mu_schedule(mu_init, mu_factor, T)
     iters = [int(max_iter) if i == T - 1 else int(warm_iter) for i in range(T)]
     Wd = torch.zeros(batch, d, d, dtype=torch.float64, device=device)
+    mask_exc, mask_inc = _batch_masks(exclude_edges, include_edges, d, device)
     res = _run_small(covd, Wd, lam, mus, ss[:T], iters, lr=lr, tol=tol, beta1=beta_1, beta2=beta_2,
-                     checkpoint=checkpoint, retry=True)
+                     checkpoint=checkpoint, retry=True, mask_exc=mask_exc, mask_inc=mask_inc)
+    _warn_retry_limit(res.status)
     W_raw = res.W.cpu().numpy()
     W_est = W_raw.copy()
     W_est[np.abs(W_est) < w_threshold] = 0
@@ -492,6 +551,7 @@ class DagmaLinear:
             self.stage_iters = [int(x) for x in stats[:, 0]]
             self.stage_stats = stats
             self.status = int(res.status.item())
+            _warn_retry_limit(res.status)
             self._record_log(res)
             self.W_est = res.W[0].cpu().numpy().astype(self.dtype)
             fin = res.final[0].cpu().numpy()

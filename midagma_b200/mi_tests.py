@@ -74,16 +74,22 @@ class _GramBank:
         med = float(srt[m // 2].item()) if m % 2 else 0.5 * float((srt[m // 2 - 1] + srt[m // 2]).item())
         return med if med > 0 else 1.0
 
-    def dots(self, pairs: List[Tuple[int, int]], perms: np.ndarray) -> np.ndarray:
-        """[len(pairs), P] values of (1/n^2) sum Kc_i o (P Lc_j P^T); perms: [len(pairs), P, n] int."""
-        n, q, P = self.n, len(pairs), perms.shape[1]
+    def dots(self, pairs: List[Tuple[int, int]], perms) -> np.ndarray:
+        """[len(pairs), P] values of (1/n^2) sum Kc_i o (P Lc_j P^T).  ``perms``: a [len(pairs), P, n] int array, or a
+        ``_PermStream`` that draws the permutations of the next pairs on demand -- host memory then stays at one
+        launch's worth (<= 256 MB) however many pairs there are, and the RNG stream is consumed in pair order
+        exactly as the reference does (mi_tests.py:124-127, 186-197)."""
+        lazy = isinstance(perms, _PermStream)
+        n, q, P = self.n, len(pairs), (perms.P if lazy else perms.shape[1])
         out = np.empty((q, P))
         step = max(1, min(q, (256 << 20) // max(1, P * n * 4)))            # <= 256 MB of permutations per launch
         for q0 in range(0, q, step):
             sub = pairs[q0:q0 + step]
             vi = torch.tensor([self.slot[i] for i, _ in sub], dtype=torch.int32, device="cuda")
             vj = torch.tensor([self.slot[j] for _, j in sub], dtype=torch.int32, device="cuda")
-            pd = torch.from_numpy(np.ascontiguousarray(perms[q0:q0 + step], dtype=np.int32)).cuda()
+            block = perms.take(len(sub)) if lazy else perms[q0:q0 + step]
+            pd = torch.from_numpy(np.ascontiguousarray(block, dtype=np.int32)).cuda()
+            del block
             res = torch.empty(len(sub) * P, dtype=torch.float64, device="cuda")
             wsb = self.lib.dagma_mi_perm_workspace_bytes(n, len(sub), P)
             ws = torch.empty(wsb // 8 + 1, dtype=torch.float64, device="cuda")
@@ -142,6 +148,16 @@ def _draw_perms(rng: np.random.Generator, n: int, num_perm: int) -> np.ndarray:
     for p in range(num_perm):
         out[p + 1] = rng.permutation(n)
     return out
+
+
+class _PermStream:
+    """The permutations of consecutive pairs, drawn block by block from ONE generator (pair order = stream order)."""
+
+    def __init__(self, rng: np.random.Generator, n: int, num_perm: int):
+        self.rng, self.n, self.num_perm, self.P = rng, n, num_perm, num_perm + 1
+
+    def take(self, count: int) -> np.ndarray:
+        return np.stack([_draw_perms(self.rng, self.n, self.num_perm) for _ in range(count)])
 
 
 def permutation_pvalue(stat_fn, x: np.ndarray, y: np.ndarray, *, num_perm: int = 200,
@@ -255,8 +271,7 @@ def test_pairwise_independence(X: np.ndarray, pairs: Iterable[Tuple[int, int]], 
         return []
     rng = np.random.default_rng(seed)
     n = X.shape[0]
-    perms = np.stack([_draw_perms(rng, n, num_perm) for _ in pairs])
-    stats = _pair_stats(X, pairs, test, perms)
+    stats = _pair_stats(X, pairs, test, _PermStream(rng, n, num_perm))
     out = []
     for q, (i, j) in enumerate(pairs):
         ge = int((stats[q, 1:] >= stats[q, 0]).sum())

@@ -96,8 +96,8 @@ class DagmaMLP(nn.Module):
 
     # ---- flat parameter vector  theta = [W1 | b1 | fc2.0.weight | fc2.0.bias | fc2.1.weight | ...]
     def _params(self):
-        if self.fc1.bias is None or any(fc.bias is None for fc in self.fc2):
-            raise NotImplementedError("the B200 path implements bias=True (the reference's default)")
+        # bias=False never gets here: like the reference, the constructor fails in nn.init.zeros_(self.fc1.bias)
+        # (nonlinear.py:38, AttributeError) -- DagmaMLP only exists with biases; LocallyConnected alone takes bias=False
         out = [self.fc1.weight, self.fc1.bias]
         for fc in self.fc2:
             out += [fc.weight, fc.bias]
@@ -423,6 +423,7 @@ class DagmaNonlinear:
         else:
             ValueError("s should be a list, int, or float.")
         self.stage_iters = []
+        self.minimize_calls = []          # (lr, s, success, lr_decay) of every minimize call, retries included
         for i in range(int(T)):
             self.vprint(f'\nDagma iter t={i+1} -- mu: {mu}', 30 * '-')
             success, s_cur = False, s[i]
@@ -432,6 +433,7 @@ class DagmaNonlinear:
             while success is False:
                 before = self.n_iters
                 success = self.minimize(inner_iter, lr, lambda1, lambda2, mu, s_cur, lr_decay)
+                self.minimize_calls.append((float(lr), float(s_cur), int(bool(success)), int(bool(lr_decay))))
                 if success is False:
                     self.model.load_state_dict(model_copy.state_dict().copy())
                     lr *= 0.5

@@ -76,7 +76,11 @@ def fit_batch_sharded(X=None, lambda1=0.03, *, cov=None, group=None, solver=None
     if device is not None:
         kw["device"] = device
     local_in = np.asarray(src)[idx] if not isinstance(src, torch.Tensor) else src[torch.as_tensor(idx)]
-    W_local = solver(local_in, lam, **kw) if X is not None else solver(None, lam, cov=local_in, **kw)
+    if len(idx) == 0:                     # fewer problems than ranks: an empty share still joins the gather
+        d = int(np.shape(src)[-1])
+        W_local = np.zeros((0, d, d))
+    else:
+        W_local = solver(local_in, lam, **kw) if X is not None else solver(None, lam, cov=local_in, **kw)
     W_local = torch.as_tensor(np.ascontiguousarray(W_local))
     if ws > 1 and dist.get_backend(group) == "nccl":
         W_local = W_local.cuda()

@@ -84,3 +84,15 @@ def test_structured_logger_sinks(tmp_path):
     off = StructuredLogger(build_default_logger(name="t_logger", stream=False), LogConfig(enabled=False))
     off.emit("x", {"a": 1})
     assert off._rows == [] and off.run_dir is None
+
+
+def test_mlp_without_bias_fails_like_the_reference():
+    """The reference's DagmaMLP cannot be built with bias=False: its constructor calls nn.init.zeros_(self.fc1.bias)
+    unconditionally (src/dagma/nonlinear.py:36-38) and dies with AttributeError on None.  The drop-in keeps that --
+    it must not quietly accept a configuration the reference rejects.  LocallyConnected alone does take bias=False
+    (locally_connected.py:38-43; GPU test in tests/test_scale_gpu.py)."""
+    from midagma_b200.nonlinear import DagmaMLP, LocallyConnected
+    with pytest.raises(AttributeError):
+        DagmaMLP([5, 4, 1], bias=False)
+    lc = LocallyConnected(5, 4, 3, bias=False)
+    assert lc.bias is None and lc.weight.shape == (5, 4, 3)

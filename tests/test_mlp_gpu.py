@@ -22,7 +22,7 @@ def _model_from(g, prefix="init."):
     return model
 
 
-@pytest.mark.parametrize("name", ["mlp_d7", "mlp_d40", "mlp_deep_d6", "mlp_deep4_d5", "mlp_lin_d6"])
+@pytest.mark.parametrize("name", ["mlp_d7", "mlp_d40", "mlp_c3_n2000", "mlp_deep_d6", "mlp_deep4_d5", "mlp_lin_d6"])
 def test_mlp_value_grad_steps_vs_reference(golden, name):
     from midagma_b200.nonlinear import DagmaNonlinear, _MlpEngine, F_MU, F_S, F_LAM1, F_LAM2, F_OBJ, F_SCORE, F_H
     g = golden(name)

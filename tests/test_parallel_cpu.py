@@ -52,6 +52,9 @@ def _worker(rank, ws, port, out_dir):
     W_all = parallel.fit_batch_sharded(Xs, lams, solver=solver, **kw)
     ref = solver(Xs, lams, **kw)
     assert W_all.shape == (n_prob, d, d) and np.array_equal(W_all, ref)
+    # fewer problems than ranks: the rank with an empty share still joins the gather (no hang, no solver call)
+    W_one = parallel.fit_batch_sharded(Xs[:1], lams[:1], solver=solver, **kw)
+    assert W_one.shape == (1, d, d) and np.array_equal(W_one[0], ref[0])
     # --- (e2) row-sharded logistic score: partial X^T sigmoid(XW) summed == full gradient
     X, _ = simulate.make_linear_problem(8, 2, 101, "ER", "logistic", 3)
     W = np.random.default_rng(0).normal(size=(8, 8)) * 0.1
