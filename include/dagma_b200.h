@@ -228,6 +228,28 @@ int dagma_tcc_assemble_f64(dagma_stream_t stream, int d, const double* w_dev, co
 int dagma_tcc_fold_f64(dagma_stream_t stream, int d, const double* w_dev, const double* g_dev, double sign,
                        int accumulate, double* out_dev);
 
+/* ---- the fork's spectral trek-cycle-coupling penalty ---------------------------
+ * Replaces: perron_eig_with_gradA(method="power")           src/notreks/notreks.py:178-194
+ *           and, iterated to convergence on A + shift I, the Perron pair the eig methods return (:196-231)
+ * n_iter steps of v <- A v / (||A v|| + eps), u <- A^T u / (||A^T u|| + eps) from the all-ones vectors (start = 0)
+ * or from the given unit vectors (start = 1); one pass over A per step serves both chains.  square != 0: the
+ * matrix is a_dev o a_dev.  scal_dev[0..3] = rho = v.(A v) / (v.v + eps), u.v, u.u, v.v.                        */
+size_t dagma_power_workspace_bytes(int n);
+int dagma_perron_power_f64(dagma_stream_t stream, int n, const double* a_dev, int lda, int square, double shift,
+                           int n_iter, double eps, int start, double* v_dev, double* u_dev, double* scal_dev,
+                           double* ws_dev, size_t ws_bytes);
+/* y = A x (or (A o A) x): the Rayleigh baseline u.(B u) of the "approx_trek_graph" version   notreks.py:365   */
+int dagma_matvec_f64(dagma_stream_t stream, int n, const double* a_dev, int lda, int square, const double* x_dev,
+                     double* y_dev);
+/* out4 = [x.y, x.x, y.y, |x - y|^2] (fixed-order sums)                                                        */
+int dagma_vec_dots_f64(dagma_stream_t stream, int n, const double* x_dev, const double* y_dev, double* out4_dev);
+/* out (+)= num / (den_dev[0] + eps) * 2 W o (a1 b1^T + a2 b2^T): d rho / dA = u v^T / (u.v) folded onto W through
+ * A11 = W o W, A22 = (W o W)^T without forming the 2d x 2d outer product     notreks.py:236, 278-287, 343-371
+ * (w_dev = NULL: the factor 2 W is left out -- the d / d(W o W) form the fused update kernel consumes)          */
+int dagma_rank2_fold_f64(dagma_stream_t stream, int d, const double* w_dev, const double* a1_dev,
+                         const double* b1_dev, const double* a2_dev, const double* b2_dev, double num,
+                         const double* den_dev, double eps, int accumulate, double* out_dev);
+
 /* ---- data staging in front of the path ---------------------------------------------
  * Replaces: X -= X.mean(0) (in place) and cov = X^T X / n   src/dagma/linear.py:410-411, 428
  * x_dev [batch][n][d] (centred in place when center != 0), cov_dev [batch][d][d].     */

@@ -50,6 +50,15 @@ class LargeLinearEngine:
         self.X = model._X_dev.contiguous() if self.loss_type == "logistic" else None
         self.mask_exc, self.mask_inc = model._mask_exc, model._mask_inc
         self.group = group                       # torch.distributed group when rows of X are sharded
+        # the per-iteration all-reduce of the d x d partial gradient is captured INSIDE the iteration's CUDA graph when
+        # the backend is NCCL (graph-capturable): the sharded iteration then costs one graph launch like the
+        # single-GPU one instead of ~6 kernel launches + one NCCL launch from the host (DAGMA_GRAPH_NCCL=0: eager)
+        self._graph_collectives = False
+        if group is not None:
+            import os
+            import torch.distributed as dist
+            self._graph_collectives = (dist.get_backend(group) == "nccl"
+                                       and os.environ.get("DAGMA_GRAPH_NCCL", "1") != "0")
         self.n_total = getattr(model, "_n_total", self.n)
         d = self.d
         f64 = dict(dtype=torch.float64, device=self.dev)
@@ -78,19 +87,39 @@ class LargeLinearEngine:
         closed-form adjoints instead of autograd, d pst / d W = 2 W o trek_GT^T -- for ``seq="inv"`` one more fused
         inverse and four DMMA GEMMs per iteration, GEMM chains for the other series."""
         self.trek = plan
+        self.tcc = None
         if plan is None:
+            return
+        if plan["kind"] == "tcc":
+            # spectral TCC as the reference's dispatch calls it (notreks.py:699-707); with notreks.FORWARD_TCC_CONFIG the
+            # regulariser's own version / method; a log-det TCC regulariser has no fused form here
+            from . import notreks
+            from ._tcc import SpectralTcc
+            kw = notreks._tcc_call_args(plan["reg"], notreks.FORWARD_TCC_CONFIG)
+            if kw.pop("cycle_penalty", "spectral") != "spectral":
+                raise NotImplementedError("a log-det TCC regulariser inside minimize: use trek_cycle_coupling_value_gradW")
+            kw.pop("s", None)
+            self.tcc = SpectralTcc(self.d, plan["I"], **kw)
+            self.trek_GT = torch.empty(self.d, self.d, dtype=torch.float64, device=self.dev)
             return
         from ._pst import PstEngine
         self.pst = PstEngine(self.d, plan["I"], plan["seq"], plan["agg"], eps_inv=plan["eps_inv"], K_log=plan["K_log"])
         self.trek_GT = self.pst.GT
 
     def _trek_grad(self):
-        """trek_GT (consumed by the update kernel) at the current W; no host synchronisation (graph-captured)."""
+        """trek_GT (consumed by the update kernel) at the current W; no host synchronisation for PST and for TCC with
+        the power method (graph-captured); the converged Perron iteration of the eig methods polls the host."""
+        if self.tcc is not None:
+            self.tcc.compute(self.W, out=self.trek_GT, fold_w=False)
+            return
         self.pst.grad(self.W)
 
     def _trek_value(self) -> float:
         if self.trek is None:
             return 0.0
+        if self.tcc is not None:
+            self.tcc.compute(self.W, out=self.tcc.grad, fold_w=True)
+            return float(self.tcc.value().item())
         return float(self.pst.value(self.W).item())
 
     def stale(self, model) -> bool:
@@ -182,8 +211,12 @@ class LargeLinearEngine:
         self._update()
 
     def _replay(self, s: float, n: int):
-        if self.group is not None:               # NCCL inside the sequence: launch eagerly
+        if self.group is not None and not self._graph_collectives:   # NCCL outside a graph: launch eagerly
             for _ in range(n):
+                self._iteration(s)
+            return
+        if self.tcc is not None and self.tcc.method != "power" and self._trek_opt():
+            for _ in range(n):                   # the converged Perron iteration polls the host: not capturable
                 self._iteration(s)
             return
         if self._graph is None or self._graph_s != s:

@@ -284,19 +284,21 @@ def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1
 def _trek_plan(tr) -> typing.Optional[dict]:
     """Which trek regulariser the accelerated path carries: PST with any series (``inv``, ``log``,
     ``exp``, ``binom``) and any scalar aggregation (``mean``, ``sum``, ``max``, ``lse``)
-    (src/notreks/notreks.py:454-619), in mode "opt" or "log".  A disabled regulariser or an empty pair list is the
-    reference's no-op branch (notreks.py:684-689).  TCC goes through ``trek_value_grad`` with the reference's
-    default ``cycle_penalty="spectral"`` (a dense non-symmetric eigendecomposition), which stays out of scope."""
+    (src/notreks/notreks.py:454-619), or TCC (spectral by the reference's dispatch, notreks.py:699-707), in mode "opt"
+    or "log".  A disabled regulariser or an empty pair list is the reference's no-op branch (notreks.py:684-689)."""
     if tr is None or not tr.enabled():
         return None
     I = tr.cfg.get("I") if tr.cfg is not None else None
     if I is None or len(I) == 0:
         return None
     name = tr.name.lower().strip()
+    if name == "tcc":
+        I_np = np.asarray(I, dtype=np.int64)
+        if I_np.ndim != 2 or I_np.shape[1] != 2:
+            raise ValueError("I must be array-like of shape (m,2)")
+        return {"kind": "tcc", "I": I_np, "weight": float(tr.weight), "mode": tr.mode, "reg": tr}
     if name != "pst":
-        raise NotImplementedError(
-            f"trek regulariser {tr.name!r} is outside the B200 hot path (SURVEY.md 8f3): the reference dispatches TCC "
-            "to the spectral penalty (LAPACK geev); only PST is accelerated")
+        raise ValueError(f"Unknown trek regularizer: {tr.name}. Has to be in ['pst', 'tcc']")   # notreks.py:664
     kwargs = dict(tr.cfg.get("kwargs", {}) or {})
     seq = str(tr.cfg.get("seq", "exp")).lower().strip()
     agg = str(kwargs.pop("agg", "mean")).lower().strip()
@@ -316,8 +318,8 @@ def _trek_plan(tr) -> typing.Optional[dict]:
     I_np = np.asarray(I, dtype=np.int64)
     if I_np.ndim != 2 or I_np.shape[1] != 2:
         raise ValueError("I must be array-like of shape (m,2)")
-    return {"I": I_np, "seq": seq, "agg": agg, "eps_inv": eps_inv, "K_log": K_log, "weight": float(tr.weight),
-            "mode": tr.mode}
+    return {"kind": "pst", "I": I_np, "seq": seq, "agg": agg, "eps_inv": eps_inv, "K_log": K_log,
+            "weight": float(tr.weight), "mode": tr.mode}
 
 
 # =============================================================================
@@ -332,7 +334,7 @@ class DagmaLinear:
         self.dtype = dtype
         self.vprint = print if verbose else lambda *a, **k: None
         self.trek_reg = trek_reg
-        self._trek_plan = _trek_plan(trek_reg)          # None, or the PST plan (TCC: NotImplementedError)
+        self._trek_plan = _trek_plan(trek_reg)          # None, or the PST / TCC plan
         self._torch_dtype = torch.double
         self._device = torch.device("cuda")
         # telemetry: same defaults as the reference (linear.py:65-67) -- a logger that is silent unless verbose

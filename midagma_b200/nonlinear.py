@@ -170,6 +170,13 @@ class _MlpEngine:
         self.state_host = torch.zeros(ST_DOUBLES, dtype=torch.float64).pin_memory()
         self.ws = torch.empty(self.lib.dagma_large_workspace_bytes(d) // 8 + 8, **f64)
         self.group, self.graph = group, None
+        # NCCL all-reduces are captured inside the iteration graph (DAGMA_GRAPH_NCCL=0: eager launches)
+        self._graph_collectives = False
+        if group is not None:
+            import os
+            import torch.distributed as dist
+            self._graph_collectives = (dist.get_backend(group) == "nccl"
+                                       and os.environ.get("DAGMA_GRAPH_NCCL", "1") != "0")
         self._side = None
         if X is not None:
             self.X = X
@@ -306,7 +313,7 @@ class _MlpEngine:
             torch.distributed.all_reduce(self.grads, group=self.group)
 
     def replay(self, s: float, n: int):
-        if self.group is not None:
+        if self.group is not None and not self._graph_collectives:
             for _ in range(n):
                 self.iteration(s)
             return

@@ -10,8 +10,11 @@ In scope:
 * PST penalties, every series (``inv``, ``log``, ``exp``, ``binom``) and aggregation (``mean``, ``sum``, ``max``,
   ``lse``): value and closed-form gradient on the inverse + GEMM kernels (``_pst.PstEngine``)   notreks.py:454-619
 
-The spectral TCC penalty (dense non-symmetric eigendecomposition, LAPACK geev in the reference) is outside the
-accelerated path and raises ``NotImplementedError``.
+* the spectral TCC penalty (``perron_eig_with_gradA``, ``trek_cycle_coupling_value_gradW(cycle_penalty="spectral")``,
+  a ``TCCRegularizer`` through ``trek_value_grad`` / ``DagmaLinear``) by power iteration on device (``_tcc``)
+                                                                                        notreks.py:156-239, 340-378
+* ``FORWARD_TCC_CONFIG`` / ``trek_value_grad(..., forward_tcc_config=True)``: the reference's dispatch drops a TCC
+  regulariser's ``cycle_penalty`` / ``version`` / ``method`` / ``s`` (notreks.py:699-707, Q14); the flag forwards them.
 """
 from __future__ import annotations
 
@@ -25,6 +28,11 @@ from . import _lib
 from .linear import logdet_inv
 
 TrekRegularizerNames = ["pst", "tcc"]
+
+# Q14: `trek_value_grad` of the reference calls the TCC penalty with its DEFAULT cycle_penalty
+# ("spectral"), version ("approx_trek_graph") and method ("eig_numpy") whatever the regulariser object says
+# (notreks.py:699-707).  False keeps that behaviour (drop-in parity); True forwards the regulariser's own settings.
+FORWARD_TCC_CONFIG = False
 
 
 @dataclass(frozen=True)
@@ -55,6 +63,7 @@ class TCCRegularizer(TrekRegularizer):
                  weight: float = 1.0, w: float = 1.0, s: float = 1.0, n_iter: int = 10, eps: float = 1e-12,
                  mode="opt", name: str = "tcc"):
         object.__setattr__(self, "cycle_penalty", cycle_penalty)
+        object.__setattr__(self, "method", method)     # never read by the reference ("eig_troch" is its default, Q14)
         object.__setattr__(self, "name", name)
         object.__setattr__(self, "mode", mode)
         object.__setattr__(self, "weight", float(weight))
@@ -85,14 +94,38 @@ def _indicator_from_pairs(I, d: int) -> torch.Tensor:
     return S
 
 
+def perron_eig_with_gradA(A: torch.Tensor, *, method="eig_torch", n_iter: int = 50,
+                          eps: float = 1e-12) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(rho, u, v, d rho / dA = u v^T / (u.v + eps)) of a non-negative matrix (notreks.py:156-239).
+    ``method="power"``: the reference's n_iter-step power iteration; the eig methods: the same Perron pair by power
+    steps iterated to convergence (see ``_tcc``)."""
+    if A.ndim != 2 or A.shape[0] != A.shape[1]:
+        raise ValueError("A must be square")
+    if method not in ("power", "eig_torch", "eig_numpy"):
+        raise ValueError("method must be one of {'power','eig_torch','eig_numpy'}")
+    from ._tcc import PerronSolver
+    Ad = _dev64(A)
+    sol = PerronSolver(Ad.shape[0])
+    if method == "power":
+        sol.power(Ad, n_iter, eps)
+    else:
+        sol.converged(Ad, eps)
+    G = torch.outer(sol.u, sol.v) / (sol.scal[1] + eps)
+    to = lambda t: t.clone().to(A.device, A.dtype)  # noqa: E731
+    return to(sol.scal[0]), to(sol.u), to(sol.v), to(G)
+
+
 def trek_cycle_coupling_value_gradW(W: torch.Tensor, I, *, w: float = 1.0, cycle_penalty="spectral",
                                     version="approx_trek_graph", method="eig_numpy", n_iter: int = 50,
                                     s: float = 1.0, eps: float = 1e-12) -> Tuple[torch.Tensor, torch.Tensor]:
-    """TCC penalty on the 2d x 2d block matrix; only ``cycle_penalty="logdet"`` is accelerated."""
+    """TCC penalty on the 2d x 2d block matrix (notreks.py:291-413): spectral (Perron root) or log-det."""
     if W.ndim != 2 or W.shape[0] != W.shape[1]:
         raise ValueError("W must be square")
     if cycle_penalty == "spectral":
-        raise NotImplementedError("the spectral TCC penalty is outside the B200 hot path (SURVEY.md 8f3)")
+        from ._tcc import SpectralTcc
+        eng = SpectralTcc(W.shape[0], I, w=w, version=version, method=method, n_iter=n_iter, eps=eps)
+        grad = eng.compute(_dev64(W))
+        return eng.value().to(W.device, W.dtype), grad.clone().to(W.device, W.dtype)
     if cycle_penalty != "logdet":
         raise ValueError("cycle_penalty must be one of {'spectral','logdet'}")
     if version in ("exact_original_graph", "approx_trek_graph"):
@@ -190,14 +223,41 @@ def pst_inv_value_grad(W, I, *, agg: str = "mean", eps_inv: float = 1e-8, want_g
     return pst_value_grad(W, I, seq="inv", agg=agg, eps_inv=eps_inv, want_grad=want_grad)
 
 
+def _tcc_call_args(tr, forward: bool) -> dict:
+    """What ``trek_cycle_coupling_value_gradW`` is called with for a TCC regulariser: the reference passes only I, w,
+    n_iter, eps (notreks.py:699-707); with ``forward`` also the regulariser's cycle_penalty / version / method / s."""
+    cfg = tr.cfg
+    kw = dict(w=cfg.get("w", 1.0), n_iter=cfg.get("n_iter", 10), eps=cfg.get("eps", 1e-12))
+    if forward:
+        kw["cycle_penalty"] = getattr(tr, "cycle_penalty", "spectral")
+        kw["version"] = cfg.get("version", "approx_trek_graph")
+        kw["s"] = cfg.get("s", 1.0)
+        method = getattr(tr, "method", "eig_numpy")
+        kw["method"] = method if method in ("power", "eig_torch", "eig_numpy") else "eig_numpy"   # "eig_troch" typo
+    return kw
+
+
 def trek_value_grad(W: np.ndarray, tr: Optional[TrekRegularizer], *, torch_dtype: torch.dtype = torch.double,
-                    device: Optional[torch.device] = None) -> Tuple[float, np.ndarray]:
-    """(value, grad) of a trek regulariser (notreks.py:667-736): the no-op branch and every PST penalty."""
+                    device: Optional[torch.device] = None,
+                    forward_tcc_config: Optional[bool] = None) -> Tuple[float, np.ndarray]:
+    """(value, grad) of a trek regulariser (notreks.py:667-736): the no-op branch, every PST penalty, and TCC."""
     from .linear import _trek_plan
     W_np = np.asarray(W)
-    plan = _trek_plan(tr)               # None: disabled / empty I; NotImplementedError for TCC (spectral default)
+    plan = _trek_plan(tr)               # None: disabled / empty I
     if plan is None:
         return 0.0, np.zeros_like(W_np)
+    if plan["kind"] == "tcc":
+        import contextlib
+        import io
+        forward = FORWARD_TCC_CONFIG if forward_tcc_config is None else bool(forward_tcc_config)
+        kw = _tcc_call_args(tr, forward)
+        with contextlib.nullcontext() if kw.get("cycle_penalty") == "logdet" else contextlib.redirect_stdout(io.StringIO()):
+            pen, grad = trek_cycle_coupling_value_gradW(torch.as_tensor(np.ascontiguousarray(W_np), dtype=torch.double),
+                                                        np.asarray(tr.cfg["I"]), **kw)
+        val = float(pen.item())
+        if tr.mode != "opt":
+            return val, np.zeros_like(W_np)
+        return val, grad.numpy().astype(W_np.dtype, copy=False)
     val, grad = pst_value_grad(W_np, plan["I"], seq=plan["seq"], agg=plan["agg"], eps_inv=plan["eps_inv"],
                                K_log=plan["K_log"], want_grad=(tr.mode == "opt"))
     if tr.mode != "opt":

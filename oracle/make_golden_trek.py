@@ -134,7 +134,66 @@ def pst_series():
     print("wrote pst_series.npz")
 
 
+def tcc_spectral():
+    """tests/golden/tcc_spectral.npz: the spectral trek-cycle-coupling penalty of the reference
+    (notreks.py:156-239 perron_eig_with_gradA, :340-378) -- every version x (power, eig_numpy) at a fixed W with a
+    simple Perron root, the Perron pairs themselves, `trek_value_grad` with a TCCRegularizer (the dispatch that ignores
+    the regulariser's cycle_penalty / version / s, :699-707, Q14) and a short `minimize` trajectory in mode "opt"."""
+    import contextlib
+    import io
+    import torch
+    d, n = 10, 300
+    rng = np.random.default_rng(21)
+    pairs = np.array([(i, j) for i in range(d) for j in range(i + 1, d) if rng.random() < 0.3], dtype=np.int64)
+    W = rng.uniform(-0.8, 0.8, size=(d, d)) * (rng.random((d, d)) < 0.45)
+    np.fill_diagonal(W, 0.0)
+    out = {"pairs": pairs, "W": W}
+    Wt = torch.from_numpy(W)
+    versions = ("DAG_learning", "exact_trek_graph", "exact_original_graph", "approx_trek_graph")
+    errors = {}
+    for method, n_iter in (("power", 50), ("power", 7), ("eig_numpy", 50), ("eig_torch", 50)):
+        for version in versions:
+            key = f"{method}{n_iter if method == 'power' else ''}_{version}"
+            try:
+                pen, g = ref_nt.trek_cycle_coupling_value_gradW(Wt, pairs, w=0.7, cycle_penalty="spectral",
+                                                                version=version, method=method, n_iter=n_iter)
+                out[f"pen_{key}"], out[f"grad_{key}"] = np.array(pen.item()), g.numpy()
+            except Exception as e:                              # noqa: BLE001
+                errors[key] = type(e).__name__
+    # the Perron pairs (2d x 2d block matrix built as the reference does, :319-337)
+    W2 = Wt * Wt
+    S = torch.zeros(d, d, dtype=torch.double)
+    S[pairs[:, 0], pairs[:, 1]] = 1.0
+    A = torch.cat([torch.cat([W2, 0.7 * S], dim=1), torch.cat([torch.eye(d, dtype=torch.double), W2.T], dim=1)], dim=0)
+    out["A"] = A.numpy()
+    for method, n_iter in (("power", 50), ("power", 7), ("eig_numpy", 50)):
+        rho, u, v, G = ref_nt.perron_eig_with_gradA(A, method=method, n_iter=n_iter)
+        tag = f"{method}{n_iter if method == 'power' else ''}"
+        out[f"rho_{tag}"], out[f"u_{tag}"], out[f"v_{tag}"], out[f"G_{tag}"] = np.array(rho.item()), u.numpy(), v.numpy(), G.numpy()
+    # dispatch through trek_value_grad: cycle_penalty / version / s of the regulariser are ignored (Q14)
+    for mode in ("opt", "log"):
+        reg = ref_nt.TCCRegularizer(I=pairs, cycle_penalty="logdet", version="DAG_learning", weight=0.3, w=0.7, s=0.8,
+                                    n_iter=10, mode=mode)
+        v, g = ref_nt.trek_value_grad(W, reg)
+        out[f"tvg_val_{mode}"], out[f"tvg_grad_{mode}"] = np.array(v), g
+    # short minimize trajectory, TCC in mode "opt"
+    stages = [(1.0, 150, 1.0, 3e-4), (0.1, 150, 0.9, 3e-4)]
+    reg = ref_nt.TCCRegularizer(I=pairs, weight=0.5, w=0.7, n_iter=10, mode="opt")
+    with contextlib.redirect_stdout(io.StringIO()):
+        X, Ws, oks, rows = run(d, n, 13, reg, stages)
+    out["fit_X"], out["fit_W"], out["fit_ok"] = X, Ws, np.array(oks)
+    out["fit_trek_vals"] = np.array([float(r["reg_trek_value"]) for r in rows])
+    out["stages"] = np.array(stages)
+    out["errors_json"] = np.array(json.dumps(errors))
+    np.savez_compressed(os.path.join(GOLD, "tcc_spectral.npz"), **out)
+    print("wrote tcc_spectral.npz; reference errors:", errors, "fit ok", oks, "trek", out["fit_trek_vals"])
+    print({k: float(out[k]) for k in out if k.startswith("pen_")})
+
+
 if __name__ == "__main__":
+    if "--tcc-spectral" in sys.argv:
+        tcc_spectral()
+        sys.exit(0)
     if "--pst-series" in sys.argv:
         pst_series()
     else:
