@@ -14,9 +14,16 @@ for every problem, i.e. 4096 x 1000 inner Adam iterations per GPU per step.
              buffers (H2D of W and cov, kernel, D2H of W inside the timed region)
     roofline: 4 d^3 flop per iteration (inverse 2d^3 + cov@(I-W) 2d^3) against the FP64
              pipe peak measured live with the DFMA/DMMA yardstick kernels
-    cpu_baseline / --impl reference: the numpy restatement of the reference
-             (oracle/linear_ref.py, bit-identical to it in the build container) on the
-             host cores, one single-threaded-BLAS process per core, bounded sample.
+    cpu_baseline / --impl reference: the UNMODIFIED reference class (dagma.linear.DagmaLinear
+             imported from /root/reference/src, kind "reference") when that tree exists, else the
+             numpy restatement of it (oracle/linear_ref.py, bit-identical to it in the build
+             container, kind "port" -- /root/reference does not exist on the GPU box); one
+             single-threaded-BLAS process per host core, bounded sample.
+    parity_sample: 32 of the 4096 problems of the full default fit against the fits of the unmodified
+             reference recorded in tests/golden/fit_c4_sample32.npz (edge sets, |dW| next to the
+             reference's own inv(M.T).T round-off envelope).
+    c5 / c2 / c3 / c1: the other configs of BASELINE.json (own roofline / e2e / CPU sample each);
+    with --gpus N > 1 also the row-sharded C2 / C3 iterations and a strong-scaling C4 step.
 """
 from __future__ import annotations
 
@@ -49,28 +56,79 @@ def make_covs(n_seeds: int, seed0: int):
 
 
 # --------------------------------------------------------------------------- CPU arm
+REFERENCE_SRC = "/root/reference/src"
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_SRC, "dagma", "linear.py"))
+
+
+class _Bar:
+    def update(self, *_a, **_k):
+        pass
+
+
+def _reference_minimize(X, lam, iters):
+    """`iters` inner iterations of the UNMODIFIED reference DagmaLinear.minimize (set-up as fit() does, linear.py:406-429)."""
+    import numpy as np
+    sys.dont_write_bytecode = True
+    if REFERENCE_SRC not in sys.path:
+        sys.path.insert(0, REFERENCE_SRC)
+    from dagma.linear import DagmaLinear as RefLinear
+    m = RefLinear("l2")
+    m.X, m.lambda1, m.checkpoint = X, lam, ITERS_PER_STEP
+    m.n, m.d = X.shape
+    m.Id = np.eye(m.d)
+    m.X -= X.mean(axis=0, keepdims=True)
+    m.exc_r = m.exc_c = m.inc_r = m.inc_c = None
+    m.cov = X.T @ X / float(m.n)
+    calls = [0]
+    adam = m._adam_update
+
+    def tap(*a, **k):
+        calls[0] += 1
+        return adam(*a, **k)
+
+    m._adam_update = tap
+    t0 = time.perf_counter()
+    m.minimize(np.zeros((m.d, m.d)), 1.0, iters, 1.0, lr=3e-4, tol=0.0, pbar=_Bar())
+    return calls[0], time.perf_counter() - t0
+
+
 def _cpu_worker(args):
-    seed, lam, iters = args
+    seed, lam, iters, kind = args
     import numpy as np
     from threadpoolctl import threadpool_limits
     from oracle import simulate
-    from oracle.linear_ref import OracleLinear
     with threadpool_limits(limits=1):
         X, _ = simulate.make_linear_problem(D, K_EDGES, N_SAMPLES, "ER", "gauss", seed)
+        if kind == "reference":
+            return _reference_minimize(X, lam, iters)
+        from oracle.linear_ref import OracleLinear
         o = OracleLinear("l2").prepare(X, lam, checkpoint=ITERS_PER_STEP)
         t0 = time.perf_counter()
         o.minimize(np.zeros((D, D)), 1.0, iters, 1.0, 3e-4, tol=0.0)
         return o.last_iters, time.perf_counter() - t0
 
 
-def cpu_rate(iters: int, rounds: int = 1):
-    """problem-iterations/s of the oracle port with one single-thread process per host core."""
+def cpu_kind() -> str:
+    return "reference" if reference_available() else "port"
+
+
+def cpu_what(kind: str) -> str:
+    return ("the unmodified reference dagma.linear.DagmaLinear.minimize (numpy/scipy)" if kind == "reference" else
+            "oracle/linear_ref.py (numpy/scipy restatement of the reference)")
+
+
+def cpu_rate(iters: int, rounds: int = 1, kind: str = None):
+    """problem-iterations/s of the CPU implementation with one single-thread process per host core."""
     import multiprocessing as mp
+    kind = kind or cpu_kind()
     cores = len(os.sched_getaffinity(0))
-    jobs = [(1000 + i, LAMBDAS[i % 4], iters) for i in range(cores * rounds)]
+    jobs = [(1000 + i, LAMBDAS[i % 4], iters, kind) for i in range(cores * rounds)]
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(1000, 0.02, 5)] * cores)          # spawn + import warm-up
+        pool.map(_cpu_worker, [(1000, 0.02, 5, kind)] * cores)    # spawn + import warm-up
         t0 = time.perf_counter()
         res = pool.map(_cpu_worker, jobs, chunksize=1)
         wall = time.perf_counter() - t0
@@ -93,7 +151,9 @@ def run_reference(args):
     total_wall = sum(r[2] for r in rates)
     total_done = sum(r[1] for r in rates)
     value = total_done / total_wall
-    sample = f"{cores} problems (one per core) x {iters} inner iterations per step, single-thread BLAS per process"
+    kind = cpu_kind()
+    sample = (f"{cores} problems (one per core) x {iters} inner iterations per step of {cpu_what(kind)}, "
+              "single-thread BLAS per process")
     line = {
         "impl": "reference", "metric": "DagmaLinear inner Adam iters/sec (batched d=64)", "value": value,
         "unit": "problem-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -101,7 +161,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C4: DagmaLinear l2 minimize, ER4 d=64 n=1000, mu=1 s=1 lr=3e-4", "d": D,
                    "n": N_SAMPLES, "iters_per_problem_per_step": iters},
-        "cpu_baseline": {"value": value, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "problem-iterations/s", "cores": cores, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "problem-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -169,7 +229,83 @@ def fp64_peak_tflops(torch, _lib, sms):
             torch.cuda.synchronize()
             tbest = min(tbest, e0.elapsed_time(e1) * 1e-3)
         best[name] = flops(ctas, threads, iters) / tbest / 1e12
+    # cuBLAS DGEMM 8192^3 through torch.matmul: the practical FP64 tensor peak SURVEY.md 7.3 asks the bench to record
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    tbest = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        tbest = min(tbest, e0.elapsed_time(e1) * 1e-3)
+    best["cublas_dgemm_8192"] = 2.0 * n ** 3 / tbest / 1e12
+    del a, b, c
     return best
+
+
+def traffic_from_profile(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, parsed from the committed ncu summary
+    that profiles/roofline_sources.json names for it (None when there is no capture)."""
+    import re
+    try:
+        src = json.load(open(os.path.join(ROOT, "profiles", "roofline_sources.json")))[kernel]
+        text = open(os.path.join(ROOT, src["file"])).read()
+    except (OSError, KeyError, ValueError):
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        m = re.search(re.escape(name) + r" \[(\w+)\] = ([0-9.,]+)", text)
+        if not m:
+            return None, None
+        total += float(m.group(2).replace(",", "")) * unit[m.group(1)]
+    return total, src
+
+
+def parity_sample(W_raw, stage_iters):
+    """The fitted W of the sampled problems of the 4096-batch against the full default fits of the UNMODIFIED
+    reference (tests/golden/fit_c4_sample32.npz, oracle/make_golden_scale.py c4): per-problem edge-set identity,
+    |dW| next to the reference's own round-off envelope (the same fit with inv(M.T).T)."""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "fit_c4_sample32.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    probs = [int(p) for p in g["problems"]]
+    if max(probs) >= len(W_raw):
+        return None
+    Wr, Wt = g["W_reference"], g["W_transposed"]
+    rows, n_same, n_env_same = [], 0, 0
+    for k, p in enumerate(probs):
+        W = W_raw[p]
+        e_gpu, e_ref, e_tr = np.abs(W) >= 0.3, np.abs(Wr[k]) >= 0.3, np.abs(Wt[k]) >= 0.3
+        diff = int((e_gpu != e_ref).sum())
+        env_diff = int((e_tr != e_ref).sum())
+        n_same += diff == 0
+        n_env_same += env_diff == 0
+        ref_iters = [int(c[0]) for c in g["calls_reference"][k] if c[0] >= 0]
+        row = {"problem": p, "edge_diff": diff, "max_abs_dW": float(np.abs(W - Wr[k]).max()),
+               "envelope_max_abs_dW": float(np.abs(Wt[k] - Wr[k]).max()), "envelope_edge_diff": env_diff,
+               "stage_iters": [int(x) for x in stage_iters[p]], "reference_stage_iters": ref_iters}
+        if diff:
+            bad = np.argwhere(e_gpu != e_ref)
+            row["exceptions"] = [{"edge": [int(i), int(j)], "W_gpu": float(W[i, j]), "W_ref": float(Wr[k][i, j]),
+                                  "margin_ref": float(abs(abs(Wr[k][i, j]) - 0.3))} for i, j in bad[:8]]
+        rows.append(row)
+    dws = np.array([r["max_abs_dW"] for r in rows])
+    envs = np.array([r["envelope_max_abs_dW"] for r in rows])
+    return {"problems": len(probs), "identical_edge_sets": int(n_same), "reference_envelope_identical_edge_sets": int(n_env_same),
+            "max_abs_dW_median": float(np.median(dws)), "max_abs_dW_max": float(dws.max()),
+            "envelope_median": float(np.median(envs)), "envelope_max": float(envs.max()),
+            "same_stage_lengths": int(sum(r["stage_iters"] == r["reference_stage_iters"] for r in rows)),
+            "source": "tests/golden/fit_c4_sample32.npz (unmodified reference; envelope = the reference with inv(M.T).T)",
+            "per_problem": rows}
 
 
 def bench_c5(torch, _lib, peak_tflops, with_cpu):
@@ -211,22 +347,60 @@ def bench_c5(torch, _lib, peak_tflops, with_cpu):
     t_it = timed(eng._graph)
     t_inv = timed(graph_of(lambda: eng._inverse(1.0)))
     t_gemm = timed(graph_of(lambda: eng._score_T()))
+    inv_tf = 2.0 * d ** 3 / t_inv / 1e12
+    traffic, src = traffic_from_profile("outer_step_kernel")
     out = {"workload": "C5: single DagmaLinear l2 problem, SF4 d=2000 n=20000, mu=1 s=1 lr=3e-4 (graph-replayed inner iteration)",
            "ms_per_iter": t_it * 1e3, "iters_per_s": 1.0 / t_it, "flop_per_iter": 4.0 * d ** 3,
            "tflops": 4.0 * d ** 3 / t_it / 1e12, "frac_of_fp64_peak": 4.0 * d ** 3 / t_it / 1e12 / peak_tflops,
-           "inverse_ms": t_inv * 1e3, "inverse_tflops": 2.0 * d ** 3 / t_inv / 1e12,
-           "inverse_frac_of_fp64_peak": 2.0 * d ** 3 / t_inv / 1e12 / peak_tflops,
-           "score_gemm_ms": t_gemm * 1e3, "score_gemm_tflops": 2.0 * d ** 3 / t_gemm / 1e12}
+           "inverse_ms": t_inv * 1e3, "inverse_tflops": inv_tf,
+           "inverse_frac_of_fp64_peak": inv_tf / peak_tflops,
+           "score_gemm_ms": t_gemm * 1e3, "score_gemm_tflops": 2.0 * d ** 3 / t_gemm / 1e12,
+           "roofline": {"bound": "tensor", "achieved": inv_tf, "peak": peak_tflops, "unit": "TFLOP/s",
+                        "frac": inv_tf / peak_tflops,
+                        # per LAUNCH of outer_step_kernel (one of the 8 outer steps of an inverse): 2 d^3 / 8 flop
+                        "traffic": traffic, "traffic_source": src,
+                        "kernel": "outer_step_kernel x ceil(d / 256) launches = one blocked inverse (2 d^3 flop)",
+                        "flop_per_unit": 2.0 * d ** 3, "units_per_launch": 1.0 / 8}}
+    # ---- e2e: the call a reference user makes -- host X in, thresholded W_est out (reduced schedule of the parity
+    # fixture: warm_iter = max_iter = 500; H2D of X, centring + covariance, 2500 iterations with their checkpoint
+    # objective evaluations, D2H of W and of the centred X inside the timed region)
+    del eng
+    model = DagmaLinear("l2")
+    Xh = X.copy()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    W_est = model.fit(Xh, lambda1=0.02, warm_iter=500, max_iter=500, s=[1.0, .9, .8, .7, .6])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    iters = int(sum(model.stage_iters))
+    out["e2e"] = {"value": iters / wall, "unit": "inner iterations/s", "wall_s": wall, "inner_iters": iters,
+                  "h2d_bytes": int(X.nbytes), "d2h_bytes": int(X.nbytes + 8 * d * d * 6),
+                  "what": "DagmaLinear('l2').fit(X, lambda1=0.02, warm_iter=500, max_iter=500) on host arrays"}
+    gpath = os.path.join(ROOT, "tests", "golden", "fit_c5_reduced.npz")
+    if os.path.exists(gpath):
+        g = np.load(gpath)
+        W_ref = np.zeros(d * d)
+        W_ref[g["w_idx"]] = g["w_val"]
+        W_ref = W_ref.reshape(d, d)
+        big = np.abs(W_ref) >= 0.05
+        out["parity"] = {"edge_set_distance": int(((W_est != 0) != (np.abs(W_ref) >= 0.3)).sum()),
+                         "edges": int((W_est != 0).sum()), "reference_edges": int(g["nnz_est"]),
+                         "max_abs_dW_on_ref_entries_ge_0.05": float(np.abs(model.W_raw - W_ref)[big].max()),
+                         "stage_iters": model.stage_iters, "reference_wall_s": float(g["wall_s"]),
+                         "source": "tests/golden/fit_c5_reduced.npz (the same fit by the unmodified reference)"}
+        out["e2e"]["speedup_vs_reference_fit_wall"] = float(g["wall_s"]) / wall
     if with_cpu:
         from oracle.linear_ref import OracleLinear
         o = OracleLinear("l2").prepare(X, 0.02, checkpoint=1000)
         Wc = W.copy()
         o.minimize(Wc, 1.0, 1, 1.0, 3e-4, tol=0.0)
+        n_cpu = 30
         t0 = time.perf_counter()
-        o.minimize(Wc, 1.0, 8, 1.0, 3e-4, tol=0.0)
-        cpu = (time.perf_counter() - t0) / 8
+        o.minimize(Wc, 1.0, n_cpu, 1.0, 3e-4, tol=0.0)
+        cpu = (time.perf_counter() - t0) / n_cpu
         out["cpu_ms_per_iter"] = cpu * 1e3
-        out["cpu_sample"] = f"8 iterations of oracle/linear_ref.py with all host BLAS threads ({len(os.sched_getaffinity(0))} cores)"
+        out["cpu_sample"] = (f"{n_cpu} iterations of oracle/linear_ref.py with all host BLAS threads "
+                             f"({len(os.sched_getaffinity(0))} cores)")
         out["speedup_vs_cpu"] = cpu / t_it
     return out
 
@@ -332,6 +506,91 @@ def bench_c2_c3(torch, with_cpu):
     return out
 
 
+def bench_sharded(torch, dist, rank, world, dev):
+    """SURVEY.md 8e2 on N GPUs (every rank calls this): the row-sharded C2 (logistic d=100) and C3 (MLP [40,10,1])
+    inner iterations -- rows of X split contiguously, ONE sum all-reduce of the d x d (parameter-sized) partial
+    gradient per iteration, captured inside the iteration's CUDA graph -- timed with CUDA events (max over ranks)
+    next to the same iterations un-sharded on one GPU, with |dW| between the two after the timed iterations; the C2
+    pair is repeated at larger n (rows tiled) to locate the n above which sharding pays."""
+    import numpy as np
+    from oracle import simulate
+    from midagma_b200 import DagmaLinear, parallel
+    from midagma_b200.nonlinear import DagmaMLP, DagmaNonlinear
+
+    def rmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_linear(X, shard, iters):
+        m = DagmaLinear("logistic")
+        Xl = X
+        if shard:
+            m.shard_rows()
+            Xl = X[parallel.row_shard(X.shape[0], rank, world)]
+        m.fit(np.ascontiguousarray(Xl), lambda1=0.02, T=1, warm_iter=0, max_iter=0, checkpoint=10 ** 9)
+        d = X.shape[1]
+        W = np.zeros((d, d))
+        m.minimize(W, 1.0, 100, 1.0, lr=3e-4, tol=0.0)            # graph capture + warm-up
+        W[...] = 0.0
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m.minimize(W, 1.0, iters, 1.0, lr=3e-4, tol=0.0)
+        e1.record()
+        torch.cuda.synchronize()
+        return rmax(e0.elapsed_time(e1) * 1e-3) / iters, W
+
+    out = {"n_gpus": world, "all_reduce": "torch.distributed NCCL sum all-reduce captured inside the iteration's CUDA graph"}
+    X, _ = simulate.config_c2(0)
+    rows = []
+    for mult in (1, 4, 16, 64):
+        Xn = np.tile(X, (mult, 1)) if mult > 1 else X
+        iters = 1000 if mult <= 4 else 200
+        t_sh, W_sh = time_linear(Xn, True, iters)
+        t_1, W_1 = time_linear(Xn, False, iters)
+        rows.append({"n": int(Xn.shape[0]), "us_per_iter_sharded": t_sh * 1e6, "us_per_iter_one_gpu": t_1 * 1e6,
+                     "speedup": t_1 / t_sh, "max_abs_dW_vs_one_gpu": float(np.abs(W_sh - W_1).max()), "iters": iters})
+        del Xn
+    out["c2_sharded"] = {"workload": "C2: DagmaLinear logistic d=100, rows sharded over the GPUs (n = 10 000 is BASELINE's size; "
+                                     "larger n: the same rows tiled)",
+                         "iters_per_s": 1e6 / rows[0]["us_per_iter_sharded"], "by_n": rows,
+                         "crossover_n": next((r["n"] for r in rows if r["speedup"] >= 1.0), None)}
+    # ---- C3
+    Xn, _ = simulate.config_c3(0)
+    n, d, m1 = Xn.shape[0], Xn.shape[1], 10
+
+    def time_mlp(shard, iters):
+        torch.manual_seed(0)
+        model = DagmaMLP(dims=[d, m1, 1], bias=True)
+        eq = DagmaNonlinear(model)
+        Xl = Xn
+        if shard:
+            eq.group, eq.n_total = dist.group.WORLD, n
+            Xl = Xn[parallel.row_shard(n, rank, world)]
+        eq.X = torch.from_numpy(np.ascontiguousarray(Xl)).cuda()
+        eq.checkpoint = 10 ** 9
+        state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        eq.minimize(100, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0)
+        model.load_state_dict(state)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eq.minimize(iters, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0)
+        e1.record()
+        torch.cuda.synchronize()
+        return rmax(e0.elapsed_time(e1) * 1e-3) / iters, model.fc1.weight.detach().clone()
+
+    t_sh, w_sh = time_mlp(True, 1000)
+    t_1, w_1 = time_mlp(False, 1000)
+    out["c3_sharded"] = {"workload": "C3: DagmaMLP [40, 10, 1] n=2000, rows sharded over the GPUs",
+                         "iters_per_s": 1.0 / t_sh, "us_per_iter_sharded": t_sh * 1e6, "us_per_iter_one_gpu": t_1 * 1e6,
+                         "speedup": t_1 / t_sh, "max_abs_dfc1_vs_one_gpu": float((w_sh - w_1).abs().max().item())}
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -424,28 +683,63 @@ def run_b200(args):
     e2e_value = total_iters / dt_e2e
 
     extra = {}
+    if world > 1:
+        # ---- strong scaling of the same workload: 4096 problems in total, 4096 / N per GPU (2 CTAs per SM: 512
+        # equal-length problems are 1.73 waves of 296 resident CTAs -- the second wave bounds the step)
+        n_loc = max(nprob // world, 1)
+        Ws = torch.zeros(n_loc, D, D, dtype=torch.float64, device=dev)
+
+        def sstep():
+            return _run_small(cov[:n_loc], Ws, lam[:n_loc], [1.0], [1.0], [ITERS_PER_STEP], lr=3e-4, tol=0.0, beta1=0.99,
+                              beta2=0.999, checkpoint=ITERS_PER_STEP, retry=False, want_final=False)
+        sstep()
+        sync()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            sstep()
+        s1.record()
+        sync()
+        dt_s = rmax(s0.elapsed_time(s1) * 1e-3)
+        strong = {"problems_total": n_loc * world, "problems_per_gpu": n_loc,
+                  "value": float(n_loc) * world * ITERS_PER_STEP * args.steps / dt_s, "unit": "problem-iterations/s",
+                  "ms_per_step": 1e3 * dt_s / args.steps, "resident_ctas_per_gpu": 2 * sms,
+                  "waves": n_loc / (2.0 * sms)}
+        del Ws
+        sharded = bench_sharded(torch, dist, rank, world, dev) if args.sharded else None
+        if rank == 0:
+            extra["strong_scaling"] = strong
+            if sharded:
+                extra.update({k: v for k, v in sharded.items() if k in ("c2_sharded", "c3_sharded")})
     if rank == 0:
         peaks = fp64_peak_tflops(torch, _lib, sms)
         peak = max(peaks.values())
         per_gpu_rate = nprob * ITERS_PER_STEP / (sum(kernel_ms) / len(kernel_ms) * 1e-3)
         achieved = per_gpu_rate * FLOP_PER_ITER / 1e12
+        traffic, tsrc = traffic_from_profile("fit_small_dmma_kernel")
+        if not (nprob == 4096 and ITERS_PER_STEP == 1000):
+            traffic = None                       # the capture is of this configuration only
         extra["roofline"] = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this configuration (4096 problems x 1000
-            # iterations), ncu --set full capture of round 1: profiles/small_fit_dmma_d64_r1_final.txt
-            "traffic": 375.0e6 if (nprob == 4096 and ITERS_PER_STEP == 1000) else None,
+            # iterations), parsed from the committed ncu --set full summary named in profiles/roofline_sources.json
+            "traffic": traffic, "traffic_source": tsrc,
             "traffic_unit": "bytes per launch (algorithmic I/O: cov + W in, W out = 402.7e6)",
             "kernel": "fit_small_dmma_kernel (one launch per step)",
-            "peak_source": "measured live: FP64 pipe yardsticks " + json.dumps({k: round(v, 2) for k, v in peaks.items()})
-                           + " TFLOP/s (MEASURED_PEAKS.json has no FP64 entry; FP64 tensor = FP64 FMA rate on B200)",
+            "peak_source": "measured live: FP64 pipe yardsticks and cuBLAS DGEMM 8192^3 "
+                           + json.dumps({k: round(v, 2) for k, v in peaks.items()})
+                           + " TFLOP/s; denominator = the largest (MEASURED_PEAKS.json has no FP64 entry; FP64 tensor = "
+                             "FP64 FMA rate on B200)",
+            "fp64_peaks_tflops": {k: round(v, 3) for k, v in peaks.items()},
             "flop_per_unit": FLOP_PER_ITER, "units_per_launch": nprob * ITERS_PER_STEP,
         }
         if args.cpu_baseline:
-            rate, cores, cdone, cwall = cpu_rate(args.cpu_iters)
+            kind = cpu_kind()
+            rate, cores, cdone, cwall = cpu_rate(args.cpu_iters, kind=kind)
             extra["cpu_baseline"] = {
-                "value": rate, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
+                "value": rate, "unit": "problem-iterations/s", "cores": cores, "kind": kind,
                 "sample": f"{cores} problems (one per core) x {args.cpu_iters} iterations, {cwall:.1f} s wall, "
-                          "oracle/linear_ref.py (numpy/scipy restatement of the reference), 1 BLAS thread per process"}
+                          f"{cpu_what(kind)}, 1 BLAS thread per process"}
         if args.full_fit and world == 1:
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -456,6 +750,10 @@ def run_b200(args):
                                  "iters_per_s": info["total_iters"] / wall,
                                  "status_nonzero": int((info["status"] != 0).sum()),
                                  "mean_edges": float((W_est != 0).sum(axis=(1, 2)).mean())}
+            ps = parity_sample(info["W_raw"], info["stage_iters"])
+            if ps is not None:
+                extra["parity_sample"] = ps
+            del W_est, info
 
         if args.c5 and world == 1:
             del W_host, cov_host
@@ -495,6 +793,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-full-fit", dest="full_fit", action="store_false")
     ap.add_argument("--no-c5", dest="c5", action="store_false", help="skip the single d=2000 problem (C5)")
+    ap.add_argument("--no-sharded", dest="sharded", action="store_false",
+                    help="N > 1: skip the row-sharded C2 / C3 iterations")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

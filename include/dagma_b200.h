@@ -155,6 +155,11 @@ int dagma_linear_apply_dir_f64(dagma_stream_t stream, int d, const void* state_d
 /* checkpoint reductions: l2 score 1/2 tr((I-W)^T cov (I-W)) and sum|W|   linear.py:85-87, 129 */
 int dagma_linear_objective_f64(dagma_stream_t stream, int d, void* state_dev, const double* w_dev,
                                const double* t_dev, const double* cov_dev, int l2);
+/* the same on a grid of CTAs (fixed-order two-level sum); ws_dev: dagma_linear_objective_workspace_bytes() bytes, the
+ * first 8 zero before the first call                                                        */
+size_t dagma_linear_objective_workspace_bytes(void);
+int dagma_linear_objective_ws_f64(dagma_stream_t stream, int d, void* state_dev, const double* w_dev,
+                                  const double* t_dev, const double* cov_dev, int l2, double* ws_dev, size_t ws_bytes);
 /* out = scale * sum(logaddexp(0, R) - X o R)      src/dagma/linear.py:91                 */
 int dagma_logistic_loss_f64(dagma_stream_t stream, int n, int d, const double* x_dev, const double* r_dev,
                             double scale, double* partial_dev, int n_partial, double* out_dev);

@@ -75,6 +75,7 @@ class LargeLinearEngine:
         if self.X is not None:
             self.R = torch.empty(self.n, d, **f64)
             self.partial = torch.empty(1024, **f64)
+        self.obj_ws = torch.zeros(self.lib.dagma_linear_objective_workspace_bytes() // 8 + 1, **f64)
         self._graph = None
         self._side = None
         self._model_cov_ptr = model._cov_dev.data_ptr()
@@ -251,15 +252,12 @@ class LargeLinearEngine:
         self._inverse(s)
         if self.loss_type == "l2":
             self._score_T()
-            _lib.check(self.lib.dagma_linear_objective_f64(_lib.stream_ptr(), self.d, self.state.data_ptr(),
-                                                           self.W.data_ptr(), self.T.data_ptr(), self.cov.data_ptr(), 1),
-                       "dagma_linear_objective_f64")
+            self._objective_sums(self.W, True)
             st, *_ = self._pull()
             score = float(st[F_SCORE])
         else:
             score = self._logistic_loss(self.W)
-            _lib.check(self.lib.dagma_linear_objective_f64(_lib.stream_ptr(), self.d, self.state.data_ptr(),
-                                                           self.W.data_ptr(), None, None, 0), "dagma_linear_objective_f64")
+            self._objective_sums(self.W, False)
             st, *_ = self._pull()
         h, l1 = float(st[F_H]), float(st[F_L1])
         obj = mu * (score + lambda1 * l1) + h
@@ -267,6 +265,13 @@ class LargeLinearEngine:
         if self._trek_opt():
             obj = obj + self.trek["weight"] * self.last_trek_val
         return obj, score, h
+
+    def _objective_sums(self, W, l2: bool):
+        """score_acc = 1/2 sum (I - W) o (cov - T) (l2 only) and l1_acc = sum |W| into the state block."""
+        _lib.check(self.lib.dagma_linear_objective_ws_f64(
+            _lib.stream_ptr(), self.d, self.state.data_ptr(), W.data_ptr(), self.T.data_ptr() if l2 else None,
+            self.cov.data_ptr() if l2 else None, int(l2), self.obj_ws.data_ptr(), self.obj_ws.numel() * 8),
+            "dagma_linear_objective_ws_f64")
 
     def _logistic_loss(self, W) -> float:
         gemm(self.X, W, self.R)
@@ -286,9 +291,7 @@ class LargeLinearEngine:
         if self.loss_type == "l2":
             gemm(self.cov, W, G, alpha=1.0, beta=-1.0)                 # cov W - cov = -cov (I - W)
             gemm(self.cov, W, self.T)
-            _lib.check(self.lib.dagma_linear_objective_f64(_lib.stream_ptr(), self.d, self.state.data_ptr(),
-                                                           W.data_ptr(), self.T.data_ptr(), self.cov.data_ptr(), 1),
-                       "dagma_linear_objective_f64")
+            self._objective_sums(W, True)
             st, *_ = self._pull()
             return float(st[F_SCORE]), G
         loss = self._logistic_loss(W)

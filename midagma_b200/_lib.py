@@ -64,6 +64,9 @@ EXPORTS = {
                                              C.c_double]),
     "dagma_linear_objective_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int]),
+    "dagma_linear_objective_workspace_bytes": (C.c_size_t, []),
+    "dagma_linear_objective_ws_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_void_p, C.c_size_t]),
     "dagma_logistic_loss_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
                                           C.c_void_p, C.c_int, C.c_void_p]),
     "dagma_adam_direction_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

@@ -2178,6 +2178,48 @@ __global__ void __launch_bounds__(1024) linear_objective_kernel(LinState* st, in
     }
 }
 
+// The same reductions over row blocks on many CTAs (a 32 MB pass at d = 2000: 2.6 ms on one CTA, HBM-bound on a grid):
+// CTA b sums the rows b, b + grid, ... (no 64-bit divide), writes its pair of partial sums, and the CTA that takes the
+// last ticket adds the partials in CTA order -- fixed order, so the result does not depend on the schedule.
+// ws: [0] ticket (unsigned, zero on entry, re-armed on exit), [1 + 2 b], [2 + 2 b] partials.
+__global__ void __launch_bounds__(256) linear_objective_mb_kernel(LinState* st, int d, const double* __restrict__ W,
+                                                                  const double* __restrict__ T,
+                                                                  const double* __restrict__ cov, int l2,
+                                                                  double* __restrict__ ws) {
+    __shared__ double red[96];
+    __shared__ unsigned s_last;
+    const int tid = threadIdx.x;
+    double sc = 0.0, l1 = 0.0, z = 0.0;
+    for (int r = blockIdx.x; r < d; r += gridDim.x) {
+        const size_t row = (size_t)r * d;
+        for (int c = tid; c < d; c += 256) {
+            const double w = W[row + c];
+            l1 += fabs(w);
+            if (l2) sc = fma(((r == c) ? 1.0 : 0.0) - w, cov[row + c] - T[row + c], sc);
+        }
+    }
+    block_sum3<256>(sc, l1, z, red, tid);
+    if (tid == 0) {
+        ws[1 + 2 * blockIdx.x] = sc;
+        ws[2 + 2 * blockIdx.x] = l1;
+        __threadfence();
+        s_last = (atomicAdd(reinterpret_cast<unsigned*>(ws), 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (unsigned k = 0; k < gridDim.x; ++k) {
+            a += __ldcg(ws + 1 + 2 * k);
+            b += __ldcg(ws + 2 + 2 * k);
+        }
+        st->score_acc = 0.5 * a;
+        st->l1_acc = b;
+        *reinterpret_cast<unsigned*>(ws) = 0u;
+    }
+}
+
 // partial[b] = sum over a slice of (logaddexp(0, R) - X o R)   (linear.py:91); finished by a 1-block pass
 __global__ void __launch_bounds__(256) logistic_loss_kernel(const double* __restrict__ X, const double* __restrict__ R,
                                                              size_t total, double* partial) {
@@ -2325,6 +2367,22 @@ extern "C" int dagma_linear_objective_f64(dagma_stream_t stream, int d, void* st
                                           const double* t_dev, const double* cov_dev, int l2) {
     DAGMA_REQUIRE(state_dev && w_dev, "null pointer");
     linear_objective_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((LinState*)state_dev, d, w_dev, t_dev, cov_dev, l2);
+    DAGMA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" size_t dagma_linear_objective_workspace_bytes(void) { return (size_t)(2 * 592 + 2) * sizeof(double); }
+
+// multi-CTA form of dagma_linear_objective_f64; ws_dev: dagma_linear_objective_workspace_bytes() bytes whose first
+// 8 bytes are zero at the first call (the kernel leaves them zero)
+extern "C" int dagma_linear_objective_ws_f64(dagma_stream_t stream, int d, void* state_dev, const double* w_dev,
+                                             const double* t_dev, const double* cov_dev, int l2, double* ws_dev,
+                                             size_t ws_bytes) {
+    DAGMA_REQUIRE(state_dev && w_dev && ws_dev, "null pointer");
+    DAGMA_REQUIRE(ws_bytes >= dagma_linear_objective_workspace_bytes(), "workspace too small");
+    const int grid = d < 592 ? d : 592;
+    linear_objective_mb_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((LinState*)state_dev, d, w_dev, t_dev, cov_dev, l2,
+                                                                       ws_dev);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }

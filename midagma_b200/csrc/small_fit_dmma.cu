@@ -25,50 +25,72 @@ __device__ __forceinline__ double signed_const(double w, double c) {
     return zero ? 0.0 : __hiloint2double(chi, __double2loint(c));
 }
 
-// w -= lr * mhat / (sqrt(vhat) + 1e-8) for N independent entries   (linear.py:160-162, 275), written
-// stage by stage so the N Newton chains interleave.  MUFU seeds are good to 2^-20 or better
-// (measured, scripts/latency.py): rsqrt seed + two coupled iterations, reciprocal seed + one iteration
-// + one division-residual step leave errors far below 1 ulp of the quotient.
+// Scalar FP64 instructions are what the element-wise pass costs: with another CTA's DMMAs queued on the same FP64
+// pipe every one of them waits its turn (measured: 26 instructions per entry = 9.3 k clk per iteration with two CTAs
+// per SM, 3.5 k alone), so the pass is written for instruction count -- 20 per entry, none of them redundant:
+//   * moments are kept pre-divided by (1 - beta):  M = m / (1 - beta1), U = v / (1 - beta2), so that
+//       M <- beta1 M + g   (one fma),   U <- beta2 U + g^2   (one mul, one fma);
+//     mhat = M k1, vhat = U k2 with k1 = (1 - beta1) / (1 - beta1^it), k2 likewise            linear.py:158-161
+//   * sqrt(vhat): MUFU seed y ~ 1 / sqrt(x) (2^-22), s0 = x y, then two Heron steps s += (x - s^2) (y / 2) -- each two
+//     fmas, y / 2 by an exponent decrement: error 1.5 e^2 then 1.5 e^3, i.e. below one ulp
+//   * 1 / (s + 1e-8): MUFU seed + one Newton step, then the quotient is corrected by its own residual
+//   * 2 w by an exponent increment (w = +-0 stays), sign(w) constants by integer ops (signed_const)
 template <int N>
-__device__ __forceinline__ void adam_step(double* __restrict__ w, const double* __restrict__ m,
-                                          const double* __restrict__ v, double c1, double c2, double lr) {
-    double x[N], gq[N], hq[N], dn[N], r[N];
+__device__ __forceinline__ void adam_entries(double* __restrict__ w, const double* __restrict__ go, double* __restrict__ M,
+                                             double* __restrict__ U, double beta1, double beta2, double k1, double k2,
+                                             double lr) {
+    double x[N], y[N], hy[N], sq[N], dn[N], z[N];
 #pragma unroll
     for (int q = 0; q < N; ++q) {
-        x[q] = v[q] * c2;
-        double y;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x[q]));
-        if (__double2hiint(x[q]) < 0x00200000) y = 0.0;       // vhat == 0 (or denormal): sqrt -> 0, not NaN
-        gq[q] = x[q] * y;
-        hq[q] = 0.5 * y;
+        M[q] = fma(M[q], beta1, go[q]);
+        U[q] = fma(U[q], beta2, go[q] * go[q]);
+        x[q] = U[q] * k2;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[q]) : "d"(x[q]));
+        const bool tiny = __double2hiint(x[q]) < 0x00200000;                 // vhat == 0 (or denormal): sqrt -> 0, not NaN
+        hy[q] = tiny ? 0.0 : __hiloint2double(__double2hiint(y[q]) - 0x00100000, __double2loint(y[q]));
+        if (tiny) y[q] = 0.0;
+        sq[q] = x[q] * y[q];
     }
 #pragma unroll
-    for (int q = 0; q < N; ++q) {
-        const double e = fma(-gq[q], hq[q], 0.5);
-        gq[q] = fma(gq[q], e, gq[q]);
-        hq[q] = fma(hq[q], e, hq[q]);
-    }
+    for (int q = 0; q < N; ++q) sq[q] = fma(fma(-sq[q], sq[q], x[q]), hy[q], sq[q]);
 #pragma unroll
     for (int q = 0; q < N; ++q) {
-        const double e = fma(-gq[q], hq[q], 0.5);
-        gq[q] = fma(gq[q], e, gq[q]);
-        dn[q] = gq[q] + 1e-8;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[q]) : "d"(dn[q]));
+        sq[q] = fma(fma(-sq[q], sq[q], x[q]), hy[q], sq[q]);
+        dn[q] = sq[q] + 1e-8;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(z[q]) : "d"(dn[q]));
     }
 #pragma unroll
-    for (int q = 0; q < N; ++q) {
-        const double e = fma(-dn[q], r[q], 1.0);
-        r[q] = fma(r[q], e, r[q]);
-    }
+    for (int q = 0; q < N; ++q) z[q] = fma(z[q], fma(-dn[q], z[q], 1.0), z[q]);
 #pragma unroll
     for (int q = 0; q < N; ++q) {
-        const double mh = m[q] * c1;
-        const double qv = mh * r[q];
-        const double rem = fma(-qv, dn[q], mh);
-        const double dir = fma(rem, r[q], qv);
+        const double mh = M[q] * k1;
+        const double qv = mh * z[q];
+        const double dir = fma(fma(-qv, dn[q], mh), z[q], qv);
         w[q] = fma(-lr, dir, w[q]);
     }
 }
+
+// 2 w without the FP64 pipe (w = +-0 and denormals are returned unchanged; |w| never gets near either overflow)
+__device__ __forceinline__ double twice(double w) {
+    const int hi = __double2hiint(w);
+    return __hiloint2double((hi & 0x7ff00000) ? hi + 0x00100000 : hi, __double2loint(w));
+}
+
+// a + 1e-16 < 0 for a finite a, as an integer comparison of the bit patterns (a < -1e-16 exactly: the sum is exact
+// near cancellation); keeps the sign test of linear.py:226-230 off the FP64 pipe
+__device__ __forceinline__ bool below_minus_1e16(double a) {
+    return (unsigned long long)__double_as_longlong(a) > 0xBC9CD2B297D889BCull;      // bits of -1e-16
+}
+
+#ifdef DAGMA_SWEEP_TRACE
+// debug build only: phase stamps of iteration 51 of CTA 0 -> rows 16.. of g_sweep_trace
+// [0] iteration start, [1] M built, [2] sweep done, [3] score GEMM done, [4] feasibility known, [5] Adam pass done
+#define PHASE_STAMP(slot) do { if (blockIdx.x == 0 && tid == 0 && it == 50) g_sweep_trace[16 * 8 + (slot)] = clock64(); } while (0)
+#define PHASE_STAMP_END(slot) do { if (blockIdx.x == 0 && tid == 0 && it == 51) g_sweep_trace[16 * 8 + (slot)] = clock64(); } while (0)
+#else
+#define PHASE_STAMP(slot) do { } while (0)
+#define PHASE_STAMP_END(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_small_fit_args P) {
     using S = DmmaSmem;
@@ -80,6 +102,12 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
     double* red = smem + S::red;
     __shared__ unsigned s_prob;
     __shared__ uint32_t s_tmem;
+    // Adam bias correction, kept by ONE lane instead of by every thread: the running powers beta^it (double-double) and
+    // the reciprocals c = 1 / (1 - beta^it) of the iteration that is about to run, slot it & 1 (the other slot still
+    // holds the factors of the last executed step, which back-tracking needs to rebuild its direction)
+    __shared__ double s_pow[4];          // committed p1.hi, p1.lo, p2.hi, p2.lo  (= beta^it)
+    __shared__ double s_pow_next[4];     // beta^(it + 1), computed ahead
+    __shared__ double s_bias[2][2];      // [slot][c1, c2]
 
     const int tid = threadIdx.x;
     const DmmaPos ps(tid);
@@ -145,7 +173,6 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
         double last_obj = 0, last_score = 0, last_h = 0;
         int iters_max = 0, it = 0, retries = 0, backtracks = 0;
         bool in_backtrack = false;
-        DD p1{1.0, 0.0}, p2{1.0, 0.0};
 
         auto start_attempt = [&]() {
             it = 0;
@@ -153,8 +180,7 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
             obj_prev = 1e16;
             in_backtrack = false;
             backtracks = 0;
-            p1 = DD{1.0, 0.0};
-            p2 = DD{1.0, 0.0};
+            if (tid == DM_NT - 32) { s_pow[0] = 1.0; s_pow[1] = 0.0; s_pow[2] = 1.0; s_pow[3] = 0.0; }
             const double z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int q = 0; q < 4; ++q) tmem_st8(tm + 16 * q, z);
@@ -198,7 +224,7 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
         };
         // Ws += scale * dir(m, v, it): the previous Adam direction rebuilt from the moments
         auto apply_dir = [&](double scale) {
-            const double c1 = 1.0 / p1.one_minus(), c2 = 1.0 / p2.one_minus();
+            const double c1 = s_bias[it & 1][0] * (1.0 - P.beta1), c2 = s_bias[it & 1][1] * (1.0 - P.beta2);
 #pragma unroll
             for (int ti = 0; ti < 2; ++ti) {
                 TmemLoad8 lm, lv;
@@ -225,6 +251,7 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
         for (;;) {
             // ================= build M^T and run the fused sweep =================
             const double s_use = final_phase ? 1.0 : s_cur;
+            PHASE_STAMP(0);
 #pragma unroll
             for (int ti = 0; ti < 2; ++ti) {
                 const int r = ps.row(ti);
@@ -240,7 +267,20 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
 #ifdef DAGMA_SWEEP_TRACE
             sy.trace = (it == 50) ? 0 : -1;          // trace the sweep of iteration 51
 #endif
+            PHASE_STAMP(1);
+            // bias factors of iteration it + 1, by lane 0 of the last warp: at the start of the sweep that warp only
+            // waits for the first pivot block, so this costs nothing on the critical path; the sweep's barriers make
+            // the values visible to everybody before the Adam pass reads them
+            if (tid == DM_NT - 32 && !final_phase) {
+                DD q1{s_pow[0], s_pow[1]}, q2{s_pow[2], s_pow[3]};
+                q1.mul(P.beta1);
+                q2.mul(P.beta2);
+                s_pow_next[0] = q1.hi; s_pow_next[1] = q1.lo; s_pow_next[2] = q2.hi; s_pow_next[3] = q2.lo;
+                s_bias[(it + 1) & 1][0] = fast_rcp(q1.one_minus());
+                s_bias[(it + 1) & 1][1] = fast_rcp(q2.one_minus());
+            }
             dmma_sweep(a, ps, smem, d, sy);
+            PHASE_STAMP(2);
 #pragma unroll
             for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
@@ -250,6 +290,7 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                     g[ti][tj][1] = -nc.y;
                 }
             dmma_score_gemm(g, ps, smem, d);
+            PHASE_STAMP(3);
             // now: a = M^{-T},  g = cov - cov W = cov (I - W),  pinfo[0..np) = pivots
 
             // ================= objective pieces (checkpoint / final) =================
@@ -306,8 +347,9 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                 for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
                     for (int tj = 0; tj < 4; ++tj)
-                        bad |= (a[ti][tj][0] + 1e-16 < 0.0) | (a[ti][tj][1] + 1e-16 < 0.0);
+                        bad |= below_minus_1e16(a[ti][tj][0]) | below_minus_1e16(a[ti][tj][1]);
                 bad = __syncthreads_or(bad);
+                PHASE_STAMP(4);
                 if (bad) {
                     if (it == 0 || s_cur <= 0.9) {            // linear.py:231-233
                         if (P.retry_on_fail) {
@@ -350,11 +392,11 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
             {
                 // ================= gradient, Adam, step (iteration it + 1) =================
                 ++it;
-                p1.mul(P.beta1);
-                p2.mul(P.beta2);
-                const double c1 = fast_rcp(p1.one_minus()), c2 = fast_rcp(p2.one_minus());
-                const double ob1 = 1.0 - P.beta1, ob2 = 1.0 - P.beta2;
-                const double l1c = mu * lambda1, incc = -2.0 * mu * lambda1;
+                const double k1 = s_bias[it & 1][0] * (1.0 - P.beta1), k2 = s_bias[it & 1][1] * (1.0 - P.beta2);
+                if (tid == DM_NT - 32) {                       // commit beta^it (nobody else reads s_pow)
+                    s_pow[0] = s_pow_next[0]; s_pow[1] = s_pow_next[1]; s_pow[2] = s_pow_next[2]; s_pow[3] = s_pow_next[3];
+                }
+                const double l1c = mu * lambda1, incc = -2.0 * mu * lambda1, nmu = -mu;
 #pragma unroll
                 for (int ti = 0; ti < 2; ++ti) {
                     TmemLoad8 lm, lv;
@@ -371,21 +413,21 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                     // Gobj = -mu cov (I - W) + mu l1 sign(W) + 2 W o (M^{-T} + 1e-16)   linear.py:248
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        go[q] = fma(-mu, g[ti][q >> 1][q & 1], signed_const(w[q], l1c));
-                        go[q] = fma(w[q] + w[q], a[ti][q >> 1][q & 1] + 1e-16, go[q]);
+                        go[q] = fma(nmu, g[ti][q >> 1][q & 1], signed_const(w[q], l1c));
+                        go[q] = fma(twice(w[q]), a[ti][q >> 1][q & 1] + 1e-16, go[q]);
                         if (incbits >> (ti * 8 + q) & 1u) go[q] += signed_const(w[q], incc);
                     }
                     lm.finish();
                     lv.finish();
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        mn[q] = fma(lm.get(q), P.beta1, ob1 * go[q]);
-                        vn[q] = fma(lv.get(q), P.beta2, ob2 * (go[q] * go[q]));
+                        mn[q] = lm.get(q);
+                        vn[q] = lv.get(q);
                     }
+                    adam_entries<4>(w, go, mn, vn, P.beta1, P.beta2, k1, k2, lr);
+                    adam_entries<4>(w + 4, go + 4, mn + 4, vn + 4, P.beta1, P.beta2, k1, k2, lr);
                     tmem_st8(tm + 32 * ti, mn);
                     tmem_st8(tm + 32 * ti + 16, vn);
-                    adam_step<4>(w, mn, vn, c1, c2, lr);
-                    adam_step<4>(w + 4, mn + 4, vn + 4, c1, c2, lr);
 #pragma unroll
                     for (int tj = 0; tj < 4; ++tj) {
                         double2 t = make_double2(w[2 * tj], w[2 * tj + 1]);
@@ -396,6 +438,7 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                 }
                 tmem_wait_st();
                 __syncthreads();
+                PHASE_STAMP_END(5);
                 continue;
             }
 

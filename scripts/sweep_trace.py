@@ -19,6 +19,9 @@ lib.dagma_debug_sweep_trace.argtypes = [C.c_void_p]
 print("rc", lib.dagma_debug_sweep_trace(buf))
 t = np.array(buf[:], dtype=np.int64).reshape(64, 8)
 print("step: diag[wait_enter->wait_exit | ->tile_dmma | ->inverse | ->publish+arrive]   other[wait | work]   step period (diag exit-to-exit)")
+ph = t[16]
+print(f"phases of iteration 51 (clk): build M {ph[1]-ph[0]} | sweep {ph[2]-ph[1]} | score GEMM {ph[3]-ph[2]} | feasibility "
+      f"{ph[4]-ph[3]} | Adam pass {ph[5]-ph[4]} | whole iteration {ph[5]-ph[0]}")
 for b in range(7):
     r = t[b]
     nxt = t[b + 1][1] if b + 1 < 8 else 0

@@ -93,8 +93,8 @@ def test_dmma_masks_match_oracle(d):
         assert m.W_raw[i, j] == 0.0
     assert simulate.edge_set_distance(W, W_ref) == 0
     # the same masks through fit_batch (shared by the batch)
-    Wb = fit_batch(np.stack([X, X]), lambda1=0.03, s=(1.0, 0.9), exclude_edges=exc, include_edges=inc, **kw)
+    Wb = fit_batch(np.stack([X, X]), s=(1.0, 0.9), exclude_edges=exc, include_edges=inc, **kw)
     assert np.array_equal(Wb[0], W) and np.array_equal(Wb[1], W)
     # without masks the answer differs (the masks are not silently ignored)
-    W0 = fit_batch(X[None], lambda1=0.03, s=(1.0, 0.9), **kw)
+    W0 = fit_batch(X[None], s=(1.0, 0.9), **kw)
     assert not np.array_equal(W0[0], W)

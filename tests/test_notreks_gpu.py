@@ -42,5 +42,6 @@ def test_trek_value_grad_noop():
     v, gr = notreks.trek_value_grad(Ws, notreks.PSTRegularizer(I=[(0, 1)], weight=0.1))
     rv, rg, _ = pst_value_grad(Ws, [(0, 1)], seq="exp", agg="mean")
     assert abs(v - rv) <= 1e-12 * abs(rv) and np.abs(gr - rg).max() <= 1e-12 * np.abs(rg).max()
-    with pytest.raises(NotImplementedError):                      # TCC: the reference dispatches to the spectral penalty
-        notreks.trek_value_grad(W, notreks.TCCRegularizer(I=[(0, 1)], weight=0.1))
+    # TCC: dispatched to the spectral penalty as in the reference (parity: tests/test_tcc_spectral_gpu.py)
+    v, gr = notreks.trek_value_grad(W, notreks.TCCRegularizer(I=np.array([(0, 1)]), weight=0.1))
+    assert np.isfinite(v) and gr.shape == W.shape

@@ -35,8 +35,8 @@ def test_pst_inv_value_grad(golden, agg):
     v3, g3 = trek_value_grad(g["pst_W"], PSTRegularizer(I=np.zeros((0, 2), dtype=np.int64), seq="inv", weight=1.0))
     assert v3 == 0.0 and not g3.any()
     from midagma_b200.notreks import TCCRegularizer
-    with pytest.raises(NotImplementedError):                          # TCC dispatches to the spectral penalty (geev)
-        trek_value_grad(g["pst_W"], TCCRegularizer(I=g["pairs"], weight=1.0))
+    v4, g4 = trek_value_grad(g["pst_W"], TCCRegularizer(I=g["pairs"], weight=1.0, mode="log"))   # spectral TCC, value only
+    assert np.isfinite(v4) and not g4.any()
 
 
 @pytest.mark.parametrize("case", ["plain", "pst_opt", "pst_log", "pst_opt_sum"])
