@@ -82,6 +82,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
                  ::"r"(addr), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ bool mbar_test(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// Work a warp can do while it waits for the step barrier of the sweep (see dmma_block_step): `more()` -- is there a
+// unit left, `unit()` -- do one.  The default has none.
+struct NoFill {
+    __device__ __forceinline__ bool more() const { return false; }
+    __device__ __forceinline__ void unit() {}
+};
+
 // The diagonal warp of block `b` inverts the pivot block P = A[K,K] = its accumulator tile (TI, TJ):
 // lane (qr, qc) holds P[qr][2qc], P[qr][2qc+1].  Two phases of four pivots, each a FRACTION-FREE
 // Gauss-Jordan in natural pivot order over all 8 rows: rows i != k become p_k row_i - x_ik row_k, so no
@@ -122,7 +136,11 @@ __device__ __forceinline__ void stage_pivot_block(const double (&a)[2][4][2], co
             const double Dp = D * p;
             D = (kk >= ie) ? Dp : D;
             E *= p;
-            // on the chain: one multiply, one fma, one select per element
+            // on the chain: one multiply, one fma, one select per element.  (A variant with five instead of seven
+            // FP64 instructions per pivot -- the pivot-column lanes fed through the same fma by operand selects, the row
+            // scales rebuilt after the phase -- was measured 16 % SLOWER, 1.55 k against 1.34 k clk per block
+            // inversion inside the sweep: the selects and the late row scale sit on the dependency chain, and the chain
+            // is bound by latency, not by issue slots.)
             const double t0 = fma(-c, r0, p * x0), t1 = fma(-c, r1, p * x1);
             x0 = (ik || j0k) ? alt0 : t0;
             x1 = (ik || j1k) ? alt1 : t1;
@@ -191,6 +209,10 @@ __device__ long long g_sweep_trace[64 * 8];
 #define SWEEP_STAMP(slot, cond) do { } while (0)
 #endif
 
+#ifndef DAGMA_SWEEP_JIT_ROWS
+#define DAGMA_SWEEP_JIT_ROWS 0       // 1: pivot-row fragments loaded tile by tile inside the block step
+#endif
+
 #ifndef DAGMA_STAGE_INTERLEAVE
 #define DAGMA_STAGE_INTERLEAVE 1     // 1: the diagonal warp issues its publish-critical DMMAs inside the pivot-block chain
 #endif
@@ -212,9 +234,9 @@ struct SweepSync {        // per-thread view of the step barrier
 // CS = Cpub (-Q) for 8 rows is ONE accumulator tile: the B fragments carry -Q[:, n/2] in the even and
 // -Q[:, 4 + n/2] in the odd columns n, so that c0 / c1 of lane (qr, qc) are CS[qr][qc] / CS[qr][4 + qc]
 // = exactly its A fragments for the two k-slabs of the rank-8 update.
-template <int B>
+template <int B, class Fill>
 __device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], const DmmaPos& ps, double* sm, int nb,
-                                                SweepSync& sy) {
+                                                SweepSync& sy, Fill& fill) {
     constexpr int CUR = B & 1;
     constexpr int BN = (B + 1) & 7;                                   // next block
     constexpr int TIN = BN & 1, TJN = BN & 3;
@@ -229,27 +251,45 @@ __device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], const Dmma
 #endif
     SWEEP_STAMP(0, trc_diag);
     SWEEP_STAMP(5, trc_other);
+    // Every warp but the one that is about to run the pivot chain of this step spends the wait on independent work
+    // (the fit kernel: k-blocks of the score GEMM) -- one unit at a time, polling the barrier in between, so the step
+    // starts at most one unit late for warps that are off the critical path and not at all late for the chain.
+    if (!diag_next)
+        while (fill.more() && !mbar_test(sy.bar, sy.phase)) fill.unit();
     mbar_wait(sy.bar, sy.phase);
     sy.phase ^= 1u;
     SWEEP_STAMP(1, trc_diag);
     SWEEP_STAMP(6, trc_other);
-    double bq[2], ac[2][2], br[2][4], acs[2][2];
+    double bq[2], ac[2][2], acs[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) bq[kk] = qb[32 * kk + ps.lane];
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) ac[ti][kk] = cb[kk * (DM_DP * 4) + ps.row(ti) * 4 + ps.qc];
+#if DAGMA_SWEEP_JIT_ROWS
+    // the pivot-row fragments are fetched tile by tile (two 8-byte loads in front of the two DMMAs that use them)
+    // instead of all eight up front: 12 registers fewer are live across the step -- room for the accumulators of
+    // the filler work (the score GEMM of the fit kernel)
+    const double* rbl = rb + ps.qc * DM_LD + 32 * ps.wc + ps.qr;
+    auto upd = [&](int ti, int tj) {
+        const double b0 = rbl[8 * tj], b1 = rbl[4 * DM_LD + 8 * tj];
+        dmma(a[ti][tj][0], a[ti][tj][1], acs[ti][0], b0);
+        dmma(a[ti][tj][0], a[ti][tj][1], acs[ti][1], b1);
+    };
+#else
+    double br[2][4];
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
         for (int tj = 0; tj < 4; ++tj) br[kk][tj] = rb[(4 * kk + ps.qc) * DM_LD + 32 * ps.wc + 8 * tj + ps.qr];
-    auto cs1 = [&](int ti) { acs[ti][0] = 0.0; acs[ti][1] = 0.0; dmma(acs[ti][0], acs[ti][1], ac[ti][0], bq[0]); };
-    auto cs2 = [&](int ti) { dmma(acs[ti][0], acs[ti][1], ac[ti][1], bq[1]); };
     auto upd = [&](int ti, int tj) {
         dmma(a[ti][tj][0], a[ti][tj][1], acs[ti][0], br[0][tj]);
         dmma(a[ti][tj][0], a[ti][tj][1], acs[ti][1], br[1][tj]);
     };
+#endif
+    auto cs1 = [&](int ti) { dmma(acs[ti][0], acs[ti][1], ac[ti][0], bq[0]); };
+    auto cs2 = [&](int ti) { dmma(acs[ti][0], acs[ti][1], ac[ti][1], bq[1]); };
     // ---- the serial chain first: CS of the next pivot rows, the next pivot block itself
     cs1(TIN);
     cs2(TIN);
@@ -297,21 +337,27 @@ __device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], const Dmma
 // a := a^{-1} on the leading 8*ceil(d/8) block (padding inside the last pivot block must
 // carry a unit diagonal).  pinfo[k] = fraction-free pivots (see stage_pivot_block), k < 8*ceil(d/8).
 // All warps must have passed a __syncthreads since the last use of the line buffers.
-__device__ __forceinline__ void dmma_sweep(double (&a)[2][4][2], const DmmaPos& ps, double* sm, int d, SweepSync& sy) {
+template <class Fill>
+__device__ __forceinline__ void dmma_sweep(double (&a)[2][4][2], const DmmaPos& ps, double* sm, int d, SweepSync& sy,
+                                           Fill& fill) {
     const int nb = (d + DM_PB - 1) / DM_PB;
     if (ps.wr == 0 && ps.wc == 0) stage_pivot_block<0, 0>(a, ps, sm, 0, 0, [](int) {});
     publish_block<0>(a, ps, sm);
     __syncwarp();
     if (ps.lane == 0) mbar_arrive(sy.bar);
-    dmma_block_step<0>(a, ps, sm, nb, sy);
-    if (nb > 1) dmma_block_step<1>(a, ps, sm, nb, sy);
-    if (nb > 2) dmma_block_step<2>(a, ps, sm, nb, sy);
-    if (nb > 3) dmma_block_step<3>(a, ps, sm, nb, sy);
-    if (nb > 4) dmma_block_step<4>(a, ps, sm, nb, sy);
-    if (nb > 5) dmma_block_step<5>(a, ps, sm, nb, sy);
-    if (nb > 6) dmma_block_step<6>(a, ps, sm, nb, sy);
-    if (nb > 7) dmma_block_step<7>(a, ps, sm, nb, sy);
+    dmma_block_step<0>(a, ps, sm, nb, sy, fill);
+    if (nb > 1) dmma_block_step<1>(a, ps, sm, nb, sy, fill);
+    if (nb > 2) dmma_block_step<2>(a, ps, sm, nb, sy, fill);
+    if (nb > 3) dmma_block_step<3>(a, ps, sm, nb, sy, fill);
+    if (nb > 4) dmma_block_step<4>(a, ps, sm, nb, sy, fill);
+    if (nb > 5) dmma_block_step<5>(a, ps, sm, nb, sy, fill);
+    if (nb > 6) dmma_block_step<6>(a, ps, sm, nb, sy, fill);
+    if (nb > 7) dmma_block_step<7>(a, ps, sm, nb, sy, fill);
     __syncthreads();
+}
+__device__ __forceinline__ void dmma_sweep(double (&a)[2][4][2], const DmmaPos& ps, double* sm, int d, SweepSync& sy) {
+    NoFill none;
+    dmma_sweep(a, ps, sm, d, sy, none);
 }
 
 // g += (-cov) W over the k range 4*ceil(d/4): 16 independent DMMA per k-block and warp, no serial chain --
@@ -322,6 +368,17 @@ __device__ __forceinline__ void dmma_score_gemm(double (&g)[2][4][2], const Dmma
 #pragma unroll 1
     for (int kb = 0; kb < nk; ++kb) gemm_chunk(g, ps, sm, kb);
 }
+
+// The score GEMM as filler work of the sweep: one k-block (8 DMMA) per unit; what the waits did not absorb is finished
+// after the sweep.
+struct ScoreFill {
+    double (&g)[2][4][2];
+    const DmmaPos& ps;
+    const double* sm;
+    int kb, nk;
+    __device__ __forceinline__ bool more() const { return kb < nk; }
+    __device__ __forceinline__ void unit() { gemm_chunk(g, ps, sm, kb++); }
+};
 
 // ---------------------------------------------------------------- tensor memory (TMEM) scratch
 // Thread-private spill space: warp w owns TMEM lanes 32(w%4)..+31 (hardware rule for

@@ -11,8 +11,18 @@
 //   * Adam moments live in tensor memory (tcgen05.ld/st), W and -cov in shared memory,
 //     M^{-T} and cov (I - W) in registers.
 #include "common.cuh"
+#ifndef DAGMA_FIT_GEMM_IN_SWEEP
+#define DAGMA_FIT_GEMM_IN_SWEEP 1     // 1: the score GEMM fills the waits of the sweep; 0: a separate phase after it
+#endif
+#ifndef DAGMA_SWEEP_JIT_ROWS
+#define DAGMA_SWEEP_JIT_ROWS DAGMA_FIT_GEMM_IN_SWEEP   // the filler's accumulators need the registers of the row fragments
+#endif
 #include "small_dmma.cuh"
 #include "small_fit_internal.h"
+
+#ifndef DAGMA_FIT_GEMM_IN_SWEEP
+#define DAGMA_FIT_GEMM_IN_SWEEP 1     // 1: the score GEMM fills the waits of the sweep; 0: a separate phase after it
+#endif
 #include "../../include/dagma_b200.h"
 
 namespace dagma {
@@ -279,17 +289,31 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                 s_bias[(it + 1) & 1][0] = fast_rcp(q1.one_minus());
                 s_bias[(it + 1) & 1][1] = fast_rcp(q2.one_minus());
             }
+            auto init_g = [&]() {
+#pragma unroll
+                for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                    for (int tj = 0; tj < 4; ++tj) {
+                        const double2 nc = *reinterpret_cast<const double2*>(ncov + ps.row(ti) * LD + ps.col(tj));
+                        g[ti][tj][0] = __hiloint2double(__double2hiint(nc.x) ^ (int)0x80000000, __double2loint(nc.x));   // -nc: sign
+                        g[ti][tj][1] = __hiloint2double(__double2hiint(nc.y) ^ (int)0x80000000, __double2loint(nc.y));   // bit, not FP64
+                    }
+            };
+#if DAGMA_FIT_GEMM_IN_SWEEP
+            // g = cov - cov W rides inside the sweep: the warps that wait for the pivot chain of a block step work on
+            // k-blocks of the score GEMM instead (it needs only W and cov), so the GEMM is off the critical path
+            init_g();
+            ScoreFill fill{g, ps, smem, 0, (d + 3) >> 2};
+            dmma_sweep(a, ps, smem, d, sy, fill);
+            PHASE_STAMP(2);
+#pragma unroll 1
+            while (fill.more()) fill.unit();
+#else
             dmma_sweep(a, ps, smem, d, sy);
             PHASE_STAMP(2);
-#pragma unroll
-            for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-                for (int tj = 0; tj < 4; ++tj) {
-                    const double2 nc = *reinterpret_cast<const double2*>(ncov + ps.row(ti) * LD + ps.col(tj));
-                    g[ti][tj][0] = -nc.x;
-                    g[ti][tj][1] = -nc.y;
-                }
+            init_g();
             dmma_score_gemm(g, ps, smem, d);
+#endif
             PHASE_STAMP(3);
             // now: a = M^{-T},  g = cov - cov W = cov (I - W),  pinfo[0..np) = pivots
 
@@ -415,7 +439,11 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                     for (int q = 0; q < 8; ++q) {
                         go[q] = fma(nmu, g[ti][q >> 1][q & 1], signed_const(w[q], l1c));
                         go[q] = fma(twice(w[q]), a[ti][q >> 1][q & 1] + 1e-16, go[q]);
-                        if (incbits >> (ti * 8 + q) & 1u) go[q] += signed_const(w[q], incc);
+                    }
+                    if (P.mask_inc_dev) {            // uniform branch: no predicated FP64 issue slots without include edges
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (incbits >> (ti * 8 + q) & 1u) go[q] += signed_const(w[q], incc);
                     }
                     lm.finish();
                     lv.finish();

@@ -120,8 +120,12 @@ class OracleLinear:
                 self.events.append(("lr_halved", it, lr))
             if self.loss_type == "l2":
                 G_score = -mu * self.cov @ (self.Id - W)    # :244
-            else:
+            elif getattr(self, "logistic_route", "reference") == "reference":
                 G_score = mu / self.n * self.X.T @ expit(self.X @ W) - mu * self.cov   # :246
+            else:
+                # round-off-equivalent route (sum first, scale afterwards) -- NOT what the reference does; used by
+                # the tests to measure the reference's own round-off envelope
+                G_score = (self.X.T @ expit(self.X @ W)) * (mu / self.n) - mu * self.cov
             sgn = np.sign(W)
             Gobj = G_score + mu * self.lambda1 * sgn + 2 * W * M.T + mask_inc * sgn   # :248 (Q1,Q5)
             grad = self.adam_update(Gobj, it, b1, b2)       # :272
