@@ -28,6 +28,7 @@ typedef void* dagma_stream_t;            /* a cudaStream_t (0 = default stream) 
 #define DAGMA_SMALL_MAX_D   64           /* fused on-chip fit path: d <= 64      */
 #define DAGMA_ONCHIP_INV_MAX_D 128       /* on-chip logdet+inverse: d <= 128     */
 #define DAGMA_MAX_STAGES    16
+#define DAGMA_DIAG_COLS     11           /* columns of a checkpoint telemetry row (ckpt_diag_dev)        */
 
 /* per-problem status bits written by the fit / minimize kernels */
 #define DAGMA_ST_OK            0
@@ -93,11 +94,20 @@ typedef struct dagma_small_fit_args {
     double*  ckpt_log_dev;        /* [batch][cap][6]: stage, iter, obj, score, h, lr       */
     int32_t* ckpt_count_dev;      /* [batch]                                               */
     uint32_t* work_counter_dev;   /* one zero-initialised uint32 (work queue head)         */
+    /* optional telemetry of the checkpoint iterations (the fork's `minimize.checkpoint` event,
+       src/dagma/linear.py:262-273, 307-324), one row per ckpt_log row, or NULL:
+       [batch][cap][DAGMA_DIAG_COLS] = ||Gobj||, ||G_score||, ||G_h||, ||G_l1||, ||G_inc||, ||Adam direction||,
+       ||W||, sum|W|, max|W|, min nonzero |W| (after the step), seconds since the minimize call started   */
+    double*  ckpt_diag_dev;
 } dagma_small_fit_args;
 
 int dagma_linear_fit_small_f64(dagma_stream_t stream, const dagma_small_fit_args* args);
 /* launch geometry chosen for (d): CTAs, threads, dynamic shared memory bytes */
 int dagma_linear_fit_small_geometry(int d, int batch, int* ctas, int* threads, size_t* smem_bytes);
+
+/* max number of CTAs of the last 32 < d <= DAGMA_SMALL_MAX_D fit launch that shared one SM, counted by the kernel
+ * itself (the geometry above assumes 2 for that path); synchronises with the device                          */
+int dagma_fit_dmma_residency(int* out_host);
 
 /* ---- host-buffer convenience: the call a reference user makes --------------------
  * Replaces: DagmaLinear.fit for a batch of problems given host covariances; does

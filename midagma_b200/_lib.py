@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("DAGMA_B200_LIB") or os.path.join(_HERE, "lib", "libda
 MAX_STAGES = 16
 SMALL_MAX_D = 64
 ONCHIP_INV_MAX_D = 128
+DIAG_COLS = 11
 
 ST_OK, ST_OUT_OF_DOMAIN, ST_LR_UNDERFLOW, ST_RETRY_LIMIT = 0, 1, 2, 4
 
@@ -30,6 +31,7 @@ class SmallFitArgs(C.Structure):
         ("mask_exc", C.c_void_p), ("mask_inc", C.c_void_p),
         ("status", C.c_void_p), ("stage_stats", C.c_void_p), ("final", C.c_void_p),
         ("ckpt_log", C.c_void_p), ("ckpt_count", C.c_void_p), ("work_counter", C.c_void_p),
+        ("ckpt_diag", C.c_void_p),
     ]
 
 
@@ -44,6 +46,7 @@ EXPORTS = {
     "dagma_linear_fit_small_f64": (C.c_int, [C.c_void_p, C.POINTER(SmallFitArgs)]),
     "dagma_linear_fit_small_geometry": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                                   C.POINTER(C.c_size_t)]),
+    "dagma_fit_dmma_residency": (C.c_int, [C.POINTER(C.c_int)]),
     "dagma_linear_fit_small_host_f64": (C.c_int, [C.c_void_p, C.POINTER(SmallFitArgs)]),
     "dagma_gemm_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),

@@ -56,6 +56,10 @@ class PerronSolver:
         """The Perron pair a dense eigensolver returns, by power steps on A + shift I; returns the iterations used."""
         self._run(A, square, 0.0, 8, eps, 0)
         rho0 = abs(float(self.scal[0].item()))
+        if not rho0 > 1e-200:
+            # nilpotent matrix (e.g. the block matrix at W = 0 with an acyclic pair set): rho = 0, the iterates vanish
+            # and every eigenvector choice gives the same (zero) fold-back 2 W o (...) -- nothing to converge to
+            return 8
         shift = 0.25 * rho0                                     # breaks periodicity, keeps most of the spectral gap
         total = 8
         for _ in range(EIG_MAX_CHUNKS):

@@ -52,8 +52,9 @@ extern "C" int dagma_linear_fit_small_host_f64(dagma_stream_t stream_, const dag
     const size_t n_mat = B * dd * sizeof(double);
     const size_t n_stats = B * (size_t)(a.n_stages > 0 ? a.n_stages : 1) * 8 * sizeof(double);
     const size_t n_log = B * (size_t)a.ckpt_log_cap * 6 * sizeof(double);
+    const size_t n_diag = host->ckpt_diag_dev ? B * (size_t)a.ckpt_log_cap * DAGMA_DIAG_COLS * sizeof(double) : 0;
     size_t total = 2 * n_mat + B * sizeof(double) + 2 * dd + B * sizeof(int32_t) + n_stats +
-                   2 * B * sizeof(double) + n_log + B * sizeof(int32_t) + 64 + 16 * 256;
+                   2 * B * sizeof(double) + n_log + n_diag + B * sizeof(int32_t) + 64 + 17 * 256;
     unsigned char* base = nullptr;
     DAGMA_CUDA_OK(cudaMallocAsync((void**)&base, total, stream));
     size_t off = 0;
@@ -67,6 +68,7 @@ extern "C" int dagma_linear_fit_small_host_f64(dagma_stream_t stream_, const dag
     double* stats_d = (double*)take(n_stats);
     double* final_d = (double*)take(2 * B * sizeof(double));
     double* log_d = a.ckpt_log_cap > 0 ? (double*)take(n_log) : nullptr;
+    double* diag_d = n_diag ? (double*)take(n_diag) : nullptr;
     int32_t* cnt_d = (int32_t*)take(B * sizeof(int32_t));
     uint32_t* ctr_d = (uint32_t*)take(64);
     int rc = 0;
@@ -82,13 +84,14 @@ extern "C" int dagma_linear_fit_small_host_f64(dagma_stream_t stream_, const dag
     if (inc_d) H2D(inc_d, host->mask_inc_dev, dd);
     a.cov_dev = cov_d; a.w_dev = w_d; a.lambda1_dev = lam_d; a.mask_exc_dev = exc_d; a.mask_inc_dev = inc_d;
     a.status_dev = status_d; a.stage_stats_dev = stats_d; a.final_dev = host->final_dev ? final_d : nullptr;
-    a.ckpt_log_dev = log_d; a.ckpt_count_dev = cnt_d; a.work_counter_dev = ctr_d;
+    a.ckpt_log_dev = log_d; a.ckpt_count_dev = cnt_d; a.work_counter_dev = ctr_d; a.ckpt_diag_dev = diag_d;
     if (!rc) rc = dagma_linear_fit_small_f64(stream, &a);
     D2H(host->w_dev, w_d, n_mat);
     D2H(host->status_dev, status_d, B * sizeof(int32_t));
     D2H(host->stage_stats_dev, stats_d, n_stats);
     D2H(host->final_dev, final_d, 2 * B * sizeof(double));
     if (log_d) D2H(host->ckpt_log_dev, log_d, n_log);
+    if (diag_d) D2H(host->ckpt_diag_dev, diag_d, n_diag);
     D2H(host->ckpt_count_dev, cnt_d, B * sizeof(int32_t));
 #undef H2D
 #undef D2H

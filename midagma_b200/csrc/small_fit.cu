@@ -108,8 +108,10 @@ __global__ void __launch_bounds__(C::NT, 1) fit_small_kernel(const dagma_small_f
         bool in_backtrack = false;
         DD p1{1.0, 0.0}, p2{1.0, 0.0};
 
+        unsigned long long t_attempt = 0;        // %globaltimer at the start of the minimize call (telemetry)
         auto start_attempt = [&]() {
             it = 0;
+            t_attempt = global_ns();
             lr = lr_adam;
             obj_prev = 1e16;
             in_backtrack = false;
@@ -297,6 +299,8 @@ __global__ void __launch_bounds__(C::NT, 1) fit_small_kernel(const dagma_small_f
                 const double c1 = 1.0 / p1.one_minus(), c2 = 1.0 / p2.one_minus();
                 const double ob1 = 1.0 - P.beta1, ob2 = 1.0 - P.beta2;
                 const double l1c = mu * lambda1, incc = -2.0 * mu * lambda1;
+                const bool diag_now = P.ckpt_diag_dev != nullptr && (it % P.checkpoint == 0 || it == iters_max);
+                FitDiag dg;
                 // transpose M^{-1} through shared memory: aT[i][j] = Minv[col][row]
 #pragma unroll
                 for (int i = 0; i < RM; ++i)
@@ -322,10 +326,19 @@ __global__ void __launch_bounds__(C::NT, 1) fit_small_kernel(const dagma_small_f
                         double wn = w - lr * dir;
                         if (excbits >> (i * RN + j) & 1u) wn = 0.0;
                         wrow[j] = wn;
+                        if (diag_now) {
+                            dg.grad(go, -mu * g[i][j], 2.0 * w * (minvT + 1e-16), w != 0.0,
+                                    (incbits >> (i * RN + j) & 1u) != 0u);
+                            dg.step(dir, wn);
+                        }
                     }
                     store_rowfrag<C>(wrow, wp, tx);
                 }
                 __syncthreads();
+                if (diag_now)
+                    dg.finish<NT>(red, tid, l1c, incc, 1e-9 * (double)(global_ns() - t_attempt),
+                                  n_ckpt < P.ckpt_log_cap
+                                      ? P.ckpt_diag_dev + ((size_t)b * P.ckpt_log_cap + n_ckpt) * DAGMA_DIAG_COLS : nullptr);
                 continue;
             }
 

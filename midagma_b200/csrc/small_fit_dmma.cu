@@ -102,6 +102,16 @@ __device__ __forceinline__ bool below_minus_1e16(double a) {
 #define PHASE_STAMP_END(slot) do { } while (0)
 #endif
 
+// Residency probe: how many CTAs of the fit kernel are on one SM at the same time (max over SMs, over the last launch).
+// The launch geometry assumes two (registers, shared memory and tensor memory are sized for exactly that), the occupancy
+// API of driver 580 answers 1 for this kernel, so the kernel counts for itself and dagma_fit_dmma_residency() reports it
+// (tests/test_dmma_cold_gpu.py asserts 2).  Two atomics per CTA lifetime.
+__device__ int g_fit_resident[512];
+__device__ int g_fit_max_resident;
+
+// DIAG: the instantiation that also writes the telemetry rows (ckpt_diag_dev); the plain one carries none of that code,
+// so switching logging on costs the logged run a few registers and the unlogged run nothing.
+template <bool DIAG>
 __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_small_fit_args P) {
     using S = DmmaSmem;
     constexpr int NT = DM_NT, LD = DM_LD;
@@ -123,6 +133,11 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
     const DmmaPos ps(tid);
     const int d = P.d;
     const int np = 4 * ((d + 3) >> 2);          // pivots swept (d rounded up to the block size)
+    unsigned my_sm = 0;
+    if (tid == 0) {
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(my_sm));
+        atomicMax(&g_fit_max_resident, atomicAdd(&g_fit_resident[my_sm & 511u], 1) + 1);
+    }
     const size_t dd = (size_t)d * d;
 
     // ---- step barrier of the sweep: one arrival per warp
@@ -184,8 +199,10 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
         int iters_max = 0, it = 0, retries = 0, backtracks = 0;
         bool in_backtrack = false;
 
+        unsigned long long t_attempt = 0;        // %globaltimer at the start of the minimize call (telemetry)
         auto start_attempt = [&]() {
             it = 0;
+            t_attempt = global_ns();
             lr = lr_adam;
             obj_prev = 1e16;
             in_backtrack = false;
@@ -421,6 +438,62 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                     s_pow[0] = s_pow_next[0]; s_pow[1] = s_pow_next[1]; s_pow[2] = s_pow_next[2]; s_pow[3] = s_pow_next[3];
                 }
                 const double l1c = mu * lambda1, incc = -2.0 * mu * lambda1, nmu = -mu;
+                if (DIAG && P.ckpt_diag_dev != nullptr && (it % P.checkpoint == 0 || it == iters_max)) {
+                    // Telemetry row of this checkpoint iteration (cold: once per `checkpoint` iterations): read-only
+                    // passes that repeat the arithmetic of the step on the side, three sums per pass so that the
+                    // accumulators do not add to the register pressure of the hot loop below.
+                    double acc[10];
+#pragma unroll
+                    for (int pass = 0; pass < 4; ++pass) {
+                        double x = 0.0, y = 0.0, z = (pass == 3) ? 1.7976931348623157e308 : 0.0;
+#pragma unroll
+                        for (int ti = 0; ti < 2; ++ti) {             // (static indices: a and g stay in registers)
+                            TmemLoad8 lm, lv;
+                            lm.issue(tm + 32 * ti);
+                            lv.issue(tm + 32 * ti + 16);
+                            lm.finish();
+                            lv.finish();
+                            const double* wp = Ws + ps.row(ti) * LD;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const double w = wp[ps.col(q >> 1) + (q & 1)];
+                                const double gs = nmu * g[ti][q >> 1][q & 1];
+                                const double gh = twice(w) * (a[ti][q >> 1][q & 1] + 1e-16);
+                                const bool inc = (incbits >> (ti * 8 + q) & 1u) != 0u;
+                                const double go = gs + signed_const(w, l1c) + gh + (inc ? signed_const(w, incc) : 0.0);
+                                if (pass == 0) {
+                                    x = fma(go, go, x); y = fma(gs, gs, y); z = fma(gh, gh, z);
+                                } else {
+                                    const double Mn = fma(lm.get(q), P.beta1, go), Un = fma(lv.get(q), P.beta2, go * go);
+                                    const double dir = fast_div(Mn * k1, fast_sqrt_nonneg(Un * k2) + 1e-8);
+                                    const bool exc = (excbits >> (ti * 8 + q) & 1u) != 0u;
+                                    const double aw = fabs(exc ? 0.0 : fma(-lr, dir, w));
+                                    if (pass == 1) {
+                                        x += (w != 0.0) ? 1.0 : 0.0; y += (w != 0.0 && inc) ? 1.0 : 0.0; z = fma(dir, dir, z);
+                                    } else if (pass == 2) {
+                                        x = fma(aw, aw, x); y += aw;
+                                    } else {
+                                        x = fmax(x, aw); if (aw > 0.0) z = fmin(z, aw);
+                                    }
+                                }
+                            }
+                        }
+                        if (pass < 3) {
+                            block_sum3<NT>(x, y, z, red, tid);
+                            acc[3 * pass] = x; acc[3 * pass + 1] = y; acc[3 * pass + 2] = z;
+                        } else {
+                            acc[8] = block_max<NT>(x, red, tid);
+                            acc[9] = block_min<NT>(z, red, tid);
+                        }
+                    }
+                    if (tid == 0 && n_ckpt < P.ckpt_log_cap) {
+                        double* row = P.ckpt_diag_dev + ((size_t)b * P.ckpt_log_cap + n_ckpt) * DAGMA_DIAG_COLS;
+                        row[0] = sqrt(acc[0]); row[1] = sqrt(acc[1]); row[2] = sqrt(acc[2]);
+                        row[3] = fabs(l1c) * sqrt(acc[3]); row[4] = fabs(incc) * sqrt(acc[4]); row[5] = sqrt(acc[5]);
+                        row[6] = sqrt(acc[6]); row[7] = acc[7]; row[8] = acc[8]; row[9] = (acc[8] > 0.0) ? acc[9] : 0.0;
+                        row[10] = 1e-9 * (double)(global_ns() - t_attempt);
+                    }
+                }
 #pragma unroll
                 for (int ti = 0; ti < 2; ++ti) {
                     TmemLoad8 lm, lv;
@@ -494,10 +567,12 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
     tmem_fence_before();
     __syncthreads();
     if (ps.warp == 0) tmem_free(tmem_base);
+    if (tid == 0) atomicSub(&g_fit_resident[my_sm & 511u], 1);
 }
 
 #ifdef DAGMA_SWEEP_TRACE
 }  // namespace dagma
+
 extern "C" int dagma_debug_sweep_trace(long long* out_host) {
     return (int)cudaMemcpyFromSymbol(out_host, dagma::g_sweep_trace, sizeof(long long) * 64 * 8);
 }
@@ -506,8 +581,11 @@ namespace dagma {
 
 int fit_dmma_geometry(int batch, int sms, int* ctas, int* threads, size_t* smem_bytes) {
     constexpr size_t bytes = DmmaSmem::bytes;
-    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_dmma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_dmma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
+    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    DAGMA_CUDA_OK(cudaFuncSetAttribute(fit_small_dmma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
     // Two CTAs per SM by construction: __launch_bounds__(256, 2) caps registers at 128 (2 x 256 x 128
     // = the whole file), 2 x 80.8 KB of shared memory fit the 228 KB carve-out and 2 x 128 TMEM columns
@@ -515,7 +593,7 @@ int fit_dmma_geometry(int batch, int sms, int* ctas, int* threads, size_t* smem_
     // driver 580 although two are resident -- ncu: sm__warps_active 25 % = 16 warps; if only one fitted,
     // the work-queue loop would still be correct, the surplus CTAs just start late.)
     int per_sm = 0;
-    DAGMA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_small_dmma_kernel, DM_NT, bytes));
+    DAGMA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_small_dmma_kernel<false>, DM_NT, bytes));
     if (per_sm < 1) return set_error(-5, "DMMA fit kernel does not fit on an SM");
     per_sm = 2;
     long n = (long)sms * per_sm;
@@ -530,9 +608,23 @@ int launch_fit_dmma(cudaStream_t stream, const dagma_small_fit_args& a, int sms)
     int ctas = 0;
     int rc = fit_dmma_geometry(a.batch, sms, &ctas, nullptr, nullptr);
     if (rc) return rc;
-    fit_small_dmma_kernel<<<ctas, DM_NT, DmmaSmem::bytes, stream>>>(a);
+    void* maxp = nullptr;
+    DAGMA_CUDA_OK(cudaGetSymbolAddress(&maxp, g_fit_max_resident));
+    DAGMA_CUDA_OK(cudaMemsetAsync(maxp, 0, sizeof(int), stream));
+    if (a.ckpt_diag_dev)
+        fit_small_dmma_kernel<true><<<ctas, DM_NT, DmmaSmem::bytes, stream>>>(a);
+    else
+        fit_small_dmma_kernel<false><<<ctas, DM_NT, DmmaSmem::bytes, stream>>>(a);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 }  // namespace dagma
+
+// max number of CTAs of the last 32 < d <= 64 fit launch that shared an SM (synchronises with the device)
+extern "C" int dagma_fit_dmma_residency(int* out_host) {
+    DAGMA_REQUIRE(out_host != nullptr, "null pointer");
+    DAGMA_CUDA_OK(cudaDeviceSynchronize());
+    DAGMA_CUDA_OK(cudaMemcpyFromSymbol(out_host, dagma::g_fit_max_resident, sizeof(int)));
+    return 0;
+}

@@ -324,6 +324,74 @@ __device__ __forceinline__ double block_min(double x, double* red, int tid) {
     return m;
 }
 
+template <int NTHREADS>
+__device__ __forceinline__ double block_max(double x, double* red, int tid) {
+    constexpr int NW = NTHREADS / 32;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, off));
+    const int w = tid >> 5;
+    if ((tid & 31) == 0) red[w] = x;
+    __syncthreads();
+    double m = red[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) m = fmax(m, red[i]);
+    __syncthreads();
+    return m;
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Telemetry of a checkpoint iteration (the fork's `minimize.checkpoint` row, src/dagma/linear.py:262-273, 307-324):
+// per-thread partial sums over the thread's entries, reduced over the CTA by `finish` into one row of
+// DAGMA_DIAG_COLS doubles.  Only the iterations that end a checkpoint interval pay for it (a uniform branch).
+struct FitDiag {
+    double go2 = 0.0, gs2 = 0.0, gh2 = 0.0, nl1 = 0.0, ninc = 0.0, dir2 = 0.0, w2 = 0.0, wabs = 0.0, wmax = 0.0,
+           wmin = 1.7976931348623157e308;
+    // gradient pieces of one entry: total, score part, acyclicity part; w != 0 / included edge for the l1 parts
+    __device__ __forceinline__ void grad(double go, double gs, double gh, bool nonzero, bool inc) {
+        go2 = fma(go, go, go2);
+        gs2 = fma(gs, gs, gs2);
+        gh2 = fma(gh, gh, gh2);
+        nl1 += nonzero ? 1.0 : 0.0;
+        ninc += (nonzero && inc) ? 1.0 : 0.0;
+    }
+    // Adam direction of the entry and the entry of W after the step (and the exclusion mask)
+    __device__ __forceinline__ void step(double dir, double w_new) {
+        dir2 = fma(dir, dir, dir2);
+        w2 = fma(w_new, w_new, w2);
+        const double aw = fabs(w_new);
+        wabs += aw;
+        wmax = fmax(wmax, aw);
+        if (aw > 0.0) wmin = fmin(wmin, aw);
+    }
+    template <int NT>
+    __device__ __forceinline__ void finish(double* red, int tid, double l1c, double incc, double seconds, double* row) {
+        block_sum3<NT>(go2, gs2, gh2, red, tid);
+        block_sum3<NT>(nl1, ninc, dir2, red, tid);
+        double z = 0.0;
+        block_sum3<NT>(w2, wabs, z, red, tid);
+        wmax = block_max<NT>(wmax, red, tid);
+        wmin = block_min<NT>(wmin, red, tid);
+        if (tid == 0 && row) {
+            row[0] = sqrt(go2);
+            row[1] = sqrt(gs2);
+            row[2] = sqrt(gh2);
+            row[3] = fabs(l1c) * sqrt(nl1);
+            row[4] = fabs(incc) * sqrt(ninc);
+            row[5] = sqrt(dir2);
+            row[6] = sqrt(w2);
+            row[7] = wabs;
+            row[8] = wmax;
+            row[9] = (wmax > 0.0) ? wmin : 0.0;
+            row[10] = seconds;
+        }
+    }
+};
+
 struct DD {   // double-double running power beta^k
     double hi, lo;
     __device__ __forceinline__ void mul(double b) {

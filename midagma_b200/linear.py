@@ -53,11 +53,12 @@ class SmallFitResult(typing.NamedTuple):
     final: torch.Tensor         # [batch, 2] (h(W, s=1), score(W))
     ckpt_log: typing.Optional[torch.Tensor]
     ckpt_count: typing.Optional[torch.Tensor]
+    ckpt_diag: typing.Optional[torch.Tensor] = None   # [batch, cap, 11] telemetry rows (include/dagma_b200.h)
 
 
 def _run_small(cov: torch.Tensor, W: torch.Tensor, lambda1: torch.Tensor, mus, ss, iters, *, lr, tol,
                beta1, beta2, checkpoint, retry, mask_exc=None, mask_inc=None, ckpt_log_cap=0,
-               want_final=True) -> SmallFitResult:
+               want_final=True, want_diag=False) -> SmallFitResult:
     """Launch ``dagma_linear_fit_small_f64`` on device tensors (W is updated in place)."""
     _lib.require_device()
     lib = _lib.load()
@@ -66,7 +67,7 @@ def _run_small(cov: torch.Tensor, W: torch.Tensor, lambda1: torch.Tensor, mus, s
     if T > _lib.MAX_STAGES:
         return _run_small_chunked(cov, W, lambda1, mus, ss, iters, lr=lr, tol=tol, beta1=beta1, beta2=beta2,
                                   checkpoint=checkpoint, retry=retry, mask_exc=mask_exc, mask_inc=mask_inc,
-                                  ckpt_log_cap=ckpt_log_cap, want_final=want_final)
+                                  ckpt_log_cap=ckpt_log_cap, want_final=want_final, want_diag=want_diag)
     assert cov.is_cuda and W.is_cuda and cov.dtype == torch.float64 and W.dtype == torch.float64
     assert cov.is_contiguous() and W.is_contiguous() and lambda1.is_contiguous()
     dev = cov.device
@@ -80,10 +81,13 @@ def _run_small(cov: torch.Tensor, W: torch.Tensor, lambda1: torch.Tensor, mus, s
     stats = torch.zeros(batch, max(T, 1), 8, dtype=torch.float64, device=dev)
     final = torch.zeros(batch, 2, dtype=torch.float64, device=dev)
     counter = torch.zeros(16, dtype=torch.int32, device=dev)
-    log = cnt = None
+    log = cnt = diag = None
     if ckpt_log_cap > 0:
         log = torch.zeros(batch, ckpt_log_cap, 6, dtype=torch.float64, device=dev)
         cnt = torch.zeros(batch, dtype=torch.int32, device=dev)
+        if want_diag:
+            diag = torch.zeros(batch, ckpt_log_cap, _lib.DIAG_COLS, dtype=torch.float64, device=dev)
+    a.ckpt_diag = diag.data_ptr() if diag is not None else None
     a.cov, a.lambda1, a.w = cov.data_ptr(), lambda1.data_ptr(), W.data_ptr()
     a.mask_exc = mask_exc.data_ptr() if mask_exc is not None else None
     a.mask_inc = mask_inc.data_ptr() if mask_inc is not None else None
@@ -93,7 +97,7 @@ def _run_small(cov: torch.Tensor, W: torch.Tensor, lambda1: torch.Tensor, mus, s
     a.ckpt_count = cnt.data_ptr() if cnt is not None else None
     a.work_counter = counter.data_ptr()
     _lib.check(lib.dagma_linear_fit_small_f64(_lib.stream_ptr(), C.byref(a)), "dagma_linear_fit_small_f64")
-    return SmallFitResult(W, status, stats, final, log, cnt)
+    return SmallFitResult(W, status, stats, final, log, cnt, diag)
 
 
 def _run_small_chunked(cov, W, lambda1, mus, ss, iters, *, ckpt_log_cap=0, want_final=True, **kw) -> SmallFitResult:
@@ -109,20 +113,24 @@ def _run_small_chunked(cov, W, lambda1, mus, ss, iters, *, ckpt_log_cap=0, want_
     for p in parts[1:]:
         status |= p.status
     stats = torch.cat([p.stage_stats for p in parts], dim=1)
-    log = cnt = None
+    log = cnt = diag = None
     if ckpt_log_cap > 0:
         # rows keep their launch-local stage index; shift it to the global one and pack the launches back to back
         batch = cov.shape[0]
         log = torch.zeros(batch, ckpt_log_cap * len(parts), 6, dtype=torch.float64, device=cov.device)
         cnt = torch.zeros(batch, dtype=torch.int32, device=cov.device)
+        if parts[0].ckpt_diag is not None:
+            diag = torch.zeros(batch, ckpt_log_cap * len(parts), _lib.DIAG_COLS, dtype=torch.float64, device=cov.device)
         for k, p in enumerate(parts):
             rows = p.ckpt_log.clone()
             rows[:, :, 0] += k * step
             for b in range(batch):
                 n, c = int(p.ckpt_count[b]), int(cnt[b])
                 log[b, c:c + n] = rows[b, :n]
+                if diag is not None:
+                    diag[b, c:c + n] = p.ckpt_diag[b, :n]
                 cnt[b] = c + n
-    return SmallFitResult(W, status, stats, parts[-1].final, log, cnt)
+    return SmallFitResult(W, status, stats, parts[-1].final, log, cnt, diag)
 
 
 def center_cov(X: torch.Tensor, center: bool) -> torch.Tensor:
@@ -253,7 +261,11 @@ def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1
     else:
         covd = _as_dev(cov, device)
     batch, d, _ = covd.shape
-    assert d <= _lib.SMALL_MAX_D, "fit_batch uses the on-chip path (d <= 64)"
+    if d > _lib.SMALL_MAX_D:
+        return _fit_batch_large(covd, lambda1, w_threshold=w_threshold, T=T, mu_init=mu_init, mu_factor=mu_factor, s=s,
+                                warm_iter=warm_iter, max_iter=max_iter, lr=lr, checkpoint=checkpoint, beta_1=beta_1,
+                                beta_2=beta_2, return_info=return_info, exclude_edges=exclude_edges,
+                                include_edges=include_edges)
     lam = _lam_dev(lambda1, batch, device)
     T = int(T)
     ss = list(s) if isinstance(s, (list, tuple)) else T * [s]
@@ -277,6 +289,33 @@ def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1
             "stage_stats": stats, "h_final": fin[:, 0], "score_final": fin[:, 1],
             "total_iters": int(stats[:, :, 0].sum())}
     return W_est, info
+
+
+def _fit_batch_large(covd, lambda1, *, w_threshold, return_info, **fit_kw):
+    """``fit_batch`` beyond the on-chip size (d > 64): the problems run one after the other on the multi-CTA engine
+    (blocked inverse + score GEMM + fused update, one CUDA-graph replay per inner iteration) -- the same code path as
+    ``DagmaLinear.fit`` at that size, fed with the covariance instead of the data."""
+    batch, d, _ = covd.shape
+    lam = np.broadcast_to(np.asarray(lambda1.cpu() if isinstance(lambda1, torch.Tensor) else lambda1,
+                                     dtype=np.float64), (batch,))
+    W_raw = np.empty((batch, d, d))
+    stage_iters, h_fin, sc_fin = [], [], []
+    for b in range(batch):
+        m = DagmaLinear("l2")
+        kw = dict(fit_kw)
+        kw["s"] = list(kw["s"]) if isinstance(kw["s"], (list, tuple)) else kw["s"]
+        m._fit_from_cov(covd[b], float(lam[b]), **kw)
+        W_raw[b] = m.W_raw
+        stage_iters.append(m.stage_iters)
+        h_fin.append(m.h_final)
+        sc_fin.append(m.score_final)
+    W_est = W_raw.copy()
+    W_est[np.abs(W_est) < w_threshold] = 0
+    if not return_info:
+        return W_est
+    si = np.array(stage_iters, dtype=np.int64)
+    return W_est, {"W_raw": W_raw, "status": np.zeros(batch, dtype=np.int32), "stage_iters": si,
+                   "h_final": np.array(h_fin), "score_final": np.array(sc_fin), "total_iters": int(si.sum())}
 
 
 # =============================================================================
@@ -360,10 +399,10 @@ class DagmaLinear:
         return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(self._device)
 
     def _small_ok(self) -> bool:
-        # the one-launch on-chip path keeps nothing in HBM between checkpoints: runs with telemetry or with a trek
-        # regulariser go through the multi-CTA engine, whose whole state is device-resident and host-visible
+        # the one-launch on-chip path; telemetry rows are produced inside the kernel at the checkpoint iterations, so
+        # logging does not change the route -- only a trek regulariser does (its series need the multi-CTA GEMMs)
         return (self.loss_type == 'l2' and self.d <= _lib.SMALL_MAX_D and self._group is None
-                and not self._log_cfg.enabled and self._trek_plan is None)
+                and self._trek_plan is None)
 
     def _large_engine(self):
         from ._large import LargeLinearEngine
@@ -416,11 +455,12 @@ class DagmaLinear:
             res = _run_small(self._cov_dev[None], Wd, self._lam_dev, [mu], [s], [int(max_iter)], lr=lr, tol=tol,
                              beta1=beta_1, beta2=beta_2, checkpoint=self.checkpoint, retry=False,
                              mask_exc=self._mask_exc, mask_inc=self._mask_inc,
-                             ckpt_log_cap=int(max_iter) // max(int(self.checkpoint), 1) + 2, want_final=False)
+                             ckpt_log_cap=int(max_iter) // max(int(self.checkpoint), 1) + 2, want_final=False,
+                             want_diag=self._log_cfg.enabled)
             W[...] = res.W[0].cpu().numpy()
             status = int(res.status.item())
             iters_done = int(res.stage_stats[0, 0, 0].item())
-            self._record_log(res)
+            self._record_log(res, [mu], [s])
         else:
             log = []
             status, iters_done = self._large_engine().minimize(
@@ -460,52 +500,61 @@ class DagmaLinear:
             })
         return emit
 
-    def _record_log(self, res: SmallFitResult) -> None:
+    def _record_log(self, res: SmallFitResult, mus=None, ss=None) -> None:
+        """Checkpoint rows of an on-chip run: the (stage, iter, obj, score, h, lr) log and, with logging enabled, the
+        fork's 25-key ``minimize.checkpoint`` event per row (linear.py:279-326) from the kernel's telemetry rows."""
         if res.ckpt_log is None:
             return
         n = int(res.ckpt_count[0].item())
         rows = res.ckpt_log[0, :n].cpu().numpy()
         self.checkpoint_log.extend(map(tuple, rows))
-        for st, it, obj, score, h, lr in rows:
+        diag = res.ckpt_diag[0, :n].cpu().numpy() if res.ckpt_diag is not None else None
+        for k, (st, it, obj, score, h, lr) in enumerate(rows):
             self.vprint(f'\nInner iteration {int(it)}\n\th(W_est): {h:.4e}\n\tscore(W_est): {score:.4e}\n\tobj: {obj:.4e}')
+            if diag is None or not self._log_cfg.enabled:
+                continue
+            dg = diag[k]
+            t = min(int(st), len(mus) - 1)
+            # the value of s a retried stage ended with is what its later rows ran at; rows of failed attempts carry
+            # the s of that attempt only up to the 0.1 steps of the retries (the kernel reports the final one)
+            self._slog.emit("minimize.checkpoint", {
+                "iter": int(it), "stage": int(getattr(self, "_stage", 0)), "elapsed_sec": float(dg[10]),
+                "obj_total": float(obj), "score_datafit": float(score),
+                "reg_dag_name": "dagma_logdet", "reg_dag_value": float(h), "reg_dag_cfg": {"s": float(ss[t])},
+                "reg_trek_name": self.trek_reg.name if self.trek_reg is not None else "none", "reg_trek_value": 0.0,
+                "reg_trek_cfg": ({k_: v for k_, v in self.trek_reg.cfg.items() if k_ != "I"}
+                                 if self.trek_reg is not None else {}),
+                "trek_mode": self.trek_reg.mode if self.trek_reg is not None else "off",
+                "trek_weight": float(self.trek_reg.weight) if self.trek_reg is not None else 0.0,
+                "mu": float(mus[t]), "lr": float(lr),
+                "w_norm": float(dg[6]), "w_abs_sum": float(dg[7]), "max_abs_w": float(dg[8]),
+                "min_abs_w_nonzero": float(dg[9]),
+                "grad_raw_norm": float(dg[0]), "grad_step_norm": float(dg[5]), "step_norm": float(lr * dg[5]),
+                "grad_score_norm": float(dg[1]), "grad_dag_norm": float(dg[2]), "grad_l1_norm": float(dg[3]),
+                "grad_inc_norm": float(dg[4]), "grad_trek_norm": 0.0,
+            })
 
-    # ------------------------------------------------------------------ fit (linear.py:335-462)
-    def fit(self, X: np.ndarray, lambda1: float = 0.03, w_threshold: float = 0.3, T: int = 5,
-            mu_init: float = 1.0, mu_factor: float = 0.1,
-            s: typing.Union[typing.List[float], float] = [1.0, .9, .8, .7, .6],
-            warm_iter: int = 3e4, max_iter: int = 6e4, lr: float = 0.0003, checkpoint: int = 1000,
-            beta_1: float = 0.99, beta_2: float = 0.999,
-            exclude_edges: typing.Optional[typing.List[typing.Tuple[int, int]]] = None,
-            include_edges: typing.Optional[typing.List[typing.Tuple[int, int]]] = None) -> np.ndarray:
-        _lib.require_device()
-        t0 = time.time()
-        self.X, self.lambda1, self.checkpoint = X, lambda1, checkpoint
-        self.n, self.d = X.shape
+    def _fit_from_cov(self, cov_dev: torch.Tensor, lambda1: float, *, T=5, mu_init=1.0, mu_factor=0.1,
+                      s=(1.0, .9, .8, .7, .6), warm_iter=3e4, max_iter=6e4, lr=0.0003, checkpoint=1000, beta_1=0.99,
+                      beta_2=0.999, exclude_edges=None, include_edges=None) -> np.ndarray:
+        """The path-following loop of ``fit`` (l2) from a device covariance instead of the data (batched entry point)."""
+        assert self.loss_type == 'l2'
+        self.X, self.lambda1, self.checkpoint = None, lambda1, checkpoint
+        self.d = int(cov_dev.shape[0])
+        self.n = self._n_total = 0
         self.Id = np.eye(self.d).astype(self.dtype)
         self.checkpoint_log = []
+        self._X_dev = None
+        self._cov_dev = cov_dev.contiguous()
+        self.cov = self._cov_dev.cpu().numpy()
+        self._run_path(lambda1, T, mu_init, mu_factor, s, warm_iter, max_iter, lr, checkpoint, beta_1, beta_2,
+                       exclude_edges, include_edges)
+        self.W_raw = self.W_est.copy()
+        return self.W_raw
 
-        # centring + covariance on device; the centred X is copied back into the caller's
-        # array to keep the reference's in-place side effect (linear.py:410-411, Q8)
-        Xd = self._dev(X)[None].contiguous()
-        self._n_total = self.n
-        if self._group is None:
-            cov = center_cov(Xd, center=(self.loss_type == 'l2'))
-        else:                                   # row-sharded: global n, global column means, summed cov
-            from .parallel import allreduce_sum_
-            nt = allreduce_sum_(torch.tensor([float(self.n)], dtype=torch.float64, device=self._device), self._group)
-            self._n_total = int(nt.item())
-            if self.loss_type == 'l2':
-                mean = allreduce_sum_(Xd[0].sum(dim=0), self._group) / self._n_total
-                Xd[0] -= mean
-            cov = center_cov(Xd, center=False)
-            cov *= self.n / self._n_total
-            allreduce_sum_(cov, self._group)
-        if self.loss_type == 'l2':
-            self.X[...] = Xd[0].cpu().numpy()
-        self._X_dev = Xd[0]
-        self._cov_dev = cov[0]
-        self.cov = cov[0].cpu().numpy()
-
+    def _run_path(self, lambda1, T, mu_init, mu_factor, s, warm_iter, max_iter, lr, checkpoint, beta_1, beta_2,
+                  exclude_edges, include_edges) -> None:
+        """linear.py:413-457: masks, the (mu, s) schedule, the stage loop with retries, final h / score."""
         self.exc_r, self.exc_c = None, None
         self.inc_r, self.inc_c = None, None
         if exclude_edges is not None:
@@ -545,7 +594,8 @@ class DagmaLinear:
             cap = sum(it // max(int(checkpoint), 1) + 2 for it in iters)
             res = _run_small(self._cov_dev[None], Wd, self._lam_dev, mus, s[:T], iters, lr=lr, tol=1e-6,
                              beta1=beta_1, beta2=beta_2, checkpoint=checkpoint, retry=True,
-                             mask_exc=self._mask_exc, mask_inc=self._mask_inc, ckpt_log_cap=min(cap, 4096))
+                             mask_exc=self._mask_exc, mask_inc=self._mask_inc, ckpt_log_cap=min(cap, 4096),
+                             want_diag=self._log_cfg.enabled)
             stats = res.stage_stats[0].cpu().numpy()
             for i in range(T):
                 if stats[i, 6] > 0:
@@ -554,7 +604,7 @@ class DagmaLinear:
             self.stage_stats = stats
             self.status = int(res.status.item())
             _warn_retry_limit(res.status)
-            self._record_log(res)
+            self._record_log(res, mus, [float(x) for x in stats[:, 2]])
             self.W_est = res.W[0].cpu().numpy().astype(self.dtype)
             fin = res.final[0].cpu().numpy()
             self.h_final, self.score_final = float(fin[0]), float(fin[1])
@@ -578,6 +628,46 @@ class DagmaLinear:
             self.h_final, _ = self._h(self.W_est)
             self.score_final, _ = self._score(self.W_est)
             del eng
+
+    # ------------------------------------------------------------------ fit (linear.py:335-462)
+    def fit(self, X: np.ndarray, lambda1: float = 0.03, w_threshold: float = 0.3, T: int = 5,
+            mu_init: float = 1.0, mu_factor: float = 0.1,
+            s: typing.Union[typing.List[float], float] = [1.0, .9, .8, .7, .6],
+            warm_iter: int = 3e4, max_iter: int = 6e4, lr: float = 0.0003, checkpoint: int = 1000,
+            beta_1: float = 0.99, beta_2: float = 0.999,
+            exclude_edges: typing.Optional[typing.List[typing.Tuple[int, int]]] = None,
+            include_edges: typing.Optional[typing.List[typing.Tuple[int, int]]] = None) -> np.ndarray:
+        _lib.require_device()
+        t0 = time.time()
+        self.X, self.lambda1, self.checkpoint = X, lambda1, checkpoint
+        self.n, self.d = X.shape
+        self.Id = np.eye(self.d).astype(self.dtype)
+        self.checkpoint_log = []
+
+        # centring + covariance on device; the centred X is copied back into the caller's
+        # array to keep the reference's in-place side effect (linear.py:410-411, Q8)
+        Xd = self._dev(X)[None].contiguous()
+        self._n_total = self.n
+        if self._group is None:
+            cov = center_cov(Xd, center=(self.loss_type == 'l2'))
+        else:                                   # row-sharded: global n, global column means, summed cov
+            from .parallel import allreduce_sum_
+            nt = allreduce_sum_(torch.tensor([float(self.n)], dtype=torch.float64, device=self._device), self._group)
+            self._n_total = int(nt.item())
+            if self.loss_type == 'l2':
+                mean = allreduce_sum_(Xd[0].sum(dim=0), self._group) / self._n_total
+                Xd[0] -= mean
+            cov = center_cov(Xd, center=False)
+            cov *= self.n / self._n_total
+            allreduce_sum_(cov, self._group)
+        if self.loss_type == 'l2':
+            self.X[...] = Xd[0].cpu().numpy()
+        self._X_dev = Xd[0]
+        self._cov_dev = cov[0]
+        self.cov = cov[0].cpu().numpy()
+
+        self._run_path(lambda1, T, mu_init, mu_factor, s, warm_iter, max_iter, lr, checkpoint, beta_1, beta_2,
+                       exclude_edges, include_edges)
         self.W_raw = self.W_est.copy()
         self.W_est[np.abs(self.W_est) < w_threshold] = 0
         self._slog.close()                                  # linear.py:460

@@ -43,5 +43,11 @@ err2 = np.abs(A_rows - A_full).max()
 assert err2 < 1e-9, err2
 dist.barrier()
 if rank == 0:
-    print(f"mgpu_check ok on {ws} GPUs: batch identical, logistic |dW|={err:.2e}, mlp |dW|={err2:.2e}")
+    print(f"mgpu_check ok on {ws} GPUs: batch identical, logistic |dW|={err:.2e}, mlp |dW|={err2:.2e}", flush=True)
+# the engines hold CUDA graphs with captured NCCL all-reduces: release them before the communicator goes away
+# (destroy_process_group with such graphs still alive does not return)
+del eq, m1, m2
+import gc
+gc.collect()
+torch.cuda.synchronize()
 dist.destroy_process_group()

@@ -33,14 +33,23 @@ for line in out.splitlines():
 
 def demangle(name):
     try:
-        return subprocess.run(["cu++filt", name], capture_output=True, text=True).stdout.strip().split("(")[0]
+        full = subprocess.run(["cu++filt", name], capture_output=True, text=True).stdout.strip()
     except OSError:
         return name
+    if not full.endswith(")"):
+        return full
+    depth = 0                                   # cut the trailing parameter list (template arguments may hold parentheses)
+    for i in range(len(full) - 1, -1, -1):
+        depth += full[i] == ")"
+        depth -= full[i] == "("
+        if depth == 0:
+            return full[:i]
+    return full
 
 
 print(f"# {os.path.relpath(lib, ROOT)}: SASS opcode counts per kernel (cuobjdump -sass; static counts, not executed counts)")
 print("# STL / LDL = local-memory stores / loads (register spills or stack arrays); UTC = tcgen05 alloc / dealloc / etc.")
 print(f"{'kernel':64s} " + " ".join(f"{c:>7s}" for c in COLS))
 for k, c in sorted(counts.items(), key=lambda kv: -kv[1]["DMMA"]):
-    name = demangle(k).replace("dagma::", "")
+    name = demangle(k).replace("dagma::", "").replace("(bool)1", "true").replace("(bool)0", "false")
     print(f"{name[:64]:64s} " + " ".join(f"{c[col]:7d}" for col in COLS))

@@ -37,8 +37,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_mirror_layout():
     from midagma_b200 import _lib
     a = _lib.SmallFitArgs
-    # 6 int32 (24 B), 4 doubles, 2 x 16 doubles, 16 int32, 11 pointers
-    assert C.sizeof(a) == 24 + 4 * 8 + 2 * 16 * 8 + 16 * 4 + 11 * 8
+    # 6 int32 (24 B), 4 doubles, 2 x 16 doubles, 16 int32, 12 pointers
+    assert C.sizeof(a) == 24 + 4 * 8 + 2 * 16 * 8 + 16 * 4 + 12 * 8
     assert a.mu.offset == 56 and a.iters.offset == 56 + 256 and a.cov.offset == 56 + 256 + 64
 
 

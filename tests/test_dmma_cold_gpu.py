@@ -100,3 +100,21 @@ def test_dmma_masks_match_oracle(d):
     _, info0 = fit_batch(X[None], s=(1.0, 0.9), return_info=True, **kw)
     assert not np.array_equal(info0["W_raw"][0], m.W_raw)
     assert any(info0["W_raw"][0][i, j] != 0.0 for (i, j) in exc)
+
+
+def test_dmma_two_ctas_per_sm_are_resident():
+    """The launch geometry of the 32 < d <= 64 kernel assumes two CTAs per SM (registers, shared memory and tensor
+    memory are sized for exactly that) although the occupancy API answers 1: the kernel counts for itself."""
+    import ctypes as C
+    import torch
+    from midagma_b200 import _lib, minimize_batch
+    sms = _lib.require_device()
+    d, nprob = 64, 2 * sms
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(nprob, 100, d))
+    cov = np.einsum("bni,bnj->bij", X, X) / 100
+    minimize_batch(np.zeros((nprob, d, d)), cov, 0.02, 1.0, 300, 1.0, 3e-4, tol=0.0)
+    got = C.c_int(-1)
+    _lib.check(_lib.load().dagma_fit_dmma_residency(C.byref(got)), "dagma_fit_dmma_residency")
+    print("CTAs of the fit kernel per SM:", got.value)
+    assert got.value == 2

@@ -204,3 +204,25 @@ def test_fit_d200_blocked_short_schedule():
     print("d=200 edge diff", simulate.edge_set_distance(W, W_ref), "max|dW|", np.abs(W - W_ref).max(), m.stage_iters)
     assert simulate.edge_set_distance(W, W_ref) == 0
     assert np.abs(W - W_ref).max() <= 1e-6
+
+
+def test_fit_batch_beyond_onchip_size():
+    """fit_batch / the batched entry accept d > 64 (the reference's fit takes any d, linear.py:335): problems run one
+    after the other on the multi-CTA engine and equal DagmaLinear.fit on the same data."""
+    from midagma_b200 import DagmaLinear, fit_batch
+    d = 72
+    kw = dict(T=2, warm_iter=150, max_iter=200, checkpoint=50)
+    Xs, Ws = [], []
+    for p, lam in ((0, 0.02), (1, 0.04)):
+        X, _ = simulate.make_linear_problem(d, 2, 400, "ER", "gauss", 30 + p)
+        Xs.append(X)
+        m = DagmaLinear("l2")
+        m.fit(X.copy(), lambda1=lam, s=[1.0, .9], **kw)
+        Ws.append(m.W_raw)
+    exc = ((0, 1), (5, 9))
+    W_est, info = fit_batch(np.stack(Xs), np.array([0.02, 0.04]), s=(1.0, .9), return_info=True, **kw)
+    assert info["stage_iters"].tolist() == [[150, 200], [150, 200]]
+    for b in range(2):
+        assert np.abs(info["W_raw"][b] - Ws[b]).max() <= 1e-12
+    _, info_x = fit_batch(np.stack(Xs), np.array([0.02, 0.04]), s=(1.0, .9), return_info=True, exclude_edges=exc, **kw)
+    assert all(info_x["W_raw"][b][i, j] == 0.0 for b in range(2) for (i, j) in exc)

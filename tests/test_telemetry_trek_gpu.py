@@ -74,19 +74,67 @@ def test_checkpoint_events_and_trajectory(golden, case):
     assert list(cols["iter"]) == [int(x) for x in ref[:, 0]]
 
 
-def test_telemetry_small_d_fit_routes_through_engine():
-    """With telemetry on, a d <= 64 fit runs on the multi-CTA engine (state visible at checkpoints) and recovers
-    the same graph as the one-launch on-chip path."""
+def test_telemetry_stays_on_the_onchip_kernel():
+    """With telemetry on, a d <= 64 fit still runs as ONE launch of the on-chip kernel (the telemetry rows are produced
+    inside it at the checkpoint iterations): bit-identical W with and without logging, rows at every checkpoint."""
     from midagma_b200 import DagmaLinear
     from midagma_b200.logger import LogConfig
     from oracle import simulate
     X, _ = simulate.config_c1(3)
-    a = DagmaLinear("l2").fit(X.copy(), lambda1=0.02, T=2, warm_iter=2000, max_iter=3000, s=[1.0, 0.9])
+    ma = DagmaLinear("l2")
+    a = ma.fit(X.copy(), lambda1=0.02, T=2, warm_iter=2000, max_iter=3000, s=[1.0, 0.9])
     rows = []
     cfg = LogConfig(enabled=True, store_jsonl=False, callback=rows.append)
-    b = DagmaLinear("l2", log_cfg=cfg).fit(X.copy(), lambda1=0.02, T=2, warm_iter=2000, max_iter=3000, s=[1.0, 0.9])
-    assert rows and rows[0]["iter"] == 1000
-    assert simulate.edge_set_distance(a, b) == 0
+    mb = DagmaLinear("l2", log_cfg=cfg)
+    b = mb.fit(X.copy(), lambda1=0.02, T=2, warm_iter=2000, max_iter=3000, s=[1.0, 0.9])
+    assert mb._large is None                                   # the multi-CTA engine was never built
+    assert np.array_equal(ma.W_raw, mb.W_raw) and np.array_equal(a, b)
+    assert [r["iter"] for r in rows] == [int(x[1]) for x in mb.checkpoint_log] and len(rows) >= 4
+    assert rows[0]["iter"] == 1000 and rows[0]["mu"] == 1.0 and rows[-1]["mu"] == 0.1
+    assert rows[0]["reg_dag_cfg"] == {"s": 1.0} and rows[-1]["reg_dag_cfg"] == {"s": 0.9}
+    assert all(r["elapsed_sec"] > 0 for r in rows) and rows[1]["elapsed_sec"] > rows[0]["elapsed_sec"]
+
+
+@pytest.mark.parametrize("d", [12, 24, 40, 64])
+def test_onchip_telemetry_rows_vs_oracle(d):
+    """The kernel's telemetry rows (scalar kernel d <= 32, tensor-core kernel above) against the same quantities
+    computed from the oracle's iteration trace (src/dagma/linear.py:262-273, 307-324), with include / exclude edges."""
+    from midagma_b200 import DagmaLinear
+    from midagma_b200.logger import LogConfig
+    from oracle import simulate
+    from oracle.linear_ref import OracleLinear
+    import scipy.linalg as sla
+    X, W_true = simulate.make_linear_problem(d, 2, 300, "ER", "gauss", 40 + d)
+    edges = np.argwhere(W_true != 0)
+    inc = ((int(edges[0][0]), int(edges[0][1])), (int(edges[1][0]), int(edges[1][1])))
+    exc = ((int(edges[2][0]), int(edges[2][1])), (0, d - 1))
+    mu, s, lr, ck, iters, lam = 0.5, 0.9, 3e-4, 60, 150, 0.03
+    o = OracleLinear("l2").prepare(X.copy(), lam, checkpoint=ck, exclude_edges=exc, include_edges=inc)
+    o.trace = []
+    W_ref, _ = o.minimize(np.zeros((d, d)), mu, iters, s, lr)
+    rows = []
+    m = DagmaLinear("l2", log_cfg=LogConfig(enabled=True, store_jsonl=False, callback=rows.append))
+    m.fit(X.copy(), lambda1=lam, T=1, warm_iter=0, max_iter=0, checkpoint=ck, exclude_edges=exc, include_edges=inc)
+    W, ok = m.minimize(np.zeros((d, d)), mu, iters, s, lr)
+    assert ok and np.abs(W - W_ref).max() <= 1e-9
+    assert [r["iter"] for r in rows] == [60, 120, 150]
+    mask_inc = np.zeros((d, d))
+    mask_inc[tuple(zip(*inc))] = -2 * mu * lam
+    mask_exc = np.ones((d, d))
+    mask_exc[tuple(zip(*exc))] = 0.0
+    for r in rows:
+        t = o.trace[r["iter"] - 1]
+        Wb, Gobj, dirn = t["W_before"], t["Gobj"], t["dir"]
+        M = sla.inv(s * np.eye(d) - Wb * Wb) + 1e-16
+        Wn = (Wb - t["lr"] * dirn) * mask_exc
+        nz = np.abs(Wn[Wn != 0])
+        want = {"grad_raw_norm": np.linalg.norm(Gobj), "grad_score_norm": np.linalg.norm(-mu * o.cov @ (np.eye(d) - Wb)),
+                "grad_dag_norm": np.linalg.norm(2 * Wb * M.T), "grad_l1_norm": np.linalg.norm(mu * lam * np.sign(Wb)),
+                "grad_inc_norm": np.linalg.norm(mask_inc * np.sign(Wb)), "grad_step_norm": np.linalg.norm(dirn),
+                "step_norm": t["lr"] * np.linalg.norm(dirn), "w_norm": np.linalg.norm(Wn), "w_abs_sum": np.abs(Wn).sum(),
+                "max_abs_w": np.abs(Wn).max(), "min_abs_w_nonzero": nz.min() if nz.size else 0.0, "lr": t["lr"], "mu": mu}
+        for k, v in want.items():
+            assert abs(r[k] - v) <= 1e-9 * max(abs(v), 1e-12), (d, r["iter"], k, r[k], v)
 
 
 @pytest.mark.parametrize("seq", ["inv", "log", "exp", "binom"])
