@@ -119,21 +119,45 @@ class DagmaMLP(nn.Module):
         eng = _MlpEngine(self, _cuda64(x))
         return eng.forward().to(x.device)
 
+    def _aux(self) -> "_MlpEngine":
+        """One data-less engine per model for the helper calls below (its buffers -- among them the workspace of the
+        inverse -- are allocated once); the parameters are re-read on every call.
+
+        These helpers run under ``torch.no_grad()`` and return tensors detached from the parameters: the kernels carry
+        the closed-form backward, there is no autograd graph (``model.h_func(s).backward()`` as in reference-style
+        user code is not supported; ``DagmaNonlinear.minimize`` / ``fit`` is the optimiser)."""
+        eng = self.__dict__.get("_aux_engine")
+        if eng is None:
+            eng = _MlpEngine(self, None)
+            self.__dict__["_aux_engine"] = eng             # not a module attribute: stays out of state_dict / deepcopy
+        else:
+            eng.theta.copy_(self.pack())
+        return eng
+
+    def __deepcopy__(self, memo):
+        import copy as _copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != "_aux_engine":
+                new.__dict__[k] = _copy.deepcopy(v, memo)
+        return new
+
     @torch.no_grad()
     def h_func(self, s: float = 1.0) -> torch.Tensor:
-        eng = _MlpEngine(self, None)
+        eng = self._aux()
         eng.h(s)
         st = eng.pull()[0]
         return torch.tensor(float(st[F_H]), dtype=torch.float64)
 
     @torch.no_grad()
     def fc1_l1_reg(self) -> torch.Tensor:
-        eng = _MlpEngine(self, None)
-        return torch.tensor(eng.l1(), dtype=torch.float64)
+        return torch.tensor(self._aux().l1(), dtype=torch.float64)
 
     @torch.no_grad()
     def fc1_to_adj(self) -> np.ndarray:                        # [j * m1, i] -> [i, j]
-        eng = _MlpEngine(self, None)
+        eng = self._aux()
         eng.adj()
         return np.sqrt(eng.A.cpu().numpy())
 
