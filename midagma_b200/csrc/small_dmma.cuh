@@ -214,7 +214,7 @@ __device__ long long g_sweep_trace[64 * 8];
 #endif
 
 #ifndef DAGMA_STAGE_INTERLEAVE
-#define DAGMA_STAGE_INTERLEAVE 1     // 1: the diagonal warp issues its publish-critical DMMAs inside the pivot-block chain
+#define DAGMA_STAGE_INTERLEAVE 1     // diagonal warp: its publish-critical DMMAs 1 inside / 0 after / 2 before the pivot-block chain
 #endif
 
 struct SweepSync {        // per-thread view of the step barrier
@@ -306,8 +306,12 @@ __device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], const Dmma
         else if (k == 5) upd(TIN ^ 1, TJN);
     };
     if (diag_next) {
-#if DAGMA_STAGE_INTERLEAVE
+#if DAGMA_STAGE_INTERLEAVE == 1
         stage_pivot_block<TIN, TJN>(a, ps, sm, B + 1, CUR ^ 1, portion);
+#elif DAGMA_STAGE_INTERLEAVE == 2
+#pragma unroll
+        for (int k = 0; k < 6; ++k) portion(k);          // the other publish-critical tiles first, then a clean chain
+        stage_pivot_block<TIN, TJN>(a, ps, sm, B + 1, CUR ^ 1, [](int) {});
 #else
         stage_pivot_block<TIN, TJN>(a, ps, sm, B + 1, CUR ^ 1, [](int) {});
 #pragma unroll

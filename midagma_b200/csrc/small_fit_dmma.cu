@@ -19,6 +19,9 @@
 #endif
 #include "small_dmma.cuh"
 #include "small_fit_internal.h"
+#ifndef DAGMA_ADAM_GROUP
+#define DAGMA_ADAM_GROUP 4            // entries whose rsqrt / rcp Newton chains are interleaved in the element-wise pass
+#endif
 
 #ifndef DAGMA_FIT_GEMM_IN_SWEEP
 #define DAGMA_FIT_GEMM_IN_SWEEP 1     // 1: the score GEMM fills the waits of the sweep; 0: a separate phase after it
@@ -525,8 +528,9 @@ __global__ void __launch_bounds__(DM_NT, 2) fit_small_dmma_kernel(const dagma_sm
                         mn[q] = lm.get(q);
                         vn[q] = lv.get(q);
                     }
-                    adam_entries<4>(w, go, mn, vn, P.beta1, P.beta2, k1, k2, lr);
-                    adam_entries<4>(w + 4, go + 4, mn + 4, vn + 4, P.beta1, P.beta2, k1, k2, lr);
+#pragma unroll
+                    for (int q0 = 0; q0 < 8; q0 += DAGMA_ADAM_GROUP)     // Newton chains of a group interleave
+                        adam_entries<DAGMA_ADAM_GROUP>(w + q0, go + q0, mn + q0, vn + q0, P.beta1, P.beta2, k1, k2, lr);
                     tmem_st8(tm + 32 * ti, mn);
                     tmem_st8(tm + 32 * ti + 16, vn);
 #pragma unroll
