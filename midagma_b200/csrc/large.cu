@@ -149,7 +149,7 @@ struct TileStepArgs {
 //   tile_out = tile_in + CS_i R_j        (two 64^3 DMMA products).
 // Reading the old state from Ain (through L2) and writing the new one to Aout (ping-pong) removes every hazard;
 // the redundancy (nblk^2 sweeps, nblk CS products) runs in parallel on otherwise idle SMs.
-constexpr size_t TILE_STEP_SMEM_BYTES = DmmaSmem::bytes;
+
 
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }   // L2: written by other CTAs
 
@@ -190,28 +190,55 @@ __global__ void outer_trace_begin_kernel(int step) {
 #define FT_MIN(k, slot) do { } while (0)
 #endif
 
+#ifndef DAGMA_TILE_STEP_PREFETCH
+#define DAGMA_TILE_STEP_PREFETCH 1   // 1: A[I,K] / A[K,J] land in shared memory by cp.async WHILE the sweep runs; 0: loads between the phases
+#endif
+// shared memory of a tile step (doubles): the two operand tiles sit where the fit kernel keeps -cov and W, which the
+// sweep does not touch; Q goes on top of the sweep's line buffers once the sweep is over; the step barrier of the
+// sweep lives behind it (it must survive from one tile step to the next)
+constexpr int TS_CS = DmmaSmem::ncov, TS_R = DmmaSmem::W, TS_Q = DmmaSmem::rbuf;
+constexpr int TS_MBAR = TS_Q + DM_DP * DM_LD;
+constexpr int TS_TOTAL = TS_MBAR + 2;
+static_assert(TS_MBAR >= DmmaSmem::total && TS_MBAR % 2 == 0, "the barrier is outside everything the sweep writes");
+
 __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj, double* psm, SweepSync& sy) {
     using S = DmmaSmem;
     constexpr int LD = DM_LD;
-    double* Cs = psm + S::ncov;     // [64][68]  Cpub rows of this tile, later CS
-    double* Qs = psm + S::W;        // [64][68]  Q, later the Rpub columns of this tile
+    double* Cs = psm + TS_CS;       // [64][68]  A[I,K] - [bi == kb] I, later CS
+    double* Rs = psm + TS_R;        // [64][68]  A[K,J] + [bj == kb] I
+    double* Qs = psm + TS_Q;        // [64][68]  Q (after the sweep)
     const int tid = threadIdx.x;
     const DmmaPos ps(tid);
     const int n = P.n, k0 = P.kb * NB;
     const int kn = min(NB, n - k0);
     const int r0 = bi * NB, c0 = bj * NB;
+    const bool vec = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.Ain) & 15) == 0);
 
-    // ---- P into the accumulator layout (identity padding); Cpub rows and Rpub columns into shared memory
+#if DAGMA_TILE_STEP_PREFETCH
+    // ---- both operand tiles are requested now and land during the sweep (zero fill outside the matrix / the block)
+    load_slab<NB, NB, DM_NT>(smem_u32(Cs), LD, P.Ain, n, r0, k0, n, k0 + kn, vec, tid);
+    load_slab<NB, NB, DM_NT>(smem_u32(Rs), LD, P.Ain, n, k0, c0, k0 + kn, n, vec, tid);
+    cp_async_commit();
+#endif
+    // ---- P into the accumulator layout (identity padding)
     double a[2][4][2], acc[2][4][2];
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
-        for (int tj = 0; tj < 4; ++tj)
+        for (int tj = 0; tj < 4; ++tj) {
+            const int r = ps.row(ti), c = ps.col(tj);
+            if (vec) {                                  // n even: c and c + 1 are inside or outside together
+                double2 v = make_double2((r == c) ? 1.0 : 0.0, (r == c + 1) ? 1.0 : 0.0);
+                if (r < kn && c < kn) v = __ldcg(reinterpret_cast<const double2*>(&P.Ain[(size_t)(k0 + r) * n + k0 + c]));
+                a[ti][tj][0] = v.x;
+                a[ti][tj][1] = v.y;
+            } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int r = ps.row(ti), c = ps.col(tj) + e;
-                a[ti][tj][e] = (r < kn && c < kn) ? ldcg(&P.Ain[(size_t)(k0 + r) * n + k0 + c]) : ((r == c) ? 1.0 : 0.0);
+                for (int e = 0; e < 2; ++e)
+                    a[ti][tj][e] = (r < kn && c + e < kn) ? ldcg(&P.Ain[(size_t)(k0 + r) * n + k0 + c + e]) : ((r == c + e) ? 1.0 : 0.0);
             }
+        }
+#if !DAGMA_TILE_STEP_PREFETCH
     {   // all 16 loads of a thread in flight before the first use
         double v[16];
 #pragma unroll
@@ -222,15 +249,39 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
-            if (bi == P.kb && r == c && r < kn) v[q] -= 1.0;
-            Cs[r * LD + c] = -v[q];
+            Cs[r * LD + c] = v[q];
         }
     }
+#endif
     __syncthreads();
     OT_TILE(0);
     dmma_sweep(a, ps, psm, kn, sy);
     OT_TILE(1);
-    if (bi == 0 && bj == 0 && tid < 4 * ((kn + 3) >> 2)) P.pivots[k0 + tid] = psm[S::pinfo + tid];
+    const bool piv_out = (bi == 0 && bj == 0 && tid < 4 * ((kn + 3) >> 2));
+    const double piv = piv_out ? psm[S::pinfo + tid] : 0.0;          // Q is about to overwrite the line buffers
+#if DAGMA_TILE_STEP_PREFETCH
+    cp_async_wait<0>();
+#else
+    {
+        double w[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
+            w[q] = (r < kn && c0 + c < n) ? ldcg(&P.Ain[(size_t)(k0 + r) * n + c0 + c]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
+            Rs[r * LD + c] = w[q];
+        }
+    }
+#endif
+    __syncthreads();                 // the copies of every thread have landed; the pivots are in registers
+    if (piv_out) P.pivots[k0 + tid] = piv;
+    if (tid < kn) {                  // the two identities of the publish trick
+        if (bi == P.kb) Cs[tid * LD + tid] -= 1.0;
+        if (bj == P.kb) Rs[tid * LD + tid] += 1.0;
+    }
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
@@ -240,7 +291,23 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
             *reinterpret_cast<double2*>(Qs + r * LD + c) = make_double2(in0 ? a[ti][tj][0] : 0.0, in1 ? a[ti][tj][1] : 0.0);
         }
     __syncthreads();
-    // ---- CS = (-Cpub) Q   (warp tile 16 x 32, 16 k-blocks of 4)
+    // the old tile travels while the first product runs
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) {
+            const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
+            if (vec) {
+                double2 v = make_double2(0.0, 0.0);
+                if (r < n && c < n) v = __ldcg(reinterpret_cast<const double2*>(&P.Ain[(size_t)r * n + c]));
+                a[ti][tj][0] = v.x;
+                a[ti][tj][1] = v.y;
+            } else {
+                a[ti][tj][0] = (r < n && c < n) ? ldcg(&P.Ain[(size_t)r * n + c]) : 0.0;
+                a[ti][tj][1] = (r < n && c + 1 < n) ? ldcg(&P.Ain[(size_t)r * n + c + 1]) : 0.0;
+            }
+        }
+    // ---- CS = -((A[I,K] - dI) Q)   (warp tile 16 x 32, 16 k-blocks of 4; the sign costs nothing: rounding is symmetric)
     auto product = [&](const double* Am, const double* Bm) {
 #pragma unroll 4
         for (int kk = 0; kk < NB; kk += 4) {
@@ -260,42 +327,31 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
 #pragma unroll
         for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
     product(Cs, Qs);
-    __syncthreads();                 // every warp is done reading Cpub and Q
+    __syncthreads();                 // every warp is done reading A[I,K] and Q
     OT_TILE(2);
-    {
-        double w[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
-            w[q] = (r < kn && c0 + c < n) ? ldcg(&P.Ain[(size_t)(k0 + r) * n + c0 + c]) : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int e = tid + q * DM_NT, r = e >> 6, c = e & 63;
-            if (bj == P.kb && r == c && r < kn) w[q] += 1.0;
-            Qs[r * LD + c] = w[q];
-        }
-    }
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
         for (int tj = 0; tj < 4; ++tj) {
-            *reinterpret_cast<double2*>(Cs + ps.row(ti) * LD + ps.col(tj)) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
-            const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);          // accumulators restart from the old tile
-            acc[ti][tj][0] = (r < n && c < n) ? ldcg(&P.Ain[(size_t)r * n + c]) : 0.0;
-            acc[ti][tj][1] = (r < n && c + 1 < n) ? ldcg(&P.Ain[(size_t)r * n + c + 1]) : 0.0;
+            *reinterpret_cast<double2*>(Cs + ps.row(ti) * LD + ps.col(tj)) = make_double2(-acc[ti][tj][0], -acc[ti][tj][1]);
+            acc[ti][tj][0] = a[ti][tj][0];                              // accumulators restart from the old tile
+            acc[ti][tj][1] = a[ti][tj][1];
         }
     __syncthreads();
     OT_TILE(3);
     // ---- tile_out = tile_in + CS R
-    product(Cs, Qs);
+    product(Cs, Rs);
 #pragma unroll
     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
         for (int tj = 0; tj < 4; ++tj) {
             const int r = r0 + ps.row(ti), c = c0 + ps.col(tj);
-            if (r < n && c < n) P.Aout[(size_t)r * n + c] = acc[ti][tj][0];
-            if (r < n && c + 1 < n) P.Aout[(size_t)r * n + c + 1] = acc[ti][tj][1];
+            if (vec) {
+                if (r < n && c < n) *reinterpret_cast<double2*>(&P.Aout[(size_t)r * n + c]) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+            } else {
+                if (r < n && c < n) P.Aout[(size_t)r * n + c] = acc[ti][tj][0];
+                if (r < n && c + 1 < n) P.Aout[(size_t)r * n + c + 1] = acc[ti][tj][1];
+            }
         }
     OT_TILE(4);
 }
@@ -303,7 +359,7 @@ __device__ __forceinline__ void tile_step(const TileStepArgs& P, int bi, int bj,
 
 __global__ void __launch_bounds__(DM_NT, 1) inv_tile_step_kernel(const TileStepArgs P) {
     extern __shared__ __align__(16) double psm[];
-    SweepSync sy{smem_u32(psm + DmmaSmem::mbar), 0u};
+    SweepSync sy{smem_u32(psm + TS_MBAR), 0u};
     if (threadIdx.x == 0) mbar_init(sy.bar, DM_NT / 32);
     tile_step(P, blockIdx.y, blockIdx.x, psm, sy);
 }
@@ -344,7 +400,7 @@ __device__ __forceinline__ void server_role(const ServerArgs& P, int rank, unsig
     const int tid = threadIdx.x;
     const int bi = rank / P.nblk, bj = rank % P.nblk;
     const int n = P.n;
-    SweepSync sy{smem_u32(psm + S::mbar), 0u};
+    SweepSync sy{smem_u32(psm + TS_MBAR), 0u};
     if (tid == 0) mbar_init(sy.bar, DM_NT / 32);
 
     server_barrier(P.counter, nctas, P.err);
@@ -384,14 +440,23 @@ struct OuterArgs {
     double* CSn; double* Rn;                // next:    d x kn1 (ld = kn1), kn1 x d (ld = d)
     int k1, kn1;                            // first column and width of the next block (kn1 = 0: last step)
     const double* Qn;                       // where the server leaves Q' (kn1 x kn1, ld = kn1)
-    unsigned* sync;                         // [0] server barrier [1] queue [2] err [3] col strip [4] row strip [5] server done [6] CS' queue
+    unsigned* sync;                         // [0] server barrier [1] queue [2] err [3] col strip [4] row strip [5] server done [6] CS' / CS queue [7] CS tiles done
     int* sm_busy;                           // [SM id] 1 while a server CTA runs there; [SM_SLOTS + SM id] CS' role claimed
     int nserver;
     ServerArgs srv;
     int use_tma;                            // update tiles fed by TMA (gemm_tma.cuh) instead of cp.async
     int sleep;                              // 1: a worker CTA that shares its SM with a look-ahead CTA sleeps meanwhile
+    // cs_head = 1: the step forms ITS OWN CS = -(A[:,K] - E) Q at its start (Q = Qc, left behind by the look-ahead of
+    // the previous step) instead of the previous step forming it as its tail: only the look-ahead CTAs wait for the
+    // row blocks of CS they need (rows K', first in the queue), so the product overlaps the serial chain instead of
+    // preceding it.  CSw = CS (writable), k0 = first column of K.
+    int cs_head;
+    double* CSw; const double* Qc; int k0;
+    unsigned* cs_rows;                      // [row block] CS tiles finished (cs_head)
 };
 constexpr int SM_SLOTS = 256;
+constexpr int CS_ROW_SLOTS = 256;           // row blocks of 64: d <= 16384
+constexpr int SYNC_STRIDE = 8 + 2 * SM_SLOTS + CS_ROW_SLOTS;    // unsigned words of one outer step's sync block
 // Worker side: a 256-thread CTA is TWO independent 128-thread tile engines (half = tid / 128), each the
 // main loop of gemm_f64_kernel<64, 64, 2, 2> (64 x 64 x 16 slabs, warp tile 32 x 32, 3-stage cp.async
 // pipeline, one barrier per k-slab -- a named barrier of the half).  Four engines per SM cover each
@@ -402,17 +467,27 @@ constexpr int EN_STG = EngT::A_STAGE + EngT::B_STAGE;                   // doubl
 constexpr int EN_SMEM = GSTAGES * EN_STG;                               // doubles per engine
 constexpr size_t OUTER_SMEM_BYTES = (2 * (size_t)EN_SMEM > (size_t)DmmaSmem::total ? 2 * (size_t)EN_SMEM : (size_t)DmmaSmem::total) * sizeof(double);
 static_assert(NB * NB <= EN_SMEM, "the split-K partial of a server tile is parked in the engine's stages");
+static_assert((size_t)TS_TOTAL * sizeof(double) <= OUTER_SMEM_BYTES, "a tile step fits in the shared memory of an outer-step CTA");
+constexpr size_t TILE_STEP_SMEM_BYTES = (size_t)TS_TOTAL * sizeof(double);
 
 __device__ __forceinline__ unsigned smid() {
     unsigned r;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ bool wait_count(volatile unsigned* c, unsigned target, int* err) {
+__device__ __forceinline__ bool wait_count(volatile unsigned* c, unsigned target, int* err, unsigned ns = 500) {
     unsigned spins = 0;
     while (*c < target) {
-        __nanosleep(500);
+        __nanosleep(ns);
         if (++spins > (1u << 22)) { *err = 2; return false; }
+    }
+    __threadfence();
+    return true;
+}
+__device__ __forceinline__ bool spin_count(volatile unsigned* c, unsigned target, int* err) {   // the serial chain: no sleep
+    unsigned spins = 0;
+    while (*c < target) {
+        if (++spins > (1u << 26)) { *err = 3; return false; }
     }
     __threadfence();
     return true;
@@ -546,6 +621,10 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
         const int kmid = min(kn, ((kn / 2 + GBK - 1) / GBK) * GBK);
         if (half == 0) load_acc(P.A, d, r0, c0, d, d);
         else zero_acc();
+        if (P.cs_head && kn > 0) {                // the rows of CS this tile needs: formed by the worker CTAs, first in their queue
+            if (tid == 0) (void)spin_count(P.cs_rows + r0 / NB, (unsigned)((kn + NB - 1) / NB), err);
+            __syncthreads();
+        }
         engine_gemm(acc, P.CS, kn, P.R, d, r0, c0, d, d, half ? kmid : 0, half ? kn : kmid, esm, ep, half);
         half_sync(half);
         if (half == 1) {
@@ -588,9 +667,76 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
         __syncthreads();
     }
 
-    // ================= the queue (each engine pulls its own items) =================
     const int tn = (d + NB - 1) / NB;
     const int cb1 = k1 / NB, nk1 = (kn1 + NB - 1) / NB;          // block-column range of K'
+    // ================= CS = -(A[:,K] - E) Q of THIS step (cs_head) =================
+    // One 64 x 64 tile per CTA and item, split over k between the CTA's two engines; the row blocks of K' come first
+    // (the look-ahead CTAs are waiting for exactly those), every finished tile is counted per row block and in total.
+    // Nothing writes A[:,K] before all tiles are done: the update tiles below wait for the total.
+    const int nkc = (kn + NB - 1) / NB;
+    const int n_csh = (P.cs_head && kn > 0) ? tn * nkc : 0;
+    bool cs_worker = false;
+    if (n_csh > 0 && (int)blockIdx.x >= P.nserver) {      // ONE CTA per SM: a tile alone on its SM takes half the time
+        if (tid == 0) s_tile[0] = (atomicExch(reinterpret_cast<int*>(P.sm_busy) + SM_SLOTS + (smid() % SM_SLOTS), 1) == 0) ? 1u : 0u;
+        __syncthreads();
+        cs_worker = s_tile[0] != 0u;
+        __syncthreads();
+    }
+    if (cs_worker) {
+        const int kmid = min(kn, ((kn / 2 + GBK - 1) / GBK) * GBK);
+        const int cb0 = P.k0 / NB;
+        for (;;) {
+            if (tid == 0) s_tile[0] = atomicAdd(P.sync + 6, 1u);
+            __syncthreads();
+            const int u = (int)s_tile[0];
+            __syncthreads();
+            if (u >= n_csh) break;
+            OT_MIN(9);
+            const int rb = u / nkc, jb = u % nkc;
+            const int bi = (rb < nk1) ? cb1 + rb : ((rb - nk1) < cb1 ? rb - nk1 : rb);     // rows K' first, then the others in order
+            const int r0 = bi * NB, c0 = jb * NB;
+            zero_acc();
+            engine_gemm(acc, P.A + P.k0, d, P.Qc, kn, r0, c0, d, kn, half ? kmid : 0, half ? kn : kmid, esm, ep, half);
+            half_sync(half);
+            if (half == 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<double2*>(esm + ep.row(i) * NB + ep.col(j)) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+            __syncthreads();
+            if (half == 0) {
+                const double* part = psm + EN_SMEM;
+                const bool inK = (bi >= cb0) && (bi < cb0 + nkc);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = r0 + ep.row(i), c = c0 + ep.col(j);
+                        if (r < d && c < kn) {
+                            const double2 q2 = *reinterpret_cast<const double2*>(part + ep.row(i) * NB + ep.col(j));
+                            double2 v = make_double2(-(acc[i][j][0] + q2.x), -(acc[i][j][1] + q2.y));
+                            if (inK) {
+                                const double2 q = __ldcg(reinterpret_cast<const double2*>(P.Qc + (size_t)(r - P.k0) * kn + c));
+                                v.x += q.x;
+                                v.y += q.y;
+                            }
+                            *reinterpret_cast<double2*>(P.CSw + (size_t)r * kn + c) = v;
+                        }
+                    }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(P.cs_rows + bi, 1u);
+                atomicAdd(P.sync + 7, 1u);
+            }
+            OT_MAX(10);
+        }
+    }
+
+    // ================= the queue (each engine pulls its own items) =================
     const int n_cs = tn * nk1 - nk1 * nk1;                       // column strip without the pivot block
     const int n_rs = nk1 * (tn - nk1);                           // row strip without the pivot block
     const int n_rest = (tn - nk1) * (tn - nk1);
@@ -616,6 +762,10 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
         half_sync(half);
         if (elected) {
             while (P.sleep && *busy) __nanosleep(2000);
+            if (n_csh > 0) {                     // CS of this step is complete (and, being read by TMA: ordered before the async proxy)
+                (void)wait_count(P.sync + 7, (unsigned)n_csh, err, 200);
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
             s_tile[half] = atomicAdd(P.sync + 1, 1u);
         }
         half_sync(half);
@@ -694,6 +844,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
         half_sync(half);
         if (ep.htid == 0) {
             while (P.sleep && *busy) __nanosleep(2000);
+            if (n_csh > 0) (void)wait_count(P.sync + 7, (unsigned)n_csh, err, 200);
             s_tile[half] = atomicAdd(P.sync + 1, 1u);
         }
         half_sync(half);
@@ -752,7 +903,7 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
     // its engines (split over k), so the 64 nk1-by-tn tiles spread over all SMs instead of piling up on the
     // SMs whose engines happened to finish first.
     __syncthreads();
-    if (kn1 > 0) {
+    if (kn1 > 0 && !P.cs_head) {
         if (tid == 0) s_tile[0] = (atomicExch(reinterpret_cast<int*>(P.sm_busy) + SM_SLOTS + (smid() % SM_SLOTS), 1) == 0) ? 1u : 0u;
         __syncthreads();
         const bool claimed = s_tile[0] != 0u;
@@ -1166,7 +1317,7 @@ __global__ void __launch_bounds__(DM_NT, 2) flow_inverse_kernel(const FlowArgs P
             bar_target += FL_NSRV;
             server_barrier(ctr + FlowCtr::bar, bar_target, reinterpret_cast<int*>(err));
         };
-        SweepSync sy{smem_u32(psm + DmmaSmem::mbar), 0u};
+        SweepSync sy{smem_u32(psm + TS_MBAR), 0u};
         for (int kk = 0; kk < nob; ++kk) {                 // block kk is inverted here
             const int knk = kn_of(kk), nkk = nk_of(kk), cbk = kk * NKB, k1 = kk * OB;
             double* X = P.X[kk & 1];
@@ -1644,7 +1795,7 @@ struct LargeWs {                   // offsets in doubles into the caller's works
         Pbuf4 = Pbuf3 + (size_t)OB * OB;
         pmin = Pbuf4 + (size_t)OB * OB;
         sync = pmin + MIN_PARTIALS + 8;          // barrier counter, tile queue, error flag, per-SM busy flags
-        flow = sync + 64 + SM_SLOTS;
+        flow = sync + (SYNC_STRIDE + 1) / 2 + 8;
         total = flow + (FlowCtr::total + 1) / 2;
     }
 };
@@ -1665,7 +1816,7 @@ __global__ void copy_block_kernel(const double* __restrict__ src, int lds, doubl
 // one launch for the two small fix-ups of an outer step:  CS[K,:] += Q  and  R = A[K,:] + E_K^T
 __global__ void outer_prep_kernel(const double* __restrict__ Q, double* __restrict__ CSk, int kn,
                                   const double* __restrict__ Arows, int d, int k0, double* __restrict__ R) {
-    const size_t nq = (size_t)kn * kn, total = nq + (size_t)kn * d;
+    const size_t nq = (Q != nullptr) ? (size_t)kn * kn : 0, total = nq + (size_t)kn * d;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         if (e < nq) {
             CSk[e] += Q[e];
@@ -1752,6 +1903,19 @@ static bool first_block_fused() {
 //     on par for the inverse alone (1.01 vs 0.97 ms at d = 2000) and for inverse + cov@W (1.58 vs 1.52 ms): its
 //     engines reach the same ~65 % of the DMMA pipe as the per-step kernels, so it stays opt-in,
 // 0 = plain GEMM update + chain of small kernels on a high-priority side stream
+// DAGMA_CS_HEAD (A-B timing): 0 (default) = the previous step forms the CS strip as its tail (on the serial chain);
+// 1 = every outer step forms its own CS strip at its start, rows K' first (the look-ahead chain waits only for those),
+// one CTA per SM.  Measured at d = 2000 (B200, round 2): 0.896 ms against 0.871 ms -- a 64 x 64 x 256 item of two
+// engines is bound by its 8 dependent slab round trips (17 us alone on an SM, as in the tail), so the chain starts
+// 17 us late and the overlap it buys (the tail leaves the critical path) does not pay for it.
+static int cs_head_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_CS_HEAD");
+        v = e ? atoi(e) : 0;
+    }
+    return v != 0 ? 1 : 0;
+}
 static int lookahead_mode() {
     static int v = -1;
     if (v < 0) {
@@ -1906,23 +2070,29 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
         // its CS' / R' items replace the first CS GEMM and the prep kernel; every later pair is produced by the
         // previous step
         double *CSa = CS, *Ra = Rbuf, *CSb = ws + L.CS2, *Rb = ws + L.Rbuf2;
+        const int cs_head = cs_head_mode();
         if (!fused_first) {
             const int kn = d < OB ? d : OB;
-            rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw, d, Q, kn, 0.0, CSa, kn, EPI_NONE, nullptr, 0);
-            if (rc) return rc;
-            outer_prep_kernel<<<296, 256, 0, stream>>>(Q, CSa, kn, Mw, d, 0, Ra);
+            if (!cs_head) {
+                rc = gemm_launch(stream, 0, d, kn, kn, -1.0, Mw, d, Q, kn, 0.0, CSa, kn, EPI_NONE, nullptr, 0);
+                if (rc) return rc;
+            }
+            outer_prep_kernel<<<296, 256, 0, stream>>>(cs_head ? nullptr : Q, CSa, kn, Mw, d, 0, Ra);
             DAGMA_CUDA_OK(cudaGetLastError());
         }
+        const double* Qc = Q;                              // inverse of the current pivot block (cs_head)
         for (int ob = fused_first ? -1 : 0; ob < nob; ++ob) {
             const bool pre = ob < 0;                       // the step in front of the first block
             const int k0 = pre ? 0 : ob * OB, kn = pre ? 0 : ((d - k0) < OB ? (d - k0) : OB);
             const bool more = ob + 1 < nob;
             const int k1 = pre ? 0 : k0 + OB, kn1 = more ? ((d - k1) < OB ? (d - k1) : OB) : 0;
             const int nblk1 = (kn1 + NB - 1) / NB;
-            double* Qn = (nblk1 & 1) ? Pbuf2 : Pbuf;
+            // cs_head: the step reads Qc while its look-ahead CTAs ping-pong the next block: two buffer pairs, in turn
+            const bool pair1 = cs_head && (((ob + 1) & 1) != 0);
+            double *bufA = pair1 ? ws + L.Pbuf3 : Pbuf, *bufB = pair1 ? ws + L.Pbuf4 : Pbuf2;
+            double* Qn = (nblk1 & 1) ? bufB : bufA;
             // every outer step has its own zeroed sync block (one memset for all of them: no memset node
             // between two step kernels); beyond the space of the flow counters: one memset per step
-            constexpr int SYNC_STRIDE = 8 + 2 * SM_SLOTS;
             unsigned* sync_words = sync_base;
             const int slot = ob + 1;                       // slot 0: the step in front of the first block
             if ((slot + 1) * SYNC_STRIDE <= FlowCtr::total) {
@@ -1939,8 +2109,10 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
 #endif
             OuterArgs OA{Mw, d, CSa, Ra, kn, CSb, Rb, k1, kn1, Qn, sync_words, reinterpret_cast<int*>(sync_words + 8),
                          nblk1 * nblk1,
-                         ServerArgs{Pbuf, Pbuf2, kn1, nblk1, piv + k1, sync_words, reinterpret_cast<int*>(sync_words + 2)},
-                         pre ? 0 : (tma_mode() & 1), outer_sleep()};
+                         ServerArgs{bufA, bufB, kn1, nblk1, piv + k1, sync_words, reinterpret_cast<int*>(sync_words + 2)},
+                         pre ? 0 : (tma_mode() & 1), outer_sleep(),
+                         cs_head, CSa, Qc, k0, sync_words + 8 + 2 * SM_SLOTS};
+            Qc = Qn;
             CUtensorMap mapCS, mapR;
             memset(&mapCS, 0, sizeof(mapCS));
             memset(&mapR, 0, sizeof(mapR));

@@ -12,17 +12,10 @@
 // all-reduce of [grads | S] per iteration is enough.
 #include "common.cuh"
 #include "small_gj.cuh"
+#include "mlp_state.h"
 #include "../../include/dagma_b200.h"
 
 namespace dagma {
-
-struct MlpState {            // mirrored by midagma_b200/nonlinear.py
-    double mu, s, lr, lambda1, lambda2, beta1, beta2;
-    double logabsdet, h, min_entry;       // written by the logdet kernel
-    double S, l1, obj, score;             // S = sum res^2 (this rank, then global), l1 = sum |W1|
-    double lr_gamma;                      // ExponentialLR factor applied every 1000 steps (1 = off)
-    int32_t step, halted, info, pad;
-};
 
 // A[i][j] = sum_k W1[(j*m1+k)][i]^2  (nonlinear.py:82-84)  + partial sums of |W1|
 __global__ void mlp_adj_kernel(const double* __restrict__ W1, int d, int m1, double* __restrict__ A,

@@ -109,8 +109,10 @@ def test_flow_kernel_mode():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("env", [{"DAGMA_FIRST_BLOCK": "1"}, {"DAGMA_TMA": "0"}, {"DAGMA_TMA": "3"}],
-                         ids=["first-block-step", "cp-async-only", "tma-gemm-everywhere"])
+@pytest.mark.parametrize("env", [{"DAGMA_FIRST_BLOCK": "1"}, {"DAGMA_TMA": "0"}, {"DAGMA_TMA": "3"}, {"DAGMA_CS_HEAD": "1"},
+                                 {"DAGMA_CS_HEAD": "1", "DAGMA_FIRST_BLOCK": "1", "DAGMA_TMA": "0"}],
+                         ids=["first-block-step", "cp-async-only", "tma-gemm-everywhere", "cs-strip-at-step-head",
+                              "cs-head-first-block-cp-async"])
 def test_optional_variants(env):
     """The A/B switches of the multi-CTA path stay correct: the first pivot block as a step of the persistent kernel,
     cp.async slabs everywhere, and the TMA GEMM for every product that qualifies (alpha / beta / sigmoid epilogues
