@@ -211,6 +211,19 @@ int dagma_mlp_adam_f64(dagma_stream_t stream, int d, int m1, void* state_dev, do
 /* same step over a flat theta of `total` doubles whose first d*m1*d entries are fc1.weight (any stack) */
 int dagma_mlp_adam_ex_f64(dagma_stream_t stream, int d, int m1, size_t total, void* state_dev, double* theta_dev,
                           const double* grads_dev, double* m_dev, double* v_dev, const double* minv_dev);
+/* The WHOLE iteration above -- and `iters` consecutive ones -- as ONE persistent kernel (csrc/mlp_iter.cu) for
+ * dims = [d, m1, 1], d <= 64, m1 <= 40, un-sharded rows: worker CTAs own (node slice, sample group) pairs and keep
+ * their samples in shared memory, one CTA inverts sI - A on chip, two grid barriers per iteration, every sum in a
+ * fixed order.  Replaces the loop body of DagmaNonlinear.minimize (nonlinear.py:212-225) between two checkpoints.
+ *   supported          : 1 when the shape is covered on this device (otherwise use the sequence above)
+ *   workspace_doubles  : size of part_dev
+ *   x_dev [n][d] row-major (this process's rows, n_total = n); sync_dev: 4 zeroed uint32 that live as long as the
+ *   state block; info = 99 in the state block: a grid barrier timed out (the grid was not co-resident).          */
+int dagma_mlp_iter_supported(int n, int d, int m1);
+size_t dagma_mlp_iter_workspace_doubles(int n, int d, int m1);
+int dagma_mlp_iter_f64(dagma_stream_t stream, int n, int n_total, int d, int m1, int iters, void* state_dev,
+                       double* theta_dev, double* m_dev, double* v_dev, const double* x_dev, double* part_dev,
+                       double* minv_dev, unsigned* sync_dev);
 /* General LocallyConnected stacks dims = [d, m_1, ..., 1] (nonlinear.py:39-43, 60-65), transposed activations
  * [d * width][n], one call per layer.
  *   lc_forward : in ([d*mi][n]; + bias_in for the first layer) is replaced by H = sigmoid(in);

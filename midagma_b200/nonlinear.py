@@ -194,6 +194,7 @@ class _MlpEngine:
         self.state_host = torch.zeros(ST_DOUBLES, dtype=torch.float64).pin_memory()
         self.ws = torch.empty(self.lib.dagma_large_workspace_bytes(d) // 8 + 8, **f64)
         self.group, self.graph = group, None
+        self.one_kernel = False
         # NCCL all-reduces are captured inside the iteration graph (DAGMA_GRAPH_NCCL=0: eager launches)
         self._graph_collectives = False
         if group is not None:
@@ -218,6 +219,14 @@ class _MlpEngine:
                              for l in range(self.L)] + [1])
             self.part = torch.empty(chunks * width, **f64)
             self.kws = torch.empty(148 * P * d + 8, **f64)
+            # [d, m1, 1] on one GPU: the whole iteration (and every iteration up to the next checkpoint) as one
+            # persistent kernel, csrc/mlp_iter.cu (DAGMA_MLP_FUSED=0: the launch sequence below, replayed as a graph)
+            import os
+            self.one_kernel = (self.fused and group is None and os.environ.get("DAGMA_MLP_FUSED", "1") != "0"
+                               and bool(self.lib.dagma_mlp_iter_supported(self.n, d, self.m1)))
+            if self.one_kernel:
+                self.iter_ws = torch.empty(self.lib.dagma_mlp_iter_workspace_doubles(self.n, d, self.m1), **f64)
+                self.iter_sync = torch.zeros(4, dtype=torch.int32, device="cuda")
 
     def _sptr(self, f):
         return self.state.data_ptr() + 8 * f
@@ -228,6 +237,8 @@ class _MlpEngine:
     def pull(self):
         self.state_host.copy_(self.state)
         ints = self.state_host[15:].view(torch.int32)
+        if int(ints[I_INFO]) == 99:
+            raise _lib.DagmaB200Error("dagma_mlp_iter_f64: a grid barrier timed out (the grid was not co-resident)")
         return self.state_host, int(ints[I_STEP]), int(ints[I_HALTED])
 
     # ---- pieces
@@ -337,6 +348,12 @@ class _MlpEngine:
             torch.distributed.all_reduce(self.grads, group=self.group)
 
     def replay(self, s: float, n: int):
+        if self.one_kernel:
+            _lib.check(self.lib.dagma_mlp_iter_f64(
+                _lib.stream_ptr(), self.n, self.n_total, self.d, self.m1, int(n), self.state.data_ptr(),
+                self.theta.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.X.data_ptr(), self.iter_ws.data_ptr(),
+                self.Minv.data_ptr(), self.iter_sync.data_ptr()), "dagma_mlp_iter_f64")
+            return
         if self.group is not None and not self._graph_collectives:
             for _ in range(n):
                 self.iteration(s)

@@ -103,3 +103,41 @@ def test_locally_connected_forward():
     x = torch.randn(17, 5, 4, dtype=torch.float64)
     ref = torch.matmul(x.unsqueeze(2), lc.weight.detach().unsqueeze(0)).squeeze(2) + lc.bias.detach()
     assert _relmax(lc(x).numpy(), ref.numpy()) <= 1e-14
+
+
+@pytest.mark.parametrize("d,m1,n,iters", [(40, 10, 2000, 25), (5, 3, 50, 40), (64, 7, 333, 12), (17, 40, 1000, 12),
+                                          (8, 4, 100000, 6), (33, 16, 4099, 8)],
+                         ids=["c3", "tiny", "d64-m7", "m1-40", "streamed-samples", "odd"])
+def test_one_kernel_iteration_vs_launch_sequence(d, m1, n, iters, monkeypatch):
+    """The persistent one-kernel iteration (csrc/mlp_iter.cu) against the launch sequence of csrc/mlp.cu on the same
+    start: parameters, Adam moments and the state block after `iters` iterations (different summation orders only),
+    for shapes that exercise one and several node slices, padded m-tiles, the last partial sample group and sample
+    groups that do not fit in shared memory (streamed in sub-groups)."""
+    from midagma_b200.nonlinear import (DagmaMLP, _MlpEngine, F_MU, F_S, F_LR, F_LAM1, F_LAM2, F_B1, F_B2, F_GAMMA, F_OBJ,
+                                        F_SCORE, F_H, F_SS, F_L1)
+    torch.manual_seed(d * 1000 + m1)
+    model = DagmaMLP([d, m1, 1], bias=True, dtype=torch.double)
+    with torch.no_grad():
+        model.fc1.weight.mul_(0.5).add_(0.02 * torch.randn_like(model.fc1.weight))
+        model.fc1.bias.add_(0.1 * torch.randn_like(model.fc1.bias))
+    X = torch.randn(n, d, dtype=torch.float64).cuda()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DAGMA_MLP_FUSED", mode)
+        eng = _MlpEngine(model, X)
+        assert eng.one_kernel == (mode == "1")
+        sh = eng.state_host
+        sh.zero_()
+        for f, val in ((F_MU, 0.1), (F_S, 1.0), (F_LR, 2e-3), (F_LAM1, 0.02), (F_LAM2, 0.005), (F_B1, 0.99), (F_B2, 0.999),
+                       (F_GAMMA, 1.0)):
+            sh[f] = val
+        eng.state.copy_(sh)
+        eng.replay(1.0, iters - 3)
+        eng.replay(1.0, 3)                       # a second launch continues from the state the first one left
+        st, step, halted = eng.pull()
+        assert step == iters and not halted
+        out[mode] = (eng.theta.cpu().numpy(), eng.m.cpu().numpy(), eng.v.cpu().numpy(), st.clone().numpy())
+    for a, b, what in zip(out["1"][:3], out["0"][:3], ("theta", "m", "v")):
+        assert _relmax(a, b) <= 1e-11, (what, _relmax(a, b))
+    for f in (F_OBJ, F_SCORE, F_H, F_SS, F_L1):
+        assert abs(out["1"][3][f] - out["0"][3][f]) <= 1e-11 * max(abs(out["0"][3][f]), 1e-3), f
