@@ -449,13 +449,15 @@ def bench_c2_c3(torch, with_cpu, peak_tflops=None):
     torch.cuda.synchronize()
     t = (time.perf_counter() - t0) / 4000
     flop = 4.0 * n * d * d + 2.0 * d ** 3
-    c2 = {"workload": "C2: DagmaLinear logistic, ER2 d=100 n=10000, mu=1 s=1 lr=3e-4 (4000 graph-replayed inner iterations, wall clock)",
+    c2 = {"workload": "C2: DagmaLinear logistic, ER2 d=100 n=10000, mu=1 s=1 lr=3e-4 (4000 inner iterations of DagmaLinear.minimize, "
+                      "wall clock; one persistent kernel per checkpoint interval, csrc/lin_iter.cu)",
           "us_per_iter": t * 1e6, "iters_per_s": 1.0 / t, "flop_per_iter": flop, "tflops": flop / t / 1e12}
     if peak_tflops:
         c2["roofline"] = {"bound": "tensor", "achieved": flop / t / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
                           "frac": flop / t / 1e12 / peak_tflops, "traffic": None,
-                          "note": "latency-bound chain of 6 graph nodes per iteration (the 100 x 100 inverse on one CTA beside "
-                                  "the two skinny score GEMMs), not a throughput kernel: the fraction is reported, not a target"}
+                          "note": "one persistent kernel: the iteration is bound by the on-chip inverse of the 100 x 100 matrix "
+                                  "on ONE CTA (two 64-pivot sweeps + six 64^3 products), the score products of the other "
+                                  "147 CTAs hide behind it: the fraction is reported, not a target"}
     # e2e: the call a reference user makes -- host X in, thresholded W_est out (reduced schedule T=2 x 1000 iterations)
     m2 = DagmaLinear("logistic")
     Xh = X.copy()
@@ -505,14 +507,15 @@ def bench_c2_c3(torch, with_cpu, peak_tflops=None):
     t = e0.elapsed_time(e1) * 1e-3 / 4000
     _, step, halted = eng.pull()
     flop = 2.0 * (2.0 * n * d * d * m1) + 6.0 * n * d * m1 + 2.0 * d ** 3
-    c3 = {"workload": "C3: DagmaMLP [40, 10, 1] n=2000, mu=0.1 s=1 lr=2e-4 (4000 replays of the per-iteration CUDA graph of "
-                      "DagmaNonlinear.minimize, CUDA events)",
+    c3 = {"workload": "C3: DagmaMLP [40, 10, 1] n=2000, mu=0.1 s=1 lr=2e-4 (4000 iterations of DagmaNonlinear.minimize's engine: "
+                      "one persistent kernel, csrc/mlp_iter.cu; CUDA events)",
           "us_per_iter": t * 1e6, "iters_per_s": 1.0 / t, "flop_per_iter": flop, "tflops": flop / t / 1e12,
           "iterations_done": int(step), "halted": int(halted)}
     if peak_tflops:
         c3["roofline"] = {"bound": "tensor", "achieved": flop / t / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
                           "frac": flop / t / 1e12 / peak_tflops, "traffic": None,
-                          "note": "latency-bound chain of ~10 graph nodes per iteration; the fraction is reported, not a target"}
+                          "note": "one persistent kernel, two grid barriers per iteration; bound by the 40-pivot sweep of the h CTA "
+                                  "and the barriers, not by throughput: the fraction is reported, not a target"}
     # e2e: DagmaNonlinear.fit on host X (reduced schedule T=2 x 1000 iterations), thresholded adjacency out
     torch.manual_seed(0)
     model_e = DagmaMLP(dims=[d, m1, 1], bias=True)

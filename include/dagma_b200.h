@@ -162,6 +162,23 @@ int dagma_linear_update_ex_f64(dagma_stream_t stream, int d, void* state_dev, do
 /* W += sign * lr * (previous Adam direction)     src/dagma/linear.py:235, 239           */
 int dagma_linear_apply_dir_f64(dagma_stream_t stream, int d, const void* state_dev, double* w_dev,
                                const double* m_dev, const double* v_dev, double sign);
+/* The WHOLE inner iteration -- fused inverse, score product(s), the update above -- and `iters` consecutive ones as
+ * ONE persistent kernel (csrc/lin_iter.cu) for d <= 128, l2 or logistic, un-sharded rows, no trek regulariser: one CTA
+ * inverts sI - W o W on chip while the worker CTAs form T (logistic: every worker keeps <= 72 rows of X in shared
+ * memory for the whole launch, partial X^T sigmoid(XW) per worker summed in a fixed order; l2: cov W), then every CTA
+ * updates its share of the entries; CTA 0 advances the state block.  Replaces the loop body of DagmaLinear.minimize
+ * (src/dagma/linear.py:224-276) between two checkpoints; state block, buffers and results are those of the launch
+ * sequence (inverse -> dagma_gemm_f64 -> dagma_linear_update_f64).
+ *   supported          : 1 when the shape is covered on this device (logistic: n <= 72 (SMs - 1))
+ *   workspace_doubles  : size of part_dev
+ *   x_dev [n][d] row-major (logistic only, else NULL / n = 0); sync_dev: 4 uint32 that live as long as the state
+ *   block; info = 99 in the state block: a grid barrier timed out (the grid was not co-resident).                  */
+int dagma_linear_iter_supported(int logistic, int n, int d);
+size_t dagma_linear_iter_workspace_doubles(int logistic, int n, int d);
+int dagma_linear_iter_f64(dagma_stream_t stream, int logistic, int n, int d, int iters, void* state_dev,
+                          double* w_dev, double* m_dev, double* v_dev, double* minv_dev, double* t_dev,
+                          const double* cov_dev, const double* x_dev, const uint8_t* mask_exc_dev,
+                          const uint8_t* mask_inc_dev, double* part_dev, unsigned* sync_dev);
 /* checkpoint reductions: l2 score 1/2 tr((I-W)^T cov (I-W)) and sum|W|   linear.py:85-87, 129 */
 int dagma_linear_objective_f64(dagma_stream_t stream, int d, void* state_dev, const double* w_dev,
                                const double* t_dev, const double* cov_dev, int l2);

@@ -81,6 +81,16 @@ class LargeLinearEngine:
         self._model_cov_ptr = model._cov_dev.data_ptr()
         self.launches_per_iter = None
         self._trek_setup(getattr(model, "_trek_plan", None))
+        # d <= 128, un-sharded rows, no trek regulariser: every iteration up to the next checkpoint is ONE persistent
+        # kernel, csrc/lin_iter.cu (DAGMA_LIN_FUSED=0: the launch sequence below, replayed as a graph)
+        import os
+        logistic = int(self.loss_type == "logistic")
+        self.one_kernel = (group is None and self.trek is None and os.environ.get("DAGMA_LIN_FUSED", "1") != "0"
+                           and bool(self.lib.dagma_linear_iter_supported(logistic, self.n if logistic else 0, d)))
+        if self.one_kernel:
+            self.iter_ws = torch.empty(self.lib.dagma_linear_iter_workspace_doubles(
+                logistic, self.n if logistic else 0, d), **f64)
+            self.iter_sync = torch.zeros(4, dtype=torch.int32, device=self.dev)
 
     # ------------------------------------------------------------------ trek regulariser
     def _trek_setup(self, plan):
@@ -146,6 +156,8 @@ class LargeLinearEngine:
     def _pull(self):
         self.state_host.copy_(self.state)
         ints = self.state_host[17:].view(torch.int32)
+        if int(ints[I_INFO]) == 99:
+            raise _lib.DagmaB200Error("dagma_linear_iter_f64: a grid barrier timed out (the grid was not co-resident)")
         return self.state_host, int(ints[I_IT]), int(ints[I_HALTED]), int(ints[I_INFO])
 
     # ------------------------------------------------------------------ launch sequences
@@ -211,7 +223,21 @@ class LargeLinearEngine:
         self._gradient_pieces(s)
         self._update()
 
+    def _fused_iterations(self, n: int):
+        """n inner iterations in one launch (stops early, like the sequence, once `halted` is latched)."""
+        ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        logistic = int(self.loss_type == "logistic")
+        _lib.check(self.lib.dagma_linear_iter_f64(
+            _lib.stream_ptr(), logistic, self.n if logistic else 0, self.d, int(n), self.state.data_ptr(),
+            self.W.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.Minv.data_ptr(), self.T.data_ptr(),
+            self.cov.data_ptr(), ptr(self.X), ptr(self.mask_exc), ptr(self.mask_inc), self.iter_ws.data_ptr(),
+            self.iter_sync.data_ptr()), "dagma_linear_iter_f64")
+
     def _replay(self, s: float, n: int):
+        if self.one_kernel:
+            if n > 0:
+                self._fused_iterations(n)
+            return
         if self.group is not None and not self._graph_collectives:   # NCCL outside a graph: launch eagerly
             for _ in range(n):
                 self._iteration(s)

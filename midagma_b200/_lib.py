@@ -65,6 +65,11 @@ EXPORTS = {
                                              C.c_double]),
     "dagma_linear_apply_dir_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_double]),
+    "dagma_linear_iter_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "dagma_linear_iter_workspace_doubles": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dagma_linear_iter_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dagma_linear_objective_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int]),
     "dagma_linear_objective_workspace_bytes": (C.c_size_t, []),

@@ -19,6 +19,7 @@
 #include "gemm_tma.cuh"
 #include "small_gj.cuh"
 #include "small_dmma.cuh"
+#include "lin_state.h"
 #include <cstdlib>
 #include "../../include/dagma_b200.h"
 
@@ -2216,24 +2217,7 @@ int logdet_inv_large(cudaStream_t stream, int batch, int d, double s, const doub
     return rc;
 }
 
-// ------------------------------------------------------------------ iteration state
-struct LinState {           // mirrored by midagma_b200/_large.py (all 8-byte fields first)
-    double mu, s, lr, lambda1, beta1, beta2;
-    double p1_hi, p1_lo, p2_hi, p2_lo;      // beta^it as double-double
-    double logabsdet, h, min_entry;
-    double score_acc, l1_acc, loss_acc;     // reduction outputs
-    double gscale;                          // l2: 1 (T = cov W), logistic: 1/n (T = X^T sigmoid(XW))
-    int32_t it, halted, info, pad;
-};
-
-__device__ __forceinline__ void dd_mul(double& hi, double& lo, double b) {
-    const double ph = hi * b;
-    const double pl = fma(hi, b, -ph) + lo * b;
-    const double s = ph + pl;
-    lo = pl - (s - ph);
-    hi = s;
-}
-
+// ------------------------------------------------------------------ iteration state (LinState: lin_state.h)
 // end of an inner iteration: latch `halted` when the inverse was infeasible, else advance beta^it and the counter
 __device__ __forceinline__ void linear_advance(LinState* st) {
     if (st->halted != 0) return;

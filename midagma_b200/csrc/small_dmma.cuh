@@ -213,6 +213,10 @@ __device__ long long g_sweep_trace[64 * 8];
 #define DAGMA_SWEEP_JIT_ROWS 0       // 1: pivot-row fragments loaded tile by tile inside the block step
 #endif
 
+#ifndef DAGMA_FILL_MATE_SKIP
+#define DAGMA_FILL_MATE_SKIP 0       // 1: the warp that shares the sub-partition (FP64 pipe) with the next diagonal warp does no filler work during that block step
+#endif
+
 #ifndef DAGMA_STAGE_INTERLEAVE
 #define DAGMA_STAGE_INTERLEAVE 1     // diagonal warp: its publish-critical DMMAs 1 inside / 0 after / 2 before the pivot-block chain
 #endif
@@ -254,7 +258,14 @@ __device__ __forceinline__ void dmma_block_step(double (&a)[2][4][2], const Dmma
     // Every warp but the one that is about to run the pivot chain of this step spends the wait on independent work
     // (the fit kernel: k-blocks of the score GEMM) -- one unit at a time, polling the barrier in between, so the step
     // starts at most one unit late for warps that are off the critical path and not at all late for the chain.
+#if DAGMA_FILL_MATE_SKIP
+    // warps w and w ^ 4 issue to the same sub-partition: the filler DMMAs of the mate (16 clk of the FP64 pipe each) would
+    // sit in front of the dependent FP64 instructions of the pivot chain
+    const bool mate_next = has_next && (ps.warp == ((2 * (BN >> 1) + (BN >> 2)) ^ 4));
+    if (!diag_next && !mate_next)
+#else
     if (!diag_next)
+#endif
         while (fill.more() && !mbar_test(sy.bar, sy.phase)) fill.unit();
     mbar_wait(sy.bar, sy.phase);
     sy.phase ^= 1u;

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "small_gj.cuh"
 #include "small_dmma.cuh"
+#include "small_inv2.cuh"
 #include <cstdlib>
 #include "../../include/dagma_b200.h"
 
@@ -152,22 +153,7 @@ __global__ void __launch_bounds__(DM_NT, 2) logdet_inv_dmma_kernel(const InvArgs
         __syncthreads();
     }
 }
-// 64 < d <= 128: two-by-two block Gauss-Jordan on chip.  The four 64 x 64 tiles of the (identity padded) matrix live
-// in shared memory ([64][68] doubles each, the row stride the DMMA fragment loads want); per block step kb
-//   Q = T[kb][kb]^{-1}            by the tensor-core sweep above (in registers, then to a fifth tile buffer),
-//   T[o][kb]  = -T[o][kb] Q       (new pivot column, o = 1 - kb; in place: its old value is not needed afterwards)
-//   T[o][o]  +=  T[o][kb] T[kb][o]
-//   T[kb][o]  =  Q T[kb][o]       (new pivot row, in place),       T[kb][kb] = Q
-// three 64^3 DMMA products per step instead of 64 barrier-separated rank-1 updates of the scalar sweep.
-// One 256-thread CTA per problem and SM (194 KB of shared memory).
-struct Inv2Smem {                  // offsets in doubles; the sweep's buffers keep their DmmaSmem offsets
-    static constexpr int tile = DM_DP * DM_LD;
-    static constexpr int t0 = DmmaSmem::ncov, t1 = DmmaSmem::W;
-    static constexpr int t2 = (DmmaSmem::total + 1) & ~1, t3 = t2 + tile, q = t3 + tile, piv = q + tile;
-    static constexpr int total = piv + 2 * DM_DP;
-    static constexpr size_t bytes = (size_t)total * sizeof(double);
-    __device__ static constexpr int at(int bi, int bj) { return bi == 0 ? (bj == 0 ? t0 : t1) : (bj == 0 ? t2 : t3); }
-};
+// 64 < d <= 128: two-by-two block Gauss-Jordan on chip (small_inv2.cuh), one 256-thread CTA per problem and SM
 __global__ void __launch_bounds__(DM_NT, 1) logdet_inv_dmma2_kernel(const InvArgs P) {
     extern __shared__ __align__(16) double psm[];
     using S = DmmaSmem;
@@ -175,50 +161,10 @@ __global__ void __launch_bounds__(DM_NT, 1) logdet_inv_dmma2_kernel(const InvArg
     const int tid = threadIdx.x, d = P.d;
     const DmmaPos ps(tid);
     double* red = psm + S::red;
-    double* Qs = psm + Inv2Smem::q;
     double* pv = psm + Inv2Smem::piv;
     SweepSync sy{smem_u32(psm + S::mbar), 0u};
     if (tid == 0) mbar_init(sy.bar, DM_NT / 32);
     __syncthreads();
-    double a[2][4][2];
-    auto product = [&](const double* Am, const double* Bm) {       // a += Am Bm (64 x 64 x 64), warp tile 16 x 32
-#pragma unroll 4
-        for (int kk = 0; kk < DM_DP; kk += 4) {
-            double an[2], bw[4];
-#pragma unroll
-            for (int ti = 0; ti < 2; ++ti) an[ti] = Am[ps.row(ti) * LD + kk + ps.qc];
-#pragma unroll
-            for (int tj = 0; tj < 4; ++tj) bw[tj] = Bm[(kk + ps.qc) * LD + 32 * ps.wc + 8 * tj + ps.qr];
-#pragma unroll
-            for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-                for (int tj = 0; tj < 4; ++tj) dmma(a[ti][tj][0], a[ti][tj][1], an[ti], bw[tj]);
-        }
-    };
-    auto load_acc = [&](const double* T) {
-#pragma unroll
-        for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-            for (int tj = 0; tj < 4; ++tj) {
-                const double2 v = *reinterpret_cast<const double2*>(T + ps.row(ti) * LD + ps.col(tj));
-                a[ti][tj][0] = v.x;
-                a[ti][tj][1] = v.y;
-            }
-    };
-    auto store_acc = [&](double* T, double sign) {
-#pragma unroll
-        for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-            for (int tj = 0; tj < 4; ++tj)
-                *reinterpret_cast<double2*>(T + ps.row(ti) * LD + ps.col(tj)) =
-                    make_double2(sign * a[ti][tj][0], sign * a[ti][tj][1]);
-    };
-    auto zero_acc = [&]() {
-#pragma unroll
-        for (int ti = 0; ti < 2; ++ti)
-#pragma unroll
-            for (int tj = 0; tj < 4; ++tj) a[ti][tj][0] = a[ti][tj][1] = 0.0;
-    };
     for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
         const double* A = P.a + (size_t)b * d * P.lda;
         // ---- M = (s I - A o A) / scale into the four tiles, identity padded to 128 x 128
@@ -233,34 +179,7 @@ __global__ void __launch_bounds__(DM_NT, 1) logdet_inv_dmma2_kernel(const InvArg
             psm[Inv2Smem::at(r >> 6, c >> 6) + (r & 63) * LD + (c & 63)] = v;
         }
         __syncthreads();
-#pragma unroll 1
-        for (int kb = 0; kb < 2; ++kb) {
-            const int o = 1 - kb, kn = min(DM_DP, d - DM_DP * kb);
-            double* Tkk = psm + Inv2Smem::at(kb, kb);
-            double* Tok = psm + Inv2Smem::at(o, kb);
-            double* Tko = psm + Inv2Smem::at(kb, o);
-            double* Too = psm + Inv2Smem::at(o, o);
-            load_acc(Tkk);
-            __syncthreads();
-            dmma_sweep(a, ps, psm, kn, sy);                       // a = Q (identity padded); ends with a barrier
-            if (tid < DM_DP) pv[DM_DP * kb + tid] = (tid < ((kn + 3) & ~3)) ? psm[S::pinfo + tid] : 1.0;
-            store_acc(Qs, 1.0);
-            store_acc(Tkk, 1.0);
-            __syncthreads();
-            zero_acc();
-            product(Tok, Qs);                                     // T[o][kb] Q
-            __syncthreads();
-            store_acc(Tok, -1.0);                                 // new pivot column
-            __syncthreads();
-            load_acc(Too);
-            product(Tok, Tko);
-            store_acc(Too, 1.0);
-            zero_acc();
-            product(Qs, Tko);                                     // Q T[kb][o]
-            __syncthreads();
-            store_acc(Tko, 1.0);                                  // new pivot row
-            __syncthreads();
-        }
+        inv2_block_gj(psm, ps, sy, d);
         // ---- outputs
         double ld = 0.0, zero1 = 0.0, zero2 = 0.0;
         bool badpiv = false;

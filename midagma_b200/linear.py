@@ -291,24 +291,77 @@ def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1
     return W_est, info
 
 
+def _batch_lanes(d: int, batch: int) -> int:
+    """How many problems of a d > 64 batch run side by side.  For d <= 128 a problem's inner iterations are one
+    persistent kernel of ceil(d / 8) + 1 CTAs (csrc/lin_iter.cu), each alone on its SM, so several problems fit on the
+    device at once -- one host thread and one CUDA stream per lane (DAGMA_BATCH_LANES overrides; 1 = one after the
+    other).  Beyond d = 128 the blocked inverse fills the device by itself."""
+    import os
+    env = os.environ.get("DAGMA_BATCH_LANES")
+    if env:
+        return max(1, min(int(env), batch))
+    lib = _lib.load()
+    if d > 128 or not lib.dagma_linear_iter_supported(0, 0, d) or os.environ.get("DAGMA_LIN_FUSED", "1") == "0":
+        return 1
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    ctas = (d + 7) // 8 + 1
+    return max(1, min((sms - 12) // ctas, 8, batch))       # a dozen SMs stay free for the checkpoint kernels of all lanes
+
+
 def _fit_batch_large(covd, lambda1, *, w_threshold, return_info, **fit_kw):
-    """``fit_batch`` beyond the on-chip size (d > 64): the problems run one after the other on the multi-CTA engine
-    (blocked inverse + score GEMM + fused update, one CUDA-graph replay per inner iteration) -- the same code path as
-    ``DagmaLinear.fit`` at that size, fed with the covariance instead of the data."""
+    """``fit_batch`` beyond the on-chip size (d > 64): every problem runs on the multi-CTA engine -- the same code path
+    as ``DagmaLinear.fit`` at that size, fed with the covariance instead of the data -- and ``_batch_lanes`` problems
+    run concurrently, each on its own stream (for d <= 128 the inner iterations of a problem are one persistent kernel
+    on a handful of SMs)."""
     batch, d, _ = covd.shape
     lam = np.broadcast_to(np.asarray(lambda1.cpu() if isinstance(lambda1, torch.Tensor) else lambda1,
                                      dtype=np.float64), (batch,))
     W_raw = np.empty((batch, d, d))
-    stage_iters, h_fin, sc_fin = [], [], []
-    for b in range(batch):
+    stage_iters, h_fin, sc_fin = [None] * batch, [None] * batch, [None] * batch
+
+    def solve(b):
         m = DagmaLinear("l2")
         kw = dict(fit_kw)
         kw["s"] = list(kw["s"]) if isinstance(kw["s"], (list, tuple)) else kw["s"]
         m._fit_from_cov(covd[b], float(lam[b]), **kw)
         W_raw[b] = m.W_raw
-        stage_iters.append(m.stage_iters)
-        h_fin.append(m.h_final)
-        sc_fin.append(m.score_final)
+        stage_iters[b], h_fin[b], sc_fin[b] = m.stage_iters, m.h_final, m.score_final
+
+    lanes = _batch_lanes(d, batch)
+    if lanes <= 1:
+        for b in range(batch):
+            solve(b)
+    else:
+        import threading
+        main = torch.cuda.current_stream()
+        dev = covd.device
+        todo = iter(range(batch))
+        lock = threading.Lock()
+        errors = []
+
+        def lane():
+            torch.cuda.set_device(dev)
+            st = torch.cuda.Stream(device=dev)
+            st.wait_stream(main)                                  # covd was produced on the caller's stream
+            with torch.cuda.stream(st):
+                while not errors:
+                    with lock:
+                        b = next(todo, None)
+                    if b is None:
+                        break
+                    try:
+                        solve(b)
+                    except BaseException as e:                    # noqa: BLE001 -- re-raised on the caller's thread
+                        errors.append(e)
+                st.synchronize()
+
+        threads = [threading.Thread(target=lane, daemon=True) for _ in range(lanes)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
     W_est = W_raw.copy()
     W_est[np.abs(W_est) < w_threshold] = 0
     if not return_info:
