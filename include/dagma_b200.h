@@ -179,6 +179,29 @@ int dagma_linear_iter_f64(dagma_stream_t stream, int logistic, int n, int d, int
                           double* w_dev, double* m_dev, double* v_dev, double* minv_dev, double* t_dev,
                           const double* cov_dev, const double* x_dev, const uint8_t* mask_exc_dev,
                           const uint8_t* mask_inc_dev, double* part_dev, unsigned* sync_dev);
+/* Rows of X sharded over the GPUs of ONE box, one process per GPU (the reference has no multi-device
+ * path: this replaces the all-reduce a torch.distributed port of linear.py:246 would issue every iteration).  The same
+ * persistent kernel runs on every GPU on its n_local rows; the sum of the d x d partial products over the GPUs happens
+ * inside it by plain stores / loads over NVLink peer memory, in rank order on every GPU (bit-identical replicas).
+ *   exchange_bytes : size of one GPU's exchange allocation (dagma_peer_alloc), zero on entry of the first launch
+ *   exchange_ptrs  : [nranks] host array, entry r = rank r's allocation as mapped into THIS process (entry `rank`: the
+ *                    own allocation; the others: dagma_peer_import of the handles the peers exported)
+ * All ranks must launch the same sequence of calls (same iters); a peer that does not show up ends the launch with
+ * info = 99 after a bounded wait.                                                                                  */
+size_t dagma_linear_iter_exchange_bytes(int d, int nranks);
+int dagma_linear_iter_sharded_f64(dagma_stream_t stream, int n_local, int d, int iters, void* state_dev,
+                                  double* w_dev, double* m_dev, double* v_dev, double* minv_dev, double* t_dev,
+                                  const double* cov_dev, const double* x_dev, const uint8_t* mask_exc_dev,
+                                  const uint8_t* mask_inc_dev, double* part_dev, unsigned* sync_dev, int rank,
+                                  int nranks, void* const* exchange_ptrs);
+/* Peer-visible device memory (csrc/peer.cu): an allocation of its own (zeroed), its 64-byte inter-process handle, the
+ * import of a peer's handle into this process (peer access enabled on demand) and the matching release / free.       */
+#define DAGMA_PEER_HANDLE_BYTES 64
+int dagma_peer_alloc(size_t bytes, void** out_dev);
+int dagma_peer_free(void* dev);
+int dagma_peer_export(void* dev, unsigned char* handle_out);
+int dagma_peer_import(const unsigned char* handle, void** out_dev);
+int dagma_peer_release(void* imported_dev);
 /* checkpoint reductions: l2 score 1/2 tr((I-W)^T cov (I-W)) and sum|W|   linear.py:85-87, 129 */
 int dagma_linear_objective_f64(dagma_stream_t stream, int d, void* state_dev, const double* w_dev,
                                const double* t_dev, const double* cov_dev, int l2);

@@ -81,16 +81,83 @@ class LargeLinearEngine:
         self._model_cov_ptr = model._cov_dev.data_ptr()
         self.launches_per_iter = None
         self._trek_setup(getattr(model, "_trek_plan", None))
-        # d <= 128, un-sharded rows, no trek regulariser: every iteration up to the next checkpoint is ONE persistent
-        # kernel, csrc/lin_iter.cu (DAGMA_LIN_FUSED=0: the launch sequence below, replayed as a graph)
+        # d <= 128, no trek regulariser: every iteration up to the next checkpoint is ONE persistent kernel,
+        # csrc/lin_iter.cu (DAGMA_LIN_FUSED=0: the launch sequence below, replayed as a graph).  Rows sharded over the
+        # GPUs of one box: the same kernel on every GPU, the d x d partial products summed INSIDE it over NVLink peer
+        # memory (DAGMA_LIN_PEER=0: launch sequence + NCCL all-reduce)
         import os
         logistic = int(self.loss_type == "logistic")
-        self.one_kernel = (group is None and self.trek is None and os.environ.get("DAGMA_LIN_FUSED", "1") != "0"
+        self._peer = None
+        self.one_kernel = (self.trek is None and os.environ.get("DAGMA_LIN_FUSED", "1") != "0"
                            and bool(self.lib.dagma_linear_iter_supported(logistic, self.n if logistic else 0, d)))
+        if group is not None:
+            self.one_kernel = self._peer_setup(group, self.one_kernel and logistic == 1
+                                               and os.environ.get("DAGMA_LIN_PEER", "1") != "0")
         if self.one_kernel:
             self.iter_ws = torch.empty(self.lib.dagma_linear_iter_workspace_doubles(
                 logistic, self.n if logistic else 0, d), **f64)
             self.iter_sync = torch.zeros(4, dtype=torch.int32, device=self.dev)
+
+    # ------------------------------------------------------------------ peer memory of the row-sharded fused iteration
+    def _peer_setup(self, group, want: bool) -> bool:
+        """Exchange buffers of the row-sharded persistent kernel: one allocation per GPU, mapped into every process of
+        the group through CUDA IPC handles.  Every rank takes the same decision (two small all-reduces): the peer path
+        is used only when every rank supports the shape and every mapping succeeded."""
+        import ctypes as C
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = self.dev
+
+        def agree(ok: bool) -> bool:
+            t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64,
+                             device=dev if dist.get_backend(group) == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(t.item() > 0.5)
+
+        want = want and dist.get_backend(group) == "nccl" and 2 <= world <= 8
+        if not agree(want):
+            return False
+        nbytes = self.lib.dagma_linear_iter_exchange_bytes(self.d, world)
+        own, handle, ok = C.c_void_p(), (C.c_ubyte * 64)(), nbytes > 0
+        ok = ok and self.lib.dagma_peer_alloc(nbytes, C.byref(own)) == 0
+        ok = ok and self.lib.dagma_peer_export(own, handle) == 0
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle) if ok else None, group=group)
+        ptrs, imported = (C.c_void_p * world)(), []
+        ok = ok and all(h is not None for h in handles)
+        if ok:
+            for r in range(world):
+                if r == rank:
+                    ptrs[r] = own.value
+                    continue
+                p = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                if self.lib.dagma_peer_import(buf, C.byref(p)) != 0:
+                    ok = False
+                    break
+                imported.append(p)
+                ptrs[r] = p.value
+        if not agree(ok):                        # also the barrier: every buffer is zeroed and mapped before a launch
+            for p in imported:
+                self.lib.dagma_peer_release(p)
+            if own.value:
+                self.lib.dagma_peer_free(own)
+            return False
+        self._peer = {"group": group, "rank": rank, "world": world, "own": own, "imported": imported, "ptrs": ptrs}
+        return True
+
+    def close(self):
+        """Release the peer mappings (collective: every rank of the group calls it) and free the own buffer."""
+        if self._peer is None:
+            return
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        pr, self._peer = self._peer, None
+        self.one_kernel = False
+        for p in pr["imported"]:
+            self.lib.dagma_peer_release(p)
+        dist.barrier(group=pr["group"])          # nobody maps the buffer any more
+        self.lib.dagma_peer_free(pr["own"])
 
     # ------------------------------------------------------------------ trek regulariser (SURVEY.md 8f3)
     def _trek_setup(self, plan):
@@ -227,6 +294,13 @@ class LargeLinearEngine:
         """n inner iterations in one launch (stops early, like the sequence, once `halted` is latched)."""
         ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         logistic = int(self.loss_type == "logistic")
+        if self._peer is not None:
+            _lib.check(self.lib.dagma_linear_iter_sharded_f64(
+                _lib.stream_ptr(), self.n, self.d, int(n), self.state.data_ptr(), self.W.data_ptr(), self.m.data_ptr(),
+                self.v.data_ptr(), self.Minv.data_ptr(), self.T.data_ptr(), self.cov.data_ptr(), ptr(self.X),
+                ptr(self.mask_exc), ptr(self.mask_inc), self.iter_ws.data_ptr(), self.iter_sync.data_ptr(),
+                self._peer["rank"], self._peer["world"], self._peer["ptrs"]), "dagma_linear_iter_sharded_f64")
+            return
         _lib.check(self.lib.dagma_linear_iter_f64(
             _lib.stream_ptr(), logistic, self.n if logistic else 0, self.d, int(n), self.state.data_ptr(),
             self.W.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.Minv.data_ptr(), self.T.data_ptr(),

@@ -70,6 +70,15 @@ EXPORTS = {
     "dagma_linear_iter_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dagma_linear_iter_exchange_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "dagma_linear_iter_sharded_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "dagma_peer_alloc": (C.c_int, [C.c_size_t, C.c_void_p]),
+    "dagma_peer_free": (C.c_int, [C.c_void_p]),
+    "dagma_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dagma_peer_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dagma_peer_release": (C.c_int, [C.c_void_p]),
     "dagma_linear_objective_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int]),
     "dagma_linear_objective_workspace_bytes": (C.c_size_t, []),

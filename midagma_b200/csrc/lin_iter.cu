@@ -22,9 +22,18 @@
 //   same order), CTA 0 advances the state block (beta powers as double-double, iteration counter) or latches `halted`
 //   when the inverse was infeasible, barrier.
 //
+// Rows of X sharded over the GPUs of one box (one process per GPU): the SAME kernel runs on every GPU on its rows, and
+// the one exchange step of the path -- the sum of the d x d partial products over the GPUs -- happens INSIDE it over
+// NVLink peer memory (csrc/peer.cu), no collective library call: after the fixed-order sum of its workers' partials a
+// GPU stores the d x d result into slot `rank` of EVERY GPU's exchange buffer (plain peer stores), fences at system
+// scope, and one thread raises its sequence number in every GPU's flag array; after the grid barrier each CTA waits
+// (bounded) for the sequence numbers of all peers in its LOCAL flag array and adds the slots in rank order -- the same
+// order on every GPU, so the replicas stay bit-identical without a broadcast.  The buffers alternate by the parity of
+// the sequence number: a GPU cannot be more than one exchange ahead of a peer, because it needs that peer's flag.
+//
 // The state block, the buffers and the results are those of the launch sequence (LargeLinearEngine), so back-tracking,
-// objective checkpoints and telemetry are unchanged.  Rows sharded over GPUs, trek regularisers and n beyond
-// 72 rows x (SMs - 1) workers stay on the launch sequence.
+// objective checkpoints and telemetry are unchanged.  Trek regularisers and n beyond 72 rows x (SMs - 1) workers per GPU
+// stay on the launch sequence.
 #include "common.cuh"
 #include "small_dmma.cuh"
 #include "small_inv2.cuh"
@@ -39,6 +48,7 @@ constexpr int LI_MT1 = 9;                 // m-tiles of X rows per worker (72 ro
 constexpr int LI_RB = 8 * LI_MT1;
 constexpr unsigned LI_SPIN_MAX = 1u << 22;
 constexpr int LI_MAX_D = 128;
+constexpr int LI_MAX_RANKS = 8;           // GPUs of one box that may share the rows of X
 
 struct LiPlan {
     int G, NW, NR;                        // CTAs, workers, rows of X per worker (logistic; multiple of 8)
@@ -83,6 +93,14 @@ struct LinIterArgs {
     double* part;                         // logistic: [NW][d * d] un-scaled partial products
     unsigned* sync;                       // [0] grid barrier arrivals [1] worker barrier arrivals [2] error (zeroed per launch)
     int logistic, n, d, iters, sms;
+    // rows of X sharded over `nranks` GPUs of one box (logistic only; nranks = 1: none of this is touched).
+    // xchg[r]: rank r's exchange buffer as mapped into THIS process, [2 (parity)][nranks (writer)][d * d] doubles;
+    // flags[r]: rank r's [nranks] sequence numbers (writer q's partial sums of iteration `seq` have landed in rank r's
+    // buffer); seq: this rank's count of exchanged iterations (lives as long as the buffers, never reset).
+    int rank, nranks;
+    double* xchg[LI_MAX_RANKS];
+    unsigned* flags[LI_MAX_RANKS];
+    unsigned* seq;
 };
 
 #ifdef DAGMA_LIN_TRACE
@@ -202,41 +220,31 @@ __device__ __forceinline__ void li_inverse_role(const LinIterArgs& P, double* ps
                     }
                 }
     } else {
-        // W lands in the tiles (cp.async.cg: L2, every 16-byte piece in flight at once; odd d: L2 loads in batches),
-        // then M = (s I - W o W) / 2^e in place; the padding keeps the identity of li_inverse_init
-        if ((d & 1) == 0) {
-            const int hc = d >> 1;
-            for (int r = tid >> 5; r < d; r += LI_NT / 32)
-                for (int c2 = tid & 31; c2 < hc; c2 += 32) {
-                    const int c = 2 * c2;
-                    cp_async16(smem_u32(psm + Inv2Smem::at(r >> 6, c >> 6) + (r & 63) * LD + (c & 63)),
-                               P.W + (size_t)r * d + c, true);
-                }
-            cp_async_commit();
-            cp_async_wait<0>();
-        } else {
-            const int dd = d * d;
-            for (int e0 = tid; e0 < dd; e0 += 16 * LI_NT) {
-                double t[16];
+        // M = (s I - W o W) / 2^e into the tiles: thread (warp, lane) owns the rows warp + 8 i and the columns lane + 32 j;
+        // all of its loads (L2: W changes every iteration) are in flight before the first use.  The padding keeps the
+        // identity of li_inverse_init.
+        {
+            const int lane = tid & 31, w8 = tid >> 5;
 #pragma unroll
-                for (int u = 0; u < 16; ++u) t[u] = (e0 + u * LI_NT < dd) ? __ldcg(P.W + e0 + u * LI_NT) : 0.0;
+            for (int ih = 0; ih < 2; ++ih) {                     // rows of the upper / lower tiles: 32 loads per batch
+                double t[8][4];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int e = e0 + u * LI_NT;
-                    if (e < dd) {
-                        const int r = e / d, c = e - r * d;
-                        psm[Inv2Smem::at(r >> 6, c >> 6) + (r & 63) * LD + (c & 63)] = t[u];
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = w8 + 8 * i + DM_DP * ih, c = lane + 32 * j;
+                        t[i][j] = (r < d && c < d) ? __ldcg(P.W + (size_t)r * d + c) : 0.0;
                     }
-                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = w8 + 8 * i + DM_DP * ih, c = lane + 32 * j;
+                        if (r < d && c < d)
+                            psm[Inv2Smem::at(ih, j >> 1) + (r & 63) * LD + (c & 63)] = (((r == c) ? s : 0.0) - t[i][j] * t[i][j]) * inv_scale;
+                    }
             }
         }
-        __syncthreads();
-        for (int r = tid >> 5; r < d; r += LI_NT / 32)
-            for (int c = tid & 31; c < d; c += 32) {
-                double* q2 = psm + Inv2Smem::at(r >> 6, c >> 6) + (r & 63) * LD + (c & 63);
-                const double x = *q2;
-                *q2 = (((r == c) ? s : 0.0) - x * x) * inv_scale;
-            }
         // the padding INSIDE the last pivot block comes back from the fraction-free elimination as p / p (one ulp from
         // 1): reset it, everything else of the padding is reproduced exactly
         if (tid < DM_PB && d + tid < 8 * ((d + 7) / 8)) {
@@ -245,7 +253,26 @@ __device__ __forceinline__ void li_inverse_role(const LinIterArgs& P, double* ps
         }
         __syncthreads();
         LI_STAMP(11, true);
-        inv2_block_gj(psm, ps, sy, d);
+        // the tiles of the inverse leave for global memory (and enter the minimum) straight from the accumulators of
+        // the last block step
+        inv2_block_gj(psm, ps, sy, d, [&](int bi, int bj, const double (&acc)[2][4][2], double sign) {
+            const double f = sign * inv_scale;
+#pragma unroll
+            for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                for (int tj = 0; tj < 4; ++tj) {
+                    const int r = DM_DP * bi + ps.row(ti), c = DM_DP * bj + ps.col(tj);
+                    const double m0 = f * acc[ti][tj][0], m1 = f * acc[ti][tj][1];
+                    if (r < d && c < d) {
+                        mn = fmin(mn, m0);
+                        P.Minv[(size_t)r * d + c] = m0;
+                        if (c + 1 < d) {
+                            mn = fmin(mn, m1);
+                            P.Minv[(size_t)r * d + c + 1] = m1;
+                        }
+                    }
+                }
+        });
         LI_STAMP(12, true);
         const double* pv = psm + Inv2Smem::piv;
         if (tid < 2 * DM_DP) {
@@ -253,12 +280,6 @@ __device__ __forceinline__ void li_inverse_role(const LinIterArgs& P, double* ps
             ld = (double)((tid & 3) - 2) * log(fabs(p));
             badpiv = !(p > 0.0);
         }
-        for (int r = tid >> 5; r < d; r += LI_NT / 32)
-            for (int c = tid & 31; c < d; c += 32) {
-                const double mi = psm[Inv2Smem::at(r >> 6, c >> 6) + (r & 63) * LD + (c & 63)] * inv_scale;
-                mn = fmin(mn, mi);
-                P.Minv[(size_t)r * d + c] = mi;
-            }
     }
     mn = block_min<LI_NT>(mn, red, tid);
     const int anybad = __syncthreads_or(badpiv);
@@ -412,8 +433,9 @@ __device__ __forceinline__ void li_logistic_role(const LinIterArgs& P, const LiP
 // T = sum over the workers' rows of `part`, fixed order: four lanes per entry (lane q adds the rows q, q + 4, ... --
 // all of its loads in flight at once), then (s0 + s1) + (s2 + s3)
 constexpr int LI_RED = 40;                    // rows per lane and pass: 4 x 40 >= the 147 workers of a B200
-__device__ __forceinline__ void li_reduce_partials(const LinIterArgs& P, const LiPlan& L, int cta) {
+__device__ __forceinline__ void li_reduce_partials(const LinIterArgs& P, const LiPlan& L, int cta, unsigned seq) {
     const int dd = P.d * P.d, NW = L.NW;
+    const size_t slot = ((size_t)(seq & 1u) * P.nranks + P.rank) * dd;        // sharded rows: where this GPU's sums go
     const int q = threadIdx.x & 3;
     const int rounds = (dd + NW * (LI_NT / 4) - 1) / (NW * (LI_NT / 4));       // uniform trip count: the shuffles need all lanes
     for (int rd = 0; rd < rounds; ++rd) {
@@ -431,8 +453,15 @@ __device__ __forceinline__ void li_reduce_partials(const LinIterArgs& P, const L
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (in && q == 0) P.T[e] = acc;
+        if (P.nranks == 1) {
+            if (in && q == 0) P.T[e] = acc;
+        } else if (in) {
+            // every lane of the four holds the sum: lane q serves the GPUs q, q + 4 (peer stores over NVLink; the own
+            // buffer is one of them)
+            for (int r = q; r < P.nranks; r += 4) P.xchg[r][slot + e] = acc;
+        }
     }
+    if (P.nranks > 1) __threadfence_system();
 }
 
 // ---------------------------------------------------------------- l2 worker: rows 8 cta .. 8 cta + 7 of T = cov W
@@ -485,13 +514,19 @@ struct LiScalars {
 };
 
 // ---------------------------------------------------------------- the step: linear_update_kernel, entry by entry
-__device__ __forceinline__ void li_update(const LinIterArgs& P, int cta, int G, const LiScalars& sc) {
+__device__ __forceinline__ void li_update(const LinIterArgs& P, int cta, int G, const LiScalars& sc, unsigned seq) {
     const int d = P.d, dd = d * d;
+    const double* xs = (P.nranks > 1) ? P.xchg[P.rank] + (size_t)(seq & 1u) * P.nranks * dd : nullptr;
     for (int e = cta * LI_NT + threadIdx.x; e < dd; e += G * LI_NT) {
         const int r = e / d, c = e - r * d;
         const double w = __ldcg(P.W + e);
         const double minvT = __ldcg(P.Minv + (size_t)c * d + r);
-        const double tt = __ldcg(P.T + e);
+        double tt;
+        if (P.nranks == 1) tt = __ldcg(P.T + e);
+        else {                                                  // the GPUs' sums in rank order: the same on every GPU
+            tt = 0.0;
+            for (int q = 0; q < P.nranks; ++q) tt += __ldcg(xs + (size_t)q * dd + e);
+        }
         const double sg = (w > 0.0) ? 1.0 : ((w < 0.0) ? -1.0 : 0.0);
         const double gsc = fma(sc.gscale, tt, -__ldg(P.cov + e));
         double go = fma(sc.mu, gsc, sc.mu * sc.lambda1 * sg);
@@ -508,11 +543,15 @@ __device__ __forceinline__ void li_update(const LinIterArgs& P, int cta, int G, 
     }
 }
 
+// LOGISTIC is a template parameter so that each loss carries only its own live state (the l2 workers keep 64 registers of
+// cov fragments across the whole launch)
+template <bool LOGISTIC>
 __global__ void __launch_bounds__(LI_NT, 1) linear_iter_kernel(const LinIterArgs P) {
     extern __shared__ __align__(16) double sm[];
     __shared__ LiScalars s_sc;
+    __shared__ unsigned s_seq;
     const int tid = threadIdx.x, cta = blockIdx.x, G = gridDim.x;
-    const LiPlan L = li_plan(P.logistic, P.n, P.d, P.sms);
+    const LiPlan L = li_plan(LOGISTIC ? 1 : 0, P.n, P.d, P.sms);
     const bool icta = (cta == G - 1);
     unsigned* err = P.sync + 2;
     SweepSync sy{smem_u32(sm + DmmaSmem::mbar), 0u};
@@ -528,7 +567,7 @@ __global__ void __launch_bounds__(LI_NT, 1) linear_iter_kernel(const LinIterArgs
         const int wrows = L.kd > L.NR ? L.kd : L.NR;
         for (int e = tid; e < wrows * L.ldx; e += LI_NT) sm[L.o_w + e] = 0.0;
     }
-    if (!icta && P.logistic) {
+    if (!icta && LOGISTIC) {
         // this worker's rows of X, once per launch, zero padded to [NR][ldx]
         double* Xs = sm + L.o_x;
         const int r0 = cta * L.NR;
@@ -536,7 +575,7 @@ __global__ void __launch_bounds__(LI_NT, 1) linear_iter_kernel(const LinIterArgs
             for (int c = tid & 31; c < L.ldx; c += 32)
                 Xs[r * L.ldx + c] = (r0 + r < P.n && c < P.d) ? __ldg(P.X + (size_t)(r0 + r) * P.d + c) : 0.0;
     } else if (!icta) {
-        li_l2_load(P, L, cta, cf);
+        if constexpr (!LOGISTIC) li_l2_load(P, L, cta, cf);
     }
     __syncthreads();
     unsigned bar_all = 0, bar_w = 0;
@@ -554,30 +593,64 @@ __global__ void __launch_bounds__(LI_NT, 1) linear_iter_kernel(const LinIterArgs
             sc.c1 = 1.0 / ((1.0 - sc.p1h) - sc.p1l);
             sc.c2 = 1.0 / ((1.0 - sc.p2h) - sc.p2l);
             s_sc = sc;
+            s_seq = (P.nranks > 1) ? *(volatile unsigned*)P.seq + 1u : 0u;       // CTA 0 stores it back after the barrier
         }
         if (icta) li_inverse_role(P, sm, sy, isc, ild);
-        else if (P.logistic) {
+        else if constexpr (LOGISTIC) {
             li_logistic_role(P, L, sm, cta);
             LI_STAMP(4, cta == 0);
-            li_barrier(P.sync + 1, err, (unsigned)L.NW, bar_w);
+#ifdef DAGMA_LIN_TRACE
+            if (tid == 0) {                                  // [14] last / [15] first arrival at the workers' barrier
+                const unsigned long long t = li_gtime();
+                if (cta == 0) { g_lin_trace[14] = 0ull; g_lin_trace[15] = ~0ull; }
+                atomicMax(&g_lin_trace[14], t);
+                atomicMin(&g_lin_trace[15], t);
+            }
+#endif
+            li_barrier(P.sync + 1, err, (unsigned)L.NW, bar_w);      // (publishes s_seq to the CTA as well)
             LI_STAMP(5, cta == 0);
-            li_reduce_partials(P, L, cta);
+            li_reduce_partials(P, L, cta, s_seq);
+            if (P.nranks > 1) {
+                // every worker's peer stores are fenced: raise this GPU's sequence number on every peer
+                li_barrier(P.sync + 1, err, (unsigned)L.NW, bar_w);
+                if (cta == 0 && tid < P.nranks && tid != P.rank) {
+                    __threadfence_system();                      // release: everything the barrier made visible to this thread
+                    *(volatile unsigned*)(P.flags[tid] + P.rank) = s_seq;
+                }
+            }
             LI_STAMP(6, cta == 0);
-        } else
+        } else {
             li_l2_role(P, L, sm, cta, cf);
+        }
         li_barrier(P.sync, err, (unsigned)G, bar_all);
         LI_STAMP(7, cta == 0);
         const LiScalars sc = s_sc;
+        const unsigned seq = s_seq;
+        if (P.nranks > 1) {
+            // the partial sums of every peer for this iteration have landed in the LOCAL buffer (bounded wait)
+            if (tid < P.nranks && tid != P.rank) {
+                unsigned spins = 0;
+                while ((int)(*(volatile unsigned*)(P.flags[P.rank] + tid) - seq) < 0) {
+                    if ((++spins & 63u) == 0u) {
+                        if (*(volatile unsigned*)err) break;
+                        if (spins > LI_SPIN_MAX) { atomicExch(err, 2u); break; }
+                    }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
         const bool stop = *(volatile int32_t*)&P.st->info != 0;
         if (cta == 0 && tid == 0) {                      // linear_advance: everybody has read the scalars of this iteration
             volatile LinState* st = P.st;
+            if (P.nranks > 1) *(volatile unsigned*)P.seq = seq;
             if (stop) st->halted = 1;
             else {
                 st->p1_hi = sc.p1h; st->p1_lo = sc.p1l; st->p2_hi = sc.p2h; st->p2_lo = sc.p2l;
                 st->it = st->it + 1;
             }
         }
-        if (!stop) li_update(P, cta, G, sc);
+        if (!stop) li_update(P, cta, G, sc, seq);
         if (icta) li_inverse_logdet(P, sm, isc, ild);        // h / log|det| of this iteration: nobody on the device waits for them
         LI_STAMP(8, cta == 0);
         li_barrier(P.sync, err, (unsigned)G, bar_all);
@@ -610,27 +683,76 @@ extern "C" size_t dagma_linear_iter_workspace_doubles(int logistic, int n, int d
     return (logistic ? (size_t)L.NW * d * d : 0) + 8;
 }
 
-extern "C" int dagma_linear_iter_f64(dagma_stream_t stream, int logistic, int n, int d, int iters, void* state_dev,
-                                     double* w_dev, double* m_dev, double* v_dev, double* minv_dev, double* t_dev,
-                                     const double* cov_dev, const double* x_dev, const uint8_t* mask_exc_dev,
-                                     const uint8_t* mask_inc_dev, double* part_dev, unsigned* sync_dev) {
+static int linear_iter_launch(cudaStream_t stream, int logistic, int n, int d, int iters, void* state_dev, double* w_dev,
+                              double* m_dev, double* v_dev, double* minv_dev, double* t_dev, const double* cov_dev,
+                              const double* x_dev, const uint8_t* mask_exc_dev, const uint8_t* mask_inc_dev,
+                              double* part_dev, unsigned* sync_dev, int rank, int nranks, void* const* xchg_ptrs,
+                              void* const* flag_ptrs, unsigned* seq_dev) {
     DAGMA_REQUIRE(state_dev && w_dev && m_dev && v_dev && minv_dev && t_dev && cov_dev && part_dev && sync_dev, "null pointer");
     DAGMA_REQUIRE(!logistic || x_dev, "the logistic loss needs X");
     const LiPlan L = li_plan(logistic, n, d, li_sms());
     DAGMA_REQUIRE(iters >= 0 && L.ok, "shape not supported by the fused iteration (dagma_linear_iter_supported)");
     const size_t smem = (size_t)L.smem_doubles * sizeof(double);
-    static size_t attr = 0;
-    if (smem > attr) {
-        DAGMA_CUDA_OK(cudaFuncSetAttribute(linear_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+    static size_t attr[2] = {0, 0};
+    if (smem > attr[logistic ? 1 : 0]) {
+        if (logistic)
+            DAGMA_CUDA_OK(cudaFuncSetAttribute(linear_iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+            DAGMA_CUDA_OK(cudaFuncSetAttribute(linear_iter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr[logistic ? 1 : 0] = smem;
     }
-    DAGMA_REQUIRE((double)L.G * 2.0 * (double)iters < 4.0e9, "too many iterations for one launch");
-    LinIterArgs A{(LinState*)state_dev, w_dev, m_dev, v_dev, minv_dev, t_dev, cov_dev, x_dev, mask_exc_dev, mask_inc_dev,
-                  part_dev, sync_dev, logistic, n, d, iters, li_sms()};
-    DAGMA_CUDA_OK(cudaMemsetAsync(sync_dev, 0, 4 * sizeof(unsigned), (cudaStream_t)stream));
-    linear_iter_kernel<<<L.G, LI_NT, smem, (cudaStream_t)stream>>>(A);
+    DAGMA_REQUIRE((double)L.G * 3.0 * (double)iters < 4.0e9, "too many iterations for one launch");
+    LinIterArgs A{};
+    A.st = (LinState*)state_dev;
+    A.W = w_dev; A.m = m_dev; A.v = v_dev; A.Minv = minv_dev; A.T = t_dev;
+    A.cov = cov_dev; A.X = x_dev;
+    A.mask_exc = mask_exc_dev; A.mask_inc = mask_inc_dev;
+    A.part = part_dev; A.sync = sync_dev;
+    A.logistic = logistic; A.n = n; A.d = d; A.iters = iters; A.sms = li_sms();
+    A.rank = rank; A.nranks = nranks; A.seq = seq_dev;
+    for (int r = 0; r < nranks && nranks > 1; ++r) {
+        A.xchg[r] = (double*)xchg_ptrs[r];
+        A.flags[r] = (unsigned*)flag_ptrs[r];
+    }
+    DAGMA_CUDA_OK(cudaMemsetAsync(sync_dev, 0, 4 * sizeof(unsigned), stream));
+    if (logistic) linear_iter_kernel<true><<<L.G, LI_NT, smem, stream>>>(A);
+    else linear_iter_kernel<false><<<L.G, LI_NT, smem, stream>>>(A);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int dagma_linear_iter_f64(dagma_stream_t stream, int logistic, int n, int d, int iters, void* state_dev,
+                                     double* w_dev, double* m_dev, double* v_dev, double* minv_dev, double* t_dev,
+                                     const double* cov_dev, const double* x_dev, const uint8_t* mask_exc_dev,
+                                     const uint8_t* mask_inc_dev, double* part_dev, unsigned* sync_dev) {
+    return linear_iter_launch((cudaStream_t)stream, logistic, n, d, iters, state_dev, w_dev, m_dev, v_dev, minv_dev, t_dev,
+                              cov_dev, x_dev, mask_exc_dev, mask_inc_dev, part_dev, sync_dev, 0, 1, nullptr, nullptr, nullptr);
+}
+
+extern "C" size_t dagma_linear_iter_exchange_bytes(int d, int nranks) {
+    if (d < 1 || d > LI_MAX_D || nranks < 2 || nranks > LI_MAX_RANKS) return 0;
+    return (size_t)2 * nranks * d * d * sizeof(double) + 256;
+}
+
+extern "C" int dagma_linear_iter_sharded_f64(dagma_stream_t stream, int n_local, int d, int iters, void* state_dev,
+                                             double* w_dev, double* m_dev, double* v_dev, double* minv_dev, double* t_dev,
+                                             const double* cov_dev, const double* x_dev, const uint8_t* mask_exc_dev,
+                                             const uint8_t* mask_inc_dev, double* part_dev, unsigned* sync_dev, int rank,
+                                             int nranks, void* const* exchange_ptrs) {
+    DAGMA_REQUIRE(nranks >= 2 && nranks <= LI_MAX_RANKS && rank >= 0 && rank < nranks && exchange_ptrs, "bad rank arguments");
+    // layout of a GPU's exchange allocation (dagma_linear_iter_exchange_bytes): [2][nranks][d * d] doubles, then
+    // [nranks] flags, then this GPU's own sequence counter
+    void* xp[LI_MAX_RANKS];
+    void* fp[LI_MAX_RANKS];
+    const size_t data = (size_t)2 * nranks * d * d * sizeof(double);
+    for (int r = 0; r < nranks; ++r) {
+        DAGMA_REQUIRE(exchange_ptrs[r], "null exchange pointer");
+        xp[r] = exchange_ptrs[r];
+        fp[r] = (char*)exchange_ptrs[r] + data;
+    }
+    unsigned* seq = (unsigned*)((char*)exchange_ptrs[rank] + data) + 32;
+    return linear_iter_launch((cudaStream_t)stream, 1, n_local, d, iters, state_dev, w_dev, m_dev, v_dev, minv_dev, t_dev,
+                              cov_dev, x_dev, mask_exc_dev, mask_inc_dev, part_dev, sync_dev, rank, nranks, xp, fp, seq);
 }
 
 #ifdef DAGMA_LIN_TRACE

@@ -24,7 +24,14 @@ struct Inv2Smem {                  // offsets in doubles; the sweep's buffers ke
 // The two block steps on the tiles in shared memory (all threads of a DM_NT CTA; the tiles are complete and a barrier
 // has been passed).  On return the tiles hold the inverse, pv[0 .. 127] the fraction-free pivots (1 in the padding), and
 // a barrier has been passed.
-__device__ __forceinline__ void inv2_block_gj(double* psm, const DmmaPos& ps, SweepSync& sy, int d) {
+// `final_tile(bi, bj, a, sign)` is called by every thread with the accumulators of tile (bi, bj) of the INVERSE (entry =
+// sign * a[ti][tj][e] at row 64 bi + ps.row(ti), column 64 bj + ps.col(tj) + e) when that tile is final -- results can
+// leave the CTA without a second pass over shared memory.
+struct Inv2NoOut {
+    __device__ __forceinline__ void operator()(int, int, const double (&)[2][4][2], double) const {}
+};
+template <class Out>
+__device__ __forceinline__ void inv2_block_gj(double* psm, const DmmaPos& ps, SweepSync& sy, int d, Out&& final_tile) {
     using S = DmmaSmem;
     constexpr int LD = DM_LD;
     const int tid = threadIdx.x;
@@ -93,21 +100,28 @@ __device__ __forceinline__ void inv2_block_gj(double* psm, const DmmaPos& ps, Sw
         if (tid < DM_DP) pv[DM_DP * kb + tid] = (tid < ((kn + 3) & ~3)) ? psm[S::pinfo + tid] : 1.0;
         store_acc(Qs, 1.0);
         store_acc(Tkk, 1.0);
+        if (kb == 1) final_tile(1, 1, a, 1.0);
         __syncthreads();
         zero_acc();
         product(Tok, Qs, on8, kn8, kn4);                      // T[o][kb] Q
         __syncthreads();
         store_acc(Tok, -1.0);                                 // new pivot column
+        if (kb == 1) final_tile(0, 1, a, -1.0);
         __syncthreads();
         load_acc(Too);
         product(Tok, Tko, on8, on8, kn4);
         store_acc(Too, 1.0);
+        if (kb == 1) final_tile(0, 0, a, 1.0);
         zero_acc();
         product(Qs, Tko, kn8, on8, kn4);                      // Q T[kb][o]
         __syncthreads();
         store_acc(Tko, 1.0);                                  // new pivot row
+        if (kb == 1) final_tile(1, 0, a, 1.0);
         __syncthreads();
     }
+}
+__device__ __forceinline__ void inv2_block_gj(double* psm, const DmmaPos& ps, SweepSync& sy, int d) {
+    inv2_block_gj(psm, ps, sy, d, Inv2NoOut{});
 }
 
 }  // namespace dagma

@@ -460,8 +460,17 @@ class DagmaLinear:
     def _large_engine(self):
         from ._large import LargeLinearEngine
         if self._large is None or self._large.stale(self):
+            if self._large is not None:
+                self._large.close()              # peer mappings of a row-sharded engine (collective)
             self._large = LargeLinearEngine(self, group=self._group)
         return self._large
+
+    def close(self) -> None:
+        """Release what the multi-CTA engine holds beyond plain device memory (the NVLink peer mappings of a
+        row-sharded logistic model: collective over the group).  Optional for un-sharded models."""
+        if self._large is not None:
+            self._large.close()
+            self._large = None
 
     # ------------------------------------------------------------------ _score (linear.py:70-94)
     def _score(self, W: np.ndarray) -> typing.Tuple[float, np.ndarray]:

@@ -22,6 +22,7 @@ lib.dagma_debug_lin_trace.argtypes = [C.c_void_p]
 print("rc", lib.dagma_debug_lin_trace(buf), loss, "d", d, "n", n)
 t = np.array(buf[:], dtype=np.uint64).astype(np.int64)
 names = ["start", "W staged", "Z done", "R written", "partial written", "past workers' barrier", "T reduced",
-         "past barrier 1", "step taken", "past barrier 2", "inv: start", "inv: M built", "inv: inverted", "inv: outputs"]
+         "past barrier 1", "step taken", "past barrier 2", "inv: start", "inv: M built", "inv: inverted", "inv: outputs",
+         "last arrival (workers)", "first arrival (workers)"]
 for k, nm in enumerate(names):
     print(f"{nm:24s} {(t[k] - t[0]) / 1e3:7.2f} us" if t[k] else f"{nm:24s}       -")

@@ -1,5 +1,5 @@
 """Throughput of fit_batch at 64 < d <= 128 (l2): problems side by side (one persistent kernel per problem,
-csrc/lin_iter.cu) against one after the other.  Usage: perf_midd_batch.py [d] [batch] [iters]"""
+csrc/lin_iter.cu) against one after the other.  Usage: perf_midd_batch.py [d] [batch] [iters] [lanes,lanes,...]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -12,7 +12,7 @@ rng = np.random.default_rng(0)
 Xs = rng.normal(size=(batch, 4 * d, d))
 kw = dict(T=1, warm_iter=iters, max_iter=iters, checkpoint=1000, s=(1.0,), tol=0.0, return_info=True)
 fit_batch(Xs[:2], 0.02, **dict(kw, warm_iter=100, max_iter=100))          # warm-up (module load, kernel attributes)
-for lanes in ("auto", "1"):
+for lanes in (sys.argv[4].split(",") if len(sys.argv) > 4 else ("auto", "1")):
     if lanes == "auto":
         os.environ.pop("DAGMA_BATCH_LANES", None)
     else:
