@@ -546,8 +546,10 @@ def bench_c2_c3(torch, with_cpu, peak_tflops=None):
 
 def bench_sharded(torch, dist, rank, world, dev):
     """SURVEY.md 8e2 on N GPUs (every rank calls this): the row-sharded C2 (logistic d=100) and C3 (MLP [40,10,1])
-    inner iterations -- rows of X split contiguously, ONE sum all-reduce of the d x d (parameter-sized) partial
-    gradient per iteration, captured inside the iteration's CUDA graph -- timed with CUDA events (max over ranks)
+    inner iterations -- rows of X split contiguously, ONE sum of the d x d (parameter-sized) partial gradient over the
+    GPUs per iteration: C2 inside the persistent iteration kernel over NVLink peer memory when every GPU's rows fit its
+    workers (csrc/lin_iter.cu), else and for C3 a NCCL all-reduce captured inside the iteration's CUDA graph -- timed
+    with CUDA events (max over ranks)
     next to the same iterations un-sharded on one GPU, with |dW| between the two after the timed iterations; the C2
     pair is repeated at larger n (rows tiled) to locate the n above which sharding pays."""
     import numpy as np
@@ -578,18 +580,27 @@ def bench_sharded(torch, dist, rank, world, dev):
         m.minimize(W, 1.0, iters, 1.0, lr=3e-4, tol=0.0)
         e1.record()
         torch.cuda.synchronize()
-        return rmax(e0.elapsed_time(e1) * 1e-3) / iters, W
+        eng = m._large
+        path = ("persistent kernel, cross-GPU sum over NVLink peer memory" if eng._peer is not None else
+                "persistent kernel" if eng.one_kernel else
+                "launch sequence" + (" + NCCL all-reduce in the CUDA graph" if shard else ""))
+        t = rmax(e0.elapsed_time(e1) * 1e-3) / iters
+        m.close()                                                 # peer mappings (collective)
+        return t, W, path
 
-    out = {"n_gpus": world, "all_reduce": "torch.distributed NCCL sum all-reduce captured inside the iteration's CUDA graph"}
+    out = {"n_gpus": world, "all_reduce": "C2: summed inside the persistent kernel over NVLink peer memory (plain stores + "
+                                          "sequence flags, rank order) when the rows fit, else NCCL; C3: torch.distributed NCCL sum "
+                                          "all-reduce captured inside the iteration's CUDA graph"}
     X, _ = simulate.config_c2(0)
     rows = []
-    for mult in (1, 4, 16, 64):
+    for mult in (1, 2, 4, 8, 16, 64):
         Xn = np.tile(X, (mult, 1)) if mult > 1 else X
-        iters = 1000 if mult <= 4 else 200
-        t_sh, W_sh = time_linear(Xn, True, iters)
-        t_1, W_1 = time_linear(Xn, False, iters)
+        iters = 1000 if mult <= 8 else 200
+        t_sh, W_sh, p_sh = time_linear(Xn, True, iters)
+        t_1, W_1, p_1 = time_linear(Xn, False, iters)
         rows.append({"n": int(Xn.shape[0]), "us_per_iter_sharded": t_sh * 1e6, "us_per_iter_one_gpu": t_1 * 1e6,
-                     "speedup": t_1 / t_sh, "max_abs_dW_vs_one_gpu": float(np.abs(W_sh - W_1).max()), "iters": iters})
+                     "speedup": t_1 / t_sh, "max_abs_dW_vs_one_gpu": float(np.abs(W_sh - W_1).max()), "iters": iters,
+                     "sharded_path": p_sh, "one_gpu_path": p_1})
         del Xn
     out["c2_sharded"] = {"workload": "C2: DagmaLinear logistic d=100, rows sharded over the GPUs (n = 10 000 is BASELINE's size; "
                                      "larger n: the same rows tiled)",

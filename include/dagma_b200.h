@@ -169,7 +169,9 @@ int dagma_linear_apply_dir_f64(dagma_stream_t stream, int d, const void* state_d
  * updates its share of the entries; CTA 0 advances the state block.  Replaces the loop body of DagmaLinear.minimize
  * (src/dagma/linear.py:224-276) between two checkpoints; state block, buffers and results are those of the launch
  * sequence (inverse -> dagma_gemm_f64 -> dagma_linear_update_f64).
- *   supported          : 1 when the shape is covered on this device (logistic: n <= 72 (SMs - 1))
+ *   supported          : 1 when the shape is covered on this device (logistic: n <= 72 (SMs - 1), the rows stay resident
+ *                        in shared memory; DAGMA_LIN_STREAM=1 opts in to streaming more rows through it every iteration,
+ *                        measured slower than the launch sequence)
  *   workspace_doubles  : size of part_dev
  *   x_dev [n][d] row-major (logistic only, else NULL / n = 0); sync_dev: 4 uint32 that live as long as the state
  *   block; info = 99 in the state block: a grid barrier timed out (the grid was not co-resident).                  */

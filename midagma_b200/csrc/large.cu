@@ -117,6 +117,9 @@ static int gemm_launch(cudaStream_t stream, int transA, int M, int N, int K, dou
 
 // ------------------------------------------------------------------ blocked inverse
 constexpr int NB = 64;
+#ifndef DAGMA_PDL_DEFAULT
+#define DAGMA_PDL_DEFAULT 0
+#endif
 #ifndef DAGMA_TMA_DEFAULT
 #define DAGMA_TMA_DEFAULT 5      // outer-step update tiles + long stand-alone GEMMs (see tma_mode)
 #endif
@@ -587,6 +590,12 @@ __global__ void __launch_bounds__(DM_NT, 2) outer_step_kernel(const OuterArgs P,
         tm_prefetch_map(&mapR);
     }
     __syncthreads();
+    // Programmatic dependent launch (DAGMA_PDL): everything above -- pipeline barriers, tensor-map prefetch -- may run
+    // while the previous outer step is still draining (its CTAs leave one by one during the CS' tail); from here on the
+    // step reads what that kernel wrote.  The trigger right behind the wait lets the NEXT step's CTAs take the slots
+    // this step's CTAs free up; they block in their own wait until this grid has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int d = P.d, kn = P.kn, k1 = P.k1, kn1 = P.kn1;
     int* err = reinterpret_cast<int*>(P.sync + 2);
     volatile int* busy = P.sm_busy + (smid() % SM_SLOTS);
@@ -1909,6 +1918,17 @@ static bool first_block_fused() {
 // one CTA per SM.  Measured at d = 2000 (B200, round 2): 0.896 ms against 0.871 ms -- a 64 x 64 x 256 item of two
 // engines is bound by its 8 dependent slab round trips (17 us alone on an SM, as in the tail), so the chain starts
 // 17 us late and the overlap it buys (the tail leaves the critical path) does not pay for it.
+// DAGMA_PDL (A-B timing): 1 = consecutive outer steps are launched with programmatic stream serialization (the next
+// step's prologue overlaps the tail of the current one), 0 = plain stream order
+static int pdl_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_PDL");
+        v = e ? atoi(e) : DAGMA_PDL_DEFAULT;
+    }
+    return v;
+}
+
 static int cs_head_mode() {
     static int v = -1;
     if (v < 0) {
@@ -2123,8 +2143,22 @@ static int gj_inplace_two_level(cudaStream_t stream, double* Mw, int d, double* 
                 rc = tm_make_b_map(&mapR, Ra, kn, d, d);
                 if (rc) return rc;
             }
-            outer_step_kernel<<<2 * sms, DM_NT, OUTER_SMEM_BYTES, stream>>>(OA, mapCS, mapR);
-            DAGMA_CUDA_OK(cudaGetLastError());
+            if (pdl_mode()) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(2 * sms);
+                cfg.blockDim = dim3(DM_NT);
+                cfg.dynamicSmemBytes = OUTER_SMEM_BYTES;
+                cfg.stream = stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                DAGMA_CUDA_OK(cudaLaunchKernelEx(&cfg, outer_step_kernel, OA, mapCS, mapR));
+            } else {
+                outer_step_kernel<<<2 * sms, DM_NT, OUTER_SMEM_BYTES, stream>>>(OA, mapCS, mapR);
+                DAGMA_CUDA_OK(cudaGetLastError());
+            }
             double* t = CSa; CSa = CSb; CSb = t;
             t = Ra; Ra = Rb; Rb = t;
         }

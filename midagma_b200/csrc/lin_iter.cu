@@ -39,6 +39,7 @@
 #include "small_inv2.cuh"
 #include "gemm_f64.cuh"
 #include "lin_state.h"
+#include <cstdlib>
 #include "../../include/dagma_b200.h"
 
 namespace dagma {
@@ -52,33 +53,57 @@ constexpr int LI_MAX_RANKS = 8;           // GPUs of one box that may share the 
 
 struct LiPlan {
     int G, NW, NR;                        // CTAs, workers, rows of X per worker (logistic; multiple of 8)
+    int SB, nsub;                         // streaming (NR > 72): rows per sub-block, sub-blocks per worker; else SB = NR, nsub = 1
     int ldx, kd;                          // row stride of the staged operands (= 4 mod 16), d rounded up to 4
-    int o_w, o_x, total;                  // shared-memory offsets / size of a worker (doubles)
+    int o_w, o_x, o_r, total;             // shared-memory offsets / size of a worker (doubles)
     int smem_doubles;                     // dynamic shared memory of the launch
+    bool stream;                          // the worker's rows do not fit: X is streamed through shared memory every iteration
     bool ok;
 };
-__host__ __device__ inline LiPlan li_plan(int logistic, int n, int d, int sms) {
+constexpr int LI_SMEM_CAP = 29000;        // doubles of shared memory a worker may plan with (227 KB = 29 056)
+constexpr int LI_MAX_ROWS = 4096;         // rows per worker in streaming mode
+__host__ __device__ inline LiPlan li_plan(int logistic, int n, int d, int sms, int allow_stream) {
     LiPlan L{};
     L.ok = false;
     if (d < 1 || d > LI_MAX_D || sms < 3) return L;
     L.ldx = 16 * ((d + 15) / 16) + 4;
     L.kd = 4 * ((d + 3) / 4);
+    L.stream = false;
     if (logistic) {
         if (n < 1) return L;
         const int per = (n + (sms - 1) - 1) / (sms - 1);
         L.NR = 8 * ((per + 7) / 8);
-        if (L.NR > LI_RB) return L;
+        L.SB = L.NR;
+        L.nsub = 1;
+        if (L.NR > LI_RB) {
+            // streaming: W, one sub-block of X and its R side by side (R cannot take the place of W, which every
+            // sub-block needs); 16-byte cp.async of the rows of X wants an even d
+            L.stream = true;
+            if (!allow_stream || (d & 1) != 0 || L.NR > LI_MAX_ROWS) return L;
+            L.SB = 8 * (((LI_SMEM_CAP - L.kd * L.ldx) / (2 * L.ldx)) / 8);
+            if (L.SB > LI_RB) L.SB = LI_RB;
+            if (L.SB < 16) return L;
+            L.nsub = (L.NR + L.SB - 1) / L.SB;
+        }
         L.NW = (n + L.NR - 1) / L.NR;
     } else {
-        L.NR = 0;
+        L.NR = L.SB = 0;
+        L.nsub = 1;
         L.NW = (d + 7) / 8;
         if (L.NW > sms - 1) return L;
     }
     L.G = L.NW + 1;
     L.o_w = 0;
-    const int wrows = L.kd > L.NR ? L.kd : L.NR;          // R (NR rows) is written over the staged W (kd rows)
-    L.o_x = wrows * L.ldx;
-    L.total = L.o_x + L.NR * L.ldx + 2;
+    if (L.stream) {
+        L.o_x = L.kd * L.ldx;
+        L.o_r = L.o_x + L.SB * L.ldx;
+        L.total = L.o_r + L.SB * L.ldx + 2;
+    } else {
+        const int wrows = L.kd > L.NR ? L.kd : L.NR;      // R (NR rows) is written over the staged W (kd rows)
+        L.o_x = wrows * L.ldx;
+        L.o_r = L.o_w;
+        L.total = L.o_x + L.NR * L.ldx + 2;
+    }
     const int inv = d <= DM_DP ? DmmaSmem::total : Inv2Smem::total;
     L.smem_doubles = L.total > inv ? L.total : inv;
     L.ok = (size_t)L.smem_doubles * sizeof(double) <= 227 * 1024;
@@ -92,7 +117,7 @@ struct LinIterArgs {
     const uint8_t *mask_exc, *mask_inc;
     double* part;                         // logistic: [NW][d * d] un-scaled partial products
     unsigned* sync;                       // [0] grid barrier arrivals [1] worker barrier arrivals [2] error (zeroed per launch)
-    int logistic, n, d, iters, sms;
+    int logistic, n, d, iters, sms, allow_stream;
     // rows of X sharded over `nranks` GPUs of one box (logistic only; nranks = 1: none of this is touched).
     // xchg[r]: rank r's exchange buffer as mapped into THIS process, [2 (parity)][nranks (writer)][d * d] doubles;
     // flags[r]: rank r's [nranks] sequence numbers (writer q's partial sums of iteration `seq` have landed in rank r's
@@ -430,6 +455,105 @@ __device__ __forceinline__ void li_logistic_role(const LinIterArgs& P, const LiP
     }
 }
 
+// ---------------------------------------------------------------- logistic worker, rows streamed (NR > 72)
+// The worker's NR rows pass through shared memory in sub-blocks of SB rows every iteration (X is constant and stays in
+// L2); W is staged once per iteration, R has its own buffer, and the warp's tiles of Gc -- all 16 m-tiles x its two
+// n-tiles -- live in registers across the sub-blocks; Z is formed four m-tiles at a time.
+__device__ __forceinline__ void li_logistic_stream_role(const LinIterArgs& P, const LiPlan& L, double* sm, int cta) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, qr = lane >> 2, qc = lane & 3;
+    const int d = P.d, ldx = L.ldx, NT = (d + 7) / 8, KT = L.kd / 4, MTd = (d + 7) / 8, hc = d >> 1;
+    double* Ws = sm + L.o_w;
+    double* Xs = sm + L.o_x;
+    double* Rs = sm + L.o_r;
+    const int nt[2] = {warp, warp + 8};
+    const bool nv[2] = {nt[0] < NT, nt[1] < NT};
+    li_stage_w(P, L, Ws);
+    double g[16][2][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) g[i][j][0] = g[i][j][1] = 0.0;
+#pragma unroll 1
+    for (int sb = 0; sb < L.nsub; ++sb) {
+        const int r0 = cta * L.NR + sb * L.SB, cnt = min(L.SB, L.NR - sb * L.SB);
+        __syncthreads();                      // the previous sub-block is done with Xs / Rs
+        for (int r = warp; r < cnt; r += LI_NT / 32)
+            for (int c2 = lane; c2 < hc; c2 += 32)
+                cp_async16(smem_u32(Xs + r * ldx + 2 * c2), P.X + (size_t)(r0 + r) * d + 2 * c2, r0 + r < P.n);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();                      // the rows (and, the first time, W) have landed for every thread
+        if (nv[0]) {
+            const int MT = cnt / 8;
+#pragma unroll 1
+            for (int mc = 0; mc < MT; mc += 4) {
+                const int mcnt = min(4, MT - mc);
+                double z[4][2][2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) z[i][j][0] = z[i][j][1] = 0.0;
+                const double* ap = Xs + (8 * mc + qr) * ldx + qc;
+                const double* bp = Ws + qc * ldx + qr;
+#pragma unroll 2
+                for (int ks = 0; ks < KT; ++ks) {
+                    double a[4], b[2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = (i < mcnt) ? ap[8 * i * ldx + 4 * ks] : 0.0;
+                    b[0] = bp[4 * ks * ldx + 8 * nt[0]];
+                    b[1] = nv[1] ? bp[4 * ks * ldx + 8 * nt[1]] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < mcnt) {
+                            dmma(z[i][0][0], z[i][0][1], a[i], b[0]);
+                            dmma(z[i][1][0], z[i][1][1], a[i], b[1]);
+                        }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (nv[j]) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (i < mcnt)
+                                *reinterpret_cast<double2*>(Rs + (8 * (mc + i) + qr) * ldx + 8 * nt[j] + 2 * qc) =
+                                    make_double2(li_sigmoid(z[i][j][0]), li_sigmoid(z[i][j][1]));
+                    }
+            }
+        }
+        __syncthreads();
+        if (nv[0]) {
+            const double* ap = Xs + qc * ldx + qr;
+            const double* bp = Rs + qc * ldx + qr;
+            const int KR = cnt / 4;
+#pragma unroll 2
+            for (int ks = 0; ks < KR; ++ks) {
+                double a[16], b[2];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a[i] = (i < MTd) ? ap[4 * ks * ldx + 8 * i] : 0.0;
+                b[0] = bp[4 * ks * ldx + 8 * nt[0]];
+                b[1] = nv[1] ? bp[4 * ks * ldx + 8 * nt[1]] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (i < MTd) {
+                        dmma(g[i][0][0], g[i][0][1], a[i], b[0]);
+                        dmma(g[i][1][0], g[i][1][1], a[i], b[1]);
+                    }
+            }
+        }
+    }
+    double* prow = P.part + (size_t)cta * d * d;
+    if (nv[0]) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int r = 8 * i + qr, c = 8 * nt[j] + 2 * qc;                 // d is even: c + 1 < d with c
+                if (i < MTd && nv[j] && r < d && c < d)
+                    *reinterpret_cast<double2*>(prow + (size_t)r * d + c) = make_double2(g[i][j][0], g[i][j][1]);
+            }
+    }
+}
+
 // T = sum over the workers' rows of `part`, fixed order: four lanes per entry (lane q adds the rows q, q + 4, ... --
 // all of its loads in flight at once), then (s0 + s1) + (s2 + s3)
 constexpr int LI_RED = 40;                    // rows per lane and pass: 4 x 40 >= the 147 workers of a B200
@@ -543,15 +667,17 @@ __device__ __forceinline__ void li_update(const LinIterArgs& P, int cta, int G, 
     }
 }
 
-// LOGISTIC is a template parameter so that each loss carries only its own live state (the l2 workers keep 64 registers of
-// cov fragments across the whole launch)
-template <bool LOGISTIC>
+// MODE (0 l2, 1 logistic with resident rows, 2 logistic with streamed rows) is a template parameter so that each variant
+// carries only its own live state (the l2 workers keep 64 registers of cov fragments across the whole launch, the
+// streaming workers 128 registers of accumulators across their sub-blocks)
+template <int MODE>
 __global__ void __launch_bounds__(LI_NT, 1) linear_iter_kernel(const LinIterArgs P) {
+    constexpr bool LOGISTIC = MODE != 0;
     extern __shared__ __align__(16) double sm[];
     __shared__ LiScalars s_sc;
     __shared__ unsigned s_seq;
     const int tid = threadIdx.x, cta = blockIdx.x, G = gridDim.x;
-    const LiPlan L = li_plan(LOGISTIC ? 1 : 0, P.n, P.d, P.sms);
+    const LiPlan L = li_plan(LOGISTIC ? 1 : 0, P.n, P.d, P.sms, P.allow_stream);
     const bool icta = (cta == G - 1);
     unsigned* err = P.sync + 2;
     SweepSync sy{smem_u32(sm + DmmaSmem::mbar), 0u};
@@ -564,10 +690,12 @@ __global__ void __launch_bounds__(LI_NT, 1) linear_iter_kernel(const LinIterArgs
         isc = li_inv_scale(P);
     } else {
         // the staging area of W: finite everywhere before the first product (see li_stage_w)
-        const int wrows = L.kd > L.NR ? L.kd : L.NR;
+        const int wrows = (MODE == 1 && L.NR > L.kd) ? L.NR : L.kd;
         for (int e = tid; e < wrows * L.ldx; e += LI_NT) sm[L.o_w + e] = 0.0;
     }
-    if (!icta && LOGISTIC) {
+    if (!icta && MODE == 2) {
+        for (int e = tid; e < 2 * L.SB * L.ldx; e += LI_NT) sm[L.o_x + e] = 0.0;     // the padding columns of Xs / Rs
+    } else if (!icta && MODE == 1) {
         // this worker's rows of X, once per launch, zero padded to [NR][ldx]
         double* Xs = sm + L.o_x;
         const int r0 = cta * L.NR;
@@ -597,7 +725,8 @@ __global__ void __launch_bounds__(LI_NT, 1) linear_iter_kernel(const LinIterArgs
         }
         if (icta) li_inverse_role(P, sm, sy, isc, ild);
         else if constexpr (LOGISTIC) {
-            li_logistic_role(P, L, sm, cta);
+            if constexpr (MODE == 2) li_logistic_stream_role(P, L, sm, cta);
+            else li_logistic_role(P, L, sm, cta);
             LI_STAMP(4, cta == 0);
 #ifdef DAGMA_LIN_TRACE
             if (tid == 0) {                                  // [14] last / [15] first arrival at the workers' barrier
@@ -675,10 +804,25 @@ static int li_sms() {
     return sms;
 }
 
-extern "C" int dagma_linear_iter_supported(int logistic, int n, int d) { return li_plan(logistic, n, d, li_sms()).ok ? 1 : 0; }
+// DAGMA_LIN_STREAM (A-B timing): 1 = logistic problems whose rows do not fit the workers' shared memory stream them
+// through it every iteration (li_logistic_stream_role); 0 (default) = such problems are reported as unsupported and keep
+// the launch sequence, whose large GEMMs are the faster route there (n = 20 000 ... 160 000 at d = 100: 88 ... 472 us per
+// iteration against 103 ... 695 streamed)
+static int li_allow_stream() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAGMA_LIN_STREAM");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+extern "C" int dagma_linear_iter_supported(int logistic, int n, int d) {
+    return li_plan(logistic, n, d, li_sms(), li_allow_stream()).ok ? 1 : 0;
+}
 
 extern "C" size_t dagma_linear_iter_workspace_doubles(int logistic, int n, int d) {
-    const LiPlan L = li_plan(logistic, n, d, li_sms());
+    const LiPlan L = li_plan(logistic, n, d, li_sms(), li_allow_stream());
     if (!L.ok) return 0;
     return (logistic ? (size_t)L.NW * d * d : 0) + 8;
 }
@@ -690,16 +834,16 @@ static int linear_iter_launch(cudaStream_t stream, int logistic, int n, int d, i
                               void* const* flag_ptrs, unsigned* seq_dev) {
     DAGMA_REQUIRE(state_dev && w_dev && m_dev && v_dev && minv_dev && t_dev && cov_dev && part_dev && sync_dev, "null pointer");
     DAGMA_REQUIRE(!logistic || x_dev, "the logistic loss needs X");
-    const LiPlan L = li_plan(logistic, n, d, li_sms());
+    const LiPlan L = li_plan(logistic, n, d, li_sms(), li_allow_stream());
     DAGMA_REQUIRE(iters >= 0 && L.ok, "shape not supported by the fused iteration (dagma_linear_iter_supported)");
     const size_t smem = (size_t)L.smem_doubles * sizeof(double);
-    static size_t attr[2] = {0, 0};
-    if (smem > attr[logistic ? 1 : 0]) {
-        if (logistic)
-            DAGMA_CUDA_OK(cudaFuncSetAttribute(linear_iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else
-            DAGMA_CUDA_OK(cudaFuncSetAttribute(linear_iter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr[logistic ? 1 : 0] = smem;
+    const int mode = logistic ? (L.stream ? 2 : 1) : 0;
+    static size_t attr[3] = {0, 0, 0};
+    if (smem > attr[mode]) {
+        const void* fn = mode == 0 ? (const void*)linear_iter_kernel<0>
+                       : mode == 1 ? (const void*)linear_iter_kernel<1> : (const void*)linear_iter_kernel<2>;
+        DAGMA_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr[mode] = smem;
     }
     DAGMA_REQUIRE((double)L.G * 3.0 * (double)iters < 4.0e9, "too many iterations for one launch");
     LinIterArgs A{};
@@ -708,15 +852,16 @@ static int linear_iter_launch(cudaStream_t stream, int logistic, int n, int d, i
     A.cov = cov_dev; A.X = x_dev;
     A.mask_exc = mask_exc_dev; A.mask_inc = mask_inc_dev;
     A.part = part_dev; A.sync = sync_dev;
-    A.logistic = logistic; A.n = n; A.d = d; A.iters = iters; A.sms = li_sms();
+    A.logistic = logistic; A.n = n; A.d = d; A.iters = iters; A.sms = li_sms(); A.allow_stream = li_allow_stream();
     A.rank = rank; A.nranks = nranks; A.seq = seq_dev;
     for (int r = 0; r < nranks && nranks > 1; ++r) {
         A.xchg[r] = (double*)xchg_ptrs[r];
         A.flags[r] = (unsigned*)flag_ptrs[r];
     }
     DAGMA_CUDA_OK(cudaMemsetAsync(sync_dev, 0, 4 * sizeof(unsigned), stream));
-    if (logistic) linear_iter_kernel<true><<<L.G, LI_NT, smem, stream>>>(A);
-    else linear_iter_kernel<false><<<L.G, LI_NT, smem, stream>>>(A);
+    if (mode == 2) linear_iter_kernel<2><<<L.G, LI_NT, smem, stream>>>(A);
+    else if (mode == 1) linear_iter_kernel<1><<<L.G, LI_NT, smem, stream>>>(A);
+    else linear_iter_kernel<0><<<L.G, LI_NT, smem, stream>>>(A);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -116,8 +116,8 @@ def test_fused_iteration_limits():
     lib = _lib.load()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     assert lib.dagma_linear_iter_supported(0, 0, 128) == 1 and lib.dagma_linear_iter_supported(0, 0, 129) == 0
-    assert lib.dagma_linear_iter_supported(1, 72 * (sms - 1), 100) == 1
-    assert lib.dagma_linear_iter_supported(1, 72 * (sms - 1) + 1, 100) == 0
+    assert lib.dagma_linear_iter_supported(1, 72 * (sms - 1), 101) == 1          # resident rows: any d
+    assert lib.dagma_linear_iter_supported(1, 72 * (sms - 1) + 1, 100) == 0      # (streamed rows: opt-in, see below)
     assert lib.dagma_linear_iter_workspace_doubles(1, 1000, 10) >= 100
 
 
@@ -143,3 +143,32 @@ def test_mid_d_batch_runs_problems_side_by_side(monkeypatch):
     assert np.array_equal(par["W_raw"], seq["W_raw"])
     assert par["stage_iters"].tolist() == seq["stage_iters"].tolist()
     assert np.array_equal(par["h_final"], seq["h_final"])
+
+
+def test_streamed_rows_variant():
+    """The opt-in variant that streams the rows of X through shared memory when they do not fit (DAGMA_LIN_STREAM=1,
+    measured slower than the launch sequence and therefore off) stays correct.  The switch is read once per process,
+    hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np\n"
+        "from oracle import simulate\n"
+        "from midagma_b200 import DagmaLinear\n"
+        "import os\n"
+        "for d, n in ((100, 20000), (128, 15001), (64, 30011), (10, 12000)):\n"
+        "    X = simulate.make_linear_problem(d, 2, n, 'ER', 'logistic', 100 + d)[0]\n"
+        "    out = []\n"
+        "    for fused in ('1', '0'):\n"
+        "        os.environ['DAGMA_LIN_FUSED'] = fused\n"
+        "        m = DagmaLinear('logistic')\n"
+        "        m.fit(X.copy(), lambda1=0.02, T=1, warm_iter=0, max_iter=0, checkpoint=50)\n"
+        "        assert m._large_engine().one_kernel == (fused == '1')\n"
+        "        W, ok = m.minimize(np.zeros((d, d)), 1.0, 130, 1.0, lr=3e-4)\n"
+        "        out.append(W)\n"
+        "    err = np.abs(out[0] - out[1]).max()\n"
+        "    print(d, n, err)\n"
+        "    assert err <= 1e-11\n")
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DAGMA_LIN_STREAM="1", PYTHONPATH=root), cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
