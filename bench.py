@@ -482,6 +482,29 @@ def bench_c2_c3(torch, with_cpu, peak_tflops=None):
         c2.update({"cpu_ms_per_iter": cpu * 1e3, "speedup_vs_cpu": cpu / t,
                    "cpu_sample": f"10 iterations of oracle/linear_ref.py with all host BLAS threads ({len(os.sched_getaffinity(0))} cores)"})
     out["c2"] = c2
+    # ---- mid-d l2 (64 < d <= 128): one persistent kernel per problem, problems of a batch side by side
+    from midagma_b200 import fit_batch
+    from midagma_b200.linear import _batch_lanes
+    db, nb, itb = 128, 16, 3000
+    rngb = np.random.default_rng(0)
+    Xb = rngb.normal(size=(nb, 4 * db, db))
+    kwb = dict(T=1, warm_iter=itb, max_iter=itb, checkpoint=1000, s=(1.0,), return_info=True)
+    fit_batch(Xb[:2], 0.02, **dict(kwb, warm_iter=100, max_iter=100))     # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, infob = fit_batch(Xb, 0.02, **kwb)
+    torch.cuda.synchronize()
+    wallb = time.perf_counter() - t0
+    lanes = _batch_lanes(db, nb)
+    out["mid_d_batch"] = {"workload": f"{nb} independent DagmaLinear l2 problems, d={db} n={4 * db}, one stage of up to {itb} "
+                                      "iterations each (fit_batch; host arrays in, W_est out)",
+                          "lanes": lanes, "wall_s": wallb, "inner_iters": int(infob["total_iters"]),
+                          "iters_per_s": infob["total_iters"] / wallb,
+                          "us_per_iter_and_lane": wallb / infob["total_iters"] * lanes * 1e6,
+                          "flop_per_iter": 4.0 * db ** 3,
+                          "what": "every problem's iterations between two checkpoints are one persistent kernel of d/8 + 1 CTAs "
+                                  "(csrc/lin_iter.cu); `lanes` problems run side by side, one stream and host thread each"}
+    del Xb
     # ---- C3
     X, _ = simulate.config_c3(0)
     d, m1, n = X.shape[1], 10, X.shape[0]

@@ -196,6 +196,14 @@ int dagma_linear_iter_sharded_f64(dagma_stream_t stream, int n_local, int d, int
                                   const double* cov_dev, const double* x_dev, const uint8_t* mask_exc_dev,
                                   const uint8_t* mask_inc_dev, double* part_dev, unsigned* sync_dev, int rank,
                                   int nranks, void* const* exchange_ptrs);
+/* Batched graph evaluation (csrc/graph_metrics.cu): the counts behind utils.count_accuracy and the test utils.is_dag
+ * (src/dagma/utils.py:245-310, 13-18; no igraph) for `batch` estimates in one launch.
+ *   est_dev  [batch][d][d] int8 in {0, 1, -1} (-1: undirected edge of a CPDAG, once per pair)
+ *   true_dev [batch][d][d] uint8 (or ONE [d][d] matrix for all problems when true_shared = 1)
+ *   counts_dev [batch][8] int32: nnz, condition positive, true positive, false positive, reverse, extra (lower
+ *   triangle of the skeleton), missing (lower), is_dag (directed support of the estimate)                            */
+int dagma_graph_metrics(dagma_stream_t stream, int batch, int d, const int8_t* est_dev, const uint8_t* true_dev,
+                        int true_shared, int* counts_dev);
 /* Peer-visible device memory (csrc/peer.cu): an allocation of its own (zeroed), its 64-byte inter-process handle, the
  * import of a peer's handle into this process (peer access enabled on demand) and the matching release / free.       */
 #define DAGMA_PEER_HANDLE_BYTES 64

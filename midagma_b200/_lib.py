@@ -74,6 +74,7 @@ EXPORTS = {
     "dagma_linear_iter_sharded_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "dagma_graph_metrics": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dagma_peer_alloc": (C.c_int, [C.c_size_t, C.c_void_p]),
     "dagma_peer_free": (C.c_int, [C.c_void_p]),
     "dagma_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
