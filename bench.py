@@ -498,7 +498,8 @@ def bench_c2_c3(torch, with_cpu, peak_tflops=None):
     lanes = _batch_lanes(db, nb)
     out["mid_d_batch"] = {"workload": f"{nb} independent DagmaLinear l2 problems, d={db} n={4 * db}, one stage of up to {itb} "
                                       "iterations each (fit_batch; host arrays in, W_est out)",
-                          "lanes": lanes, "wall_s": wallb, "inner_iters": int(infob["total_iters"]),
+                          "lanes": lanes, "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
+                          "wall_s": wallb, "inner_iters": int(infob["total_iters"]),
                           "iters_per_s": infob["total_iters"] / wallb,
                           "us_per_iter_and_lane": wallb / infob["total_iters"] * lanes * 1e6,
                           "flop_per_iter": 4.0 * db ** 3,
@@ -754,7 +755,68 @@ def run_b200(args):
     value = total_iters / dt
     e2e_value = total_iters / dt_e2e
 
+    # ---- the contract line is complete from here on; everything below adds keys to it.  A watchdog guarantees that
+    # rank 0 prints it exactly once even if an extra section hangs (e.g. a collective after a failure on one rank) or
+    # raises: the extras then carry an `extras_error` / `extras_timeout` note instead of values.
+    import threading
+    core = {
+        "metric": "DagmaLinear inner Adam iters/sec (batched d=64)", "value": value,
+        "unit": "problem-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4: batched DagmaLinear l2 minimize, ER4 d=64 n=1000, 1024 seeds x 4 lambda1",
+                   "problems_per_gpu": nprob, "d": D, "n": N_SAMPLES, "iters_per_step": ITERS_PER_STEP,
+                   "mu": 1.0, "s": 1.0, "lr": 3e-4, "l2_policy": "inputs exceed L2 (cov+W = 268 MB per GPU)",
+                   "data_gen_s": round(t_gen, 1)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "problem-iterations/s",
+                "h2d_bytes_per_step": 2 * nprob * D * D * 8 + nprob * 8, "d2h_bytes_per_step": nprob * D * D * 8},
+        "gpu_launches": args.steps,
+    }
     extra = {}
+    emit_lock, emitted = threading.Lock(), []
+
+    def emit(note=None):
+        with emit_lock:
+            if emitted:
+                return
+            emitted.append(1)
+            if rank == 0:
+                line = dict(core)
+                line.update(extra)
+                if note:
+                    line.update(note)
+                print(json.dumps(line), flush=True)
+
+    def on_timeout():
+        emit({"extras_timeout": f"an extra section did not finish within {args.extras_timeout} s: keys after the last "
+                                "completed section are missing"})
+        os._exit(0)
+
+    watchdog = threading.Timer(args.extras_timeout, on_timeout)
+    watchdog.daemon = True
+    watchdog.start()
+    try:
+        run_extras(args, torch, dist, _lib, fit_batch, _run_small, extra, locals())
+    except BaseException as e:                            # noqa: BLE001 -- reported in the line, never lost
+        extra["extras_error"] = f"{type(e).__name__}: {e}"[:500]
+        if world > 1:
+            watchdog.cancel()
+            emit()
+            os._exit(0)                                  # the other ranks may sit in a collective: their watchdogs end them
+    watchdog.cancel()
+    emit()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_extras(args, torch, dist, _lib, fit_batch, _run_small, extra, env):
+    """Everything of the bench line beyond the contract keys (see the module docstring); `env` = the locals of run_b200."""
+    import numpy as np                                    # noqa: F401
+    world, rank, dev, sms, nprob = env["world"], env["rank"], env["dev"], env["sms"], env["nprob"]
+    cov, lam, sync, rmax, kernel_ms = env["cov"], env["lam"], env["sync"], env["rmax"], env["kernel_ms"]
+    W_host, cov_host = env["W_host"], env["cov_host"]
     if world > 1:
         # ---- strong scaling of the same workload: 4096 problems in total, 4096 / N per GPU (2 CTAs per SM: 512
         # equal-length problems are 1.73 waves of 296 resident CTAs -- the second wave bounds the step)
@@ -829,29 +891,11 @@ def run_b200(args):
 
         if args.c5 and world == 1:
             del W_host, cov_host
+            env.pop("W_host", None)
+            env.pop("cov_host", None)
             extra["c5"] = bench_c5(torch, _lib, peak, args.cpu_baseline)
             extra.update(bench_c2_c3(torch, args.cpu_baseline, peak))
 
-    if rank == 0:
-        line = {
-            "metric": "DagmaLinear inner Adam iters/sec (batched d=64)", "value": value,
-            "unit": "problem-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4: batched DagmaLinear l2 minimize, ER4 d=64 n=1000, 1024 seeds x 4 lambda1",
-                       "problems_per_gpu": nprob, "d": D, "n": N_SAMPLES, "iters_per_step": ITERS_PER_STEP,
-                       "mu": 1.0, "s": 1.0, "lr": 3e-4, "l2_policy": "inputs exceed L2 (cov+W = 268 MB per GPU)",
-                       "data_gen_s": round(t_gen, 1)},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "problem-iterations/s",
-                    "h2d_bytes_per_step": 2 * nprob * D * D * 8 + nprob * 8, "d2h_bytes_per_step": nprob * D * D * 8},
-            "gpu_launches": args.steps,
-        }
-        line.update(extra)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 def main():
@@ -867,6 +911,8 @@ def main():
     ap.add_argument("--no-c5", dest="c5", action="store_false", help="skip the single d=2000 problem (C5)")
     ap.add_argument("--no-sharded", dest="sharded", action="store_false",
                     help="N > 1: skip the row-sharded C2 / C3 iterations")
+    ap.add_argument("--extras-timeout", type=float, default=1500.0,
+                    help="seconds after which the contract line is printed without the unfinished extra keys")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

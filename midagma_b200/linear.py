@@ -221,7 +221,9 @@ def minimize_batch(W, cov, lambda1, mu, max_iter, s, lr, *, tol=1e-6, beta_1=0.9
     Wd = W if on_device and W.dtype == torch.float64 and W.is_contiguous() else _as_dev(W, device)
     covd = _as_dev(cov, device)
     batch, d, _ = covd.shape
-    assert d <= _lib.SMALL_MAX_D, "minimize_batch uses the on-chip path (d <= 64)"
+    if d > _lib.SMALL_MAX_D:
+        return _minimize_batch_large(W, covd, lambda1, mu, max_iter, s, lr, tol=tol, beta_1=beta_1, beta_2=beta_2,
+                                     checkpoint=checkpoint, exclude_edges=exclude_edges, include_edges=include_edges)
     lam = _lam_dev(lambda1, batch, device)
     mask_exc, mask_inc = _batch_masks(exclude_edges, include_edges, d, device)
     res = _run_small(covd, Wd, lam, [mu], [s], [int(max_iter)], lr=lr, tol=tol, beta1=beta_1, beta2=beta_2,
@@ -308,6 +310,75 @@ def _batch_lanes(d: int, batch: int) -> int:
     return max(1, min((sms - 12) // ctas, 8, batch))       # a dozen SMs stay free for the checkpoint kernels of all lanes
 
 
+def _run_lanes(batch: int, d: int, solve, device) -> None:
+    """``solve(b)`` for every problem of a d > 64 batch, ``_batch_lanes`` of them at a time: one host thread and one
+    CUDA stream per lane (the caller's stream is waited for first; every lane is synchronised before returning)."""
+    lanes = _batch_lanes(d, batch)
+    if lanes <= 1:
+        for b in range(batch):
+            solve(b)
+        return
+    import threading
+    main = torch.cuda.current_stream()
+    todo = iter(range(batch))
+    lock = threading.Lock()
+    errors = []
+
+    def lane():
+        torch.cuda.set_device(device)
+        st = torch.cuda.Stream(device=device)
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            while not errors:
+                with lock:
+                    b = next(todo, None)
+                if b is None:
+                    break
+                try:
+                    solve(b)
+                except BaseException as e:                        # noqa: BLE001 -- re-raised on the caller's thread
+                    errors.append(e)
+            st.synchronize()
+
+    threads = [threading.Thread(target=lane, daemon=True) for _ in range(lanes)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+
+
+def _minimize_batch_large(W, covd, lambda1, mu, max_iter, s, lr, *, tol, beta_1, beta_2, checkpoint, exclude_edges,
+                          include_edges):
+    """``minimize_batch`` beyond the on-chip size: one ``DagmaLinear.minimize`` per problem on the multi-CTA engine, for
+    d <= 128 several problems side by side (one persistent kernel each, csrc/lin_iter.cu)."""
+    batch, d, _ = covd.shape
+    lam = np.broadcast_to(np.asarray(lambda1.cpu() if isinstance(lambda1, torch.Tensor) else lambda1,
+                                     dtype=np.float64), (batch,))
+    W_np = W.detach().cpu().numpy() if isinstance(W, torch.Tensor) else np.asarray(W)
+    W_out = np.array(W_np, dtype=np.float64, copy=True)
+    ok = np.zeros(batch, dtype=bool)
+    stats = np.zeros((batch, 1, 8))
+
+    def solve(b):
+        m = DagmaLinear("l2")
+        m._fit_from_cov(covd[b], float(lam[b]), T=1, warm_iter=0, max_iter=0, checkpoint=checkpoint,
+                        exclude_edges=exclude_edges, include_edges=include_edges)
+        _, ok[b] = m.minimize(W_out[b], mu, int(max_iter), s, lr=lr, tol=tol, beta_1=beta_1, beta_2=beta_2)
+        stats[b, 0, 0] = m.last_iters
+        stats[b, 0, 1], stats[b, 0, 2] = m._large.last_lr, s
+        if m.checkpoint_log:
+            stats[b, 0, 3:6] = m.checkpoint_log[-1][2:5]
+
+    _run_lanes(batch, d, solve, covd.device)
+    if isinstance(W, torch.Tensor):
+        W.copy_(torch.from_numpy(W_out))
+        return W, (torch.from_numpy(ok).to(W.device) if W.is_cuda else ok), (torch.from_numpy(stats).to(W.device) if W.is_cuda else stats)
+    W[...] = W_out
+    return W, ok, stats
+
+
 def _fit_batch_large(covd, lambda1, *, w_threshold, return_info, **fit_kw):
     """``fit_batch`` beyond the on-chip size (d > 64): every problem runs on the multi-CTA engine -- the same code path
     as ``DagmaLinear.fit`` at that size, fed with the covariance instead of the data -- and ``_batch_lanes`` problems
@@ -327,41 +398,7 @@ def _fit_batch_large(covd, lambda1, *, w_threshold, return_info, **fit_kw):
         W_raw[b] = m.W_raw
         stage_iters[b], h_fin[b], sc_fin[b] = m.stage_iters, m.h_final, m.score_final
 
-    lanes = _batch_lanes(d, batch)
-    if lanes <= 1:
-        for b in range(batch):
-            solve(b)
-    else:
-        import threading
-        main = torch.cuda.current_stream()
-        dev = covd.device
-        todo = iter(range(batch))
-        lock = threading.Lock()
-        errors = []
-
-        def lane():
-            torch.cuda.set_device(dev)
-            st = torch.cuda.Stream(device=dev)
-            st.wait_stream(main)                                  # covd was produced on the caller's stream
-            with torch.cuda.stream(st):
-                while not errors:
-                    with lock:
-                        b = next(todo, None)
-                    if b is None:
-                        break
-                    try:
-                        solve(b)
-                    except BaseException as e:                    # noqa: BLE001 -- re-raised on the caller's thread
-                        errors.append(e)
-                st.synchronize()
-
-        threads = [threading.Thread(target=lane, daemon=True) for _ in range(lanes)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
+    _run_lanes(batch, d, solve, covd.device)
     W_est = W_raw.copy()
     W_est[np.abs(W_est) < w_threshold] = 0
     if not return_info:

@@ -172,3 +172,22 @@ def test_streamed_rows_variant():
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DAGMA_LIN_STREAM="1", PYTHONPATH=root), cwd=root,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_minimize_batch_beyond_onchip_size():
+    """minimize_batch accepts d > 64: each problem equals DagmaLinear.minimize on the same covariance."""
+    from midagma_b200 import DagmaLinear, minimize_batch
+    from midagma_b200.linear import center_cov
+    import torch
+    d, batch = 72, 5
+    Xs = np.stack([simulate.make_linear_problem(d, 2, 300, "ER", "gauss", 80 + p)[0] for p in range(batch)])
+    lam = np.linspace(0.01, 0.03, batch)
+    cov = center_cov(torch.from_numpy(Xs).cuda(), center=True).cpu().numpy()
+    W0 = np.zeros((batch, d, d))
+    W, ok, stats = minimize_batch(W0, cov, lam, 1.0, 120, 1.0, 3e-4, checkpoint=50)
+    assert W is W0 and ok.all() and stats[:, 0, 0].tolist() == [120.0] * batch
+    for b in range(batch):
+        m = DagmaLinear("l2")
+        m.fit(Xs[b].copy(), lambda1=float(lam[b]), T=1, warm_iter=0, max_iter=0, checkpoint=50)
+        Wb, okb = m.minimize(np.zeros((d, d)), 1.0, 120, 1.0, lr=3e-4)
+        assert okb and np.abs(Wb - W[b]).max() <= 1e-12
