@@ -654,13 +654,32 @@ def bench_sharded(torch, dist, rank, world, dev):
         eq.minimize(iters, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0)
         e1.record()
         torch.cuda.synchronize()
-        return rmax(e0.elapsed_time(e1) * 1e-3) / iters, model.fc1.weight.detach().clone()
+        eng = eq._engine
+        path = ("persistent kernel, cross-GPU sum over NVLink peer memory" if eng._peer is not None else
+                "persistent kernel" if eng.one_kernel else
+                "launch sequence" + (" + NCCL all-reduce in the CUDA graph" if shard else ""))
+        t = rmax(e0.elapsed_time(e1) * 1e-3) / iters
+        w = model.fc1.weight.detach().clone()
+        eq.close()                                                # peer mappings (collective)
+        return t, w, path
 
-    t_sh, w_sh = time_mlp(True, 1000)
-    t_1, w_1 = time_mlp(False, 1000)
-    out["c3_sharded"] = {"workload": "C3: DagmaMLP [40, 10, 1] n=2000, rows sharded over the GPUs",
-                         "iters_per_s": 1.0 / t_sh, "us_per_iter_sharded": t_sh * 1e6, "us_per_iter_one_gpu": t_1 * 1e6,
-                         "speedup": t_1 / t_sh, "max_abs_dfc1_vs_one_gpu": float((w_sh - w_1).abs().max().item())}
+    rows3 = []
+    X3 = Xn
+    for mult in (1, 4, 16):
+        Xn = np.tile(X3, (mult, 1)) if mult > 1 else X3
+        n = Xn.shape[0]
+        t_sh, w_sh, p_sh = time_mlp(True, 1000)
+        t_1, w_1, p_1 = time_mlp(False, 1000)
+        rows3.append({"n": int(n), "us_per_iter_sharded": t_sh * 1e6, "us_per_iter_one_gpu": t_1 * 1e6, "speedup": t_1 / t_sh,
+                      "max_abs_dfc1_vs_one_gpu": float((w_sh - w_1).abs().max().item()), "sharded_path": p_sh,
+                      "one_gpu_path": p_1})
+    out["c3_sharded"] = {"workload": "C3: DagmaMLP [40, 10, 1], rows sharded over the GPUs (n = 2000 is BASELINE's size; larger "
+                                     "n: the same rows tiled)",
+                         "iters_per_s": 1e6 / rows3[0]["us_per_iter_sharded"],
+                         "us_per_iter_sharded": rows3[0]["us_per_iter_sharded"],
+                         "us_per_iter_one_gpu": rows3[0]["us_per_iter_one_gpu"], "speedup": rows3[0]["speedup"],
+                         "max_abs_dfc1_vs_one_gpu": rows3[0]["max_abs_dfc1_vs_one_gpu"], "by_n": rows3,
+                         "crossover_n": next((r["n"] for r in rows3 if r["speedup"] >= 1.0), None)}
     return out
 
 

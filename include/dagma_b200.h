@@ -274,6 +274,15 @@ size_t dagma_mlp_iter_workspace_doubles(int n, int d, int m1);
 int dagma_mlp_iter_f64(dagma_stream_t stream, int n, int n_total, int d, int m1, int iters, void* state_dev,
                        double* theta_dev, double* m_dev, double* v_dev, const double* x_dev, double* part_dev,
                        double* minv_dev, unsigned* sync_dev);
+/* The same with the rows of X sharded over the GPUs of ONE box, one process per GPU: the sums of the
+ * un-scaled gradients and of S over the GPUs happen inside the kernel over NVLink peer memory, in rank order on every
+ * GPU (bit-identical replicas, no collective call in the loop).  exchange_ptrs: as for dagma_linear_iter_sharded_f64,
+ * allocations of dagma_mlp_iter_exchange_bytes(d, m1, nranks) bytes.                                              */
+size_t dagma_mlp_iter_exchange_bytes(int d, int m1, int nranks);
+int dagma_mlp_iter_sharded_f64(dagma_stream_t stream, int n_local, int n_total, int d, int m1, int iters,
+                               void* state_dev, double* theta_dev, double* m_dev, double* v_dev, const double* x_dev,
+                               double* part_dev, double* minv_dev, unsigned* sync_dev, int rank, int nranks,
+                               void* const* exchange_ptrs);
 /* General LocallyConnected stacks dims = [d, m_1, ..., 1] (nonlinear.py:39-43, 60-65), transposed activations
  * [d * width][n], one call per layer.
  *   lc_forward : in ([d*mi][n]; + bias_in for the first layer) is replaced by H = sigmoid(in);

@@ -100,64 +100,21 @@ class LargeLinearEngine:
 
     # ------------------------------------------------------------------ peer memory of the row-sharded fused iteration
     def _peer_setup(self, group, want: bool) -> bool:
-        """Exchange buffers of the row-sharded persistent kernel: one allocation per GPU, mapped into every process of
-        the group through CUDA IPC handles.  Every rank takes the same decision (two small all-reduces): the peer path
-        is used only when every rank supports the shape and every mapping succeeded."""
-        import ctypes as C
+        """Exchange buffers of the row-sharded persistent kernel (``_peer.PeerExchange``); every rank takes the same
+        decision: the peer path is used only when every rank supports its shape and every mapping succeeded."""
+        from ._peer import PeerExchange
         import torch.distributed as dist
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        dev = self.dev
-
-        def agree(ok: bool) -> bool:
-            t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64,
-                             device=dev if dist.get_backend(group) == "nccl" else "cpu")
-            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
-            return bool(t.item() > 0.5)
-
-        want = want and dist.get_backend(group) == "nccl" and 2 <= world <= 8
-        if not agree(want):
-            return False
-        nbytes = self.lib.dagma_linear_iter_exchange_bytes(self.d, world)
-        own, handle, ok = C.c_void_p(), (C.c_ubyte * 64)(), nbytes > 0
-        ok = ok and self.lib.dagma_peer_alloc(nbytes, C.byref(own)) == 0
-        ok = ok and self.lib.dagma_peer_export(own, handle) == 0
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle) if ok else None, group=group)
-        ptrs, imported = (C.c_void_p * world)(), []
-        ok = ok and all(h is not None for h in handles)
-        if ok:
-            for r in range(world):
-                if r == rank:
-                    ptrs[r] = own.value
-                    continue
-                p = C.c_void_p()
-                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
-                if self.lib.dagma_peer_import(buf, C.byref(p)) != 0:
-                    ok = False
-                    break
-                imported.append(p)
-                ptrs[r] = p.value
-        if not agree(ok):                        # also the barrier: every buffer is zeroed and mapped before a launch
-            for p in imported:
-                self.lib.dagma_peer_release(p)
-            if own.value:
-                self.lib.dagma_peer_free(own)
-            return False
-        self._peer = {"group": group, "rank": rank, "world": world, "own": own, "imported": imported, "ptrs": ptrs}
-        return True
+        nbytes = self.lib.dagma_linear_iter_exchange_bytes(self.d, dist.get_world_size(group))
+        self._peer = PeerExchange.create(group, nbytes, self.dev, want)
+        return self._peer is not None
 
     def close(self):
         """Release the peer mappings (collective: every rank of the group calls it) and free the own buffer."""
         if self._peer is None:
             return
-        import torch.distributed as dist
-        torch.cuda.synchronize()
         pr, self._peer = self._peer, None
         self.one_kernel = False
-        for p in pr["imported"]:
-            self.lib.dagma_peer_release(p)
-        dist.barrier(group=pr["group"])          # nobody maps the buffer any more
-        self.lib.dagma_peer_free(pr["own"])
+        pr.close()
 
     # ------------------------------------------------------------------ trek regulariser (SURVEY.md 8f3)
     def _trek_setup(self, plan):
@@ -299,7 +256,7 @@ class LargeLinearEngine:
                 _lib.stream_ptr(), self.n, self.d, int(n), self.state.data_ptr(), self.W.data_ptr(), self.m.data_ptr(),
                 self.v.data_ptr(), self.Minv.data_ptr(), self.T.data_ptr(), self.cov.data_ptr(), ptr(self.X),
                 ptr(self.mask_exc), ptr(self.mask_inc), self.iter_ws.data_ptr(), self.iter_sync.data_ptr(),
-                self._peer["rank"], self._peer["world"], self._peer["ptrs"]), "dagma_linear_iter_sharded_f64")
+                self._peer.rank, self._peer.world, self._peer.ptrs), "dagma_linear_iter_sharded_f64")
             return
         _lib.check(self.lib.dagma_linear_iter_f64(
             _lib.stream_ptr(), logistic, self.n if logistic else 0, self.d, int(n), self.state.data_ptr(),

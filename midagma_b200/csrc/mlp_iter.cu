@@ -25,7 +25,13 @@
 //             The LAST CTA to reach the closing barrier writes the state block (S, score, objective, h < 0 latch,
 //             step counter, ExponentialLR) before it opens it.
 //
-// Rows sharded over GPUs and stacks other than [d, m1, 1] stay on the launch sequence of mlp.cu.
+// Rows of X sharded over the GPUs of one box (one process per GPU): the same kernel on every GPU; between the two
+// phases every CTA stores the fixed-order sums of ITS GPU's sample groups for its share of the parameters (and the
+// GPU's S) into slot `rank` of every GPU's exchange buffer over NVLink peer memory (csrc/peer.cu), one more grid barrier,
+// sequence-number flags, and phase B adds the slots in rank order -- the same order everywhere, so the replicas stay
+// bit-identical and there is no collective call in the loop (protocol and memory ordering: csrc/lin_iter.cu).
+//
+// Stacks other than [d, m1, 1] stay on the launch sequence of mlp.cu.
 #include "common.cuh"
 #include "small_dmma.cuh"
 #include "gemm_f64.cuh"
@@ -40,6 +46,7 @@ constexpr int MI_MTG = 3;         // m-tiles per warp in the gW1 product (two m-
 constexpr int MI_NTT = 8;         // n-tiles of the gW1 product: d <= 64
 constexpr int MI_KSL = 4;         // k-slices (sample ranges) of the gW1 product: warps = 2 m-groups x 4 k-slices
 constexpr unsigned MI_SPIN_MAX = 1u << 22;
+constexpr int MI_MAX_RANKS = 8;   // GPUs of one box that may share the rows of X
 constexpr size_t MI_SMEM_CAP = 200 * 1024;
 
 // How the work of an iteration is cut (host and device agree through this struct).  The MLP is locally connected:
@@ -97,6 +104,14 @@ struct MlpIterArgs {
     unsigned* sync;                        // [0] arrivals at the grid barriers of this launch [2] error (zeroed by the host per launch)
     int iters, sms;
     int h_stage;                           // doubles of the h CTA's staging buffer for fc1.weight
+    // rows of X sharded over `nranks` GPUs of one box (nranks = 1: none of this is touched) -- the protocol of
+    // csrc/lin_iter.cu: xchg[r] = rank r's exchange buffer as mapped into THIS process, [2 (parity)][nranks (writer)]
+    // [total + 1] doubles (the un-scaled gradient sums of the writer's rows, then its S); flags[r]: rank r's [nranks]
+    // sequence numbers; seq: this rank's count of exchanged iterations
+    int rank, nranks;
+    double* xchg[MI_MAX_RANKS];
+    unsigned* flags[MI_MAX_RANKS];
+    unsigned* seq;
 };
 
 #ifdef DAGMA_MLP_TRACE
@@ -451,8 +466,43 @@ __device__ __forceinline__ MiScalars mi_read_state(const MlpState* stp) {
 }
 
 // ---------------------------------------------------------------- phase B: fixed-order sums + Adam (mlp_adam_kernel)
+// the SG rows of `part` for one entry, added in order (sixteen loads in flight)
+__device__ __forceinline__ double mi_group_sum(const double* src, int SG, int W) {
+    double acc = 0.0;
+    int c = 0;
+    for (; c + 16 <= SG; c += 16) {
+        double t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = __ldcg(src + (size_t)(c + u) * W);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc += t[u];
+    }
+    {
+        double t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = (c + u < SG) ? __ldcg(src + (size_t)(c + u) * W) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            if (c + u < SG) acc += t[u];
+    }
+    return acc;
+}
+
+// sharded rows: this GPU's sums for the CTA's share of the parameters (and, by CTA 0, its S) to every GPU's buffer
+__device__ __forceinline__ void mi_publish_sums(const MlpIterArgs& P, const MiPlan& L, int cta, double S_local, unsigned seq) {
+    const int tid = threadIdx.x, d = P.d, PP = d * P.m1, W = PP * d + 2 * PP + d;
+    const size_t slot = ((size_t)(seq & 1u) * P.nranks + P.rank) * (W + 1);
+    for (int e = cta * MI_NT + tid; e < W; e += L.G * MI_NT) {
+        const double acc = mi_group_sum(P.part + e, L.SG, W);
+        for (int r = 0; r < P.nranks; ++r) P.xchg[r][slot + e] = acc;
+    }
+    if (cta == 0 && tid == 0)
+        for (int r = 0; r < P.nranks; ++r) P.xchg[r][slot + W] = S_local;
+    __threadfence_system();
+}
+
 __device__ __forceinline__ void mi_update(const MlpIterArgs& P, const MiPlan& L, int cta, double S, const MiScalars& sc,
-                                          double bc1, double bc2) {
+                                          double bc1, double bc2, unsigned seq) {
     const int tid = threadIdx.x, d = P.d, m1 = P.m1, PP = d * m1;
     const int W = PP * d + 2 * PP + d, SG = L.SG;
     const double mu = sc.mu, lr = sc.lr, b1 = sc.beta1, b2 = sc.beta2;
@@ -460,8 +510,8 @@ __device__ __forceinline__ void mi_update(const MlpIterArgs& P, const MiPlan& L,
     const double gs = mu * (double)d / S;
     const double step_size = lr / bc1, bc2s = sqrt(bc2);
     const int nW1 = PP * d;
+    const double* xs = (P.nranks > 1) ? P.xchg[P.rank] + (size_t)(seq & 1u) * P.nranks * (W + 1) : nullptr;
     for (int e = cta * MI_NT + tid; e < W; e += L.G * MI_NT) {
-        const double* src = P.part + e;
         // everything the step needs travels together with the partial sums
         const double p = P.theta[e], mo = P.m[e], vo = P.v[e];
         double hterm = 0.0;
@@ -469,22 +519,11 @@ __device__ __forceinline__ void mi_update(const MlpIterArgs& P, const MiPlan& L,
             const int row = e / d, i = e - row * d, j = row / m1;
             hterm = __ldcg(P.Minv + (size_t)j * d + i);
         }
-        double acc = 0.0;
-        int c = 0;
-        for (; c + 16 <= SG; c += 16) {                   // sixteen loads in flight, added in order
-            double t[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) t[u] = __ldcg(src + (size_t)(c + u) * W);
-#pragma unroll
-            for (int u = 0; u < 16; ++u) acc += t[u];
-        }
-        {
-            double t[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) t[u] = (c + u < SG) ? __ldcg(src + (size_t)(c + u) * W) : 0.0;
-#pragma unroll
-            for (int u = 0; u < 16; ++u)
-                if (c + u < SG) acc += t[u];
+        double acc;
+        if (P.nranks == 1) acc = mi_group_sum(P.part + e, SG, W);
+        else {                                                    // the GPUs' sums in rank order: the same on every GPU
+            acc = 0.0;
+            for (int q = 0; q < P.nranks; ++q) acc += __ldcg(xs + (size_t)q * (W + 1) + e);
         }
         double g = gs * acc;
         if (e < nW1) {
@@ -506,6 +545,7 @@ __global__ void __launch_bounds__(MI_NT, 1) mlp_iter_kernel(const MlpIterArgs P)
     extern __shared__ __align__(16) double sm[];
     __shared__ double s_S, s_bc[2];
     __shared__ MiScalars s_sc;
+    __shared__ unsigned s_seq;
     const int tid = threadIdx.x, cta = blockIdx.x, G = gridDim.x;
     const MiPlan L = mi_plan(P.n, P.d, P.m1, P.sms);
     const int d = P.d, PP = d * P.m1, W = PP * d + 2 * PP + d;
@@ -538,8 +578,11 @@ __global__ void __launch_bounds__(MI_NT, 1) mlp_iter_kernel(const MlpIterArgs P)
             atomicMin(&g_mlp_trace[15], t);
         }
 #endif
-        if (tid == 0) s_sc = mi_read_state(P.st);                     // before the barrier: CTA 0 rewrites it after it;
+        if (tid == 0) {
+            s_sc = mi_read_state(P.st);                               // before the barrier: CTA 0 rewrites it after it;
                                                                       // one thread per CTA (36 k readers of one line slow the barrier down)
+            s_seq = (P.nranks > 1) ? *(volatile unsigned*)P.seq + 1u : 0u;
+        }
         mi_grid_barrier(P.sync, (unsigned)G, bar_k);
         MI_STAMP(9, cta == 0);
         const MiScalars sc = s_sc;
@@ -562,6 +605,35 @@ __global__ void __launch_bounds__(MI_NT, 1) mlp_iter_kernel(const MlpIterArgs P)
         }
         const double h = *(volatile double*)&P.st->h;
         __syncthreads();
+        const unsigned seq = s_seq;
+        if (P.nranks > 1) {
+            // ---- rows sharded over GPUs: exchange the sums of this GPU's rows (see the file header)
+            mi_publish_sums(P, L, cta, s_S, seq);
+            mi_grid_barrier(P.sync, (unsigned)G, bar_k);              // every CTA's peer stores are fenced
+            if (cta == 0 && tid < P.nranks && tid != P.rank) {
+                __threadfence_system();                               // release
+                *(volatile unsigned*)(P.flags[tid] + P.rank) = seq;
+            }
+            if (tid < P.nranks && tid != P.rank) {
+                unsigned spins = 0;
+                while ((int)(*(volatile unsigned*)(P.flags[P.rank] + tid) - seq) < 0) {
+                    if ((++spins & 63u) == 0u) {
+                        if (*(volatile unsigned*)(P.sync + 2)) break;
+                        if (spins > MI_SPIN_MAX) { atomicExch(P.sync + 2, 2u); break; }
+                    }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+            if (tid == 0) {                                           // S over all GPUs, rank order
+                const int Wt = PP * d + 2 * PP + d;
+                const double* xs = P.xchg[P.rank] + (size_t)(seq & 1u) * P.nranks * (Wt + 1);
+                double S_all = 0.0;
+                for (int q = 0; q < P.nranks; ++q) S_all += __ldcg(xs + (size_t)q * (Wt + 1) + Wt);
+                s_S = S_all;
+            }
+            __syncthreads();
+        }
         const double S = s_S;
         const bool neg = h < 0.0;
         MI_STAMP(10, cta == 0);
@@ -570,6 +642,7 @@ __global__ void __launch_bounds__(MI_NT, 1) mlp_iter_kernel(const MlpIterArgs P)
         if (cta == 0 && tid == 0) {
             volatile MlpState* st = P.st;
             const double score = 0.5 * (double)d * log(S / (double)P.n_total);
+            if (P.nranks > 1) *(volatile unsigned*)P.seq = seq;
             st->S = S;
             st->score = score;
             st->obj = sc.mu * (score + sc.lambda1 * st->l1) + h;
@@ -579,7 +652,7 @@ __global__ void __launch_bounds__(MI_NT, 1) mlp_iter_kernel(const MlpIterArgs P)
                 if (sc.gamma != 1.0 && ((sc.step + 1) % 1000) == 0) st->lr = sc.lr * sc.gamma;
             }
         }
-        if (!neg) mi_update(P, L, cta, S, sc, s_bc[0], s_bc[1]);
+        if (!neg) mi_update(P, L, cta, S, sc, s_bc[0], s_bc[1], seq);
         MI_STAMP(11, cta == 0);
         mi_grid_barrier(P.sync, (unsigned)G, bar_k);
         MI_STAMP(12, cta == 0);
@@ -614,9 +687,10 @@ extern "C" size_t dagma_mlp_iter_workspace_doubles(int n, int d, int m1) {
     return (size_t)L.SG * W + (size_t)L.SG * L.JS + 8;
 }
 
-extern "C" int dagma_mlp_iter_f64(dagma_stream_t stream, int n, int n_total, int d, int m1, int iters, void* state_dev,
-                                  double* theta_dev, double* m_dev, double* v_dev, const double* x_dev, double* part_dev,
-                                  double* minv_dev, unsigned* sync_dev) {
+static int mlp_iter_launch(cudaStream_t stream, int n, int n_total, int d, int m1, int iters, void* state_dev,
+                           double* theta_dev, double* m_dev, double* v_dev, const double* x_dev, double* part_dev,
+                           double* minv_dev, unsigned* sync_dev, int rank, int nranks, void* const* xchg_ptrs,
+                           void* const* flag_ptrs, unsigned* seq_dev) {
     DAGMA_REQUIRE(state_dev && theta_dev && m_dev && v_dev && x_dev && part_dev && minv_dev && sync_dev, "null pointer");
     const MiPlan L = mi_plan(n, d, m1, mi_sms());
     DAGMA_REQUIRE(iters >= 0 && L.ok, "shape not supported by the fused iteration (dagma_mlp_iter_supported)");
@@ -635,14 +709,60 @@ extern "C" int dagma_mlp_iter_f64(dagma_stream_t stream, int n, int n_total, int
         DAGMA_CUDA_OK(cudaFuncSetAttribute(mlp_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    MlpIterArgs A{(MlpState*)state_dev, theta_dev, m_dev, v_dev, x_dev, n, n_total, d, m1, part_dev, minv_dev, sync_dev,
-                  iters, mi_sms(), (int)stage};
-    // 32-bit arrival counter: G * 2 * iters arrivals per launch
-    DAGMA_REQUIRE((double)L.G * 2.0 * (double)iters < 4.0e9, "too many iterations for one launch");
-    DAGMA_CUDA_OK(cudaMemsetAsync(sync_dev, 0, 4 * sizeof(unsigned), (cudaStream_t)stream));
-    mlp_iter_kernel<<<L.G, MI_NT, smem, (cudaStream_t)stream>>>(A);
+    MlpIterArgs A{};
+    A.st = (MlpState*)state_dev;
+    A.theta = theta_dev; A.m = m_dev; A.v = v_dev; A.X = x_dev;
+    A.n = n; A.n_total = n_total; A.d = d; A.m1 = m1;
+    A.part = part_dev; A.Minv = minv_dev; A.sync = sync_dev;
+    A.iters = iters; A.sms = mi_sms(); A.h_stage = (int)stage;
+    A.rank = rank; A.nranks = nranks; A.seq = seq_dev;
+    for (int r = 0; r < nranks && nranks > 1; ++r) {
+        A.xchg[r] = (double*)xchg_ptrs[r];
+        A.flags[r] = (unsigned*)flag_ptrs[r];
+    }
+    // 32-bit arrival counter: up to G * 3 * iters arrivals per launch
+    DAGMA_REQUIRE((double)L.G * 3.0 * (double)iters < 4.0e9, "too many iterations for one launch");
+    DAGMA_CUDA_OK(cudaMemsetAsync(sync_dev, 0, 4 * sizeof(unsigned), stream));
+    mlp_iter_kernel<<<L.G, MI_NT, smem, stream>>>(A);
     DAGMA_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int dagma_mlp_iter_f64(dagma_stream_t stream, int n, int n_total, int d, int m1, int iters, void* state_dev,
+                                  double* theta_dev, double* m_dev, double* v_dev, const double* x_dev, double* part_dev,
+                                  double* minv_dev, unsigned* sync_dev) {
+    return mlp_iter_launch((cudaStream_t)stream, n, n_total, d, m1, iters, state_dev, theta_dev, m_dev, v_dev, x_dev,
+                           part_dev, minv_dev, sync_dev, 0, 1, nullptr, nullptr, nullptr);
+}
+
+static size_t mi_exchange_data_bytes(int d, int m1, int nranks) {
+    const size_t W = (size_t)d * m1 * d + 2 * (size_t)d * m1 + d;
+    return (((size_t)2 * nranks * (W + 1) * sizeof(double)) + 127) & ~(size_t)127;
+}
+
+extern "C" size_t dagma_mlp_iter_exchange_bytes(int d, int m1, int nranks) {
+    if (d < 1 || d > 64 || m1 < 1 || m1 > MI_PR || nranks < 2 || nranks > MI_MAX_RANKS) return 0;
+    return mi_exchange_data_bytes(d, m1, nranks) + 256;
+}
+
+extern "C" int dagma_mlp_iter_sharded_f64(dagma_stream_t stream, int n_local, int n_total, int d, int m1, int iters,
+                                          void* state_dev, double* theta_dev, double* m_dev, double* v_dev,
+                                          const double* x_dev, double* part_dev, double* minv_dev, unsigned* sync_dev,
+                                          int rank, int nranks, void* const* exchange_ptrs) {
+    DAGMA_REQUIRE(nranks >= 2 && nranks <= MI_MAX_RANKS && rank >= 0 && rank < nranks && exchange_ptrs, "bad rank arguments");
+    // layout of a GPU's exchange allocation (dagma_mlp_iter_exchange_bytes): [2][nranks][total + 1] doubles, then
+    // [nranks] flags, then this GPU's own sequence counter
+    void* xp[MI_MAX_RANKS];
+    void* fp[MI_MAX_RANKS];
+    const size_t data = mi_exchange_data_bytes(d, m1, nranks);
+    for (int r = 0; r < nranks; ++r) {
+        DAGMA_REQUIRE(exchange_ptrs[r], "null exchange pointer");
+        xp[r] = exchange_ptrs[r];
+        fp[r] = (char*)exchange_ptrs[r] + data;
+    }
+    unsigned* seq = (unsigned*)((char*)exchange_ptrs[rank] + data) + 32;
+    return mlp_iter_launch((cudaStream_t)stream, n_local, n_total, d, m1, iters, state_dev, theta_dev, m_dev, v_dev, x_dev,
+                           part_dev, minv_dev, sync_dev, rank, nranks, xp, fp, seq);
 }
 
 #ifdef DAGMA_MLP_TRACE

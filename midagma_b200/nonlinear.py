@@ -165,7 +165,7 @@ class DagmaMLP(nn.Module):
 class _MlpEngine:
     """Device buffers + launch sequences for one (model, X) pair."""
 
-    def __init__(self, model: DagmaMLP, X: typing.Optional[torch.Tensor], group=None, n_total=None):
+    def __init__(self, model: DagmaMLP, X: typing.Optional[torch.Tensor], group=None, n_total=None, peer_cache=None):
         _lib.require_device()
         self.lib = _lib.load()
         self.model = model
@@ -195,6 +195,7 @@ class _MlpEngine:
         self.ws = torch.empty(self.lib.dagma_large_workspace_bytes(d) // 8 + 8, **f64)
         self.group, self.graph = group, None
         self.one_kernel = False
+        self._peer = None
         # NCCL all-reduces are captured inside the iteration graph (DAGMA_GRAPH_NCCL=0: eager launches)
         self._graph_collectives = False
         if group is not None:
@@ -221,9 +222,26 @@ class _MlpEngine:
             self.kws = torch.empty(148 * P * d + 8, **f64)
             # [d, m1, 1] on one GPU: the whole iteration (and every iteration up to the next checkpoint) as one
             # persistent kernel, csrc/mlp_iter.cu (DAGMA_MLP_FUSED=0: the launch sequence below, replayed as a graph)
+            # Rows sharded over the GPUs of one box: the same kernel on every GPU, the gradient sums and S summed INSIDE it
+            # over NVLink peer memory (DAGMA_MLP_PEER=0: launch sequence + NCCL all-reduces)
             import os
-            self.one_kernel = (self.fused and group is None and os.environ.get("DAGMA_MLP_FUSED", "1") != "0"
+            self.one_kernel = (self.fused and os.environ.get("DAGMA_MLP_FUSED", "1") != "0"
                                and bool(self.lib.dagma_mlp_iter_supported(self.n, d, self.m1)))
+            if group is not None:
+                # the exchange buffers outlive the engine (DagmaNonlinear re-creates it per minimize call, Q13): they
+                # are created once per (shape, group) and handed on through `peer_cache`; every rank decides alike
+                from ._peer import PeerExchange
+                import torch.distributed as dist
+                want = self.one_kernel and os.environ.get("DAGMA_MLP_PEER", "1") != "0"
+                key = (d, self.m1, dist.get_world_size(group))
+                cache = peer_cache if peer_cache is not None else {}
+                if key not in cache:
+                    nbytes = self.lib.dagma_mlp_iter_exchange_bytes(d, self.m1, key[2]) if self.fused else 0
+                    cache[key] = PeerExchange.create(group, nbytes, torch.device("cuda", torch.cuda.current_device()), True)
+                ok = PeerExchange._agree(group, torch.device("cuda", torch.cuda.current_device()),
+                                         want and cache[key] is not None)
+                self._peer = cache[key] if ok else None
+                self.one_kernel = self._peer is not None
             if self.one_kernel:
                 self.iter_ws = torch.empty(self.lib.dagma_mlp_iter_workspace_doubles(self.n, d, self.m1), **f64)
                 self.iter_sync = torch.zeros(4, dtype=torch.int32, device="cuda")
@@ -348,6 +366,13 @@ class _MlpEngine:
             torch.distributed.all_reduce(self.grads, group=self.group)
 
     def replay(self, s: float, n: int):
+        if self.one_kernel and self._peer is not None:
+            _lib.check(self.lib.dagma_mlp_iter_sharded_f64(
+                _lib.stream_ptr(), self.n, self.n_total, self.d, self.m1, int(n), self.state.data_ptr(),
+                self.theta.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.X.data_ptr(), self.iter_ws.data_ptr(),
+                self.Minv.data_ptr(), self.iter_sync.data_ptr(), self._peer.rank, self._peer.world, self._peer.ptrs),
+                "dagma_mlp_iter_sharded_f64")
+            return
         if self.one_kernel:
             _lib.check(self.lib.dagma_mlp_iter_f64(
                 _lib.stream_ptr(), self.n, self.n_total, self.d, self.m1, int(n), self.state.data_ptr(),
@@ -416,7 +441,9 @@ class DagmaNonlinear:
     def minimize(self, max_iter: float, lr: float, lambda1: float, lambda2: float, mu: float, s: float,
                  lr_decay: float = False, tol: float = 1e-6, pbar=None) -> bool:
         self.vprint(f'\nMinimize s={s} -- lr={lr}')
-        eng = _MlpEngine(self.model, self.X, self.group, self.n_total)     # optimizer re-created (Q13)
+        if getattr(self, "_peer_cache", None) is None:
+            self._peer_cache = {}
+        eng = _MlpEngine(self.model, self.X, self.group, self.n_total, peer_cache=self._peer_cache)   # optimizer re-created (Q13)
         sh = eng.state_host
         sh.zero_()
         for f, val in ((F_MU, mu), (F_S, s), (F_LR, lr), (F_LAM1, lambda1), (F_LAM2, lambda2), (F_B1, 0.99),
@@ -448,6 +475,14 @@ class DagmaNonlinear:
         if pbar is not None:
             pbar.update(max_iter)
         return ok
+
+    def close(self) -> None:
+        """Release the NVLink peer mappings of a row-sharded model (collective over the group; optional otherwise)."""
+        cache, self._peer_cache = getattr(self, "_peer_cache", None) or {}, {}
+        self._engine = None
+        for px in cache.values():
+            if px is not None:
+                px.close()
 
     def fit(self, X: typing.Union[torch.Tensor, np.ndarray], lambda1: float = .02, lambda2: float = .005,
             T: int = 4, mu_init: float = .1, mu_factor: float = .1, s: float = 1.0, warm_iter: int = 5e4,

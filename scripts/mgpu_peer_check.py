@@ -83,6 +83,80 @@ for mult in (1, 2, 4, 8):
     if rank == 0:
         print(f"d=100 n={n} on {ws} GPUs: sharded ({k_p}) {t_p:.1f} us/iter | sharded NCCL ({k_n}) {t_n:.1f} | one GPU ({k_1}) "
               f"{t_1:.1f} | |dW| vs one GPU {np.abs(W_p - W_1).max():.1e}", flush=True)
+# ---- the MLP (DagmaNonlinear, dims [d, m1, 1]): the same exchange inside csrc/mlp_iter.cu
+from midagma_b200.nonlinear import DagmaMLP, DagmaNonlinear
+
+
+def mlp_fit(Xn, mode, dims, **kw):
+    os.environ["DAGMA_MLP_PEER"] = "1" if mode == "peer" else "0"
+    torch.manual_seed(0)
+    model = DagmaMLP(dims)
+    eq = DagmaNonlinear(model)
+    Xl = Xn
+    if mode != "one":
+        eq.group, eq.n_total = dist.group.WORLD, Xn.shape[0]
+        Xl = Xn[parallel.row_shard(Xn.shape[0], rank, ws)]
+    A = eq.fit(Xl, w_threshold=0.0, **kw)
+    used = eq._engine is not None and eq._engine._peer is not None
+    eq.close()
+    return A, used
+
+
+for d, m1, n in ((12, 4, 1001), (40, 10, 2000)):
+    Xn, _ = simulate.config_c3(seed=0, n=n, d=d)
+    kw = dict(lambda1=0.02, lambda2=0.005, T=2, warm_iter=120, max_iter=150, checkpoint=50)
+    A_one, _ = mlp_fit(Xn, "one", [d, m1, 1], **kw)
+    A_peer, used = mlp_fit(Xn, "peer", [d, m1, 1], **kw)
+    A_nccl, used0 = mlp_fit(Xn, "nccl", [d, m1, 1], **kw)
+    assert used and not used0, (used, used0)
+    e1, e2 = np.abs(A_peer - A_one).max(), np.abs(A_peer - A_nccl).max()
+    t = torch.from_numpy(np.ascontiguousarray(A_peer)).cuda()
+    allw = [torch.empty_like(t) for _ in range(ws)]
+    dist.all_gather(allw, t)
+    same = all(torch.equal(allw[0], a) for a in allw)
+    if rank == 0:
+        print(f"MLP parity [{d}, {m1}, 1] n={n}: |dA| peer vs one GPU {e1:.2e}, peer vs NCCL sequence {e2:.2e}, replicas identical: {same}",
+              flush=True)
+    assert e1 < 1e-9 and e2 < 1e-9 and same
+
+
+def mlp_time(Xn, mode, iters):
+    os.environ["DAGMA_MLP_PEER"] = "1" if mode == "peer" else "0"
+    d = Xn.shape[1]
+    torch.manual_seed(0)
+    model = DagmaMLP([d, 10, 1])
+    eq = DagmaNonlinear(model)
+    Xl = Xn
+    if mode != "one":
+        eq.group, eq.n_total = dist.group.WORLD, Xn.shape[0]
+        Xl = Xn[parallel.row_shard(Xn.shape[0], rank, ws)]
+    eq.X = torch.from_numpy(np.ascontiguousarray(Xl)).cuda()
+    if mode == "one":
+        eq.n_total = Xn.shape[0]
+    eq.checkpoint = 10 ** 9
+    eq.minimize(100, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    eq.minimize(iters, 2e-4, 0.02, 0.005, 0.1, 1.0, tol=0.0)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eng = eq._engine
+    kind = "peer kernel" if eng._peer is not None else ("one kernel" if eng.one_kernel else "launch sequence")
+    eq.close()
+    return t.item() / iters * 1e6, kind
+
+
+X3, _ = simulate.config_c3(0)
+for mult in (1, 4, 16):
+    Xn = np.tile(X3, (mult, 1))
+    t_p, k_p = mlp_time(Xn, "peer", 1000)
+    t_n, k_n = mlp_time(Xn, "nccl", 1000)
+    t_1, k_1 = mlp_time(Xn, "one", 1000)
+    if rank == 0:
+        print(f"MLP [40, 10, 1] n={Xn.shape[0]} on {ws} GPUs: sharded ({k_p}) {t_p:.1f} us/iter | sharded NCCL ({k_n}) {t_n:.1f} | "
+              f"one GPU ({k_1}) {t_1:.1f}", flush=True)
 dist.barrier()
 import gc
 gc.collect()
