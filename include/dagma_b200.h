@@ -212,6 +212,9 @@ int dagma_peer_free(void* dev);
 int dagma_peer_export(void* dev, unsigned char* handle_out);
 int dagma_peer_import(const unsigned char* handle, void** out_dev);
 int dagma_peer_release(void* imported_dev);
+/* a non-blocking stream of its own for one lane of a mid-d batch (midagma_b200.linear._run_lanes)                     */
+int dagma_stream_create(void** out_stream);
+int dagma_stream_destroy(void* stream);
 /* checkpoint reductions: l2 score 1/2 tr((I-W)^T cov (I-W)) and sum|W|   linear.py:85-87, 129 */
 int dagma_linear_objective_f64(dagma_stream_t stream, int d, void* state_dev, const double* w_dev,
                                const double* t_dev, const double* cov_dev, int l2);

@@ -80,6 +80,8 @@ EXPORTS = {
     "dagma_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dagma_peer_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dagma_peer_release": (C.c_int, [C.c_void_p]),
+    "dagma_stream_create": (C.c_int, [C.c_void_p]),
+    "dagma_stream_destroy": (C.c_int, [C.c_void_p]),
     "dagma_linear_objective_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int]),
     "dagma_linear_objective_workspace_bytes": (C.c_size_t, []),

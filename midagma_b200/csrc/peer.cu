@@ -46,3 +46,19 @@ extern "C" int dagma_peer_release(void* imported_dev) {
     if (imported_dev) DAGMA_CUDA_OK(cudaIpcCloseMemHandle(imported_dev));
     return 0;
 }
+
+// A stream of its own for a batch lane (linear._run_lanes): created when the lane starts, so that consecutive lanes get
+// consecutive hardware work queues -- streams handed out by a framework's pool were created long before, interleaved
+// with other streams, and several of them can share a queue, which serialises the lanes' long persistent kernels.
+extern "C" int dagma_stream_create(void** out_stream) {
+    DAGMA_REQUIRE(out_stream, "null pointer");
+    cudaStream_t st = nullptr;
+    DAGMA_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *out_stream = (void*)st;
+    return 0;
+}
+
+extern "C" int dagma_stream_destroy(void* stream) {
+    if (stream) DAGMA_CUDA_OK(cudaStreamDestroy((cudaStream_t)stream));
+    return 0;
+}

@@ -318,15 +318,24 @@ def _run_lanes(batch: int, d: int, solve, device) -> None:
         for b in range(batch):
             solve(b)
         return
+    import ctypes as C
     import threading
+    lib = _lib.load()
     main = torch.cuda.current_stream()
     todo = iter(range(batch))
     lock = threading.Lock()
     errors = []
+    # one fresh stream per lane, created back to back: consecutive hardware work queues (streams from torch's pool were
+    # created long ago, interleaved with others; several can share a queue and serialise the lanes' persistent kernels)
+    raw = []
+    for _ in range(lanes):
+        p = C.c_void_p()
+        _lib.check(lib.dagma_stream_create(C.byref(p)), "dagma_stream_create")
+        raw.append(p)
 
-    def lane():
+    def lane(k):
         torch.cuda.set_device(device)
-        st = torch.cuda.Stream(device=device)
+        st = torch.cuda.ExternalStream(raw[k].value, device=device)
         st.wait_stream(main)
         with torch.cuda.stream(st):
             while not errors:
@@ -340,11 +349,14 @@ def _run_lanes(batch: int, d: int, solve, device) -> None:
                     errors.append(e)
             st.synchronize()
 
-    threads = [threading.Thread(target=lane, daemon=True) for _ in range(lanes)]
+    threads = [threading.Thread(target=lane, args=(k,), daemon=True) for k in range(lanes)]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
+    torch.cuda.synchronize()
+    for p in raw:
+        lib.dagma_stream_destroy(p)
     if errors:
         raise errors[0]
 

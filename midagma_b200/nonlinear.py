@@ -389,9 +389,8 @@ class _MlpEngine:
             torch.cuda.synchronize()
             for dst, src in zip((self.theta, self.m, self.v, self.state), snap):
                 dst.copy_(src)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.iteration(s)
+            from ._large import capture_graph
+            self.graph = capture_graph(lambda: self.iteration(s))
         for _ in range(n):
             self.graph.replay()
 
