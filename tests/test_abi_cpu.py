@@ -96,3 +96,25 @@ def test_mlp_without_bias_fails_like_the_reference():
         DagmaMLP([5, 4, 1], bias=False)
     lc = LocallyConnected(5, 4, 3, bias=False)
     assert lc.bias is None and lc.weight.shape == (5, 4, 3)
+
+
+def test_batch_lanes_and_value_checks_on_cpu(monkeypatch):
+    """Host-side decisions that need no device: how many problems of a mid-d batch run side by side, and the input
+    checks of utils.count_accuracy (src/dagma/utils.py:269-278)."""
+    import numpy as np
+    from midagma_b200 import utils
+    from midagma_b200.linear import _batch_lanes
+    monkeypatch.delenv("DAGMA_BATCH_LANES", raising=False)
+    assert _batch_lanes(200, 16) == 1                      # beyond d = 128 the blocked inverse fills the device
+    monkeypatch.setenv("DAGMA_BATCH_LANES", "3")
+    assert _batch_lanes(100, 16) == 3 and _batch_lanes(100, 2) == 2
+    B = np.zeros((4, 4), dtype=np.int64)
+    B[0, 1] = 1
+    assert utils._check_values(B) is False
+    B[1, 2] = -1
+    assert utils._check_values(B) is True
+    B[2, 1] = -1
+    with pytest.raises(ValueError, match="only appear once"):
+        utils._check_values(B)
+    with pytest.raises(ValueError, match="value in"):
+        utils._check_values(2 * np.abs(B))
