@@ -191,3 +191,21 @@ def test_minimize_batch_beyond_onchip_size():
         m.fit(Xs[b].copy(), lambda1=float(lam[b]), T=1, warm_iter=0, max_iter=0, checkpoint=50)
         Wb, okb = m.minimize(np.zeros((d, d)), 1.0, 120, 1.0, lr=3e-4)
         assert okb and np.abs(Wb - W[b]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("d", [1, 8, 20, 48, 64])
+def test_fused_iteration_l2_small_d(monkeypatch, d):
+    """The l2 branch of the persistent kernel at d <= 64 (tensor-core sweep in the inverse CTA) -- reachable through the
+    C ABI, while DagmaLinear itself uses the on-chip fit kernel there: forced here, against the launch sequence and
+    the oracle."""
+    from midagma_b200 import DagmaLinear
+    monkeypatch.setattr(DagmaLinear, "_small_ok", lambda self: False)
+    X = _problem("l2", d, 150, 40 + d) if d > 1 else np.random.default_rng(0).normal(size=(150, 1))
+    a, _ = _run(monkeypatch, True, "l2", X, 0.02, {})
+    b, _ = _run(monkeypatch, False, "l2", X, 0.02, {})
+    o = OracleLinear("l2").prepare(X.copy(), 0.02, checkpoint=50)
+    W = np.zeros((d, d))
+    for (mu, s, iters), (Wa, oka, ita, _), (Wb, okb, itb, _) in zip(STAGES, a, b):
+        W, ok = o.minimize(W.copy(), mu, iters, s, 3e-4)
+        assert oka == okb == ok and ita == itb == o.last_iters
+        assert np.abs(Wa - Wb).max() <= 1e-11 and np.abs(Wa - W).max() <= 1e-9
