@@ -307,6 +307,24 @@ class LargeLinearEngine:
         for _ in range(n):
             self._graph.replay()
 
+    PROBE = 64       # graph path: iterations between two looks at the `halted` latch
+
+    def _replay_probed(self, s: float, n: int):
+        """``_replay`` of n iterations.  The persistent kernel leaves its loop by itself once an inverse is infeasible;
+        graph replays cannot, and every replay after the latch is a full inverse + score product that changes nothing
+        (up to checkpoint - 1 of them).  So the graph path looks at the latch every ``PROBE`` iterations -- one 80-byte
+        read-back per 64 iterations (at d = 2000: every 92 ms) -- and stops issuing replays once it is set."""
+        if self.one_kernel or n <= self.PROBE:
+            self._replay(s, n)
+            return
+        done = 0
+        while done < n:
+            k = min(self.PROBE, n - done)
+            self._replay(s, k)
+            done += k
+            if done < n and self._pull()[2]:
+                break
+
     def _snapshot(self):
         self._snap = (self.W.clone(), self.m.clone(), self.v.clone(), self.state.clone())
 
@@ -439,7 +457,7 @@ class LargeLinearEngine:
             chunk_end = min((it_done // checkpoint + 1) * checkpoint, max_iter)
             diag = None
             if telemetry is None:
-                self._replay(s, chunk_end - it_done)
+                self._replay_probed(s, chunk_end - it_done)
             else:                                # the last iteration of the chunk also reports its gradient norms
                 if chunk_end - it_done > 1:
                     self._replay(s, chunk_end - it_done - 1)

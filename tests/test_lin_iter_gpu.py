@@ -93,13 +93,15 @@ def test_fused_iteration_vs_oracle_logistic(monkeypatch):
     assert err <= 1e-9
 
 
-def test_fused_iteration_backtracking_and_failure(monkeypatch):
+@pytest.mark.parametrize("iters,checkpoint", [(30, 20), (200, 150)])
+def test_fused_iteration_backtracking_and_failure(monkeypatch, iters, checkpoint):
     """lr = 1: the inverse turns infeasible inside a launch, the kernel latches `halted`, the host halves lr exactly as
-    linear.py:230-241 and relaunches; infeasible start: untouched W, ok = False."""
+    linear.py:230-241 and relaunches; infeasible start: untouched W, ok = False.  (200, 150): the checkpoint interval is
+    longer than the launch sequence's probe interval of the latch, LargeLinearEngine._replay_probed.)"""
     d = 70
     X, _ = simulate.make_linear_problem(d, 2, 300, "ER", "gauss", 4)
-    a, ma = _run(monkeypatch, True, "l2", X, 0.0, {}, lr=1.0, stages=((1.0, 1.0, 30),), checkpoint=20)
-    b, mb = _run(monkeypatch, False, "l2", X, 0.0, {}, lr=1.0, stages=((1.0, 1.0, 30),), checkpoint=20)
+    a, ma = _run(monkeypatch, True, "l2", X, 0.0, {}, lr=1.0, stages=((1.0, 1.0, iters),), checkpoint=checkpoint)
+    b, mb = _run(monkeypatch, False, "l2", X, 0.0, {}, lr=1.0, stages=((1.0, 1.0, iters),), checkpoint=checkpoint)
     assert a[0][1] == b[0][1] and a[0][2] == b[0][2]
     assert ma._large.last_lr == mb._large.last_lr and ma._large.last_lr < 1.0
     assert np.abs(a[0][0] - b[0][0]).max() <= 1e-9
