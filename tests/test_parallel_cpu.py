@@ -73,6 +73,13 @@ def _worker(rank, ws, port, out_dir):
     loc = torch.full((len(parallel.problem_shard(7, rank, ws)), 2), float(rank))
     full = parallel.gather_problems(loc, 7)
     assert full[:, 0].tolist() == [float(p % ws) for p in range(7)]
+    # --- peer-memory exchange of the persistent kernels: the decision is collective; without NCCL every rank gets None
+    # (the engines then keep the launch sequence + all-reduce), also when only one rank does not want it
+    from midagma_b200._peer import PeerExchange
+    assert PeerExchange.create(dist.group.WORLD, 4096, "cpu", True) is None
+    assert PeerExchange.create(dist.group.WORLD, 4096, "cpu", rank == 0) is None
+    assert PeerExchange._agree(dist.group.WORLD, "cpu", True) is True
+    assert PeerExchange._agree(dist.group.WORLD, "cpu", rank == 1) is False
     dist.barrier()
     open(os.path.join(out_dir, f"ok{rank}"), "w").close()
     dist.destroy_process_group()
