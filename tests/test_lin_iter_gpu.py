@@ -35,7 +35,8 @@ def _run(monkeypatch, fused, loss, X, lam, masks, lr=3e-4, stages=STAGES, checkp
 
 @pytest.mark.parametrize("loss,d,n", [("l2", 65, 200), ("l2", 72, 300), ("l2", 100, 400), ("l2", 127, 300), ("l2", 128, 500),
                                       ("logistic", 5, 40), ("logistic", 12, 300), ("logistic", 33, 1000),
-                                      ("logistic", 64, 2000), ("logistic", 100, 3000), ("logistic", 101, 777),
+                                      ("logistic", 64, 2000), ("logistic", 70, 900), ("logistic", 88, 1500), ("logistic", 100, 3000),
+                                      ("logistic", 101, 777), ("logistic", 120, 2500),
                                       ("logistic", 128, 10584)])
 def test_fused_iteration_matches_launch_sequence(monkeypatch, loss, d, n):
     X = _problem(loss, d, n, 100 + d)
