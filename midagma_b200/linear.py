@@ -310,6 +310,9 @@ def _batch_lanes(d: int, batch: int) -> int:
     return max(1, min((sms - 12) // ctas, 8, batch))       # a dozen SMs stay free for the checkpoint kernels of all lanes
 
 
+_LANE_STREAMS: dict = {}       # device index -> raw streams of the batch lanes (created once, reused)
+
+
 def _run_lanes(batch: int, d: int, solve, device) -> None:
     """``solve(b)`` for every problem of a d > 64 batch, ``_batch_lanes`` of them at a time: one host thread and one
     CUDA stream per lane (the caller's stream is waited for first; every lane is synchronised before returning)."""
@@ -325,10 +328,12 @@ def _run_lanes(batch: int, d: int, solve, device) -> None:
     todo = iter(range(batch))
     lock = threading.Lock()
     errors = []
-    # one fresh stream per lane, created back to back: consecutive hardware work queues (streams from torch's pool were
-    # created long ago, interleaved with others; several can share a queue and serialise the lanes' persistent kernels)
-    raw = []
-    for _ in range(lanes):
+    # one stream of its own per lane, created back to back: consecutive hardware work queues (streams from torch's pool
+    # were created long ago, interleaved with others; several can share a queue and serialise the lanes' persistent
+    # kernels).  The streams live as long as the process and are reused by later batches, so the caching allocator's
+    # blocks of a lane stay usable and no stream it has seen is ever destroyed.
+    raw = _LANE_STREAMS.setdefault(torch.device(device).index or 0, [])
+    while len(raw) < lanes:
         p = C.c_void_p()
         _lib.check(lib.dagma_stream_create(C.byref(p)), "dagma_stream_create")
         raw.append(p)
@@ -354,9 +359,6 @@ def _run_lanes(batch: int, d: int, solve, device) -> None:
         t.start()
     for t in threads:
         t.join()
-    torch.cuda.synchronize()
-    for p in raw:
-        lib.dagma_stream_destroy(p)
     if errors:
         raise errors[0]
 
