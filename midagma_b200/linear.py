@@ -218,6 +218,10 @@ def minimize_batch(W, cov, lambda1, mu, max_iter, s, lr, *, tol=1e-6, beta_1=0.9
     _lib.require_device()
     device = torch.device(device or "cuda")
     on_device = isinstance(W, torch.Tensor) and W.is_cuda
+    if _host_pipeline_ok(W, cov):
+        return _minimize_batch_host_pipelined(W, cov, lambda1, mu, max_iter, s, lr, tol=tol, beta_1=beta_1, beta_2=beta_2,
+                                              checkpoint=checkpoint, device=device, exclude_edges=exclude_edges,
+                                              include_edges=include_edges)
     Wd = W if on_device and W.dtype == torch.float64 and W.is_contiguous() else _as_dev(W, device)
     covd = _as_dev(cov, device)
     batch, d, _ = covd.shape
@@ -238,6 +242,85 @@ def minimize_batch(W, cov, lambda1, mu, max_iter, s, lr, *, tol=1e-6, beta_1=0.9
     else:
         W[...] = res.W.cpu().numpy()
     return W, ok.cpu().numpy(), res.stage_stats.cpu().numpy()
+
+
+_COPY_STREAMS: dict = {}       # device index -> (H2D stream, D2H stream) of the pipelined host path
+
+
+def _host_pipeline_ok(W, cov) -> bool:
+    """Pinned host tensors of a batch that spans several waves of resident CTAs: worth overlapping the copies."""
+    import os
+    if os.environ.get("DAGMA_HOST_PIPELINE", "1") == "0":
+        return False
+    ok = all(isinstance(t, torch.Tensor) and not t.is_cuda and t.is_pinned() and t.dtype == torch.float64
+             and t.is_contiguous() and t.dim() == 3 for t in (W, cov))
+    return ok and 32 < cov.shape[1] <= _lib.SMALL_MAX_D and cov.shape[0] >= 4 * _resident_ctas()
+
+
+def _resident_ctas() -> int:
+    """CTAs of the tensor-core fit kernel that are resident at once (two per SM)."""
+    return 2 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
+def _minimize_batch_host_pipelined(W, cov, lambda1, mu, max_iter, s, lr, *, tol, beta_1, beta_2, checkpoint, device,
+                                   exclude_edges, include_edges):
+    """``minimize_batch`` on pinned host buffers with the copies hidden behind the kernel: the batch is cut into chunks of
+    whole waves of resident CTAs (a chunk of k x 296 equal-length problems takes k wave-times whether it is launched
+    alone or as part of the batch), H2D of chunk c + 1 and D2H of chunk c - 1 run on copy streams while chunk c
+    computes.  What stays exposed is the H2D of a first, short chunk and the D2H of the last one."""
+    batch, d, _ = cov.shape
+    wave = _resident_ctas()
+    bounds, lo = [], 0
+    for size in [2 * wave] + [4 * wave] * (batch // wave):
+        if lo >= batch:
+            break
+        hi = min(batch, lo + size)
+        if batch - hi < wave:                     # no sliver at the end
+            hi = batch
+        bounds.append((lo, hi))
+        lo = hi
+    lam = _lam_dev(lambda1, batch, device)
+    mask_exc, mask_inc = _batch_masks(exclude_edges, include_edges, d, device)
+    cur = torch.cuda.current_stream()
+    key = torch.device(device).index or 0
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = (torch.cuda.Stream(), torch.cuda.Stream())
+    s_in, s_out = _COPY_STREAMS[key]
+    # the device buffers come from the CALLER's stream pool (reused from call to call: a buffer allocated under a copy
+    # stream would be a fresh cudaMalloc every time); the copy streams are told about them with record_stream
+    Wall = torch.empty(batch, d, d, dtype=torch.float64, device=device)
+    call = torch.empty(batch, d, d, dtype=torch.float64, device=device)
+    Wall.record_stream(s_in)
+    Wall.record_stream(s_out)
+    call.record_stream(s_in)
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    bufs, results = [], []
+    with torch.cuda.stream(s_in):                 # every H2D is queued up front; the chunks' kernels wait for their event
+        for lo, hi in bounds:
+            Wd, cd = Wall[lo:hi], call[lo:hi]
+            Wd.copy_(W[lo:hi], non_blocking=True)
+            cd.copy_(cov[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+            bufs.append((Wd, cd, ev))
+    for (lo, hi), (Wd, cd, ev) in zip(bounds, bufs):
+        cur.wait_event(ev)
+        res = _run_small(cd, Wd, lam[lo:hi].contiguous(), [mu], [s], [int(max_iter)], lr=lr, tol=tol, beta1=beta_1,
+                         beta2=beta_2, checkpoint=checkpoint, retry=False, want_final=False, mask_exc=mask_exc,
+                         mask_inc=mask_inc)
+        done = torch.cuda.Event()
+        done.record(cur)
+        s_out.wait_event(done)
+        with torch.cuda.stream(s_out):
+            W[lo:hi].copy_(Wd, non_blocking=True)
+        results.append(res)
+    cur.wait_stream(s_out)
+    status = torch.cat([r.status for r in results])
+    stats = torch.cat([r.stage_stats for r in results])
+    ok = ((status & _lib.ST_OUT_OF_DOMAIN) == 0).cpu().numpy()        # (synchronises: every copy has landed)
+    torch.cuda.current_stream().synchronize()
+    return W, ok, stats.cpu().numpy()
 
 
 def fit_batch(X=None, lambda1=0.03, *, cov=None, w_threshold=0.3, T=5, mu_init=1.0, mu_factor=0.1,

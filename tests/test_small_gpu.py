@@ -195,3 +195,26 @@ def test_fit_retry_path():
     assert int(m.stage_stats[:, 6].sum()) == len(fails)
     assert abs(s_list[1] - (0.3 + 0.1 * m.stage_stats[1, 6])) < 1e-12      # caller's list mutated (Q9)
     assert simulate.edge_set_distance(W, W_ref) == 0
+
+
+def test_minimize_batch_host_pipeline(monkeypatch):
+    """Pinned host buffers of a batch of several waves: the copies are hidden behind the kernel chunk by chunk
+    (linear._minimize_batch_host_pipelined) -- bit for bit the result of copy / launch / copy."""
+    import torch
+    from midagma_b200 import minimize_batch
+    from midagma_b200.linear import _resident_ctas, _host_pipeline_ok
+    d, batch = 40, 4 * _resident_ctas() + 37
+    rng = np.random.default_rng(0)
+    Xs = rng.normal(size=(16, 120, d))
+    cov16 = np.einsum("bni,bnj->bij", Xs, Xs) / 120
+    cov = torch.from_numpy(np.ascontiguousarray(np.tile(cov16, (batch // 16 + 1, 1, 1))[:batch])).pin_memory()
+    lam = np.linspace(0.01, 0.05, batch)
+    outs = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DAGMA_HOST_PIPELINE", mode)
+        W = torch.zeros(batch, d, d, dtype=torch.float64).pin_memory()
+        assert _host_pipeline_ok(W, cov) == (mode == "1")
+        Wr, ok, st = minimize_batch(W, cov, lam, 1.0, 60, 1.0, 3e-4, checkpoint=20)
+        assert Wr is W and ok.all() and st.shape == (batch, 1, 8) and (st[:, 0, 0] == 60).all()
+        outs.append(W.clone())
+    assert torch.equal(outs[0], outs[1]) and float(outs[0].abs().max()) > 0.0
