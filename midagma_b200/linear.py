@@ -262,16 +262,12 @@ def _resident_ctas() -> int:
     return 2 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
 
 
-def _minimize_batch_host_pipelined(W, cov, lambda1, mu, max_iter, s, lr, *, tol, beta_1, beta_2, checkpoint, device,
-                                   exclude_edges, include_edges):
-    """``minimize_batch`` on pinned host buffers with the copies hidden behind the kernel: the batch is cut into chunks of
-    whole waves of resident CTAs (a chunk of k x 296 equal-length problems takes k wave-times whether it is launched
-    alone or as part of the batch), H2D of chunk c + 1 and D2H of chunk c - 1 run on copy streams while chunk c
-    computes.  What stays exposed is the H2D of a first, short chunk and the D2H of the last one."""
-    batch, d, _ = cov.shape
-    wave = _resident_ctas()
+def _pipeline_chunks(batch: int, wave: int) -> list:
+    """[lo, hi) ranges of the pipelined host path: a first chunk of two waves of resident CTAs (its H2D is the part of
+    the copies that stays exposed), then chunks of four waves; a remainder of less than one wave joins the chunk in
+    front of it.  Whole waves: k x `wave` equal-length problems take k wave-times alone or as part of the batch."""
     bounds, lo = [], 0
-    for size in [2 * wave] + [4 * wave] * (batch // wave):
+    for size in [2 * wave] + [4 * wave] * (batch // max(wave, 1) + 1):
         if lo >= batch:
             break
         hi = min(batch, lo + size)
@@ -279,6 +275,17 @@ def _minimize_batch_host_pipelined(W, cov, lambda1, mu, max_iter, s, lr, *, tol,
             hi = batch
         bounds.append((lo, hi))
         lo = hi
+    return bounds
+
+
+def _minimize_batch_host_pipelined(W, cov, lambda1, mu, max_iter, s, lr, *, tol, beta_1, beta_2, checkpoint, device,
+                                   exclude_edges, include_edges):
+    """``minimize_batch`` on pinned host buffers with the copies hidden behind the kernel: the batch is cut into chunks of
+    whole waves of resident CTAs (a chunk of k x 296 equal-length problems takes k wave-times whether it is launched
+    alone or as part of the batch), H2D of chunk c + 1 and D2H of chunk c - 1 run on copy streams while chunk c
+    computes.  What stays exposed is the H2D of a first, short chunk and the D2H of the last one."""
+    batch, d, _ = cov.shape
+    bounds = _pipeline_chunks(batch, _resident_ctas())
     lam = _lam_dev(lambda1, batch, device)
     mask_exc, mask_inc = _batch_masks(exclude_edges, include_edges, d, device)
     cur = torch.cuda.current_stream()

@@ -118,3 +118,15 @@ def test_batch_lanes_and_value_checks_on_cpu(monkeypatch):
         utils._check_values(B)
     with pytest.raises(ValueError, match="value in"):
         utils._check_values(2 * np.abs(B))
+
+
+def test_pipeline_chunks():
+    """Chunks of the copy / compute pipeline of minimize_batch: whole waves, contiguous, complete, no sliver."""
+    from midagma_b200.linear import _pipeline_chunks
+    w = 296
+    assert _pipeline_chunks(4096, w) == [(0, 592), (592, 1776), (1776, 2960), (2960, 4096)]
+    for batch in (4 * w, 4 * w + 1, 5 * w - 1, 6 * w, 6 * w + 7, 10 * w + 295, 32768, 1):
+        b = _pipeline_chunks(batch, w)
+        assert b[0][0] == 0 and b[-1][1] == batch and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert all((hi - lo) % w == 0 for lo, hi in b[:-1])
+        assert all(hi - lo >= min(w, batch) for lo, hi in b)
